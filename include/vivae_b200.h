@@ -1,0 +1,142 @@
+/*
+ * vivae_b200 -- C ABI of the B200-native (sm_100a) ViVAE hot path.
+ *
+ * The reference (saeyslab/ViVAE) is pure Python and has no FFI layer; its
+ * boundary for this path is three Python call sites.  Each entry point below
+ * names the reference interface it replaces (file:line in /root/reference).
+ * The binding a reference maintainer would add is a ctypes stub; see
+ * INTEGRATION.md.  Plain pointers and sizes only -- no torch / C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative VVB_E* code;
+ *     vvb_last_error() gives the message for the calling thread.
+ *   - "*_host" functions take HOST pointers, do their own device allocation,
+ *     H2D / D2H copies and synchronise before returning (the drop-in path).
+ *   - "*_device" functions take DEVICE pointers on the current CUDA device,
+ *     enqueue work on `stream` (a cudaStream_t passed as void*, NULL = legacy
+ *     default stream) and do NOT synchronise unless stated.
+ *   - matrices are dense row-major; `n` rows, `d` columns.
+ */
+#ifndef VIVAE_B200_H
+#define VIVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VVB_OK 0
+#define VVB_EINVAL (-1)   /* bad argument (maps to Python ValueError)            */
+#define VVB_ECUDA (-2)    /* CUDA runtime error (maps to Python RuntimeError)    */
+#define VVB_ENOMEM (-3)   /* host or device allocation failed                    */
+#define VVB_ENOTSUP (-4)  /* valid request outside the implemented envelope      */
+
+/* kNN algorithm selector */
+#define VVB_KNN_AUTO 0    /* tensor-core screening + FP32 re-rank + certify/fallback */
+#define VVB_KNN_BRUTE 1   /* FP32 FFMA brute force (the exactness fallback, usable on its own) */
+#define VVB_KNN_TENSOR 2  /* force the tensor-core path (error if unsupported shape) */
+
+/* smooth() sweep semantics */
+#define VVB_SMOOTH_GAUSS_SEIDEL 0 /* the reference's in-place sweep (knn.py:173-184) */
+#define VVB_SMOOTH_JACOBI 1       /* every row reads the previous sweep (NOT the reference) */
+
+/* quartet-loss distance functions (losses.py:140-177) */
+#define VVB_DIST_EUCLIDEAN 0
+#define VVB_DIST_COSINE 1
+
+/* counters filled by the kNN entry points (all optional: pass NULL) */
+typedef struct vvb_knn_stats {
+  int64_t rows;            /* query rows processed                                  */
+  int64_t rows_fallback;   /* rows whose certificate failed and were recomputed by
+                              the FP32 brute-force kernel                           */
+  int32_t algo_used;       /* VVB_KNN_BRUTE or VVB_KNN_TENSOR                       */
+  int32_t candidates;      /* m: candidates kept per row by the screening kernel    */
+  float ms_prepare;        /* device time, operand preparation (centre/scale/split) */
+  float ms_screen;         /* device time, tensor-core distance GEMM + select       */
+  float ms_rerank;         /* device time, FP32 re-rank + certify                   */
+  float ms_fallback;       /* device time, brute-force fallback                     */
+  int64_t kernel_launches; /* kernels launched by this call                         */
+} vvb_knn_stats;
+
+int vvb_version(void);
+const char *vvb_last_error(void);
+/* number of kernels launched by this library in the calling process so far */
+int64_t vvb_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * make_knn  -- replaces the cache-miss branch of
+ *   /root/reference/src/vivae/knn.py:133-141
+ *   (pynndescent.NNDescent(x, n_neighbors=k+1).query(x, k=k+1), int64 cast,
+ *    correct_knn_for_duplicates), made EXACT:
+ *   for every query row i, all rows j != i ranked by the FP32 key (d2(i,j), j),
+ *   d2 = left-to-right fmaf chain over coordinates of (x_ic - x_jc)^2;
+ *   column 0 is i itself with distance 0; dist = sqrtf(d2).
+ *
+ *   x        (n, d) float32, row-major           -- the database AND the query set
+ *   q0, nq   query rows [q0, q0+nq) (row sharding; q0=0,nq=n for everything)
+ *   idx_out  (nq, k+1) int64   -- global row indices, like knn.py:137
+ *   dist_out (nq, k+1) float32 -- knn.py:135-136 leaves distances float32
+ * ------------------------------------------------------------------------ */
+int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, int64_t nq,
+                      int algo, int64_t *idx_out_host, float *dist_out_host, vvb_knn_stats *stats);
+
+/* bytes of device workspace vvb_make_knn_device needs for these sizes */
+int vvb_make_knn_workspace_bytes(int64_t n, int d, int k, int64_t nq, int algo, size_t *bytes);
+
+/* same contract with device-resident buffers; synchronises `stream` before
+ * returning only if `stats` is non-NULL (the timings need it). */
+int vvb_make_knn_device(const float *x_dev, int64_t n, int d, int k, int64_t q0, int64_t nq,
+                        int algo, int64_t *idx_out_dev, float *dist_out_dev, void *workspace_dev,
+                        size_t workspace_bytes, void *stream, vvb_knn_stats *stats);
+
+/* ------------------------------------------------------------------------
+ * smooth -- replaces the sweep loop of /root/reference/src/vivae/knn.py:173-185
+ *   (argument validation and ensure_valid_knn, knn.py:165-171, stay in Python).
+ *   Row i moves by `coef` toward the mean of rows idx[i, 0:k]; in
+ *   VVB_SMOOTH_GAUSS_SEIDEL mode rows j < i are read already-updated, exactly
+ *   as the reference's aliased in-place loop does.  Arithmetic per element:
+ *   sequential sum in neighbour order, true divide by k, then
+ *   r + (target - r) * coef as three separately rounded operations.
+ *
+ *   elem_size 4 = float32, 8 = float64 (dtype follows x, like the reference)
+ *   idx (n, ld_idx) int64, ld_idx >= k ; out (n, d) same dtype, must not alias x
+ * ------------------------------------------------------------------------ */
+int vvb_smooth_host(const void *x_host, int elem_size, int64_t n, int d, const int64_t *idx_host,
+                    int64_t ld_idx, int k, double coef, int n_iter, int mode, void *out_host);
+
+int vvb_smooth_workspace_bytes(int elem_size, int64_t n, int d, int n_iter, size_t *bytes);
+
+int vvb_smooth_device(const void *x_dev, int elem_size, int64_t n, int d, const int64_t *idx_dev,
+                      int64_t ld_idx, int k, double coef, int n_iter, int mode, void *out_dev,
+                      void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
+ * quartet ("stochastic MDS") loss -- replaces MDSLoss.__call__,
+ *   /root/reference/src/vivae/losses.py:266-349, and its autograd backward.
+ *
+ *   x (B, D) float32, z (B, L) float32 on the device.
+ *   perms: n_sampling device pointers (array on the HOST) to int64 permutations
+ *          of range(B); a NULL entry means identity (losses.py:328-331).
+ *   loss_out : device float32 scalar  = mean over passes of (B/nq) * mean_q cost_q
+ *   grad_unit: device (B, L) float32 or NULL -- d(loss)/dz for grad_output = 1
+ *              (rows 4*nq..B-1 get 0).
+ *   workspace: at least vvb_quartet_workspace_bytes(B) bytes.
+ *   B < 4 gives NaN like the reference (mean over zero quartets).
+ * ------------------------------------------------------------------------ */
+size_t vvb_quartet_workspace_bytes(int64_t B);
+
+int vvb_quartet_loss_fwd_device(const float *x_dev, const float *z_dev, int64_t B, int D, int L,
+                                const int64_t *const *perms, int n_sampling, int metric_hd,
+                                int metric_ld, float *loss_out_dev, float *grad_unit_dev,
+                                void *workspace_dev, void *stream);
+
+/* grad_z = grad_unit * (*grad_out_dev)   (grad_out is the upstream 0-dim gradient) */
+int vvb_quartet_loss_bwd_device(const float *grad_unit_dev, const float *grad_out_dev, int64_t count,
+                                float *grad_z_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIVAE_B200_H */

@@ -183,6 +183,26 @@ def gen_fit(vv):
     print("fit_a:", buf.getvalue().strip().splitlines()[-1])
 
 
+def gen_fit_cpu(vv):
+    """Seeded CPU `fit` WITHOUT the quartet term: exercises loader / optimiser / loss
+    bookkeeping only, so the product's host-side training loop can be compared bit for
+    bit on a CPU-only box (no custom kernel involved)."""
+    import io
+    from contextlib import redirect_stdout
+
+    X = mixture(300, 9, 4, seed=21)
+    model = vv.ViVAE(input_dim=9, latent_dim=2, random_state=5)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        model.fit(X, n_epochs=3, batch_size=64, lam_mds=0.0, lam_kldiv=0.5, verbose=True)
+    emb = model.transform(X)
+    emb_b = model.transform(X, batch_size=100)
+    assert np.array_equal(emb, emb_b) or np.allclose(emb, emb_b, atol=1e-6)
+    np.savez_compressed(os.path.join(GOLD, "fit_cpu_nomds.npz"), X=X, emb=emb, log=buf.getvalue(),
+                        keys=np.array(list(model.net.state_dict().keys())))
+    print("fit_cpu_nomds:", buf.getvalue().strip().splitlines()[-1])
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     orc.build()
@@ -191,6 +211,7 @@ def main():
     gen_quartet(vv)
     gen_validators(vv)
     gen_fit(vv)
+    gen_fit_cpu(vv)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,177 @@
+"""CPU tests: the C-ABI library loads and exports what include/vivae_b200.h declares
+(no compute call is made), and the host-side mirror of the reference API behaves like
+the reference (validators, error messages, state_dict layout, training bookkeeping)."""
+
+import ctypes
+import io
+import os
+import re
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+import vivae_b200 as vv
+from vivae_b200 import _lib
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "vivae_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vvb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _header_functions()
+    assert len(names) >= 12
+    assert os.path.isfile(_lib.LIB_PATH), "libvivae_b200.so not built (run __graft_entry__.build())"
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for nm in names:
+        assert hasattr(raw, nm), f"{nm} declared in the header but not exported"
+    assert sorted(_lib.SYMBOLS) == names, "ctypes table and header disagree"
+    lib = _lib.load()
+    assert lib.vvb_version() >= 100
+    assert lib.vvb_launch_count() == 0 or lib.vvb_launch_count() > 0
+
+
+def test_library_is_sm100a_with_native_code():
+    # the .so must carry sm_100a SASS (no PTX-only / other-arch build)
+    import subprocess
+
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cuda_means_loud_failure_not_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    x = np.random.default_rng(0).standard_normal((64, 4)).astype(np.float32)
+    with pytest.raises(RuntimeError):
+        vv.make_knn(x, k=5, verbose=False)
+    idx = np.tile(np.arange(64)[:, None], (1, 6))
+    dist = np.zeros((64, 6), dtype=np.float32)
+    with pytest.raises(RuntimeError):
+        vv.smooth(x, [idx, dist], k=5, coef=1.0)
+    z = torch.zeros(8, 2, requires_grad=True)
+    with pytest.raises(RuntimeError):
+        vv.MDSLoss()(torch.zeros(8, 4), z)
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "vivae_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("brute-force oracle", ""), f"{f} mentions the oracle"
+
+
+# ------------------------------------------------------------------ argument errors
+def test_make_knn_and_smooth_argument_errors_match_reference_messages():
+    x = np.zeros((10, 3), dtype=np.float32)
+    for bad_k in (0, 10, 11):
+        with pytest.raises(ValueError, match=r"`k` must be between 1 and \(n-1\)"):
+            vv.make_knn(x, k=bad_k, verbose=False)
+    idx = np.tile(np.arange(10)[:, None], (1, 4))
+    dist = np.zeros((10, 4), dtype=np.float32)
+    knn = [idx, dist]
+    with pytest.raises(ValueError, match=r"`k` must be between 1 and \(n-1\)"):
+        vv.smooth(x, knn, k=10)
+    with pytest.raises(ValueError, match="`coef` must be more than 0. and at most 1."):
+        vv.smooth(x, knn, k=3, coef=1.5)
+    with pytest.raises(ValueError, match="`n_iter` must be at least 1 and at most 10000"):
+        vv.smooth(x, knn, k=3, coef=0.5, n_iter=0)
+    with pytest.raises(TypeError):  # knn.py:167 compares None < 0. before anything else
+        vv.smooth(x, knn, k=3, coef=None)
+    with pytest.raises(ValueError, match="list of 2 np.ndarray"):
+        vv.smooth(x, [idx], k=3, coef=0.5)
+    with pytest.raises(ValueError, match="as many rows"):
+        vv.smooth(x, [idx[:5], dist[:5]], k=3, coef=0.5)
+    with pytest.raises(ValueError, match="must include self"):
+        vv.smooth(x, [idx, dist + 1.0], k=3, coef=0.5)
+    with pytest.raises(ValueError, match="coercible to integer"):
+        vv.smooth(x, [idx.astype(np.float64) + 0.5, dist], k=3, coef=0.5)
+
+
+def test_validators_match_reference_fixture():
+    g = np.load(os.path.join(GOLDEN, "validators.npz"))
+    fixed = vv.ensure_valid_knn(50, [g["swapped"].copy(), g["dist"].copy()])
+    assert np.array_equal(fixed[0], g["fixed_idx"]) and np.array_equal(fixed[1], g["fixed_dist"])
+    fl = vv.ensure_valid_knn(50, [g["idx"].astype(np.float64), g["dist"].astype(np.float64)])
+    assert np.array_equal(fl[0], g["float_idx"]) and str(fl[0].dtype) == str(g["float_idx_dtype"])
+    ok = vv.ensure_valid_knn(50, [g["idx"].copy(), g["dist"].copy()])
+    assert np.array_equal(ok[0], g["idx"])
+    # self missing from a row: the reference raises ValueError as well
+    bad = g["idx"].copy()
+    bad[7, 0] = 8
+    with pytest.raises(ValueError):
+        vv.ensure_valid_knn(50, [bad, g["dist"].copy()])
+
+
+def test_knn_cache_file_format_round_trip(tmp_path):
+    # load branch of make_knn (knn.py:122-131): float64 (2, n, k+1) file -> int64 idx, float64 dist
+    n, k = 12, 3
+    idx = np.tile(np.arange(n)[:, None], (1, k + 1)).astype(np.int64)
+    dist = np.abs(np.random.default_rng(0).standard_normal((n, k + 1))).astype(np.float32)
+    dist[:, 0] = 0
+    f = str(tmp_path / "knn.npy")
+    np.save(f, [idx, dist])
+    raw = np.load(f)
+    assert raw.dtype == np.float64 and raw.shape == (2, n, k + 1)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        got = vv.make_knn(np.zeros((n, 2), dtype=np.float32), fname=f, k=k)
+    assert "Loading k-NNG" in buf.getvalue()
+    assert got[0].dtype == np.int64 and np.array_equal(got[0], idx)
+    assert got[1].dtype == np.float64 and np.allclose(got[1], dist)
+    assert isinstance(vv.make_knn(np.zeros((n, 2), dtype=np.float32), fname=f, k=k, as_tuple=True, verbose=False), tuple)
+
+
+# ---------------------------------------------------------------------- model side
+def test_autoencoder_layout_matches_reference_state_dict():
+    g = np.load(os.path.join(GOLDEN, "fit_cpu_nomds.npz"))
+    with torch.device("cpu"):
+        net = vv.Autoencoder(input_dim=9, latent_dim=2, hidden_dims=[32, 64, 128, 32], variational=True)
+    assert list(net.state_dict().keys()) == [str(k) for k in g["keys"]]
+    assert sum(p.numel() for p in vv.Autoencoder(50, 2, [32, 64, 128, 32], True).parameters()) == 32630
+
+
+def test_fit_errors():
+    m = vv.ViVAE(input_dim=4)
+    with pytest.raises(ValueError, match="No data to train on"):
+        m.train_epoch()
+    with pytest.raises(ValueError, match="Mismatch between data dimensionality"):
+        m.fit(np.zeros((8, 5), dtype=np.float32), n_epochs=1, verbose=False)
+    with pytest.raises(ValueError, match="Decoder geometric loss"):
+        m.fit(np.zeros((8, 4), dtype=np.float32), n_epochs=1, lam_geom=1.0, lam_recon=0.0, verbose=False)
+    assert "not trained" in str(m) and "ViVAE(input_dim=4" in repr(m)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU bit-exactness check (device RNG differs on CUDA)")
+def test_cpu_fit_without_quartet_term_is_bit_identical_to_reference():
+    """Loader order, RNG consumption, Adam, KL / MSE terms and the epoch log line
+    reproduce the reference exactly when no custom kernel is involved."""
+    g = np.load(os.path.join(GOLDEN, "fit_cpu_nomds.npz"))
+    m = vv.ViVAE(input_dim=9, latent_dim=2, random_state=5)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        m.fit(g["X"], n_epochs=3, batch_size=64, lam_mds=0.0, lam_kldiv=0.5, verbose=True)
+    assert buf.getvalue() == str(g["log"])
+    assert np.array_equal(m.transform(g["X"]), g["emb"])
+    assert np.array_equal(m.transform(g["X"], batch_size=100), g["emb"]) or np.allclose(
+        m.transform(g["X"], batch_size=100), g["emb"], atol=1e-6)
+    assert m.trained and m.decoder_active
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only variant of the reference's own smoke test")
+def test_reference_smoke_test_shape_cpu():
+    # /root/reference/tests/tests.py:5-15 with the quartet term off (it needs the GPU)
+    np.random.seed(1)
+    x = np.random.rand(50, 2).astype(np.float32)
+    model = vv.ViVAE(input_dim=x.shape[1], latent_dim=2)
+    model.fit(x, n_epochs=1, lam_recon=1.0, lam_kldiv=0.1, lam_geom=1.0, lam_egeom=1.0, lam_mds=0.0, batch_size=2,
+              verbose=False)
+    emb = model.transform(x)
+    assert emb.shape == (50, 2)

@@ -1,0 +1,340 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the
+C ABI (`vivae_b200` -> ctypes -> libvivae_b200.so), against the CPU oracle and the
+golden vectors recorded from the unmodified reference.
+
+Bars (BASELINE.json north_star): neighbour indices bit-exact; smoothed values
+bit-exact in Gauss-Seidel mode (bar: 1e-5 relative); quartet loss and gradient within
+1e-4 relative."""
+
+import glob
+import io
+import os
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as orc
+from conftest import GOLDEN
+
+import vivae_b200 as vv
+
+pytestmark = pytest.mark.gpu
+
+SMOOTH = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "smooth_*.npz")))
+QUARTET = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "quartet_*.npz")))
+
+
+def clustered(n, d, n_clusters, seed, scale=5.0):
+    """PCA-like synthetic cells: Gaussian mixture with a decaying per-dimension spectrum."""
+    rng = np.random.default_rng(seed)
+    spec = scale / np.sqrt(1.0 + np.arange(d))
+    centres = rng.standard_normal((n_clusters, d)) * spec
+    lab = rng.integers(0, n_clusters, size=n)
+    return (centres[lab] + 0.3 * spec * rng.standard_normal((n, d))).astype(np.float32)
+
+
+def tie_data(n, d, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, 4, size=(n, d)).astype(np.float32)
+    dup = rng.choice(n, size=max(2, n // 100), replace=False)
+    x[dup] = x[dup[0]]  # 1 % exact duplicates of one point
+    return x
+
+
+def assert_knn_equal(got, want):
+    gi, gd = got
+    wi, wd = want
+    assert gi.dtype == np.int64 and gd.dtype == np.float32
+    bad = np.flatnonzero((gi != wi).any(axis=1))
+    assert bad.size == 0, f"{bad.size} rows differ, first {bad[:5]}: got {gi[bad[0]]} want {wi[bad[0]]}"
+    assert np.array_equal(gd, wd), f"distances differ, max abs {np.abs(gd - wd).max()}"
+
+
+# ============================================================================ kNN
+@pytest.mark.parametrize("algo", ["brute", "auto"])
+@pytest.mark.parametrize("n,d,k,kind", [
+    (3000, 50, 50, "clustered"),
+    (2000, 38, 100, "clustered"),
+    (1500, 7, 10, "ties"),
+    (600, 3, 50, "ties"),
+    (257, 100, 17, "clustered"),   # d not a multiple of 16
+    (129, 1, 5, "gauss"),          # d = 1
+    (64, 5, 63, "gauss"),          # k = n-1
+    (2, 4, 1, "gauss"),            # smallest legal problem
+])
+def test_knn_bit_exact_vs_oracle(algo, n, d, k, kind):
+    if kind == "clustered":
+        x = clustered(n, d, 8, seed=n + d)
+    elif kind == "ties":
+        x = tie_data(n, d, seed=n + d)
+    else:
+        x = np.random.default_rng(n + d).standard_normal((n, d)).astype(np.float32)
+    st = {}
+    got = vv.make_knn(x, k=k, verbose=False, algo=algo, stats=st)
+    assert_knn_equal(got, orc.knn(x, k))
+    assert st["rows"] == n and st["kernel_launches"] >= 1
+    assert np.array_equal(got[0][:, 0], np.arange(n)) and np.all(got[1][:, 0] == 0)
+
+
+@pytest.mark.parametrize("algo", ["brute", "auto"])
+def test_knn_large_offset_data_and_float64_input(algo):
+    # un-centred data far from the origin (worst case for a GEMM-expansion distance) and
+    # float64 input (R/reticulate passes doubles): coerced to float32 like pynndescent does
+    x = clustered(4000, 50, 6, seed=3).astype(np.float64) + 1000.0
+    got = vv.make_knn(x, k=30, verbose=False, algo=algo)
+    assert_knn_equal(got, orc.knn(x.astype(np.float32), 30))
+
+
+@pytest.mark.parametrize("algo", ["brute", "auto"])
+def test_knn_many_duplicates_more_than_k(algo):
+    # 200 copies of one point with k = 20: ties at distance 0 must resolve to the LOWEST indices
+    x = clustered(1000, 10, 3, seed=9)
+    x[300:500] = x[300]
+    got = vv.make_knn(x, k=20, verbose=False, algo=algo)
+    assert_knn_equal(got, orc.knn(x, 20))
+    assert np.array_equal(got[0][450, :4], [450, 300, 301, 302])
+
+
+@pytest.mark.parametrize("algo", ["brute", "auto"])
+def test_knn_query_row_shard_through_c_abi(algo):
+    from vivae_b200.knn import _knn_host
+
+    x = clustered(5000, 50, 5, seed=12)
+    want = orc.knn(x, 25)
+    for q0, nq in ((0, 1000), (1000, 3000), (4000, 1000), (4999, 1), (17, 0)):
+        gi, gd = _knn_host(x, 25, q0, nq, algo, None)
+        assert gi.shape == (nq, 26)
+        assert np.array_equal(gi, want[0][q0:q0 + nq]) and np.array_equal(gd, want[1][q0:q0 + nq])
+
+
+def test_knn_medium_scale_properties_and_sampled_oracle():
+    """200k x 50, k=50 (too big for a full CPU oracle in seconds): size-independent
+    properties on all rows + bit-exact check of a query sample against the oracle."""
+    n, d, k = 200_000, 50, 50
+    x = clustered(n, d, 30, seed=1)
+    st = {}
+    idx, dist = vv.make_knn(x, k=k, verbose=False, stats=st)
+    assert np.array_equal(idx[:, 0], np.arange(n)) and np.all(dist[:, 0] == 0)
+    assert np.all(np.diff(dist, axis=1) >= 0)                       # sortedness
+    assert idx.min() >= 0 and idx.max() < n
+    srt = np.sort(idx, axis=1)
+    assert np.all(srt[:, 1:] != srt[:, :-1])                        # no repeated neighbour
+    rng = np.random.default_rng(0)
+    rows = rng.choice(n, 64, replace=False)
+    d_chk = np.sqrt(((x[rows, None, :].astype(np.float64) - x[idx[rows]].astype(np.float64)) ** 2).sum(-1))
+    np.testing.assert_allclose(dist[rows], d_chk, rtol=2e-6, atol=1e-6)
+    for q0 in (0, 77_777, n - 256):
+        wi, wd = orc.knn(x, k, q0, q0 + 256)
+        assert np.array_equal(idx[q0:q0 + 256], wi) and np.array_equal(dist[q0:q0 + 256], wd)
+    print("knn stats:", st)
+
+
+def test_make_knn_cache_write_then_load(tmp_path):
+    x = clustered(500, 8, 3, seed=4)
+    f = str(tmp_path / "graph.npy")
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        a = vv.make_knn(x, fname=f, k=12)
+        b = vv.make_knn(x, fname=f, k=12)
+    assert buf.getvalue().split() == ["Constructing", "k-NNG", "Loading", "k-NNG"]
+    raw = np.load(f)
+    assert raw.dtype == np.float64 and raw.shape == (2, 500, 13)     # the reference's cache format
+    assert np.array_equal(a[0], b[0]) and np.allclose(a[1], b[1])
+    out = vv.smooth(x, b, k=10, coef=1.0)                            # loaded object is a valid `knn`
+    assert out.shape == x.shape
+
+
+# ========================================================================= smooth
+@pytest.mark.parametrize("name", SMOOTH)
+def test_smooth_bit_exact_vs_reference_golden(name):
+    g = np.load(os.path.join(GOLDEN, name))
+    out = vv.smooth(g["x"], [g["idx"].astype(np.int64), g["dist"]], k=int(g["k"]), coef=float(g["coef"]),
+                    n_iter=int(g["n_iter"]))
+    assert out.dtype == g["out"].dtype
+    assert np.array_equal(out, g["out"]), f"max abs diff {np.abs(out - g['out']).max()}"
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("order", ["random", "sorted"])
+def test_smooth_bit_exact_vs_oracle_100k(dtype, order):
+    """100k x 50, k=50.  'sorted' orders rows along coordinate 0 (trajectory-like data), the
+    adversarial case for the dependency depth of the Gauss-Seidel sweep."""
+    n, d, k = 100_000, 50, 50
+    x = clustered(n, d, 20, seed=5)
+    if order == "sorted":
+        x = x[np.argsort(x[:, 0])]
+    idx, dist = vv.make_knn(x, k=k, verbose=False)
+    xin = x.astype(dtype)
+    for coef, n_iter in ((1.0, 1), (0.1, 2)):
+        out = vv.smooth(xin, [idx, dist], k=k, coef=coef, n_iter=n_iter)
+        want = orc.smooth(xin, idx, k, coef, n_iter)
+        assert out.dtype == dtype
+        assert np.array_equal(out, want), f"{(out != want).sum()} elements differ, max abs {np.abs(out - want).max()}"
+    assert np.array_equal(xin, x.astype(dtype))  # input not mutated
+
+
+def test_smooth_jacobi_mode_and_wide_rows():
+    x = clustered(3000, 300, 5, seed=8)  # d > 128: several column passes per row
+    idx, dist = vv.make_knn(x, k=20, verbose=False)
+    for mode, m in (("gauss_seidel", 0), ("jacobi", 1)):
+        out = vv.smooth(x, [idx, dist], k=15, coef=0.7, n_iter=2, mode=mode)
+        assert np.array_equal(out, orc.smooth(x, idx, 15, 0.7, 2, mode=m))
+    with pytest.raises(ValueError):
+        vv.smooth(x, [idx, dist], k=15, mode="nope")
+
+
+def test_smooth_is_identity_for_coef_zero_and_idempotent_on_constant_data():
+    x = clustered(2000, 12, 3, seed=2)
+    knn = vv.make_knn(x, k=10, verbose=False)
+    assert np.array_equal(vv.smooth(x, knn, k=10, coef=0.0), x)
+    c = np.full((500, 6), 3.25, dtype=np.float32)
+    idx = np.stack([np.roll(np.arange(500), -s) for s in range(8)], axis=1)
+    assert np.array_equal(vv.smooth(c, [idx, np.zeros((500, 8), np.float32)], k=8, coef=1.0, n_iter=3), c)
+
+
+# ======================================================================== quartet
+@pytest.mark.parametrize("name", QUARTET)
+def test_quartet_loss_and_grad_vs_reference_golden(name):
+    g = np.load(os.path.join(GOLDEN, name))
+    ns = int(g["n_sampling"])
+    dev = torch.device("cuda")
+    x = torch.tensor(g["x"], device=dev)
+    z = torch.tensor(g["z"], device=dev, requires_grad=True)
+    perms = [None] + [torch.tensor(g["perms"][i], device=dev) for i in range(ns - 1)]
+    loss = vv.quartet_loss(x, z, str(g["hd"]), str(g["ld"]), perms)
+    (loss * 3.0).backward()  # upstream gradient != 1 (lam_mds multiplies outside the op, network.py:286)
+    grad = z.grad.cpu().numpy() / 3.0
+    # vs the float32 reference (the 1e-4 bar) ...
+    np.testing.assert_allclose(loss.item(), float(g["loss_f32"]), rtol=1e-4)
+    scale = np.abs(g["grad_f32"]).max()
+    np.testing.assert_allclose(grad, g["grad_f32"], rtol=1e-4, atol=1e-4 * scale)
+    # ... and vs the float64 oracle, live
+    ol, og = orc.quartet_loss(g["x"], g["z"], str(g["hd"]), str(g["ld"]), [None] + list(g["perms"]))
+    np.testing.assert_allclose(loss.item(), ol, rtol=1e-4)
+    np.testing.assert_allclose(grad, og, rtol=1e-4, atol=1e-4 * scale)
+
+
+def test_quartet_small_batches_nan_and_zero_grad_rows():
+    dev = torch.device("cuda")
+    x = torch.randn(3, 5, device=dev)
+    z = torch.randn(3, 2, device=dev, requires_grad=True)
+    loss = vv.MDSLoss()(x, z)
+    assert torch.isnan(loss)  # B < 4: mean over zero quartets, as in the reference
+    loss.backward()
+    assert torch.all(z.grad == 0)
+    x = torch.randn(10, 5, device=dev)
+    z = torch.randn(10, 2, device=dev, requires_grad=True)
+    vv.MDSLoss()(x, z).backward()
+    assert torch.all(z.grad[8:] == 0) and torch.any(z.grad[:8] != 0)
+    with pytest.raises(ValueError, match="Invalid distance function"):
+        vv.MDSLoss()(x, z, distf_hd="manhattan")
+
+
+def test_quartet_is_deterministic_and_resampling_uses_global_rng():
+    dev = torch.device("cuda")
+    x = torch.randn(1024, 50, device=dev)
+    z0 = torch.randn(1024, 2, device=dev)
+    outs = []
+    for _ in range(3):
+        torch.manual_seed(5)
+        z = z0.clone().requires_grad_(True)
+        loss = vv.MDSLoss()(x, z, n_sampling=4)
+        loss.backward()
+        outs.append((loss.item(), z.grad.clone()))
+    assert outs[0][0] == outs[1][0] == outs[2][0]
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][1], outs[2][1])
+    # same draws as the reference: pass i>0 consumes torch.randperm(B) from the global generator
+    torch.manual_seed(5)
+    perms = [None] + [torch.randperm(1024, device=dev) for _ in range(3)]
+    z = z0.clone().requires_grad_(True)
+    assert vv.quartet_loss(x, z, perms=perms).item() == outs[0][0]
+
+
+def test_quartet_large_batch_against_oracle():
+    rng = np.random.default_rng(3)
+    B, D, L = 1 << 16, 50, 2
+    x = clustered(B, D, 10, seed=6)
+    z = rng.standard_normal((B, L)).astype(np.float32)
+    zt = torch.tensor(z, device="cuda", requires_grad=True)
+    loss = vv.quartet_loss(torch.tensor(x, device="cuda"), zt)
+    loss.backward()
+    ol, og = orc.quartet_loss(x, z)
+    np.testing.assert_allclose(loss.item(), ol, rtol=1e-4)
+    np.testing.assert_allclose(zt.grad.cpu().numpy(), og, rtol=1e-4, atol=1e-4 * np.abs(og).max())
+
+
+# ============================================================================ fit
+def test_reference_smoke_test_on_gpu():
+    """/root/reference/tests/tests.py:5-15, verbatim settings (batch_size=2 -> the quartet term
+    is NaN in the log exactly as in the reference, weights stay finite)."""
+    np.random.seed(1)
+    x = np.random.rand(50, 2).astype(np.float32)
+    model = vv.ViVAE(input_dim=x.shape[1], latent_dim=2)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        model.fit(x, n_epochs=1, lam_recon=1.0, lam_kldiv=0.1, lam_geom=1.0, lam_egeom=1.0, lam_mds=1.0, batch_size=2)
+    emb = model.transform(x)
+    assert emb.shape[0] == x.shape[0] and emb.shape[1] == 2
+    assert np.all(np.isfinite(emb)) and "mds: nan" in buf.getvalue()
+
+
+def test_fit_replay_matches_reference_run():
+    """Replay the recorded reference run (tests/golden/fit_a.npz: initial weights, loader
+    permutations and reparameterisation noise) through the product's training loop on the GPU."""
+    g = np.load(os.path.join(GOLDEN, "fit_a.npz"))
+    dev = torch.device("cuda")
+    model = vv.ViVAE(input_dim=g["X"].shape[1], latent_dim=2, random_state=3)
+    sd = {k[len("init__"):]: torch.tensor(g[k], device=dev) for k in g.files if k.startswith("init__")}
+    model.net.load_state_dict(sd)
+    loader_perms = [g["perms"][0], g["perms"][2]]  # every epoch draws two, the 2nd is unused (see DeviceBatchLoader)
+    eps = torch.tensor(g["eps"], device=dev)
+    cursor = {"perm": 0, "eps": 0}
+
+    def next_perm():
+        p = torch.tensor(loader_perms[cursor["perm"]], device=dev)
+        cursor["perm"] += 1
+        return p
+
+    real_randn_like = torch.randn_like
+
+    def replay_randn_like(t, *a, **k):
+        e = eps[cursor["eps"]:cursor["eps"] + t.shape[0]].reshape(t.shape)
+        cursor["eps"] += t.shape[0]
+        return e
+
+    # first call builds the loader; install the replay hooks by running zero epochs first
+    model.fit(g["X"], n_epochs=0, batch_size=int(g["batch_size"]), lam_mds=float(g["lam_mds"]), verbose=False)
+    model.data_loader._perm_override = next_perm
+    torch.randn_like = replay_randn_like
+    buf = io.StringIO()
+    try:
+        with redirect_stdout(buf):
+            for epoch in (1, 2):
+                losses = model.train_epoch(lam_mds=float(g["lam_mds"]))
+                print(f"{losses['recon']/epoch:.4f} {losses['kldiv']/epoch:.4f} {losses['mds']/epoch:.4f}")
+    finally:
+        torch.randn_like = real_randn_like
+    assert cursor["eps"] == eps.shape[0]
+    ref_lines = [ln.split("\t") for ln in str(g["log"]).strip().splitlines()]
+    got = [[float(v) for v in ln.split()] for ln in buf.getvalue().strip().splitlines()]
+    for ref, mine in zip(ref_lines, got):
+        want = [float(ref[1].split()[1]), float(ref[2].split()[1]), float(ref[5].split()[1])]
+        np.testing.assert_allclose(mine, want, rtol=2e-3, atol=2e-4)
+    emb = model.transform(g["X"])
+    # 10 optimiser steps in FP32 on different hardware: compare at 1e-2 of the embedding's spread
+    assert np.abs(emb - g["emb"]).max() < 1e-2 * np.abs(g["emb"]).max()
+
+
+def test_full_pipeline_through_public_api():
+    x = clustered(20_000, 38, 12, seed=10)
+    knn = vv.make_knn(x, k=50, verbose=False)
+    xd = vv.smooth(x, knn, k=50, coef=1.0, n_iter=1)
+    model = vv.ViVAE(input_dim=38, random_state=1)
+    before = vv._lib.launch_count()
+    model.fit(xd, n_epochs=2, batch_size=512, lam_mds=10.0, verbose=False)
+    assert vv._lib.launch_count() - before >= 2 * 2 * 40  # fused quartet fwd + bwd kernel per batch
+    emb = model.transform(xd)
+    assert emb.shape == (20_000, 2) and np.all(np.isfinite(emb))
+    assert model.trained and model.decoder_active

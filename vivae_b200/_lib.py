@@ -1,0 +1,110 @@
+"""ctypes binding of the C ABI in include/vivae_b200.h (libvivae_b200.so).
+
+There is no CPU fallback: if the shared library is missing, or a compute entry
+point is called without a CUDA device, the call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvivae_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+OK, EINVAL, ECUDA, ENOMEM, ENOTSUP = 0, -1, -2, -3, -4
+KNN_ALGOS = {"auto": 0, "brute": 1, "tensor": 2}
+SMOOTH_MODES = {"gauss_seidel": 0, "jacobi": 1}
+DIST_FUNCS = {"euclidean": 0, "cosine": 1}
+
+
+class KnnStats(ctypes.Structure):
+    """Mirror of `vvb_knn_stats`."""
+
+    _fields_ = [
+        ("rows", ctypes.c_int64),
+        ("rows_fallback", ctypes.c_int64),
+        ("algo_used", ctypes.c_int32),
+        ("candidates", ctypes.c_int32),
+        ("ms_prepare", ctypes.c_float),
+        ("ms_screen", ctypes.c_float),
+        ("ms_rerank", ctypes.c_float),
+        ("ms_fallback", ctypes.c_float),
+        ("kernel_launches", ctypes.c_int64),
+    ]
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+# every symbol include/vivae_b200.h declares: (restype, argtypes)
+_i64, _int, _dbl, _vp, _sz = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t
+SYMBOLS = {
+    "vvb_version": (_int, []),
+    "vvb_last_error": (ctypes.c_char_p, []),
+    "vvb_launch_count": (_i64, []),
+    "vvb_make_knn_host": (_int, [_vp, _i64, _int, _int, _i64, _i64, _int, _vp, _vp, ctypes.POINTER(KnnStats)]),
+    "vvb_make_knn_workspace_bytes": (_int, [_i64, _int, _int, _i64, _int, ctypes.POINTER(_sz)]),
+    "vvb_make_knn_device": (_int, [_vp, _i64, _int, _int, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp,
+                                   ctypes.POINTER(KnnStats)]),
+    "vvb_smooth_host": (_int, [_vp, _int, _i64, _int, _vp, _i64, _int, _dbl, _int, _int, _vp]),
+    "vvb_smooth_workspace_bytes": (_int, [_int, _i64, _int, _int, ctypes.POINTER(_sz)]),
+    "vvb_smooth_device": (_int, [_vp, _int, _i64, _int, _vp, _i64, _int, _dbl, _int, _int, _vp, _vp, _sz, _vp]),
+    "vvb_quartet_workspace_bytes": (_sz, [_i64]),
+    "vvb_quartet_loss_fwd_device": (_int, [_vp, _vp, _i64, _int, _int, _vp, _int, _int, _int, _vp, _vp, _vp, _vp]),
+    "vvb_quartet_loss_bwd_device": (_int, [_vp, _vp, _i64, _vp, _vp]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libvivae_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC, "-j", str(os.cpu_count() or 4)], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise RuntimeError("building libvivae_b200.so failed")
+    return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library; raise (never fall back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(vivae_b200 has no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError if the ABI and the header disagree
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return load().vvb_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    """Translate a VVB_E* status into the reference's exception conventions."""
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc == EINVAL:
+        raise ValueError(msg)
+    if rc == ENOMEM:
+        raise MemoryError(msg)
+    if rc == ENOTSUP:
+        raise NotImplementedError(msg)
+    raise RuntimeError(msg)
+
+
+def launch_count() -> int:
+    return int(load().vvb_launch_count())

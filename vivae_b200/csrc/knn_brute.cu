@@ -1,0 +1,177 @@
+// Exact FP32 brute-force kNN (the exactness fallback of the tensor-core path, and a
+// complete make_knn on its own).
+//
+// Contract (include/vivae_b200.h): neighbours of row i are all
+// j != i ranked by (d2, j), d2 = acc after `for c: t = x_ic - x_jc; acc = fmaf(t,t,acc)`
+// in FP32, evaluated left to right.  Zero-padding the coordinate loop is exact
+// (fmaf(0,0,acc) == acc), which is what lets the kernel work in 16-column chunks.
+//
+// Layout: one thread owns one query row (its running threshold `tau` and candidate
+// count live in registers), a CTA of 128 threads sweeps the database in tiles of
+// 32 rows x 16 columns staged in shared memory and read back as warp-wide
+// broadcasts.  Candidates that beat `tau` are appended to the row's buffer in
+// global memory (L2 resident); when a buffer is nearly full the warp sorts it
+// cooperatively in registers (bitonic, 64-bit (key,idx) composites), keeps the best
+// k and tightens `tau`.  Because the database is swept in increasing j and admission
+// is a strict `<`, ties are broken towards the lower index, as the contract demands.
+#include "common.cuh"
+
+namespace vvb {
+
+constexpr int BR_THREADS = 128;
+constexpr int BR_TJ = 32;  // database rows per tile
+constexpr int BR_DC = 16;  // coordinates per chunk
+
+template <int E>
+__global__ void __launch_bounds__(BR_THREADS) knn_brute_kernel(
+    const float *__restrict__ x, int64_t n, int d, const int64_t *__restrict__ qrows, int64_t q0,
+    int64_t nq, int k, float *__restrict__ cand_key, uint32_t *__restrict__ cand_idx,
+    int64_t *__restrict__ out_idx, float *__restrict__ out_dist, int64_t out_row0) {
+  constexpr int CAP = 32 * E;
+  __shared__ __align__(16) float ys[BR_TJ][BR_DC];
+
+  const int lane = threadIdx.x & 31;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * BR_THREADS + threadIdx.x;
+  const bool active = t < nq;
+  const int64_t grow = active ? (qrows ? qrows[t] : q0 + t) : -1;
+  const float *xq = x + (active ? grow : 0) * d;
+  float *ck = cand_key + t * CAP;  // workspace is sized for gridDim.x * BR_THREADS rows
+  uint32_t *ci = cand_idx + t * CAP;
+
+  float tau = active ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
+  int cnt = 0;
+
+  for (int64_t j0 = 0; j0 < n; j0 += BR_TJ) {
+    // ---- make room for up to BR_TJ admissions (warp-cooperative sort + truncate)
+    unsigned need = __ballot_sync(FULL, cnt > CAP - BR_TJ);
+    while (need) {
+      const int src = __ffs(need) - 1;
+      need &= need - 1;
+      const int64_t tt = __shfl_sync(FULL, t, src);
+      const int c = __shfl_sync(FULL, cnt, src);
+      int nc;
+      const float thr = warp_sort_truncate<E>(cand_key + tt * CAP, cand_idx + tt * CAP, c, k, lane, &nc);
+      if (lane == src) {
+        cnt = nc;
+        tau = thr;
+      }
+    }
+
+    float acc[BR_TJ];
+#pragma unroll
+    for (int r = 0; r < BR_TJ; ++r) acc[r] = 0.0f;
+
+    for (int c0 = 0; c0 < d; c0 += BR_DC) {
+      __syncthreads();  // previous chunk fully consumed
+#pragma unroll
+      for (int it = 0; it < (BR_TJ * BR_DC) / BR_THREADS; ++it) {
+        const int e = it * BR_THREADS + threadIdx.x;
+        const int r = e / BR_DC, c = e % BR_DC;
+        const int64_t j = j0 + r;
+        float v = 0.0f;
+        if (j < n && c0 + c < d) v = __ldg(x + j * d + c0 + c);
+        ys[r][c] = v;
+      }
+      float xr[BR_DC];
+#pragma unroll
+      for (int c = 0; c < BR_DC; ++c) xr[c] = (active && c0 + c < d) ? __ldg(xq + c0 + c) : 0.0f;
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < BR_TJ; ++r) {
+#pragma unroll
+        for (int c4 = 0; c4 < BR_DC / 4; ++c4) {
+          const float4 y = *reinterpret_cast<const float4 *>(&ys[r][c4 * 4]);
+          float tdiff;
+          tdiff = __fsub_rn(xr[c4 * 4 + 0], y.x); acc[r] = __fmaf_rn(tdiff, tdiff, acc[r]);
+          tdiff = __fsub_rn(xr[c4 * 4 + 1], y.y); acc[r] = __fmaf_rn(tdiff, tdiff, acc[r]);
+          tdiff = __fsub_rn(xr[c4 * 4 + 2], y.z); acc[r] = __fmaf_rn(tdiff, tdiff, acc[r]);
+          tdiff = __fsub_rn(xr[c4 * 4 + 3], y.w); acc[r] = __fmaf_rn(tdiff, tdiff, acc[r]);
+        }
+      }
+    }
+
+    // ---- admission: strict `<` against the row's threshold, self excluded
+#pragma unroll
+    for (int r = 0; r < BR_TJ; ++r) {
+      const int64_t j = j0 + r;
+      if (acc[r] < tau && j < n && j != grow) {
+        ck[cnt] = acc[r];
+        ci[cnt] = static_cast<uint32_t>(j);
+        ++cnt;
+      }
+    }
+  }
+
+  // ---- finalize: sort every row of this warp and emit [self, k best]
+  for (int src = 0; src < 32; ++src) {
+    const int64_t tt = __shfl_sync(FULL, t, src);
+    const int c = __shfl_sync(FULL, cnt, src);
+    const int64_t g = __shfl_sync(FULL, grow, src);
+    if (tt >= nq) continue;  // warp-uniform
+    float *rk = cand_key + tt * CAP;
+    uint32_t *ri = cand_idx + tt * CAP;
+    int nc;
+    (void)warp_sort_truncate<E>(rk, ri, c, k, lane, &nc);
+    int64_t *oi = out_idx + (g - out_row0) * (k + 1);
+    float *od = out_dist + (g - out_row0) * (k + 1);
+    if (lane == 0) {
+      oi[0] = g;
+      od[0] = 0.0f;
+    }
+    for (int p = lane; p < k; p += 32) {
+      if (p < nc) {
+        oi[p + 1] = ri[p];
+        od[p + 1] = __fsqrt_rn(rk[p]);
+      } else {  // fewer than k admissible neighbours (NaN input): mark clearly
+        oi[p + 1] = -1;
+        od[p + 1] = __int_as_float(0x7fc00000);
+      }
+    }
+  }
+}
+
+size_t brute_workspace_bytes(int64_t nq, int k) {
+  const int64_t rows = (nq + BR_THREADS - 1) / BR_THREADS * BR_THREADS;
+  int cap = 128;
+  while (cap < k + BR_TJ + 32) cap *= 2;
+  return align_up(static_cast<size_t>(rows) * cap * sizeof(float), 256) +
+         align_up(static_cast<size_t>(rows) * cap * sizeof(uint32_t), 256) + 256;
+}
+
+// Launch the brute-force kernel for `nq` query rows (contiguous from q0, or listed in
+// qrows_dev) against the n database rows of x_dev.  Output row of query `g` is g - out_row0.
+int launch_knn_brute(const float *x_dev, int64_t n, int d, int k, const int64_t *qrows_dev,
+                     int64_t q0, int64_t nq, int64_t *out_idx, float *out_dist, int64_t out_row0,
+                     void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (nq == 0) return VVB_OK;
+  VVB_REQUIRE(n <= 0xffffffffLL, "brute kNN: n=%lld exceeds the 32-bit candidate index", (long long)n);
+  VVB_REQUIRE(k + BR_TJ + 32 <= 2048, "brute kNN: k=%d above the supported maximum of 1984", k);
+  VVB_REQUIRE(workspace_bytes >= brute_workspace_bytes(nq, k), "brute kNN: workspace too small");
+  const int64_t rows = (nq + BR_THREADS - 1) / BR_THREADS * BR_THREADS;
+  int cap = 128;
+  while (cap < k + BR_TJ + 32) cap *= 2;
+  Carver cv(workspace);
+  float *ck = cv.take<float>(static_cast<size_t>(rows) * cap);
+  uint32_t *ci = cv.take<uint32_t>(static_cast<size_t>(rows) * cap);
+  const unsigned grid = static_cast<unsigned>(rows / BR_THREADS);
+#define VVB_BRUTE_CASE(EE)                                                                         \
+  case 32 * EE:                                                                                    \
+    knn_brute_kernel<EE><<<grid, BR_THREADS, 0, stream>>>(x_dev, n, d, qrows_dev, q0, nq, k, ck,   \
+                                                          ci, out_idx, out_dist, out_row0);        \
+    break;
+  switch (cap) {
+    VVB_BRUTE_CASE(4)
+    VVB_BRUTE_CASE(8)
+    VVB_BRUTE_CASE(16)
+    VVB_BRUTE_CASE(32)
+    VVB_BRUTE_CASE(64)
+    default:
+      set_error("brute kNN: unsupported candidate capacity %d", cap);
+      return VVB_ENOTSUP;
+  }
+#undef VVB_BRUTE_CASE
+  VVB_CHECK_LAUNCH();
+  return VVB_OK;
+}
+
+}  // namespace vvb

@@ -1,0 +1,250 @@
+// Quartet ("stochastic MDS") loss, fused forward + gradient.
+// Replaces MDSLoss.__call__ (/root/reference/src/vivae/losses.py:266-349), which costs
+// ~1.5k ATen dispatches per batch for forward+backward.
+//
+// One warp per quartet q of a sampling pass: rows perm[a*nq + q], a = 0..3
+// (losses.py:326,332-336).  The six pairs, in the order of losses.py:234,263, are
+// (0,1) (1,2) (2,3) (0,2) (0,3) (1,3).  Lanes stride over the D (and L) coordinates,
+// partial sums are combined with xor-shuffles, then every lane holds the six
+// high-dimensional and six latent distances and evaluates
+//     cost_q = sum_p (dz_p/S - dx_p/X)^2,   X = sum_p dx_p,  S = sum_p dz_p
+// and the closed-form gradient
+//     dC/d(dz_p) = (2/S) (e_p - sum_p' e_p' dz_p'/S),   e_p = dz_p/S - dx_p/X.
+// Each row belongs to exactly one quartet per pass, so gradient rows are written
+// without atomics and the result is run-to-run deterministic (VIVAE_DETERMINISTIC).
+// The scalar loss is reduced in a fixed order by the last CTA to finish.
+#include "common.cuh"
+
+namespace vvb {
+
+constexpr int QT_THREADS = 256;  // 8 quartets per CTA
+constexpr int QT_WARPS = QT_THREADS / 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// Reduced pair statistics of four rows: for euclidean the six squared distances, for
+// cosine additionally the four squared norms and six dot products.
+struct QuadStats {
+  float sq[6];   // sum (a-b)^2
+  float dot[6];  // sum a*b        (cosine only)
+  float nrm[4];  // sum a*a        (cosine only)
+};
+
+template <int METRIC>
+__device__ __forceinline__ void quad_stats(const float *base, const int64_t (&r)[4], int dim, int lane,
+                                           QuadStats &s) {
+#pragma unroll
+  for (int p = 0; p < 6; ++p) s.sq[p] = 0.f, s.dot[p] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) s.nrm[a] = 0.f;
+  for (int c = lane; c < dim; c += 32) {
+    const float v0 = __ldg(base + r[0] * dim + c), v1 = __ldg(base + r[1] * dim + c);
+    const float v2 = __ldg(base + r[2] * dim + c), v3 = __ldg(base + r[3] * dim + c);
+    if (METRIC == VVB_DIST_EUCLIDEAN) {
+      float t;
+      t = v0 - v1; s.sq[0] = fmaf(t, t, s.sq[0]);
+      t = v1 - v2; s.sq[1] = fmaf(t, t, s.sq[1]);
+      t = v2 - v3; s.sq[2] = fmaf(t, t, s.sq[2]);
+      t = v0 - v2; s.sq[3] = fmaf(t, t, s.sq[3]);
+      t = v0 - v3; s.sq[4] = fmaf(t, t, s.sq[4]);
+      t = v1 - v3; s.sq[5] = fmaf(t, t, s.sq[5]);
+    } else {
+      s.nrm[0] = fmaf(v0, v0, s.nrm[0]); s.nrm[1] = fmaf(v1, v1, s.nrm[1]);
+      s.nrm[2] = fmaf(v2, v2, s.nrm[2]); s.nrm[3] = fmaf(v3, v3, s.nrm[3]);
+      s.dot[0] = fmaf(v0, v1, s.dot[0]); s.dot[1] = fmaf(v1, v2, s.dot[1]);
+      s.dot[2] = fmaf(v2, v3, s.dot[2]); s.dot[3] = fmaf(v0, v2, s.dot[3]);
+      s.dot[4] = fmaf(v0, v3, s.dot[4]); s.dot[5] = fmaf(v1, v3, s.dot[5]);
+    }
+  }
+  if (METRIC == VVB_DIST_EUCLIDEAN) {
+#pragma unroll
+    for (int p = 0; p < 6; ++p) s.sq[p] = warp_sum(s.sq[p]);
+  } else {
+#pragma unroll
+    for (int p = 0; p < 6; ++p) s.dot[p] = warp_sum(s.dot[p]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) s.nrm[a] = warp_sum(s.nrm[a]);
+  }
+}
+
+template <int METRIC>
+__device__ __forceinline__ void pair_dists(const QuadStats &s, float (&dist)[6]) {
+  constexpr int pa[6] = {0, 1, 2, 0, 0, 1};
+  constexpr int pb[6] = {1, 2, 3, 2, 3, 3};
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    if (METRIC == VVB_DIST_EUCLIDEAN) {
+      dist[p] = sqrtf(fmaxf(s.sq[p], 1e-9f));  // losses.py:154-159
+    } else {
+      const float ca = fmaxf(sqrtf(s.nrm[pa[p]]), 1e-8f), cb = fmaxf(sqrtf(s.nrm[pb[p]]), 1e-8f);
+      dist[p] = 1.0f - s.dot[p] / (ca * cb);  // losses.py:176 (ATen clamps each norm at eps=1e-8)
+    }
+  }
+}
+
+template <int MHD, int MLD>
+__global__ void __launch_bounds__(QT_THREADS) quartet_fwd_kernel(
+    const float *__restrict__ x, const float *__restrict__ z, int64_t B, int D, int L,
+    const int64_t *__restrict__ perm, float *__restrict__ cost_q, float *__restrict__ grad_unit,
+    int accumulate, float grad_scale, float pass_weight, float *__restrict__ loss_out,
+    int accumulate_loss, unsigned int *__restrict__ done_counter) {
+  constexpr int pa[6] = {0, 1, 2, 0, 0, 1};
+  constexpr int pb[6] = {1, 2, 3, 2, 3, 3};
+  const int64_t nq = B / 4;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * QT_WARPS + warp;
+
+  if (q < nq) {
+    int64_t r[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) r[a] = perm ? perm[a * nq + q] : a * nq + q;
+
+    QuadStats sx, sz;
+    quad_stats<MHD>(x, r, D, lane, sx);
+    quad_stats<MLD>(z, r, L, lane, sz);
+    float dx[6], dz[6];
+    pair_dists<MHD>(sx, dx);
+    pair_dists<MLD>(sz, dz);
+    float X = 0.f, S = 0.f;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) X += dx[p], S += dz[p];
+    float e[6], cost = 0.f, er = 0.f;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      e[p] = dz[p] / S - dx[p] / X;
+      cost = fmaf(e[p], e[p], cost);
+      er = fmaf(e[p], dz[p] / S, er);
+    }
+    if (lane == 0) cost_q[q] = cost;
+
+    if (grad_unit != nullptr) {
+      float w[6];
+#pragma unroll
+      for (int p = 0; p < 6; ++p) w[p] = (2.0f / S) * (e[p] - er) * grad_scale;
+      for (int c = lane; c < L; c += 32) {
+        float zv[4], g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) zv[a] = __ldg(z + r[a] * L + c);
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          const int a = pa[p], b = pb[p];
+          if (MLD == VVB_DIST_EUCLIDEAN) {
+            // d sqrt(max(s,1e-9))/dz_a = (z_a - z_b)/dist when s > 1e-9, else 0
+            if (sz.sq[p] > 1e-9f) {
+              const float t = w[p] * (zv[a] - zv[b]) / dz[p];
+              g[a] += t;
+              g[b] -= t;
+            }
+          } else {
+            const float na = sqrtf(sz.nrm[a]), nb = sqrtf(sz.nrm[b]);
+            const float ca = fmaxf(na, 1e-8f), cb = fmaxf(nb, 1e-8f);
+            const float inv = 1.0f / (ca * cb);
+            // cos = dot/(ca cb);  d(1-cos)/dz_a = -(z_b/(ca cb) - dot/(ca^2 cb) * z_a/|a|)
+            const float da = na > 0.f ? zv[a] / na : 0.f, db = nb > 0.f ? zv[b] / nb : 0.f;
+            g[a] -= w[p] * (zv[b] * inv - sz.dot[p] * inv / ca * da);
+            g[b] -= w[p] * (zv[a] * inv - sz.dot[p] * inv / cb * db);
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          float *gp = grad_unit + r[a] * L + c;
+          *gp = accumulate ? (*gp + g[a]) : g[a];
+        }
+      }
+    }
+  }
+
+  // ---- deterministic loss reduction by the last CTA
+  __shared__ bool is_last;
+  __shared__ float red[QT_THREADS];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(done_counter, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float part = 0.f;
+  for (int64_t i = threadIdx.x; i < nq; i += QT_THREADS) part += __ldcg(cost_q + i);
+  red[threadIdx.x] = part;
+  __syncthreads();
+#pragma unroll
+  for (int o = QT_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    // pass loss = mean_q(cost) * B / nq  (losses.py:263,339-343); pass_weight = 1/n_sampling
+    const float pass = red[0] / static_cast<float>(nq) * static_cast<float>(B) / static_cast<float>(nq);
+    const float contrib = pass * pass_weight;
+    *loss_out = accumulate_loss ? (*loss_out + contrib) : contrib;
+    *done_counter = 0;  // ready for the next launch on this stream
+  }
+}
+
+__global__ void quartet_nan_kernel(float *loss_out) { *loss_out = __int_as_float(0x7fc00000); }
+
+__global__ void scale_by_scalar_kernel(const float *__restrict__ g, const float *__restrict__ s,
+                                       int64_t count, float *__restrict__ out) {
+  const float f = __ldg(s);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = g[i] * f;
+}
+
+size_t quartet_workspace_bytes(int64_t B) {
+  // [done counter (256 B)][cost_q: B/4 floats]
+  return 256 + align_up(static_cast<size_t>(B / 4 + 1) * sizeof(float), 256);
+}
+
+int launch_quartet_fwd(const float *x, const float *z, int64_t B, int D, int L, const int64_t *const *perms,
+                       int n_sampling, int mhd, int mld, float *loss_out, float *grad_unit, void *workspace,
+                       cudaStream_t st) {
+  VVB_REQUIRE(B >= 0 && D >= 1 && L >= 1 && n_sampling >= 1, "quartet loss: bad shape arguments");
+  VVB_REQUIRE((mhd == 0 || mhd == 1) && (mld == 0 || mld == 1), "Invalid distance function specification for MDS loss");
+  const int64_t nq = B / 4;
+  if (grad_unit && B > 0) VVB_CUDA(cudaMemsetAsync(grad_unit, 0, static_cast<size_t>(B) * L * sizeof(float), st));
+  if (nq == 0) {  // mean over zero quartets: NaN, like the reference
+    quartet_nan_kernel<<<1, 1, 0, st>>>(loss_out);
+    VVB_CHECK_LAUNCH();
+    return VVB_OK;
+  }
+  unsigned int *counter = static_cast<unsigned int *>(workspace);
+  float *cost_q = reinterpret_cast<float *>(static_cast<char *>(workspace) + 256);
+  VVB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+  const unsigned grid = static_cast<unsigned>((nq + QT_WARPS - 1) / QT_WARPS);
+  const float grad_scale = static_cast<float>(static_cast<double>(B) / (static_cast<double>(nq) * nq) / n_sampling);
+  const float pass_weight = 1.0f / static_cast<float>(n_sampling);
+  for (int s = 0; s < n_sampling; ++s) {
+    const int64_t *perm = perms ? perms[s] : nullptr;
+#define VVB_QT_LAUNCH(A, Bm)                                                                              \
+  quartet_fwd_kernel<A, Bm><<<grid, QT_THREADS, 0, st>>>(x, z, B, D, L, perm, cost_q, grad_unit, s > 0,  \
+                                                         grad_scale, pass_weight, loss_out, s > 0, counter)
+    if (mhd == 0 && mld == 0) VVB_QT_LAUNCH(0, 0);
+    else if (mhd == 0 && mld == 1) VVB_QT_LAUNCH(0, 1);
+    else if (mhd == 1 && mld == 0) VVB_QT_LAUNCH(1, 0);
+    else VVB_QT_LAUNCH(1, 1);
+#undef VVB_QT_LAUNCH
+    VVB_CHECK_LAUNCH();
+  }
+  return VVB_OK;
+}
+
+int launch_quartet_bwd(const float *grad_unit, const float *grad_out, int64_t count, float *grad_z,
+                       cudaStream_t st) {
+  if (count <= 0) return VVB_OK;
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  scale_by_scalar_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(grad_unit, grad_out, count, grad_z);
+  VVB_CHECK_LAUNCH();
+  return VVB_OK;
+}
+
+}  // namespace vvb

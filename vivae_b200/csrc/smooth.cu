@@ -1,0 +1,183 @@
+// kNN smoother -- reproduces /root/reference/src/vivae/knn.py:173-185 on the GPU.
+//
+// The reference's sweep is in place (res aliases y), so row i reads rows j < i that
+// were ALREADY updated in the same sweep (Gauss-Seidel).  That
+// dependency DAG only points to lower row indices, which permits a sync-free design:
+//   * two arrays per sweep: `prev` (values before the sweep) and `next` (after);
+//     row i reads neighbour j from `next` if j < i (after j's done-flag is published)
+//     and from `prev` otherwise -- exactly what the sequential loop observes;
+//   * one warp per row, rows handed out in increasing order through an atomic ticket,
+//     so a warp only ever waits on rows whose owner is already running: no deadlock,
+//     whatever the grid size or the row order of the data.
+// Arithmetic per element matches NumPy's: sequential sum over the k gathered rows in
+// neighbour order (starting from the first row, not from zero), true division by k,
+// then r + (target - r) * coef as three separately rounded operations (no FMA).
+// VVB_SMOOTH_JACOBI (every row reads `prev`) is the documented non-parity variant.
+#include "common.cuh"
+
+namespace vvb {
+
+constexpr int SM_THREADS = 256;
+constexpr int SM_ROWS_PER_TICKET = 4;
+constexpr int SM_UNROLL = 8;  // neighbour rows in flight per warp
+
+template <typename T> struct Arith;
+template <> struct Arith<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <> struct Arith<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+
+// DPL = columns per lane held in registers (a warp covers 32*DPL columns per pass)
+template <typename T, int DPL, bool GS>
+__global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
+    const T *__restrict__ prev, T *next, const int64_t *__restrict__ idx, int64_t ld_idx, int64_t n,
+    int d, int k, T coef, int *flags, int epoch, unsigned long long *ticket) {
+  const int lane = threadIdx.x & 31;
+  const T kk = static_cast<T>(k);
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(ticket, 1ull) * SM_ROWS_PER_TICKET;
+    base = __shfl_sync(FULL, base, 0);
+    if (base >= static_cast<unsigned long long>(n)) break;
+    const int64_t row_end = min(static_cast<int64_t>(base) + SM_ROWS_PER_TICKET, n);
+    for (int64_t i = static_cast<int64_t>(base); i < row_end; ++i) {
+      const int64_t *nb = idx + i * ld_idx;
+      if (GS) {
+        // wait until every lower-indexed neighbour has been published in this sweep
+        for (int jb = 0; jb < k; jb += 32) {
+          const int jj = jb + lane;
+          if (jj < k) {
+            const int64_t j = nb[jj];
+            if (j < i) {
+              while (ld_acquire(flags + j) < epoch) __nanosleep(40);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      for (int c0 = 0; c0 < d; c0 += 32 * DPL) {
+        T acc[DPL];
+        bool first = true;
+        for (int jb = 0; jb < k; jb += SM_UNROLL) {
+          T v[SM_UNROLL][DPL];
+#pragma unroll
+          for (int u = 0; u < SM_UNROLL; ++u) {
+            if (jb + u < k) {
+              const int64_t j = nb[jb + u];  // warp-uniform broadcast load
+              const bool from_next = GS && (j < i);
+              const T *src = (from_next ? static_cast<const T *>(next) : prev) + j * d;
+#pragma unroll
+              for (int q = 0; q < DPL; ++q) {
+                const int c = c0 + q * 32 + lane;
+                T val = T(0);
+                if (c < d) val = from_next ? __ldcg(src + c) : __ldg(src + c);
+                v[u][q] = val;
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < SM_UNROLL; ++u) {
+            if (jb + u < k) {
+#pragma unroll
+              for (int q = 0; q < DPL; ++q) acc[q] = first ? v[u][q] : Arith<T>::add(acc[q], v[u][q]);
+              first = false;
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < DPL; ++q) {
+          const int c = c0 + q * 32 + lane;
+          if (c < d) {
+            const T r = __ldg(prev + i * d + c);
+            const T target = Arith<T>::div(acc[q], kk);
+            const T vec = Arith<T>::sub(target, r);
+            const T prod = Arith<T>::mul(vec, coef);
+            next[i * d + c] = Arith<T>::add(r, prod);
+          }
+        }
+      }
+      if (GS) {
+        __threadfence();  // every lane: its stores to `next` are visible device-wide ...
+        __syncwarp();
+        if (lane == 0) st_release(flags + i, epoch);  // ... before the row is published
+      }
+    }
+  }
+}
+
+template <typename T, int DPL>
+static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
+                         double coef, int n_iter, int mode, T *out, void *workspace, cudaStream_t st) {
+  // workspace: [scratch (n*d) T][flags n int][tickets n_iter u64]
+  Carver cv(workspace);
+  T *scratch = cv.take<T>(static_cast<size_t>(n) * d);
+  int *flags = cv.take<int>(static_cast<size_t>(n));
+  unsigned long long *tickets = cv.take<unsigned long long>(static_cast<size_t>(n_iter));
+  VVB_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(n) * sizeof(int), st));
+  VVB_CUDA(cudaMemsetAsync(tickets, 0, static_cast<size_t>(n_iter) * sizeof(unsigned long long), st));
+
+  int blocks_per_sm = 0;
+  auto kern_gs = smooth_sweep_kernel<T, DPL, true>;
+  auto kern_ja = smooth_sweep_kernel<T, DPL, false>;
+  VVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, mode == VVB_SMOOTH_JACOBI ? kern_ja : kern_gs,
+                                                         SM_THREADS, 0));
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  const int64_t warps_needed = (n + SM_ROWS_PER_TICKET - 1) / SM_ROWS_PER_TICKET;
+  int64_t grid = static_cast<int64_t>(sm_count()) * blocks_per_sm;
+  const int64_t max_useful = (warps_needed + SM_THREADS / 32 - 1) / (SM_THREADS / 32);
+  if (grid > max_useful) grid = max_useful;
+  if (grid < 1) grid = 1;
+
+  // ping-pong so that the LAST sweep lands in `out`:  sweep s reads a_s, writes b_s
+  const T *src = x;
+  for (int it = 0; it < n_iter; ++it) {
+    const bool to_out = ((n_iter - 1 - it) % 2) == 0;
+    T *dst = to_out ? out : scratch;
+    if (mode == VVB_SMOOTH_JACOBI)
+      kern_ja<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k,
+                                                                 static_cast<T>(coef), flags, it + 1, tickets + it);
+    else
+      kern_gs<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k,
+                                                                 static_cast<T>(coef), flags, it + 1, tickets + it);
+    VVB_CHECK_LAUNCH();
+    src = dst;
+  }
+  return VVB_OK;
+}
+
+size_t smooth_workspace_bytes(int elem_size, int64_t n, int d, int n_iter) {
+  return align_up(static_cast<size_t>(n) * d * elem_size, 256) + align_up(static_cast<size_t>(n) * sizeof(int), 256) +
+         align_up(static_cast<size_t>(n_iter) * sizeof(unsigned long long), 256) + 256;
+}
+
+int launch_smooth(const void *x, int elem_size, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
+                  double coef, int n_iter, int mode, void *out, void *workspace, size_t workspace_bytes,
+                  cudaStream_t st) {
+  VVB_REQUIRE(elem_size == 4 || elem_size == 8, "smooth: elem_size must be 4 or 8");
+  VVB_REQUIRE(n >= 1 && d >= 1 && k >= 1 && ld_idx >= k && n_iter >= 1, "smooth: bad shape arguments");
+  VVB_REQUIRE(mode == VVB_SMOOTH_GAUSS_SEIDEL || mode == VVB_SMOOTH_JACOBI, "smooth: unknown mode %d", mode);
+  VVB_REQUIRE(out != x, "smooth: out must not alias x");
+  VVB_REQUIRE(workspace_bytes >= smooth_workspace_bytes(elem_size, n, d, n_iter), "smooth: workspace too small");
+  if (elem_size == 4) {
+    const float *xf = static_cast<const float *>(x);
+    float *of = static_cast<float *>(out);
+    if (d <= 32) return launch_sweeps<float, 1>(xf, n, d, idx, ld_idx, k, coef, n_iter, mode, of, workspace, st);
+    if (d <= 64) return launch_sweeps<float, 2>(xf, n, d, idx, ld_idx, k, coef, n_iter, mode, of, workspace, st);
+    return launch_sweeps<float, 4>(xf, n, d, idx, ld_idx, k, coef, n_iter, mode, of, workspace, st);
+  }
+  const double *xd = static_cast<const double *>(x);
+  double *od = static_cast<double *>(out);
+  if (d <= 32) return launch_sweeps<double, 1>(xd, n, d, idx, ld_idx, k, coef, n_iter, mode, od, workspace, st);
+  if (d <= 64) return launch_sweeps<double, 2>(xd, n, d, idx, ld_idx, k, coef, n_iter, mode, od, workspace, st);
+  return launch_sweeps<double, 4>(xd, n, d, idx, ld_idx, k, coef, n_iter, mode, od, workspace, st);
+}
+
+}  // namespace vvb

@@ -1,0 +1,198 @@
+"""ViVAE model driver (sklearn-like `fit` / `transform`).
+
+Mirrors /root/reference/src/vivae/model.py (`ViVAE` 37-428): same constructor and method
+signatures, defaults, attributes (`net`, `data_loader`, `optimizer`, `trained`,
+`decoder_active`, `device_name`), progress line and `ValueError`s.
+
+What is re-plumbed for the GPU:
+  * batches come from ONE on-device `randperm` per epoch and one `index_select` per batch,
+    instead of the DataLoader's per-sample indexing + stack (model.py:249-254);
+  * per-term loss sums are accumulated on the device and read back once per epoch,
+    instead of three `.item()` host syncs per batch (model.py:151,157,169);
+  * the quartet term runs as one fused kernel (see `losses.MDSLoss`).
+RNG call order is the reference's: the loader permutation comes from a dedicated
+generator seeded with `random_state` (model.py:246-248), `randn_like` and the quartet
+re-sampling permutations from the global generator.
+"""
+
+from __future__ import annotations
+
+import random
+from collections.abc import Callable
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .network import Autoencoder
+
+__all__ = ["ViVAE", "DeviceBatchLoader"]
+
+
+def _device() -> torch.device:
+    from . import DEVICE
+
+    return DEVICE
+
+
+class DeviceBatchLoader:
+    """Shuffled mini-batches of a device-resident matrix.
+
+    Iterating yields 1-tuples `(batch,)` like `DataLoader(TensorDataset(X), shuffle=True)`
+    does (model.py:249-254), so `train_epoch` reads the same.  `drop_last` is False."""
+
+    def __init__(self, data: torch.Tensor, batch_size: int, generator: Optional[torch.Generator] = None,
+                 shuffle: bool = True):
+        self.data = data
+        self.batch_size = int(batch_size)
+        self.generator = generator
+        self.shuffle = shuffle
+        self._perm_override = None  # test hook: replay a recorded permutation
+
+    def __len__(self) -> int:
+        return (self.data.shape[0] + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = self.data.shape[0]
+        dev = self.data.device
+        if self._perm_override is not None:
+            perm = self._perm_override()
+        elif self.shuffle:
+            # keep the generator in lockstep with the reference's DataLoader: every epoch it draws
+            # a base seed (torch/utils/data/dataloader.py, `_base_seed`), the epoch's permutation,
+            # and -- when the sampler is exhausted -- one more, unused, permutation
+            # (RandomSampler.__iter__ ends with `randperm(n)[: num_samples % n]`).
+            torch.empty((), dtype=torch.int64, device=dev).random_(generator=self.generator)
+            perm = torch.randperm(n, generator=self.generator, device=dev)
+        else:
+            perm = torch.arange(n, device=dev)
+        for s in range(0, n, self.batch_size):
+            yield (self.data.index_select(0, perm[s:s + self.batch_size]),)
+        if self._perm_override is None and self.shuffle:
+            torch.randperm(n, generator=self.generator, device=dev)
+
+
+_TERMS = ("recon", "kldiv", "geom", "egeom", "mds", "imit")
+
+
+class ViVAE:
+    """ViVAE dimension-reduction model (reference: model.py:37-78)."""
+
+    def __init__(self, input_dim: int, latent_dim: int = 2, hidden_dims: list[int] = [32, 64, 128, 32],
+                 variational: bool = True, activation=torch.nn.GELU(), random_state: Optional[int] = None):
+        from . import DEVICE_NAME
+
+        self.random_state = random_state
+        if self.random_state is not None:
+            torch.cuda.manual_seed(self.random_state)
+            torch.manual_seed(self.random_state)
+        dev = _device()
+        # like the reference (global default device), parameters are initialised on the device RNG
+        with torch.device(dev):
+            net = Autoencoder(input_dim=input_dim, latent_dim=latent_dim, hidden_dims=hidden_dims,
+                              variational=variational, activation=activation)
+        self.net = net.to(dev)
+        self.device_name = DEVICE_NAME
+        self.data_loader = None
+        self.optimizer = None
+        self.trained = False
+        self.decoder_active = False
+
+    def __repr__(self):
+        return f"ViVAE(input_dim={self.net.input_dim}, latent_dim={self.net.latent_dim}, device={self.device_name})"
+
+    def __str__(self):
+        return f"ViVAE model {self.net.input_dim}->{self.net.latent_dim}, {'trained' if self.trained else 'not trained'}"
+
+    # ------------------------------------------------------------------ training
+    def train_epoch(self, lam_recon: float = 1.0, lam_kldiv: float = 1.0, lam_geom: float = 0.0,
+                    lam_egeom: float = 0.0, lam_mds: float = 100.0, mds_distf_hd: str = "euclidean",
+                    mds_distf_ld: str = "euclidean", mds_nsamp: int = 1, lam_imit: float = 0.0,
+                    ref_model: Optional[Callable] = None) -> dict:
+        """One pass over the data (reference: model.py:89-186); returns the per-term loss sums."""
+        if self.data_loader is None:
+            raise ValueError("No data to train on: use the `fit` or `fit_transform` method")
+        dev = next(self.net.parameters()).device
+        sums = torch.zeros(len(_TERMS), dtype=torch.float32, device=dev)
+        for batch in self.data_loader:
+            x = batch[0]
+            self.optimizer.zero_grad()
+            terms = self.net(x, lam_recon=lam_recon, lam_kldiv=lam_kldiv, lam_geom=lam_geom, lam_egeom=lam_egeom,
+                             lam_mds=lam_mds, mds_distf_hd=mds_distf_hd, mds_distf_ld=mds_distf_ld,
+                             mds_nsamp=mds_nsamp, lam_imit=lam_imit, ref_model=ref_model)
+            loss = None
+            vals = []
+            for name in _TERMS:  # same summation order as model.py:149-174
+                t = terms[name]
+                if name == "kldiv" and not self.net.variational:
+                    t = None
+                if t is None:
+                    vals.append(None)
+                    continue
+                vals.append(t.detach().reshape(()))
+                loss = t if loss is None else loss + t
+            with torch.no_grad():
+                present = [i for i, v in enumerate(vals) if v is not None]
+                if present:
+                    sums[present] += torch.stack([vals[i] for i in present])
+            loss.backward()
+            self.optimizer.step()
+        host = sums.tolist()  # the only host sync of the epoch
+        return dict(zip(_TERMS, host))
+
+    def fit(self, X: np.ndarray, n_epochs: int = 50, batch_size: int = 256, learning_rate: float = 1e-3,
+            weight_decay: float = 1e-4, lam_recon: float = 1.0, lam_kldiv: float = 1.0, lam_geom: float = 0.0,
+            lam_egeom: float = 0.0, lam_mds: float = 100.0, mds_distf_hd: str = "euclidean",
+            mds_distf_ld: str = "euclidean", mds_nsamp: int = 1, lam_imit: float = 0.0,
+            ref_model: Optional[Callable] = None, verbose: bool = True):
+        """Fit the model (reference: model.py:188-279)."""
+        if X.shape[1] != self.net.input_dim:
+            raise ValueError("Mismatch between data dimensionality and network shape")
+        if lam_geom > 0.0 and lam_recon == 0.0:
+            raise ValueError("Decoder geometric loss can only be used if reconstruction loss is used")
+
+        if self.random_state is not None:
+            np.random.seed(self.random_state)
+            torch.manual_seed(self.random_state)
+            random.seed(self.random_state)
+
+        dev = next(self.net.parameters()).device
+        g = torch.Generator(device=dev)
+        if self.random_state is not None:
+            g.manual_seed(self.random_state)
+        # whole matrix to the device once (model.py:250); float64 input is cast (the reference
+        # would raise a dtype mismatch inside nn.Linear)
+        data = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32)).to(dev)
+        self.data_loader = DeviceBatchLoader(data, batch_size=batch_size, generator=g, shuffle=True)
+        self.optimizer = torch.optim.Adam(self.net.parameters(), lr=learning_rate, weight_decay=weight_decay)
+        self.net.train()
+
+        for epoch in range(1, n_epochs + 1):
+            losses = self.train_epoch(lam_recon=lam_recon, lam_kldiv=lam_kldiv, lam_geom=lam_geom,
+                                      lam_egeom=lam_egeom, lam_mds=lam_mds, mds_distf_hd=mds_distf_hd,
+                                      mds_distf_ld=mds_distf_ld, mds_nsamp=mds_nsamp, lam_imit=lam_imit,
+                                      ref_model=ref_model)
+            if verbose:
+                # the reference divides the epoch sums by the epoch INDEX (model.py:272-275); kept as is
+                print(
+                    f"Epoch {epoch}/{n_epochs}\trecon: {losses['recon']/epoch:.4f}\tkldiv: {losses['kldiv']/epoch:.4f}\tgeom: {losses['geom']/epoch:.4f}\tegeom: {losses['egeom']/epoch:.4f}\tmds: {losses['mds']/epoch:.4f}\timit: {losses['imit']/epoch:.4f}"
+                )
+        self.trained = True
+        if lam_recon > 0.0:
+            self.decoder_active = True
+
+    def transform(self, X: np.ndarray, batch_size: Optional[int] = None) -> np.ndarray:
+        """Latent means of X (reference: model.py:281-292)."""
+        return self.net.embed(X, batch_size=batch_size)
+
+    def fit_transform(self, X: np.ndarray, n_epochs: int = 50, batch_size: int = 256, learning_rate: float = 1e-3,
+                      weight_decay: float = 1e-4, lam_recon: float = 1.0, lam_kldiv: float = 1.0,
+                      lam_geom: float = 0.0, lam_egeom: float = 0.0, lam_mds: float = 100.0,
+                      mds_distf_hd: str = "euclidean", mds_distf_ld: str = "euclidean", mds_nsamp: int = 1,
+                      lam_imit: float = 0.0, ref_model: Optional[Callable] = None, verbose: bool = True):
+        """`fit` then `transform` with the same batch size (reference: model.py:294-351)."""
+        self.fit(X, n_epochs=n_epochs, batch_size=batch_size, learning_rate=learning_rate, weight_decay=weight_decay,
+                 lam_recon=lam_recon, lam_kldiv=lam_kldiv, lam_geom=lam_geom, lam_egeom=lam_egeom, lam_mds=lam_mds,
+                 mds_distf_hd=mds_distf_hd, mds_distf_ld=mds_distf_ld, mds_nsamp=mds_nsamp, lam_imit=lam_imit,
+                 ref_model=ref_model, verbose=verbose)
+        return self.transform(X, batch_size=batch_size)
