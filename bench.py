@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the ViVAE hot path on B200: exact kNN (k=50) + smooth, cells/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): synthetic 1,000,000 cells x 50 PCs (30-cluster
+mixture with a PCA-like decaying spectrum, seed 1), exact kNN k=50, then smooth(k=50,
+coef=1, n_iter=1).  One "step" = one full pass (graph + smoothing) over all cells.
+
+Timed quantities
+  value : cells/s with the matrix already resident in HBM (CUDA events, max over ranks)
+  e2e   : cells/s through the public drop-in API (`vv.make_knn` + `vv.smooth`): HOST NumPy
+          in, HOST NumPy out, H2D/D2H copies inside the timed region (wall clock around
+          calls that synchronise internally)
+N > 1 (launched under torchrun): the query rows are sharded across ranks (strong scaling:
+total work fixed); each rank holds the whole matrix, computes the graph rows of its shard,
+the index shards are all-gathered over NCCL and the Gauss-Seidel smoother -- which does
+not shard by rows -- runs replicated on every rank.
+
+`--impl reference` times the reference's CPU path for the same metric on the host cores:
+the oracle port (oracle/, C + OpenMP) on a bounded sample -- the reference's own kNN
+(pynndescent) is not installable here and its smoother is the single-threaded Python loop
+the oracle's C function restates.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def synth_cells(n: int, d: int, seed: int = 1, n_clusters: int = 30) -> np.ndarray:
+    """C2-syn of SURVEY.md section 8(d): Gaussian mixture, per-dimension scale 5/sqrt(1+c)."""
+    rng = np.random.default_rng(seed)
+    spec = (5.0 / np.sqrt(1.0 + np.arange(d))).astype(np.float32)
+    centres = rng.standard_normal((n_clusters, d)).astype(np.float32) * spec
+    out = np.empty((n, d), dtype=np.float32)
+    chunk = 1 << 18
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        lab = rng.integers(0, n_clusters, size=e - s)
+        out[s:e] = centres[lab] + 0.3 * spec * rng.standard_normal((e - s, d), dtype=np.float32)
+    return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            j = json.load(f)
+        return {"hbm_gbs": j["hbm_gbs"], "tf": j["bf16_tflops"], "tf_sustained": j.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def cpu_baseline(x: np.ndarray, k: int, knn_queries: int, smooth_rows: int) -> dict:
+    """The oracle port of the reference path, timed on the host cores on a bounded sample:
+    brute-force kNN of `knn_queries` query rows against the FULL matrix (all threads) plus
+    the single-threaded smooth sweep over `smooth_rows` rows; per-cell costs are added."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+
+    n, d = x.shape
+    knn_queries = min(knn_queries, n)
+    smooth_rows = min(smooth_rows, n)
+    t0 = time.perf_counter()
+    orc.knn(x, k, 0, knn_queries)
+    t_knn = time.perf_counter() - t0
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, smooth_rows, size=(smooth_rows, k), dtype=np.int64)
+    idx[:, 0] = np.arange(smooth_rows)
+    xs = np.ascontiguousarray(x[:smooth_rows])
+    t0 = time.perf_counter()
+    orc.smooth(xs, idx, k, 1.0, 1)
+    t_sm = time.perf_counter() - t0
+    per_cell = t_knn / knn_queries + t_sm / smooth_rows
+    return {"value": 1.0 / per_cell, "unit": "cells/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": f"kNN: {knn_queries} query rows vs all {n} rows ({t_knn:.2f} s, OpenMP x{orc.num_threads()}); "
+                      f"smooth: {smooth_rows} rows, k={k}, 1 thread ({t_sm:.2f} s); per-cell costs added",
+            "seconds": t_knn + t_sm}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    x = synth_cells(args.n, args.d)
+    vals = []
+    base = None
+    t_all0 = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        base = cpu_baseline(x, args.k, args.cpu_knn_queries, args.cpu_smooth_rows)
+        if i >= args.warmup:
+            vals.append(base["value"])
+    v = float(np.mean(vals))
+    base["value"] = v
+    line = {
+        "impl": "reference", "metric": "cells/sec exact kNN(k=50)+smooth", "value": v, "unit": "cells/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.n / v,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": base,
+        "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_all0,
+        "note": "ms_per_step is extrapolated to the full workload from the bounded sample (brute force is linear in queries)",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_gpus: int) -> dict:
+    return {"workload": f"synthetic {args.n} cells x {args.d} PCs, exact kNN k={args.k} + smooth(k={args.k}, coef=1, n_iter=1)",
+            "n": args.n, "d": args.d, "k": args.k, "parallelism": f"query-row shards x{n_gpus}, smooth replicated",
+            "l2": "inputs larger than L2 (matrix 200 MB, graph 612 MB vs 126 MB L2)"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import vivae_b200 as vv
+    from vivae_b200 import _lib
+    from vivae_b200.device import knn_device, smooth_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, d, k = args.n, args.d, args.k
+    x_host = synth_cells(n, d)
+    x_dev = torch.from_numpy(x_host).to(dev)
+    per = (n + world - 1) // world
+    q0 = min(rank * per, n)
+    nq = min(per, n - q0)
+
+    def step_device(stats=None):
+        idx, dist_ = knn_device(x_dev, k, q0, nq, algo=args.algo, stats=stats)
+        if world > 1:
+            full = torch.empty((per * world, k + 1), dtype=torch.int64, device=dev)
+            if nq < per:
+                pad = torch.zeros((per, k + 1), dtype=torch.int64, device=dev)
+                pad[:nq] = idx
+                idx = pad
+            dist.all_gather_into_tensor(full, idx)
+            idx = full[:n]
+        out = smooth_device(x_dev, idx, k=k, coef=1.0, n_iter=1)
+        return idx, dist_, out
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        step_device()
+    sync_all()
+
+    # ---- timed region: EXACTLY `steps` steps, CUDA events on the launching stream
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clocks:
+        sync_all()
+        ev0.record()
+        for _ in range(args.steps):
+            step_device()
+        ev1.record()
+        sync_all()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms_step = ms_total / args.steps
+    value = n / (ms_step / 1e3)
+
+    # ---- per-kernel split of one more (untimed) step, for the roofline of the dominant kernel
+    st = {}
+    sync_all()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    idx_s, _ = knn_device(x_dev, k, q0, nq, algo=args.algo, stats=st)
+    e1.record()
+    idx_full = idx_s if world == 1 else None
+    torch.cuda.synchronize()
+    ms_knn = e0.elapsed_time(e1)
+    ms_smooth = None
+    if world == 1:
+        e1.record()
+        smooth_device(x_dev, idx_full, k=k, coef=1.0, n_iter=1)
+        e2.record()
+        torch.cuda.synchronize()
+        ms_smooth = e1.elapsed_time(e2)
+    peaks = measured_peaks()
+    dom_ms = st.get("ms_screen") or st.get("ms_fallback") or ms_knn
+    flops = 2.0 * nq * n * d  # ALGORITHMIC: cross-term only, unpadded d
+    achieved = flops / (dom_ms / 1e3) / 1e12
+    roofline = {"kernel": "knn_screen_tcgen05" if st.get("algo_used") == 2 else "knn_brute_ffma",
+                "bound": "tensor", "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tf"], "traffic": None, "peak_source": peaks["source"],
+                "ms": dom_ms, "algorithmic_flops": flops}
+    smooth_roof = None
+    if ms_smooth:
+        sbytes = float(n) * (k * d * 4 + k * 4 + d * 4)
+        smooth_roof = {"kernel": "smooth_sweep_gs", "bound": "hbm", "achieved": sbytes / (ms_smooth / 1e3) / 1e9,
+                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": sbytes / (ms_smooth / 1e3) / 1e9 / peaks["hbm_gbs"],
+                       "ms": ms_smooth, "algorithmic_bytes": sbytes}
+
+    # ---- end to end through the public API (host buffers in and out)
+    e2e = None
+    if not args.skip_e2e:
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        xq = x_host if world == 1 else x_host  # every rank owns the host matrix; shards by query rows
+        from vivae_b200.knn import _knn_host
+
+        def step_e2e():
+            if world == 1:
+                knn = vv.make_knn(xq, k=k, verbose=False, algo=args.algo)
+                out = vv.smooth(xq, knn, k=k, coef=1.0, n_iter=1)
+                return float(out[0, 0])
+            idx_h, dist_h = _knn_host(xq, k, q0, nq, args.algo, None)
+            return float(dist_h[0, 1]) if nq else 0.0
+
+        step_e2e()  # warm-up
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = n * d * 4 + (n * d * 4 + n * k * 8 if world == 1 else 0)
+        d2h = nq * (k + 1) * 12 + (n * d * 4 if world == 1 else 0)
+        e2e = {"value": n / dt, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "path": "vv.make_knn + vv.smooth (host NumPy in/out)" if world == 1 else
+                       "vvb_make_knn_host per rank on its query shard (host in/out); smooth not included at N>1"}
+
+    # ---- fit (secondary metric: s/epoch), rank 0 only
+    fit = None
+    if rank == 0 and not args.skip_fit:
+        rows = min(n, args.fit_rows)
+        model = vv.ViVAE(input_dim=d, random_state=1)
+        xf = x_host[:rows]
+        model.fit(xf, n_epochs=1, batch_size=args.fit_batch, lam_mds=100.0, verbose=False)  # warm-up epoch
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        t0 = time.perf_counter()
+        model.fit(xf, n_epochs=args.fit_epochs, batch_size=args.fit_batch, lam_mds=100.0, verbose=False)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.fit_epochs
+        fit = {"rows": rows, "batch_size": args.fit_batch, "s_per_epoch": dt, "cells_per_s": rows / dt,
+               "quartet_kernel_launches_per_epoch": (_lib.launch_count() - l0) / args.fit_epochs}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    base = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        base = cpu_baseline(x_host, k, args.cpu_knn_queries, args.cpu_smooth_rows)
+
+    if rank == 0:
+        line = {
+            "metric": "cells/sec exact kNN(k=50)+smooth", "value": value, "unit": "cells/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (screening operands f16 hi/lo, f32 accumulate; re-rank f32)",
+            "data": "synthetic", "config": workload_config(args, world), "clocks": clocks.summary(),
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_smooth": smooth_roof,
+            "knn_stats": st, "ms_knn": ms_knn, "ms_smooth": ms_smooth, "cpu_baseline": base, "fit": fit,
+            "parity": {"knn": "bit-exact vs FP32 brute-force oracle (tests/test_gpu_parity.py)",
+                       "smooth": "bit-exact vs reference smooth()", "quartet": "1e-4 relative"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--d", type=int, default=50)
+    ap.add_argument("--k", type=int, default=50)
+    ap.add_argument("--algo", default="auto")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-fit", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--fit-rows", type=int, default=200_000)
+    ap.add_argument("--fit-batch", type=int, default=512)
+    ap.add_argument("--fit-epochs", type=int, default=1)
+    ap.add_argument("--cpu-knn-queries", type=int, default=4096)
+    ap.add_argument("--cpu-smooth-rows", type=int, default=200_000)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.gpus != int(os.environ.get("WORLD_SIZE", "1")) and int(os.environ.get("WORLD_SIZE", "1")) == 1 and args.gpus > 1:
+            # convenience: `python bench.py --gpus N` re-launches itself under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
+            raise SystemExit(subprocess.call(cmd))
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
