@@ -91,6 +91,17 @@ int vvb_make_knn_device(const float *x_dev, int64_t n, int d, int k, int64_t q0,
                         int algo, int64_t *idx_out_dev, float *dist_out_dev, void *workspace_dev,
                         size_t workspace_bytes, void *stream, vvb_knn_stats *stats);
 
+/* Diagnostics (no reference counterpart): run only the preparation and the tensor-core
+ * screening of the VVB_KNN_TENSOR path and return the raw per-row candidate lists:
+ * cand_idx/cand_key (nq, C) with C = vvb_knn_screen_debug_capacity(), cand_cnt (nq) valid
+ * entries per row (sorted by screening key), cand_thr (nq) the final admission threshold,
+ * xnorm (nq) |x^|^2 of the scaled/centred query, scale_ymax[2] = {scale, ymax}, mu[64] the
+ * column means.  Tests use it to bound the screening error against FP64. */
+int vvb_knn_screen_debug_capacity(void);
+int vvb_knn_screen_debug_host(const float *x_host, int64_t n, int d, int k, int64_t q0, int64_t nq,
+                              uint32_t *cand_idx_out, float *cand_key_out, int32_t *cand_cnt_out,
+                              float *cand_thr_out, float *xnorm_out, float *scale_ymax_out, float *mu_out);
+
 /* ------------------------------------------------------------------------
  * smooth -- replaces the sweep loop of /root/reference/src/vivae/knn.py:173-185
  *   (argument validation and ensure_valid_knn, knn.py:165-171, stay in Python).

@@ -338,3 +338,78 @@ def test_full_pipeline_through_public_api():
     emb = model.transform(xd)
     assert emb.shape == (20_000, 2) and np.all(np.isfinite(emb))
     assert model.trained and model.decoder_active
+
+
+# ===================================================== tensor-core screening internals
+def _screen_debug(x, k, q0, nq):
+    import ctypes
+
+    lib = vv._lib.load()
+    cap = lib.vvb_knn_screen_debug_capacity()
+    n, d = x.shape
+    ci = np.zeros((nq, cap), dtype=np.uint32)
+    ck = np.zeros((nq, cap), dtype=np.float32)
+    cc = np.zeros(nq, dtype=np.int32)
+    ct = np.zeros(nq, dtype=np.float32)
+    xn = np.zeros(nq, dtype=np.float32)
+    sy = np.zeros(2, dtype=np.float32)
+    mu = np.zeros(64, dtype=np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    vv._lib.check(lib.vvb_knn_screen_debug_host(p(x), n, d, k, q0, nq, p(ci), p(ck), p(cc), p(ct), p(xn), p(sy), p(mu)))
+    return ci, ck, cc, ct, xn, float(sy[0]), float(sy[1]), mu[:d]
+
+
+@pytest.mark.parametrize("kind", ["clustered", "offset"])
+def test_screening_error_is_far_below_the_certificate_margin(kind):
+    """The certificate assumes |key + |x^|^2 - s^2 d2| <= 2^-15 (|x^| + Ymax)^2.  Measure the
+    actual tensor-core error against FP64 on the kept candidates: it must stay 8x below."""
+    n, d, k = 20_000, 50, 50
+    x = clustered(n, d, 12, seed=21)
+    if kind == "offset":
+        x = (x + 300.0).astype(np.float32)
+    nq = 1024
+    ci, ck, cc, ct, xn, s, ymax, mu = _screen_debug(x, k, 500, nq)
+    m = k + 1 + max(16, k // 4)
+    assert np.all(cc == m) and s > 0 and 16.0 < ymax <= 64.1
+    assert np.all(np.diff(ck[:, :m], axis=1) >= 0)
+    xc = (x.astype(np.float64) - mu.astype(np.float64)) * s
+    worst = 0.0
+    for t in range(0, nq, 7):
+        g = 500 + t
+        j = ci[t, :m].astype(np.int64)
+        d2 = ((xc[g][None, :] - xc[j]) ** 2).sum(1)
+        err = np.abs(ck[t, :m].astype(np.float64) + float(xn[t]) - d2)
+        bound = (np.sqrt(float(xn[t])) + ymax) ** 2
+        worst = max(worst, float((err / bound).max()))
+    print(f"screening error / (|x|+Ymax)^2 = 2^{np.log2(max(worst, 1e-30)):.1f}")
+    assert worst < 2.0 ** -18
+    # every true neighbour is among the candidates, self included
+    oi, _ = orc.knn(x, k, 500, 500 + nq)
+    for t in range(0, nq, 11):
+        assert set(oi[t].tolist()) <= set(ci[t, :m].astype(np.int64).tolist())
+
+
+def test_tensor_path_is_used_and_fallback_is_rare():
+    x = clustered(50_000, 50, 30, seed=1)
+    st = {}
+    idx, dist = vv.make_knn(x, k=50, verbose=False, algo="tensor", stats=st)
+    assert st["algo_used"] == 2 and st["candidates"] == 67
+    assert st["rows_fallback"] <= 0.01 * st["rows"], st
+    for q0 in (0, 25_000, 49_000):
+        wi, wd = orc.knn(x, 50, q0, q0 + 500)
+        assert np.array_equal(idx[q0:q0 + 500], wi) and np.array_equal(dist[q0:q0 + 500], wd)
+    with pytest.raises(NotImplementedError):
+        vv.make_knn(clustered(500, 100, 3, seed=2), k=10, verbose=False, algo="tensor")  # d > 61: brute only
+
+
+def test_certificate_rejects_adversarial_rows_and_fallback_repairs_them():
+    """Points on a fine grid far from the data's bulk: thousands of near-ties within the screening
+    error of each other.  Whatever the certificate decides, the answer must be exact."""
+    rng = np.random.default_rng(4)
+    bulk = rng.standard_normal((3000, 8)).astype(np.float32) * 50.0
+    grid = (rng.integers(0, 3, size=(3000, 8)).astype(np.float32) * 1e-3) + 40.0
+    x = np.concatenate([bulk, grid]).astype(np.float32)
+    st = {}
+    got = vv.make_knn(x, k=20, verbose=False, algo="tensor", stats=st)
+    assert_knn_equal(got, orc.knn(x, 20))
+    print("adversarial fallback rows:", st["rows_fallback"], "of", st["rows"])

@@ -43,6 +43,10 @@ bool knn_tensor_supported(int64_t n, int d, int k);
 int launch_knn_tensor(const float *x_dev, int64_t n, int d, int k, int64_t q0, int64_t nq, int64_t *out_idx,
                       float *out_dist, void *workspace, size_t workspace_bytes, cudaStream_t stream,
                       vvb_knn_stats *stats);
+int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, int64_t nq, uint32_t *cand_idx_out,
+                     float *cand_key_out, int *cand_cnt_out, float *cand_thr_out, float *xnorm_out,
+                     float *scale_ymax_out, float *mu_out);
+int knn_screen_debug_capacity();
 size_t smooth_workspace_bytes(int elem_size, int64_t n, int d, int n_iter);
 int launch_smooth(const void *x, int elem_size, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
                   double coef, int n_iter, int mode, void *out, void *workspace, size_t workspace_bytes,
@@ -196,6 +200,17 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
                            cudaMemcpyDeviceToHost, st));
   VVB_CUDA(cudaStreamSynchronize(st));
   return VVB_OK;
+}
+
+int vvb_knn_screen_debug_capacity(void) { return knn_screen_debug_capacity(); }
+
+int vvb_knn_screen_debug_host(const float *x_host, int64_t n, int d, int k, int64_t q0, int64_t nq,
+                              uint32_t *cand_idx_out, float *cand_key_out, int32_t *cand_cnt_out,
+                              float *cand_thr_out, float *xnorm_out, float *scale_ymax_out, float *mu_out) {
+  VVB_REQUIRE(x_host && cand_idx_out && cand_key_out && cand_cnt_out && cand_thr_out && xnorm_out && scale_ymax_out &&
+                  mu_out, "screen debug: null pointer argument");
+  return knn_screen_debug(x_host, n, d, k, q0, nq, cand_idx_out, cand_key_out, cand_cnt_out, cand_thr_out, xnorm_out,
+                          scale_ymax_out, mu_out);
 }
 
 // --------------------------------------------------------------------- smooth

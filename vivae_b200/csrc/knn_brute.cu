@@ -25,10 +25,15 @@ constexpr int BR_DC = 16;  // coordinates per chunk
 template <int E>
 __global__ void __launch_bounds__(BR_THREADS) knn_brute_kernel(
     const float *__restrict__ x, int64_t n, int d, const int64_t *__restrict__ qrows, int64_t q0,
-    int64_t nq, int k, float *__restrict__ cand_key, uint32_t *__restrict__ cand_idx,
-    int64_t *__restrict__ out_idx, float *__restrict__ out_dist, int64_t out_row0) {
+    int64_t nq_max, const int *__restrict__ nq_dev, int k, float *__restrict__ cand_key,
+    uint32_t *__restrict__ cand_idx, int64_t *__restrict__ out_idx, float *__restrict__ out_dist,
+    int64_t out_row0) {
   constexpr int CAP = 32 * E;
   __shared__ __align__(16) float ys[BR_TJ][BR_DC];
+  // the row count may live on the device (fallback list of the tensor-core path)
+  int64_t nq = nq_max;
+  if (nq_dev != nullptr) nq = min(nq_max, static_cast<int64_t>(*nq_dev));
+  if (static_cast<int64_t>(blockIdx.x) * BR_THREADS >= nq) return;  // whole CTA idle
 
   const int lane = threadIdx.x & 31;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * BR_THREADS + threadIdx.x;
@@ -140,9 +145,9 @@ size_t brute_workspace_bytes(int64_t nq, int k) {
 
 // Launch the brute-force kernel for `nq` query rows (contiguous from q0, or listed in
 // qrows_dev) against the n database rows of x_dev.  Output row of query `g` is g - out_row0.
-int launch_knn_brute(const float *x_dev, int64_t n, int d, int k, const int64_t *qrows_dev,
-                     int64_t q0, int64_t nq, int64_t *out_idx, float *out_dist, int64_t out_row0,
-                     void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+static int launch_knn_brute_impl(const float *x_dev, int64_t n, int d, int k, const int64_t *qrows_dev,
+                                 const int *count_dev, int64_t q0, int64_t nq, int64_t *out_idx, float *out_dist,
+                                 int64_t out_row0, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (nq == 0) return VVB_OK;
   VVB_REQUIRE(n <= 0xffffffffLL, "brute kNN: n=%lld exceeds the 32-bit candidate index", (long long)n);
   VVB_REQUIRE(k + BR_TJ + 32 <= 2048, "brute kNN: k=%d above the supported maximum of 1984", k);
@@ -156,7 +161,7 @@ int launch_knn_brute(const float *x_dev, int64_t n, int d, int k, const int64_t 
   const unsigned grid = static_cast<unsigned>(rows / BR_THREADS);
 #define VVB_BRUTE_CASE(EE)                                                                         \
   case 32 * EE:                                                                                    \
-    knn_brute_kernel<EE><<<grid, BR_THREADS, 0, stream>>>(x_dev, n, d, qrows_dev, q0, nq, k, ck,   \
+    knn_brute_kernel<EE><<<grid, BR_THREADS, 0, stream>>>(x_dev, n, d, qrows_dev, q0, nq, count_dev, k, ck, \
                                                           ci, out_idx, out_dist, out_row0);        \
     break;
   switch (cap) {
@@ -172,6 +177,21 @@ int launch_knn_brute(const float *x_dev, int64_t n, int d, int k, const int64_t 
 #undef VVB_BRUTE_CASE
   VVB_CHECK_LAUNCH();
   return VVB_OK;
+}
+
+int launch_knn_brute(const float *x_dev, int64_t n, int d, int k, const int64_t *qrows_dev, int64_t q0,
+                     int64_t nq, int64_t *out_idx, float *out_dist, int64_t out_row0, void *workspace,
+                     size_t workspace_bytes, cudaStream_t stream) {
+  return launch_knn_brute_impl(x_dev, n, d, k, qrows_dev, nullptr, q0, nq, out_idx, out_dist, out_row0, workspace,
+                               workspace_bytes, stream);
+}
+
+// rows listed in qrows_dev[0 .. *count_dev) (count known only on the device; at most max_rows)
+int launch_knn_brute_list(const float *x_dev, int64_t n, int d, int k, const int64_t *qrows_dev,
+                          const int *count_dev, int64_t max_rows, int64_t *out_idx, float *out_dist,
+                          int64_t out_row0, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return launch_knn_brute_impl(x_dev, n, d, k, qrows_dev, count_dev, 0, max_rows, out_idx, out_dist, out_row0,
+                               workspace, workspace_bytes, stream);
 }
 
 }  // namespace vvb

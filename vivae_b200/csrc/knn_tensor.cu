@@ -1,12 +1,810 @@
-// Tensor-core screening path (tcgen05 / TMEM / TMA) -- placeholder until the kernel lands.
+// Exact kNN, tensor-core path:  screening GEMM (tcgen05 / TMEM / TMA)  ->  FP32 re-rank
+// + certificate  ->  brute-force fallback for the rows the certificate rejects.
+//
+// Screening key.  Rows are mean-centred and scaled by a power of two so that the largest
+// centred norm is <= 64, then split into two FP16 numbers x^ = hi + lo (22 significant
+// bits).  For query i and database row j the tensor cores evaluate, in FP32,
+//     key(i,j) = |y^_j|^2 - 2 ( xh.yh + xh.yl + xl.yh )        ( = |x^-y^|^2 - |x^|^2 + O(2^-22) )
+// as ONE accumulation: the query operand holds [-2 xh | 1 1 1] and [-2 xl], the database
+// operand [yh | nh nl nl2] (the squared norm as a three-term FP16 sum riding in the padded
+// K slots) and [yl]; three descriptor pairs (hi,hi) (hi,lo) (lo,hi) are issued into the
+// same TMEM accumulator, so the epilogue is a bare compare of the accumulator against the
+// row's running threshold.
+//
+// Kernel shape (one CTA per SM, persistent over the database):
+//   CTA = 256 query rows (two M=128 MMAs share every database tile), database tile N=128,
+//   warp 0 lane 0 : TMA producer  (query operand once, database tiles through a 3-stage ring)
+//   warp 1 lane 0 : tcgen05.mma issuer, accumulators double-buffered in TMEM (4 x 128 columns)
+//   warp 2        : TMEM allocator
+//   warps 4..11   : epilogue -- tcgen05.ld 32x32b, ONE THREAD OWNS ONE QUERY ROW, so the
+//                   running threshold tau and the candidate count are registers; a 32-column
+//                   chunk is screened with a min-tree + one compare, survivors are appended to
+//                   the row's candidate list (global memory, L2 resident); a nearly full list is
+//                   sorted by the warp in registers and truncated to the best m, tightening tau.
+// Everything a row ever rejected has key >= its final tau, which is what the certificate uses.
+//
+// Exactness.  The re-rank kernel recomputes the contract's FP32 fmaf-chain distance for the m
+// candidates, sorts by (d2, index) and emits the k best.  Row i is certified when
+//     s^2 * D_k(i)  <  tau_i + |x^_i|^2 - eps_i,     eps_i = 2^-15 (|x^_i| + Ymax)^2
+// i.e. even after the worst-case screening error no rejected row can beat the k-th neighbour;
+// otherwise the row is recomputed by the FP32 brute-force kernel.  Results are therefore
+// identical to the brute-force contract whatever the tensor cores round.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace vvb {
-bool knn_tensor_supported(int64_t, int, int) { return false; }
-size_t knn_tensor_workspace_bytes(int64_t, int, int, int64_t) { return 256; }
-int launch_knn_tensor(const float *, int64_t, int, int, int64_t, int64_t, int64_t *, float *, void *, size_t,
-                      cudaStream_t, vvb_knn_stats *) {
-  set_error("tensor-core kNN path not built");
-  return VVB_ENOTSUP;
+
+int launch_knn_brute_list(const float *x_dev, int64_t n, int d, int k, const int64_t *qrows_dev,
+                          const int *count_dev, int64_t max_rows, int64_t *out_idx, float *out_dist,
+                          int64_t out_row0, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t brute_workspace_bytes(int64_t nq, int k);
+
+// ------------------------------------------------------------------ compile-time shape
+constexpr int TC_M = 256;            // query rows per CTA
+constexpr int TC_N = 128;            // database rows per tile
+constexpr int TC_STAGES = 3;         // database-tile ring
+constexpr int TC_THREADS = 384;      // 4 control warps + 8 epilogue warps
+constexpr int TC_ATOM_BYTES = 128 * 128;  // 128 rows x 64 fp16 (one 128B-swizzle K atom)
+constexpr int TC_OP_COLS = 128;      // operand row: [hi atom | lo atom] fp16
+constexpr int TC_CAP_E = 8;          // candidate list capacity = 32 * 8 = 256
+constexpr int TC_CAP = 32 * TC_CAP_E;
+constexpr int TC_MAX_D = 61;         // d + 3 norm slots must fit one 64-column atom
+constexpr float TC_PAD_NORM = 60000.0f;
+constexpr float TC_EPS = 1.0f / 32768.0f;  // 2^-15
+
+constexpr size_t TC_SMEM_A = 4 * TC_ATOM_BYTES;                       // [mb][atom]
+constexpr size_t TC_SMEM_B = TC_STAGES * 2 * TC_ATOM_BYTES;           // [stage][atom]
+constexpr size_t TC_SMEM_BYTES = TC_SMEM_A + TC_SMEM_B + 1024 /*align*/ + 256 /*barriers*/;
+
+static inline int tc_candidates(int k) {
+  const int slack = k / 4 > 16 ? k / 4 : 16;
+  return k + 1 + slack;
 }
+
+bool knn_tensor_supported(int64_t n, int d, int k) {
+  return d <= TC_MAX_D && tc_candidates(k) <= TC_CAP - 32 && n >= 2 && n <= 0x7fffffffLL;
+}
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzle shared-memory descriptor of one atom (8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);  // start address
+  d |= static_cast<uint64_t>(0) << 16;                     // leading byte offset (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;             // stride byte offset
+  d |= static_cast<uint64_t>(1) << 46;                     // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: FP16 x FP16 -> FP32, both operands K-major, M=128
+__host__ __device__ constexpr uint32_t make_idesc(int n_cols) {
+  return (1u << 4)                                   // c_format = F32
+         | (0u << 7) | (0u << 10)                    // a_format = b_format = F16
+         | (0u << 15) | (0u << 16)                   // K-major A and B
+         | (static_cast<uint32_t>(n_cols >> 3) << 17)  // N
+         | (static_cast<uint32_t>(128 >> 4) << 24);    // M
+}
+
+// ------------------------------------------------------------------ preparation kernels
+constexpr int PREP_BLOCKS = 256;
+
+// stage 1 of the column means: per-block partial sums in double
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float *__restrict__ x, int64_t n, int d,
+                                                            double *__restrict__ partial) {
+  // thread (c = threadIdx.x % 64, sub = threadIdx.x / 64) sums rows sub, sub+4*gridDim.x ... of column c
+  const int c = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  double acc = 0.0;
+  if (c < d)
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * 4 + sub; r < n; r += static_cast<int64_t>(gridDim.x) * 4)
+      acc += static_cast<double>(__ldg(x + r * d + c));
+  __shared__ double sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (sub == 0) partial[blockIdx.x * 64 + c] = sh[c] + sh[64 + c] + sh[128 + c] + sh[192 + c];
+}
+__global__ void colsum_final_kernel(const double *__restrict__ partial, int nblocks, int64_t n, int d,
+                                    float *__restrict__ mu, unsigned int *__restrict__ maxn2_bits) {
+  const int c = threadIdx.x;
+  if (c < 64) {
+    double acc = 0.0;
+    for (int b = 0; b < nblocks; ++b) acc += partial[b * 64 + c];
+    mu[c] = (c < d) ? static_cast<float>(acc / static_cast<double>(n)) : 0.0f;
+  }
+  if (c == 0) *maxn2_bits = 0u;
+}
+// largest squared centred norm (order-independent: atomicMax on the bits of a non-negative float)
+__global__ void __launch_bounds__(256) maxnorm_kernel(const float *__restrict__ x, int64_t n, int d,
+                                                     const float *__restrict__ mu,
+                                                     unsigned int *__restrict__ maxn2_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  float best = 0.0f;
+  for (int64_t r = warp; r < n; r += nwarps) {
+    float s = 0.0f;
+    for (int c = lane; c < d; c += 32) {
+      const float t = __ldg(x + r * d + c) - __ldg(mu + c);
+      s = fmaf(t, t, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    best = fmaxf(best, s);
+  }
+  if (lane == 0 && best > 0.0f) atomicMax(maxn2_bits, __float_as_uint(best));
+}
+
+struct PrepScalars {  // written by build_operands_kernel (block 0), read by the re-rank kernel
+  float scale;        // power of two
+  float ymax;         // largest scaled centred norm (<= 64 before rounding slack)
+};
+
+__device__ __forceinline__ float pick_scale(float maxn2) {
+  if (!(maxn2 > 0.0f)) return 1.0f;
+  const float target = 64.0f / sqrtf(maxn2);
+  int e;
+  (void)frexpf(target, &e);  // target = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.0f, e - 1);  // largest power of two <= target
+}
+
+// One warp per row: centre, scale, split into FP16 hi/lo, write the database operand row
+// (and, for rows of the query shard, the query operand row and |x^|^2).
+__global__ void __launch_bounds__(256) build_operands_kernel(
+    const float *__restrict__ x, int64_t n, int d, const float *__restrict__ mu,
+    const unsigned int *__restrict__ maxn2_bits, int64_t n_pad, __half *__restrict__ opB, int64_t q0, int64_t nq,
+    int64_t nq_pad, __half *__restrict__ opA, float *__restrict__ xnorm, PrepScalars *__restrict__ scalars) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const float maxn2 = __uint_as_float(*maxn2_bits);
+  const float s = pick_scale(maxn2);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scalars->scale = s;
+    scalars->ymax = sqrtf(maxn2) * s * 1.0001f;
+  }
+  const __half zero = __float2half_rn(0.0f);
+  // rows [0, n_pad) -> database operand; rows [n_pad, n_pad + nq_pad) -> query operand of row q0 + (r - n_pad)
+  for (int64_t w = warp; w < n_pad + nq_pad; w += nwarps) {
+    const bool is_q = w >= n_pad;
+    const int64_t local = is_q ? w - n_pad : w;
+    const int64_t src = is_q ? q0 + local : local;
+    const bool valid = is_q ? (local < nq) : (local < n);
+    __half hi[2], lo[2];
+    float nrm = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = q * 32 + lane;
+      float v = 0.0f;
+      if (valid && c < d) v = (__ldg(x + src * d + c) - __ldg(mu + c)) * s;
+      hi[q] = __float2half_rn(v);
+      const float hf = __half2float(hi[q]);
+      lo[q] = __float2half_rn(v - hf);
+      const float rep = hf + __half2float(lo[q]);
+      nrm = fmaf(rep, rep, nrm);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(FULL, nrm, o);
+    __half *row = (is_q ? opA : opB) + local * TC_OP_COLS;
+    if (is_q) {
+      if (lane == 0) xnorm[local] = nrm;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = q * 32 + lane;
+        __half h = __float2half_rn(-2.0f * __half2float(hi[q]));  // exact (power-of-two factor)
+        __half l = __float2half_rn(-2.0f * __half2float(lo[q]));
+        if (c >= d) {
+          h = (c < d + 3 && valid) ? __float2half_rn(1.0f) : zero;
+          l = zero;
+        }
+        row[c] = h;
+        row[64 + c] = l;
+      }
+    } else {
+      // squared norm as a three-term FP16 sum (33 significant bits)
+      const float base = valid ? nrm : TC_PAD_NORM;
+      const __half n0 = __float2half_rn(base);
+      const float r1 = base - __half2float(n0);
+      const __half n1 = __float2half_rn(r1);
+      const __half n2 = __float2half_rn(r1 - __half2float(n1));
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = q * 32 + lane;
+        __half h = hi[q], l = lo[q];
+        if (c >= d) {
+          h = (c == d) ? n0 : (c == d + 1) ? n1 : (c == d + 2) ? n2 : zero;
+          l = zero;
+        }
+        row[c] = h;
+        row[64 + c] = l;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ the screening kernel
+struct TcParams {
+  int64_t n;        // database rows
+  int64_t nq;       // query rows of this launch
+  int n_tiles;      // ceil(n / TC_N)
+  int ks_hi;        // k-steps (of 16) covering d + 3 columns
+  int ks_lo;        // k-steps covering d columns
+  int keep;         // m: candidates kept per row
+  float *cand_key;  // (nq_pad, TC_CAP)
+  uint32_t *cand_idx;
+  int *cand_cnt;    // (nq_pad)
+  float *cand_thr;  // (nq_pad) final admission threshold tau
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                   const __grid_constant__ CUtensorMap map_b,
+                                                                   const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // 128B swizzle needs 1024-byte aligned atoms
+  const uint32_t smem_a = base;                                 // [mb 2][atom 2] x 16 KB
+  const uint32_t smem_b = base + TC_SMEM_A;                     // [stage][atom 2] x 16 KB
+  const uint32_t bars = base + TC_SMEM_A + TC_SMEM_B;           // mbarriers (8 B each)
+  const uint32_t bar_a_full = bars;
+  const uint32_t bar_b_full = bars + 8;                         // [TC_STAGES]
+  const uint32_t bar_b_empty = bar_b_full + 8 * TC_STAGES;      // [TC_STAGES]
+  const uint32_t bar_acc_full = bar_b_empty + 8 * TC_STAGES;    // [2]
+  const uint32_t bar_acc_empty = bar_acc_full + 16;             // [2]
+  const uint32_t tmem_slot = bar_acc_empty + 16;                // u32 written by tcgen05.alloc
+  volatile uint32_t *tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t q_base = static_cast<int64_t>(blockIdx.x) * TC_M;  // first (local) query row of this CTA
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_a_full, 1);
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar_b_full + 8 * s, 1);
+      mbar_init(bar_b_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc_full + 8 * b, 1);
+      mbar_init(bar_acc_empty + 8 * b, 8);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      mbar_expect_tx(bar_a_full, 4 * TC_ATOM_BYTES);
+      for (int mb = 0; mb < 2; ++mb)
+        for (int atom = 0; atom < 2; ++atom)
+          tma_load_2d(smem_a + (mb * 2 + atom) * TC_ATOM_BYTES, &map_a, bar_a_full, atom * 64,
+                      static_cast<int>(q_base + mb * 128));
+      for (int t = 0; t < p.n_tiles; ++t) {
+        const int s = t % TC_STAGES;
+        const uint32_t ph = (t / TC_STAGES) & 1;
+        mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_b_full + 8 * s, 2 * TC_ATOM_BYTES);
+        for (int atom = 0; atom < 2; ++atom)
+          tma_load_2d(smem_b + (s * 2 + atom) * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, atom * 64, t * TC_N);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TC_N);
+      mbar_wait(bar_a_full, 0);
+      for (int t = 0; t < p.n_tiles; ++t) {
+        const int s = t % TC_STAGES;
+        const uint32_t ph = (t / TC_STAGES) & 1;
+        const int buf = t & 1;
+        const uint32_t aph = (t >> 1) & 1;
+        mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
+        mbar_wait(bar_b_full + 8 * s, ph);
+        tc_fence_after();
+        const uint64_t b_hi = make_desc(smem_b + (s * 2 + 0) * TC_ATOM_BYTES);
+        const uint64_t b_lo = make_desc(smem_b + (s * 2 + 1) * TC_ATOM_BYTES);
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((buf * 2 + mb) * TC_N);
+          const uint64_t a_hi = make_desc(smem_a + (mb * 2 + 0) * TC_ATOM_BYTES);
+          const uint64_t a_lo = make_desc(smem_a + (mb * 2 + 1) * TC_ATOM_BYTES);
+          uint32_t acc = 0;
+          for (int ks = 0; ks < p.ks_hi; ++ks) {  // [-2xh | 1 1 1] . [yh | norm]
+            tc_mma_f16(d_tmem, a_hi + 2 * ks, b_hi + 2 * ks, idesc, acc);
+            acc = 1;
+          }
+          for (int ks = 0; ks < p.ks_lo; ++ks) tc_mma_f16(d_tmem, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1);  // xh.yl
+          for (int ks = 0; ks < p.ks_lo; ++ks) tc_mma_f16(d_tmem, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1);  // xl.yh
+        }
+        tc_commit(bar_b_empty + 8 * s);       // smem stage reusable once these MMAs retire
+        tc_commit(bar_acc_full + 8 * buf);    // accumulators ready for the epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue: fused per-row top-m ===========================
+    const int ew = warp - 4;          // 0..7
+    const int quad = warp & 3;        // TMEM lane quadrant this warp may access
+    const int mb = ew >> 2;           // which M=128 block
+    const int64_t t_row = q_base + mb * 128 + quad * 32 + lane;  // local query row owned by this thread
+    const bool active = t_row < p.nq;
+    float *ck = p.cand_key + t_row * TC_CAP;
+    uint32_t *ci = p.cand_idx + t_row * TC_CAP;
+    float tau = active ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
+    int cnt = 0;
+
+    for (int t = 0; t < p.n_tiles; ++t) {
+      const int buf = t & 1;
+      const uint32_t aph = (t >> 1) & 1;
+      mbar_wait(bar_acc_full + 8 * buf, aph);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>((buf * 2 + mb) * TC_N);
+#pragma unroll 1
+      for (int chunk = 0; chunk < TC_N / 32; ++chunk) {
+        float v[32];
+        tc_ld32(t_acc + chunk * 32, v);
+        if (chunk == TC_N / 32 - 1) {  // accumulator fully drained into registers: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+        }
+        // room for up to 32 admissions
+        unsigned need = __ballot_sync(FULL, cnt > TC_CAP - 32);
+        while (need) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          const int64_t tt = __shfl_sync(FULL, t_row, src);
+          const int c = __shfl_sync(FULL, cnt, src);
+          int nc;
+          const float thr =
+              warp_sort_truncate<TC_CAP_E>(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, lane, &nc);
+          if (lane == src) {
+            cnt = nc;
+            tau = thr;
+          }
+        }
+        float mn = v[0];
+#pragma unroll
+        for (int c = 1; c < 32; ++c) mn = fminf(mn, v[c]);
+        if (mn < tau) {
+          const int64_t j0 = static_cast<int64_t>(t) * TC_N + chunk * 32;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (v[c] < tau && j0 + c < p.n) {
+              ck[cnt] = v[c];
+              ci[cnt] = static_cast<uint32_t>(j0 + c);
+              ++cnt;
+            }
+          }
+        }
+      }
+    }
+    // final: sort every row's list, keep the best m, publish count and threshold
+    for (int src = 0; src < 32; ++src) {
+      const int64_t tt = __shfl_sync(FULL, t_row, src);
+      const int c = __shfl_sync(FULL, cnt, src);
+      if (tt >= p.nq) continue;  // warp-uniform
+      int nc;
+      const float thr =
+          warp_sort_truncate<TC_CAP_E>(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, lane, &nc);
+      if (lane == 0) {
+        p.cand_cnt[tt] = nc;
+        p.cand_thr[tt] = thr;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ re-rank + certificate
+// One warp per query row.  E = ceil(m / 32).
+template <int E>
+__global__ void __launch_bounds__(256) knn_rerank_kernel(
+    const float *__restrict__ x, int64_t n, int d, int64_t q0, int64_t nq, int k,
+    const uint32_t *__restrict__ cand_idx, const int *__restrict__ cand_cnt, const float *__restrict__ cand_thr,
+    const float *__restrict__ xnorm, const PrepScalars *__restrict__ scalars, int64_t *__restrict__ out_idx,
+    float *__restrict__ out_dist, int *__restrict__ fb_count, int64_t *__restrict__ fb_rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (t >= nq) return;  // warp-uniform
+  const int64_t g = q0 + t;
+  const int cnt = cand_cnt[t];
+  const float *xq = x + g * d;
+  uint64_t key[E];
+  bool self_here = false;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int pos = e * 32 + lane;
+    key[e] = ~0ull;
+    if (pos < cnt) {
+      const uint32_t j = cand_idx[t * TC_CAP + pos];
+      const float *y = x + static_cast<int64_t>(j) * d;
+      float acc = 0.0f;
+      for (int c = 0; c < d; ++c) {  // the contract's chain: left to right, one rounding per fmaf
+        const float df = __fsub_rn(__ldg(xq + c), __ldg(y + c));
+        acc = __fmaf_rn(df, df, acc);
+      }
+      if (static_cast<int64_t>(j) == g) {
+        key[e] = 0ull;  // self sorts first
+        self_here = true;
+      } else {
+        key[e] = (static_cast<uint64_t>(__float_as_uint(acc) + 1u) << 32) | j;  // d2 >= 0: bits are monotone
+      }
+    }
+  }
+  const bool has_self = __any_sync(FULL, self_here);
+  warp_bitonic_sort<E>(key, lane);
+  const int shift = has_self ? 0 : 1;  // self absent from the list (more than m duplicates): still column 0
+  int64_t *oi = out_idx + t * (k + 1);
+  float *od = out_dist + t * (k + 1);
+  if (lane == 0) {
+    oi[0] = g;
+    od[0] = 0.0f;
+  }
+  const int pos_k = k - shift;  // sorted position of the k-th non-self neighbour
+  float dk = 0.0f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int pos = e * 32 + lane;
+    const int col = pos + shift;
+    const bool is_self = has_self && pos == 0;
+    if (col <= k && !is_self) {
+      if (pos < cnt) {
+        oi[col] = static_cast<int64_t>(static_cast<uint32_t>(key[e]));
+        od[col] = __fsqrt_rn(__uint_as_float(static_cast<uint32_t>(key[e] >> 32) - 1u));
+      } else {
+        oi[col] = -1;
+        od[col] = __int_as_float(0x7fc00000);
+      }
+    }
+    if (pos_k / 32 == e) {
+      const uint64_t kv = __shfl_sync(FULL, key[e], pos_k & 31);
+      dk = __uint_as_float(static_cast<uint32_t>(kv >> 32) - 1u);
+    }
+  }
+  // certificate: no rejected row can beat the k-th neighbour, whatever the screening rounded
+  const float thr = cand_thr[t];
+  const float xn = xnorm[t];
+  const float s = scalars->scale, ymax = scalars->ymax;
+  const float r = sqrtf(xn) + ymax;
+  const float eps = TC_EPS * r * r;
+  bool ok = cnt > pos_k;
+  if (ok && thr < __int_as_float(0x7f800000)) ok = (dk * s * s) < (thr + xn - eps);
+  if (!ok && lane == 0) {
+    const int slot = atomicAdd(fb_count, 1);
+    fb_rows[slot] = g;
+  }
+}
+
+// ------------------------------------------------------------------ host orchestration
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// operand matrix (rows, 128) fp16 row-major; box = 64 columns x 128 rows, 128B swizzle
+static int make_operand_map(CUtensorMap *map, void *ptr, int64_t rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return VVB_ECUDA;
+  }
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(TC_OP_COLS), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(TC_OP_COLS) * sizeof(__half)};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return VVB_ECUDA;
+  }
+  return VVB_OK;
+}
+
+struct TcLayout {
+  int64_t n_pad, nq_pad;
+  __half *opB, *opA;
+  double *partial;
+  float *mu;
+  unsigned int *maxn2;
+  PrepScalars *scalars;
+  float *xnorm;
+  float *cand_key;
+  uint32_t *cand_idx;
+  int *cand_cnt;
+  float *cand_thr;
+  int *fb_count;
+  int64_t *fb_rows;
+  void *brute_ws;
+  size_t brute_ws_bytes;
+  size_t total;
+};
+
+static TcLayout tc_layout(void *ws, int64_t n, int k, int64_t nq) {
+  TcLayout L;
+  L.n_pad = (n + TC_N - 1) / TC_N * TC_N;
+  L.nq_pad = (nq + TC_M - 1) / TC_M * TC_M;
+  if (L.nq_pad == 0) L.nq_pad = TC_M;
+  Carver cv(ws);
+  L.opB = cv.take<__half>(static_cast<size_t>(L.n_pad) * TC_OP_COLS);
+  L.opA = cv.take<__half>(static_cast<size_t>(L.nq_pad) * TC_OP_COLS);
+  L.partial = cv.take<double>(PREP_BLOCKS * 64);
+  L.mu = cv.take<float>(64);
+  L.maxn2 = cv.take<unsigned int>(1);
+  L.scalars = cv.take<PrepScalars>(1);
+  L.xnorm = cv.take<float>(static_cast<size_t>(L.nq_pad));
+  L.cand_cnt = cv.take<int>(static_cast<size_t>(L.nq_pad));
+  L.cand_thr = cv.take<float>(static_cast<size_t>(L.nq_pad));
+  L.fb_count = cv.take<int>(1);
+  L.fb_rows = cv.take<int64_t>(static_cast<size_t>(L.nq_pad));
+  L.cand_key = cv.take<float>(static_cast<size_t>(L.nq_pad) * TC_CAP);
+  L.cand_idx = cv.take<uint32_t>(static_cast<size_t>(L.nq_pad) * TC_CAP);
+  // the fallback's candidate lists reuse the screening lists (dead after the re-rank)
+  L.brute_ws = L.cand_key;
+  L.brute_ws_bytes = static_cast<size_t>(L.nq_pad) * TC_CAP * 8;
+  const size_t need_brute = brute_workspace_bytes(nq, k);
+  if (need_brute > L.brute_ws_bytes) {  // never for the supported k, kept for safety
+    L.brute_ws = cv.take<char>(need_brute);
+    L.brute_ws_bytes = need_brute;
+  }
+  L.total = cv.used() + 256;
+  return L;
+}
+
+size_t knn_tensor_workspace_bytes(int64_t n, int d, int k, int64_t nq) {
+  (void)d;
+  return tc_layout(nullptr, n, k, nq).total;
+}
+
+int launch_knn_tensor(const float *x_dev, int64_t n, int d, int k, int64_t q0, int64_t nq, int64_t *out_idx,
+                      float *out_dist, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                      vvb_knn_stats *stats) {
+  VVB_REQUIRE(knn_tensor_supported(n, d, k), "tensor kNN: unsupported shape n=%lld d=%d k=%d", (long long)n, d, k);
+  if (nq == 0) return VVB_OK;
+  TcLayout L = tc_layout(workspace, n, k, nq);
+  VVB_REQUIRE(workspace_bytes >= L.total, "tensor kNN: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+  const int keep = tc_candidates(k);
+
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(TC_SMEM_BYTES)));
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (stats)
+    for (auto &e : ev) VVB_CUDA(cudaEventCreate(&e));
+  auto mark = [&](int i) {
+    if (stats) cudaEventRecord(ev[i], st);
+  };
+
+  // ---- prepare: means, max centred norm, operands
+  mark(0);
+  colsum_partial_kernel<<<PREP_BLOCKS, 256, 0, st>>>(x_dev, n, d, L.partial);
+  VVB_CHECK_LAUNCH();
+  colsum_final_kernel<<<1, 64, 0, st>>>(L.partial, PREP_BLOCKS, n, d, L.mu, L.maxn2);
+  VVB_CHECK_LAUNCH();
+  const int prep_grid = sm_count() * 8;
+  maxnorm_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.mu, L.maxn2);
+  VVB_CHECK_LAUNCH();
+  build_operands_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.mu, L.maxn2, L.n_pad, L.opB, q0, nq, L.nq_pad,
+                                                   L.opA, L.xnorm, L.scalars);
+  VVB_CHECK_LAUNCH();
+  VVB_CUDA(cudaMemsetAsync(L.fb_count, 0, sizeof(int), st));
+
+  // ---- screen
+  CUtensorMap map_a, map_b;
+  int rc = make_operand_map(&map_a, L.opA, L.nq_pad);
+  if (rc) return rc;
+  rc = make_operand_map(&map_b, L.opB, L.n_pad);
+  if (rc) return rc;
+  TcParams p;
+  p.n = n;
+  p.nq = nq;
+  p.n_tiles = static_cast<int>(L.n_pad / TC_N);
+  p.ks_hi = (d + 3 + 15) / 16;
+  p.ks_lo = (d + 15) / 16;
+  p.keep = keep;
+  p.cand_key = L.cand_key;
+  p.cand_idx = L.cand_idx;
+  p.cand_cnt = L.cand_cnt;
+  p.cand_thr = L.cand_thr;
+  mark(1);
+  knn_screen_kernel<<<static_cast<unsigned>(L.nq_pad / TC_M), TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, p);
+  VVB_CHECK_LAUNCH();
+
+  // ---- re-rank + certificate
+  mark(2);
+  const unsigned rr_grid = static_cast<unsigned>((nq + 7) / 8);
+  const int e_need = (keep + 31) / 32;
+#define VVB_RR(EE)                                                                                               \
+  knn_rerank_kernel<EE><<<rr_grid, 256, 0, st>>>(x_dev, n, d, q0, nq, k, L.cand_idx, L.cand_cnt, L.cand_thr,    \
+                                                 L.xnorm, L.scalars, out_idx, out_dist, L.fb_count, L.fb_rows)
+  if (e_need <= 2) VVB_RR(2);
+  else if (e_need <= 4) VVB_RR(4);
+  else VVB_RR(8);
+#undef VVB_RR
+  VVB_CHECK_LAUNCH();
+
+  // ---- fallback: rows the certificate rejected, exact FP32 brute force (device-side count)
+  mark(3);
+  rc = launch_knn_brute_list(x_dev, n, d, k, L.fb_rows, L.fb_count, nq, out_idx, out_dist, q0, L.brute_ws,
+                             L.brute_ws_bytes, st);
+  if (rc) return rc;
+  mark(4);
+
+  if (stats) {
+    int fb = 0;
+    VVB_CUDA(cudaMemcpyAsync(&fb, L.fb_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VVB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]);
+    stats->ms_prepare = ms;
+    cudaEventElapsedTime(&ms, ev[1], ev[2]);
+    stats->ms_screen = ms;
+    cudaEventElapsedTime(&ms, ev[2], ev[3]);
+    stats->ms_rerank = ms;
+    cudaEventElapsedTime(&ms, ev[3], ev[4]);
+    stats->ms_fallback = ms;
+    stats->rows_fallback = fb;
+    stats->candidates = keep;
+    for (auto &e : ev) cudaEventDestroy(e);
+  }
+  return VVB_OK;
+}
+
+// Diagnostics: run preparation + screening only and hand the raw candidate lists back to the
+// host (tests use this to measure the screening error against FP64 and to check the lists).
+int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, int64_t nq, uint32_t *cand_idx_out,
+                     float *cand_key_out, int *cand_cnt_out, float *cand_thr_out, float *xnorm_out,
+                     float *scale_ymax_out, float *mu_out) {
+  VVB_REQUIRE(knn_tensor_supported(n, d, k) && nq >= 1 && q0 >= 0 && q0 + nq <= n, "screen debug: unsupported shape");
+  const size_t ws_bytes = knn_tensor_workspace_bytes(n, d, k, nq);
+  void *ws = nullptr, *xd = nullptr;
+  VVB_CUDA(cudaMalloc(&ws, ws_bytes));
+  VVB_CUDA(cudaMalloc(&xd, static_cast<size_t>(n) * d * sizeof(float)));
+  VVB_CUDA(cudaMemcpy(xd, x_host, static_cast<size_t>(n) * d * sizeof(float), cudaMemcpyHostToDevice));
+  TcLayout L = tc_layout(ws, n, k, nq);
+  cudaStream_t st = nullptr;
+  const float *x_dev = static_cast<const float *>(xd);
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(TC_SMEM_BYTES)));
+  colsum_partial_kernel<<<PREP_BLOCKS, 256, 0, st>>>(x_dev, n, d, L.partial);
+  colsum_final_kernel<<<1, 64, 0, st>>>(L.partial, PREP_BLOCKS, n, d, L.mu, L.maxn2);
+  const int prep_grid = sm_count() * 8;
+  maxnorm_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.mu, L.maxn2);
+  build_operands_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.mu, L.maxn2, L.n_pad, L.opB, q0, nq, L.nq_pad,
+                                                   L.opA, L.xnorm, L.scalars);
+  count_launch(4);
+  CUtensorMap map_a, map_b;
+  int rc = make_operand_map(&map_a, L.opA, L.nq_pad);
+  if (!rc) rc = make_operand_map(&map_b, L.opB, L.n_pad);
+  if (!rc) {
+    TcParams p;
+    p.n = n;
+    p.nq = nq;
+    p.n_tiles = static_cast<int>(L.n_pad / TC_N);
+    p.ks_hi = (d + 3 + 15) / 16;
+    p.ks_lo = (d + 15) / 16;
+    p.keep = tc_candidates(k);
+    p.cand_key = L.cand_key;
+    p.cand_idx = L.cand_idx;
+    p.cand_cnt = L.cand_cnt;
+    p.cand_thr = L.cand_thr;
+    knn_screen_kernel<<<static_cast<unsigned>(L.nq_pad / TC_M), TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, p);
+    count_launch();
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      set_error("screen debug: %s", cudaGetErrorString(e));
+      rc = VVB_ECUDA;
+    }
+  }
+  if (!rc) {
+    cudaMemcpy(cand_idx_out, L.cand_idx, static_cast<size_t>(nq) * TC_CAP * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(cand_key_out, L.cand_key, static_cast<size_t>(nq) * TC_CAP * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(cand_cnt_out, L.cand_cnt, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(cand_thr_out, L.cand_thr, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(xnorm_out, L.xnorm, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(scale_ymax_out, L.scalars, 2 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaMemcpy(mu_out, L.mu, 64 * sizeof(float), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(ws);
+  cudaFree(xd);
+  return rc;
+}
+
+int knn_screen_debug_capacity() { return TC_CAP; }
+
 }  // namespace vvb

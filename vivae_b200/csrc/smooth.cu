@@ -19,7 +19,7 @@ namespace vvb {
 
 constexpr int SM_THREADS = 256;
 constexpr int SM_ROWS_PER_TICKET = 4;
-constexpr int SM_UNROLL = 8;  // neighbour rows in flight per warp
+constexpr int SM_UNROLL = 16;  // neighbour rows in flight per warp
 
 template <typename T> struct Arith;
 template <> struct Arith<float> {
@@ -36,7 +36,8 @@ template <> struct Arith<double> {
 };
 
 // DPL = columns per lane held in registers (a warp covers 32*DPL columns per pass)
-template <typename T, int DPL, bool GS>
+// KPL = neighbour indices per lane held in registers (k <= 32*KPL)
+template <typename T, int DPL, int KPL, bool GS>
 __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
     const T *__restrict__ prev, T *next, const int64_t *__restrict__ idx, int64_t ld_idx, int64_t n,
     int d, int k, T coef, int *flags, int epoch, unsigned long long *ticket) {
@@ -49,15 +50,24 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
     if (base >= static_cast<unsigned long long>(n)) break;
     const int64_t row_end = min(static_cast<int64_t>(base) + SM_ROWS_PER_TICKET, n);
     for (int64_t i = static_cast<int64_t>(base); i < row_end; ++i) {
+      // the row's neighbour list, coalesced, into registers: lane l holds entries l, l+32, ...
       const int64_t *nb = idx + i * ld_idx;
+      int64_t mine[KPL];
+#pragma unroll
+      for (int q = 0; q < KPL; ++q) {
+        const int jj = q * 32 + lane;
+        mine[q] = (jj < k) ? __ldg(nb + jj) : i;
+      }
       if (GS) {
-        // wait until every lower-indexed neighbour has been published in this sweep
-        for (int jb = 0; jb < k; jb += 32) {
-          const int jj = jb + lane;
-          if (jj < k) {
-            const int64_t j = nb[jj];
-            if (j < i) {
-              while (ld_acquire(flags + j) < epoch) __nanosleep(40);
+        // wait until every lower-indexed neighbour has been published in this sweep;
+        // exponential back-off keeps thousands of waiting lanes from flooding L2 with polls
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+          if (mine[q] < i) {
+            unsigned ns = 64;
+            while (ld_acquire(flags + mine[q]) < epoch) {
+              __nanosleep(ns);
+              if (ns < 2048) ns <<= 1;
             }
           }
         }
@@ -65,30 +75,37 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
       }
       for (int c0 = 0; c0 < d; c0 += 32 * DPL) {
         T acc[DPL];
+#pragma unroll
+        for (int q = 0; q < DPL; ++q) acc[q] = T(0);
         bool first = true;
-        for (int jb = 0; jb < k; jb += SM_UNROLL) {
-          T v[SM_UNROLL][DPL];
 #pragma unroll
-          for (int u = 0; u < SM_UNROLL; ++u) {
-            if (jb + u < k) {
-              const int64_t j = nb[jb + u];  // warp-uniform broadcast load
-              const bool from_next = GS && (j < i);
-              const T *src = (from_next ? static_cast<const T *>(next) : prev) + j * d;
+        for (int kq = 0; kq < KPL; ++kq) {
+          if (kq * 32 < k) {  // warp-uniform
+            for (int jb = 0; jb < 32 && kq * 32 + jb < k; jb += SM_UNROLL) {
+              T v[SM_UNROLL][DPL];
 #pragma unroll
-              for (int q = 0; q < DPL; ++q) {
-                const int c = c0 + q * 32 + lane;
-                T val = T(0);
-                if (c < d) val = from_next ? __ldcg(src + c) : __ldg(src + c);
-                v[u][q] = val;
+              for (int u = 0; u < SM_UNROLL; ++u) {
+                const int64_t j = __shfl_sync(FULL, mine[kq], (jb + u) & 31);
+                if (kq * 32 + jb + u < k) {
+                  const bool from_next = GS && (j < i);
+                  const T *src = (from_next ? static_cast<const T *>(next) : prev) + j * d;
+#pragma unroll
+                  for (int q = 0; q < DPL; ++q) {
+                    const int c = c0 + q * 32 + lane;
+                    T val = T(0);
+                    if (c < d) val = from_next ? __ldcg(src + c) : __ldg(src + c);
+                    v[u][q] = val;
+                  }
+                }
               }
-            }
-          }
 #pragma unroll
-          for (int u = 0; u < SM_UNROLL; ++u) {
-            if (jb + u < k) {
+              for (int u = 0; u < SM_UNROLL; ++u) {
+                if (kq * 32 + jb + u < k) {
 #pragma unroll
-              for (int q = 0; q < DPL; ++q) acc[q] = first ? v[u][q] : Arith<T>::add(acc[q], v[u][q]);
-              first = false;
+                  for (int q = 0; q < DPL; ++q) acc[q] = first ? v[u][q] : Arith<T>::add(acc[q], v[u][q]);
+                  first = false;
+                }
+              }
             }
           }
         }
@@ -113,7 +130,7 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
   }
 }
 
-template <typename T, int DPL>
+template <typename T, int DPL, int KPL>
 static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
                          double coef, int n_iter, int mode, T *out, void *workspace, cudaStream_t st) {
   // workspace: [scratch (n*d) T][flags n int][tickets n_iter u64]
@@ -125,8 +142,8 @@ static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64
   VVB_CUDA(cudaMemsetAsync(tickets, 0, static_cast<size_t>(n_iter) * sizeof(unsigned long long), st));
 
   int blocks_per_sm = 0;
-  auto kern_gs = smooth_sweep_kernel<T, DPL, true>;
-  auto kern_ja = smooth_sweep_kernel<T, DPL, false>;
+  auto kern_gs = smooth_sweep_kernel<T, DPL, KPL, true>;
+  auto kern_ja = smooth_sweep_kernel<T, DPL, KPL, false>;
   VVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, mode == VVB_SMOOTH_JACOBI ? kern_ja : kern_gs,
                                                          SM_THREADS, 0));
   if (blocks_per_sm < 1) blocks_per_sm = 1;
@@ -134,6 +151,12 @@ static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64
   int64_t grid = static_cast<int64_t>(sm_count()) * blocks_per_sm;
   const int64_t max_useful = (warps_needed + SM_THREADS / 32 - 1) / (SM_THREADS / 32);
   if (grid > max_useful) grid = max_useful;
+  if (mode != VVB_SMOOTH_JACOBI) {
+    // Gauss-Seidel: rows in flight wait on each other, so keep the in-flight window a small
+    // fraction of n (waiting warps only burn issue slots and L2 polls)
+    const int64_t cap = n / (16 * SM_ROWS_PER_TICKET * (SM_THREADS / 32)) + 1;
+    if (grid > cap) grid = cap;
+  }
   if (grid < 1) grid = 1;
 
   // ping-pong so that the LAST sweep lands in `out`:  sweep s reads a_s, writes b_s
@@ -166,18 +189,26 @@ int launch_smooth(const void *x, int elem_size, int64_t n, int d, const int64_t 
   VVB_REQUIRE(mode == VVB_SMOOTH_GAUSS_SEIDEL || mode == VVB_SMOOTH_JACOBI, "smooth: unknown mode %d", mode);
   VVB_REQUIRE(out != x, "smooth: out must not alias x");
   VVB_REQUIRE(workspace_bytes >= smooth_workspace_bytes(elem_size, n, d, n_iter), "smooth: workspace too small");
+  VVB_REQUIRE(k <= 1024, "smooth: k=%d above the supported maximum of 1024", k);
+#define VVB_SM_K(T, DPL, xp, op)                                                                          \
+  do {                                                                                                    \
+    if (k <= 64) return launch_sweeps<T, DPL, 2>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, st);   \
+    if (k <= 128) return launch_sweeps<T, DPL, 4>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, st);  \
+    return launch_sweeps<T, DPL, 32>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, st);    \
+  } while (0)
   if (elem_size == 4) {
     const float *xf = static_cast<const float *>(x);
     float *of = static_cast<float *>(out);
-    if (d <= 32) return launch_sweeps<float, 1>(xf, n, d, idx, ld_idx, k, coef, n_iter, mode, of, workspace, st);
-    if (d <= 64) return launch_sweeps<float, 2>(xf, n, d, idx, ld_idx, k, coef, n_iter, mode, of, workspace, st);
-    return launch_sweeps<float, 4>(xf, n, d, idx, ld_idx, k, coef, n_iter, mode, of, workspace, st);
+    if (d <= 32) VVB_SM_K(float, 1, xf, of);
+    if (d <= 64) VVB_SM_K(float, 2, xf, of);
+    VVB_SM_K(float, 4, xf, of);
   }
   const double *xd = static_cast<const double *>(x);
   double *od = static_cast<double *>(out);
-  if (d <= 32) return launch_sweeps<double, 1>(xd, n, d, idx, ld_idx, k, coef, n_iter, mode, od, workspace, st);
-  if (d <= 64) return launch_sweeps<double, 2>(xd, n, d, idx, ld_idx, k, coef, n_iter, mode, od, workspace, st);
-  return launch_sweeps<double, 4>(xd, n, d, idx, ld_idx, k, coef, n_iter, mode, od, workspace, st);
+  if (d <= 32) VVB_SM_K(double, 1, xd, od);
+  if (d <= 64) VVB_SM_K(double, 2, xd, od);
+  VVB_SM_K(double, 4, xd, od);
+#undef VVB_SM_K
 }
 
 }  // namespace vvb
