@@ -163,6 +163,84 @@ __device__ __forceinline__ float warp_sort_truncate(float *keys, uint32_t *idxs,
   *new_cnt = nk;
   return thr;
 }
+
+// ---- per-row candidate buffer: cheap threshold selection (no sort) ------------------------
+// Keeps at least the `m` smallest keys of the row's `cnt` entries (at most `keep_max`),
+// compacts them to the front PRESERVING their order (so a buffer filled in increasing index
+// order stays in index order) and returns the new admission threshold tau with the
+// invariant  "every dropped entry has key >= tau".  Requires cnt >= m and m <= keep_max.
+//
+// The threshold is found by a bitwise binary search on the order-preserving integer image of
+// the keys: ~12 warp instructions per bit instead of a ~2.5k-instruction bitonic sort, with
+// an early exit as soon as the count of kept entries lands in [m, m + slack].
+template <int E>
+__device__ __forceinline__ float warp_select_truncate(float *keys, uint32_t *idxs, int cnt, int m, int keep_max,
+                                                      int lane, int *new_cnt) {
+  uint32_t u[E], id[E];
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int p = e * 32 + lane;
+    u[e] = 0xffffffffu;
+    id[e] = 0;
+    if (p < cnt) {
+      u[e] = f2ord(keys[p]);
+      id[e] = idxs[p];
+    }
+  }
+  const int slack = (keep_max - m) < 24 ? (keep_max - m) : 24;
+  uint32_t T = 0;       // invariant: count(u < T) < m
+  uint32_t cut = 0;     // entries with u < cut are kept
+  bool exact = true;    // loop ran to the end: T is the m-th smallest key itself
+  for (int b = 31; b >= 0; --b) {
+    const uint32_t trial = T | (1u << b);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c += (u[e] < trial) ? 1 : 0;
+    c = __reduce_add_sync(FULL, c);
+    if (c < m) {
+      T = trial;
+    } else if (c <= m + slack) {
+      cut = trial;
+      exact = false;
+      break;
+    }
+  }
+  int ties_allowed = 0;
+  if (exact) {
+    // count(u < T) < m <= count(u <= T): keep everything below T plus the first ties
+    int c_less = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c_less += (u[e] < T) ? 1 : 0;
+    c_less = __reduce_add_sync(FULL, c_less);
+    cut = T;
+    ties_allowed = keep_max - c_less;
+  }
+  __syncwarp();
+  int base = 0, ties_seen = 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int p = e * 32 + lane;
+    const bool valid = p < cnt;
+    const bool below = valid && (u[e] < cut);
+    const bool tie = exact && valid && (u[e] == cut);
+    const unsigned tb = __ballot_sync(FULL, tie);
+    const bool tie_kept = tie && (ties_seen + __popc(tb & lt_mask) < ties_allowed);
+    ties_seen += __popc(tb);
+    const bool keep = below || tie_kept;
+    const unsigned kb = __ballot_sync(FULL, keep);
+    if (keep) {
+      const int dst = base + __popc(kb & lt_mask);
+      keys[dst] = ord2f(u[e]);
+      idxs[dst] = id[e];
+    }
+    base += __popc(kb);
+  }
+  __syncwarp();
+  *new_cnt = base;
+  return ord2f(cut);
+}
 #endif  // __CUDACC__
 
 }  // namespace vvb

@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(BR_THREADS) knn_brute_kernel(
       const int64_t tt = __shfl_sync(FULL, t, src);
       const int c = __shfl_sync(FULL, cnt, src);
       int nc;
-      const float thr = warp_sort_truncate<E>(cand_key + tt * CAP, cand_idx + tt * CAP, c, k, lane, &nc);
+      const float thr =
+          warp_select_truncate<E>(cand_key + tt * CAP, cand_idx + tt * CAP, c, k, CAP - 2 * BR_TJ, lane, &nc);
       if (lane == src) {
         cnt = nc;
         tau = thr;

@@ -64,7 +64,7 @@ static inline int tc_candidates(int k) {
 }
 
 bool knn_tensor_supported(int64_t n, int d, int k) {
-  return d <= TC_MAX_D && tc_candidates(k) <= TC_CAP - 32 && n >= 2 && n <= 0x7fffffffLL;
+  return d <= TC_MAX_D && tc_candidates(k) <= TC_CAP - 64 && n >= 2 && n <= 0x7fffffffLL;
 }
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -115,8 +115,10 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// tcgen05.ld is asynchronous: tc_ld32_issue starts the load of 32 consecutive columns of this
+// thread's TMEM lane, tc_ld32_wait makes them usable.  The wait lists the registers as in/out
+// operands so that the compiler cannot move their uses above it.
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -127,9 +129,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                 "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                 "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 
 // K-major, 128B-swizzle shared-memory descriptor of one atom (8-row groups 1024 B apart)
@@ -286,6 +295,17 @@ __global__ void __launch_bounds__(256) build_operands_kernel(
   }
 }
 
+// Out-of-line list maintenance, so that the hot screening loop stays small in the instruction
+// cache.  In-sweep compaction uses the cheap threshold selection; the full sort runs once per
+// row at the end of the sweep.
+__device__ __noinline__ float tc_select_truncate(float *keys, uint32_t *idxs, int cnt, int keep, int lane,
+                                                 int *new_cnt) {
+  return warp_select_truncate<TC_CAP_E>(keys, idxs, cnt, keep, TC_CAP - 64, lane, new_cnt);
+}
+__device__ __noinline__ float tc_sort_truncate(float *keys, uint32_t *idxs, int cnt, int keep, int lane, int *new_cnt) {
+  return warp_sort_truncate<TC_CAP_E>(keys, idxs, cnt, keep, lane, new_cnt);
+}
+
 // ------------------------------------------------------------------ the screening kernel
 struct TcParams {
   int64_t n;        // database rows
@@ -409,6 +429,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     float tau = active ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
     int cnt = 0;
 
+    // One 32-column chunk: make room, then screen.  The chunk is reduced to four group minima
+    // (8 columns each) with 3-input min instructions; only groups that beat tau are expanded.
+    auto process = [&](const uint32_t(&r)[32], int64_t j0) {
+      unsigned need = __ballot_sync(FULL, cnt > TC_CAP - 32);
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int64_t tt = __shfl_sync(FULL, t_row, src);
+        const int c = __shfl_sync(FULL, cnt, src);
+        int nc;
+        const float thr = tc_select_truncate(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, lane, &nc);
+        if (lane == src) {
+          cnt = nc;
+          tau = thr;
+        }
+      }
+      float g[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float a = fminf(fminf(__uint_as_float(r[8 * q + 0]), __uint_as_float(r[8 * q + 1])),
+                              __uint_as_float(r[8 * q + 2]));
+        const float b = fminf(fminf(__uint_as_float(r[8 * q + 3]), __uint_as_float(r[8 * q + 4])),
+                              __uint_as_float(r[8 * q + 5]));
+        g[q] = fminf(fminf(a, b), fminf(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
+      }
+      const float mn = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
+      if (mn < tau) {
+        const int lim = static_cast<int>(min(static_cast<int64_t>(32), p.n - j0));  // columns that are real rows
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (g[q] < tau) {
+#pragma unroll
+            for (int c = 8 * q; c < 8 * q + 8; ++c) {
+              const float v = __uint_as_float(r[c]);
+              if (v < tau && c < lim) {
+                ck[cnt] = v;
+                ci[cnt] = static_cast<uint32_t>(j0 + c);
+                ++cnt;
+              }
+            }
+          }
+        }
+      }
+    };
+
     for (int t = 0; t < p.n_tiles; ++t) {
       const int buf = t & 1;
       const uint32_t aph = (t >> 1) & 1;
@@ -416,44 +481,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>((buf * 2 + mb) * TC_N);
+      const int64_t jt = static_cast<int64_t>(t) * TC_N;
+      // software pipeline over the four chunks: the TMEM load of chunk c+1 is in flight while
+      // chunk c is screened
+      uint32_t ra[32], rb[32];
+      tc_ld32_issue(t_acc, ra);
 #pragma unroll 1
-      for (int chunk = 0; chunk < TC_N / 32; ++chunk) {
-        float v[32];
-        tc_ld32(t_acc + chunk * 32, v);
-        if (chunk == TC_N / 32 - 1) {  // accumulator fully drained into registers: hand it back
+      for (int half = 0; half < 2; ++half) {
+        tc_ld32_wait(ra);
+        tc_ld32_issue(t_acc + half * 64 + 32, rb);
+        process(ra, jt + half * 64);
+        tc_ld32_wait(rb);
+        if (half == 0) {
+          tc_ld32_issue(t_acc + 64, ra);
+        } else {
+          // accumulator fully drained into registers: hand it back to the MMA issuer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
         }
-        // room for up to 32 admissions
-        unsigned need = __ballot_sync(FULL, cnt > TC_CAP - 32);
-        while (need) {
-          const int src = __ffs(need) - 1;
-          need &= need - 1;
-          const int64_t tt = __shfl_sync(FULL, t_row, src);
-          const int c = __shfl_sync(FULL, cnt, src);
-          int nc;
-          const float thr =
-              warp_sort_truncate<TC_CAP_E>(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, lane, &nc);
-          if (lane == src) {
-            cnt = nc;
-            tau = thr;
-          }
-        }
-        float mn = v[0];
-#pragma unroll
-        for (int c = 1; c < 32; ++c) mn = fminf(mn, v[c]);
-        if (mn < tau) {
-          const int64_t j0 = static_cast<int64_t>(t) * TC_N + chunk * 32;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            if (v[c] < tau && j0 + c < p.n) {
-              ck[cnt] = v[c];
-              ci[cnt] = static_cast<uint32_t>(j0 + c);
-              ++cnt;
-            }
-          }
-        }
+        process(rb, jt + half * 64 + 32);
       }
     }
     // final: sort every row's list, keep the best m, publish count and threshold
@@ -462,8 +509,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       const int c = __shfl_sync(FULL, cnt, src);
       if (tt >= p.nq) continue;  // warp-uniform
       int nc;
-      const float thr =
-          warp_sort_truncate<TC_CAP_E>(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, lane, &nc);
+      const float thr = tc_sort_truncate(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, lane, &nc);
       if (lane == 0) {
         p.cand_cnt[tt] = nc;
         p.cand_thr[tt] = thr;
