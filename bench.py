@@ -176,6 +176,7 @@ def run_ours(args) -> None:
     import vivae_b200 as vv
     from vivae_b200 import _lib
     from vivae_b200.device import knn_device, smooth_device
+    from vivae_b200.sharded import all_gather_rows, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -188,20 +189,12 @@ def run_ours(args) -> None:
     n, d, k = args.n, args.d, args.k
     x_host = synth_cells(n, d)
     x_dev = torch.from_numpy(x_host).to(dev)
-    per = (n + world - 1) // world
-    q0 = min(rank * per, n)
-    nq = min(per, n - q0)
+    q0, nq = shard_bounds(n, world, rank)
 
     def step_device(stats=None):
         idx, dist_ = knn_device(x_dev, k, q0, nq, algo=args.algo, stats=stats)
         if world > 1:
-            full = torch.empty((per * world, k + 1), dtype=torch.int64, device=dev)
-            if nq < per:
-                pad = torch.zeros((per, k + 1), dtype=torch.int64, device=dev)
-                pad[:nq] = idx
-                idx = pad
-            dist.all_gather_into_tensor(full, idx)
-            idx = full[:n]
+            idx = all_gather_rows(idx, n)  # the smoother needs the whole graph (NCCL all-gather)
         out = smooth_device(x_dev, idx, k=k, coef=1.0, n_iter=1)
         return idx, dist_, out
 
