@@ -64,6 +64,9 @@ int vvb_version(void);
 const char *vvb_last_error(void);
 /* number of kernels launched by this library in the calling process so far */
 int64_t vvb_launch_count(void);
+/* the *_host entry points keep their device buffers and streams between calls (grow-only);
+ * this frees them */
+int vvb_release_cached_memory(void);
 
 /* ------------------------------------------------------------------------
  * make_knn  -- replaces the cache-miss branch of

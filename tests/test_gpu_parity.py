@@ -305,6 +305,7 @@ def test_fit_replay_matches_reference_run():
         return e
 
     # first call builds the loader; install the replay hooks by running zero epochs first
+    model.use_cuda_graph = False  # the replay hook below swaps torch.randn_like per call: eager only
     model.fit(g["X"], n_epochs=0, batch_size=int(g["batch_size"]), lam_mds=float(g["lam_mds"]), verbose=False)
     model.data_loader._perm_override = next_perm
     torch.randn_like = replay_randn_like
@@ -325,6 +326,25 @@ def test_fit_replay_matches_reference_run():
     emb = model.transform(g["X"])
     # 10 optimiser steps in FP32 on different hardware: compare at 1e-2 of the embedding's spread
     assert np.abs(emb - g["emb"]).max() < 1e-2 * np.abs(g["emb"]).max()
+
+
+def test_cuda_graph_step_matches_eager_training():
+    """The captured step (forward + quartet kernel + backward + Adam) must train exactly like the
+    eager loop: same seed -> same loss log and embedding (warm-up steps are undone before capture)."""
+    x = clustered(6_000 + 37, 20, 6, seed=13)  # 37 tail rows: the short last batch runs eagerly
+    runs = []
+    for use_graph in (False, True):
+        m = vv.ViVAE(input_dim=20, random_state=11)
+        m.use_cuda_graph = use_graph
+        buf = io.StringIO()
+        with redirect_stdout(buf):
+            m.fit(x, n_epochs=3, batch_size=512, lam_mds=10.0)
+        runs.append((buf.getvalue(), m.transform(x), m._graph))
+    assert runs[0][2] is None and runs[1][2] is not None and runs[1][2][1] is not None, "graph path not taken"
+    a = [[float(t.split()[1]) for t in ln.split("\t")[1:]] for ln in runs[0][0].strip().splitlines()]
+    b = [[float(t.split()[1]) for t in ln.split("\t")[1:]] for ln in runs[1][0].strip().splitlines()]
+    np.testing.assert_allclose(a, b, rtol=1e-3, atol=1e-4)
+    assert np.abs(runs[0][1] - runs[1][1]).max() < 2e-3 * np.abs(runs[0][1]).max()
 
 
 def test_full_pipeline_through_public_api():
@@ -413,3 +433,31 @@ def test_certificate_rejects_adversarial_rows_and_fallback_repairs_them():
     got = vv.make_knn(x, k=20, verbose=False, algo="tensor", stats=st)
     assert_knn_equal(got, orc.knn(x, 20))
     print("adversarial fallback rows:", st["rows_fallback"], "of", st["rows"])
+
+
+def test_smooth_rejects_out_of_range_indices_without_touching_bad_memory():
+    x = clustered(1000, 8, 3, seed=5)
+    idx, dist = vv.make_knn(x, k=10, verbose=False)
+    bad = idx.copy()
+    bad[500, 3] = 10_000_000
+    with pytest.raises(ValueError, match="must include self"):
+        vv.smooth(x, [bad, dist], k=10, coef=1.0)
+    bad[500, 3] = -7
+    with pytest.raises(ValueError, match="must include self"):
+        vv.smooth(x, [bad, dist], k=10, coef=1.0)
+    assert np.array_equal(vv.smooth(x, [idx, dist], k=10, coef=1.0), orc.smooth(x, idx, 10, 1.0, 1))  # still healthy
+
+
+def test_make_knn_host_chunked_path_matches_oracle_samples():
+    """n above one 262,144-row chunk: exercises the chunk loop, the overlapped D2H and the cached buffers."""
+    n, k = 300_000, 20
+    x = clustered(n, 16, 25, seed=33)
+    st = {}
+    idx, dist = vv.make_knn(x, k=k, verbose=False, stats=st)
+    assert st["rows"] == n and st["algo_used"] == 2
+    for q0 in (0, 262_144 - 100, 262_144, n - 300):
+        wi, wd = orc.knn(x, k, q0, q0 + 200)
+        assert np.array_equal(idx[q0:q0 + 200], wi) and np.array_equal(dist[q0:q0 + 200], wd)
+    idx2, dist2 = vv.make_knn(x, k=k, verbose=False)  # second call reuses the cached device buffers
+    assert np.array_equal(idx, idx2) and np.array_equal(dist, dist2)
+    assert vv._lib.load().vvb_release_cached_memory() == 0

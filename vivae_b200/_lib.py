@@ -45,6 +45,7 @@ SYMBOLS = {
     "vvb_version": (_int, []),
     "vvb_last_error": (ctypes.c_char_p, []),
     "vvb_launch_count": (_i64, []),
+    "vvb_release_cached_memory": (_int, []),
     "vvb_make_knn_host": (_int, [_vp, _i64, _int, _int, _i64, _i64, _int, _vp, _vp, ctypes.POINTER(KnnStats)]),
     "vvb_make_knn_workspace_bytes": (_int, [_i64, _int, _int, _i64, _int, ctypes.POINTER(_sz)]),
     "vvb_make_knn_device": (_int, [_vp, _i64, _int, _int, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp,
@@ -108,5 +109,15 @@ def check(rc: int) -> None:
     raise RuntimeError(msg)
 
 
+_graph_replayed = 0  # kernels of this library launched through CUDA-graph replays
+
+
+def note_graph_replay(kernels: int) -> None:
+    global _graph_replayed
+    _graph_replayed += int(kernels)
+
+
 def launch_count() -> int:
-    return int(load().vvb_launch_count())
+    """Kernels of this library launched so far: direct launches (counted in C) plus the library's
+    kernel nodes inside replayed CUDA graphs (counted at capture time, added per replay)."""
+    return int(load().vvb_launch_count()) + _graph_replayed

@@ -1,7 +1,13 @@
 // extern "C" surface of libvivae_b200.so (declared in include/vivae_b200.h).
+#include <sys/mman.h>
+#include <unistd.h>
+
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -40,9 +46,12 @@ int launch_knn_brute(const float *x_dev, int64_t n, int d, int k, const int64_t 
                      size_t workspace_bytes, cudaStream_t stream);
 size_t knn_tensor_workspace_bytes(int64_t n, int d, int k, int64_t nq);
 bool knn_tensor_supported(int64_t n, int d, int k);
-int launch_knn_tensor(const float *x_dev, int64_t n, int d, int k, int64_t q0, int64_t nq, int64_t *out_idx,
-                      float *out_dist, void *workspace, size_t workspace_bytes, cudaStream_t stream,
-                      vvb_knn_stats *stats);
+int64_t knn_tensor_chunk_rows(int64_t nq);
+size_t knn_tensor_session_bytes();
+int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, int k, int64_t chunk_rows,
+                     void *workspace, size_t workspace_bytes, cudaStream_t st, vvb_knn_stats *stats);
+int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx, float *out_dist, cudaStream_t st,
+                     vvb_knn_stats *stats, bool screen_only);
 int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, int64_t nq, uint32_t *cand_idx_out,
                      float *cand_key_out, int *cand_cnt_out, float *cand_thr_out, float *xnorm_out,
                      float *scale_ymax_out, float *mu_out);
@@ -97,6 +106,119 @@ struct EventTimer {
   }
 };
 
+// Touch the pages of freshly allocated host output arrays on helper threads.
+struct HostPrefault {
+  struct Range {
+    char *p;
+    size_t bytes;
+  };
+  std::vector<Range> ranges;
+  std::vector<std::thread> threads;
+  void add(void *p, size_t bytes) {
+    if (p && bytes >= (8u << 20)) ranges.push_back({static_cast<char *>(p), bytes});
+  }
+  void start() {
+    const size_t page = static_cast<size_t>(sysconf(_SC_PAGESIZE));
+    for (const Range &r : ranges) {
+      // whole pages inside the range only: bytes outside the array are never written
+      uintptr_t lo = (reinterpret_cast<uintptr_t>(r.p) + page - 1) / page * page;
+      uintptr_t hi = (reinterpret_cast<uintptr_t>(r.p) + r.bytes) / page * page;
+      if (hi <= lo) continue;
+      madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE);  // best effort (THP = madvise)
+      const int nthreads = 4;
+      const size_t pages = (hi - lo) / page;
+      for (int t = 0; t < nthreads; ++t) {
+        const size_t p0 = pages * t / nthreads, p1 = pages * (t + 1) / nthreads;
+        threads.emplace_back([lo, page, p0, p1]() {
+          volatile char *base = reinterpret_cast<volatile char *>(lo);
+          for (size_t i = p0; i < p1; ++i) base[i * page] = 0;  // the array is an OUTPUT: contents are overwritten
+        });
+      }
+    }
+  }
+  void join() {
+    for (auto &t : threads) t.join();
+    threads.clear();
+  }
+  ~HostPrefault() { join(); }
+};
+
+// Grow-only device buffers and two streams kept between *_host calls (a 2 GB cudaMalloc/cudaFree
+// pair costs ~27 ms per call otherwise).  Released by vvb_release_cached_memory().
+struct DeviceCache {
+  std::mutex mu;
+  int device = -1;
+  void *ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  int last_rc = VVB_OK;
+  static DeviceCache &get() {
+    static DeviceCache c;
+    return c;
+  }
+  void release() {
+    for (int i = 0; i < 8; ++i) {
+      if (ptr[i]) cudaFree(ptr[i]);
+      ptr[i] = nullptr;
+      cap[i] = 0;
+    }
+    if (s_compute) cudaStreamDestroy(s_compute);
+    if (s_copy) cudaStreamDestroy(s_copy);
+    s_compute = s_copy = nullptr;
+  }
+  void check_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    if (dev != device) {
+      if (device >= 0) {
+        cudaSetDevice(device);
+        release();
+        cudaSetDevice(dev);
+      }
+      device = dev;
+    }
+  }
+  void *slot(int i, size_t bytes) {
+    check_device();
+    if (bytes == 0) bytes = 256;
+    if (cap[i] >= bytes) return ptr[i];
+    if (ptr[i]) cudaFree(ptr[i]);
+    ptr[i] = nullptr;
+    cap[i] = 0;
+    cudaError_t e = cudaMalloc(&ptr[i], bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      release();  // drop everything cached and retry once
+      e = cudaMalloc(&ptr[i], bytes);
+    }
+    if (e != cudaSuccess) {
+      ptr[i] = nullptr;
+      set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      cudaGetLastError();
+      last_rc = (e == cudaErrorMemoryAllocation) ? VVB_ENOMEM : VVB_ECUDA;
+      return nullptr;
+    }
+    cap[i] = bytes;
+    return ptr[i];
+  }
+  cudaStream_t compute_stream() {
+    check_device();
+    if (!s_compute && cudaStreamCreateWithFlags(&s_compute, cudaStreamNonBlocking) != cudaSuccess) {
+      set_error("cudaStreamCreate failed");
+      s_compute = nullptr;
+    }
+    return s_compute;
+  }
+  cudaStream_t copy_stream() {
+    check_device();
+    if (!s_copy && cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking) != cudaSuccess) {
+      set_error("cudaStreamCreate failed");
+      s_copy = nullptr;
+    }
+    return s_copy;
+  }
+};
+
 static int knn_check_args(const void *x, int64_t n, int d, int k, int64_t q0, int64_t nq, const void *idx,
                           const void *dist) {
   VVB_REQUIRE(x && idx && dist, "make_knn: null pointer argument");
@@ -135,9 +257,56 @@ int vvb_make_knn_workspace_bytes(int64_t n, int d, int k, int64_t nq, int algo, 
   int use = 0;
   int rc = resolve_algo(algo, n, d, k, &use);
   if (rc) return rc;
-  *bytes = (use == VVB_KNN_BRUTE) ? brute_workspace_bytes(nq, k) : knn_tensor_workspace_bytes(n, d, k, nq);
+  *bytes = (use == VVB_KNN_BRUTE) ? brute_workspace_bytes(knn_tensor_chunk_rows(nq), k)
+                                   : knn_tensor_workspace_bytes(n, d, k, nq);
   return VVB_OK;
 }
+
+}  // extern "C"
+
+// One pass of the graph builder over query rows [q0, q0+nq) in chunks; `after_chunk(c0, rows)` is
+// called once the work of a chunk has been ENQUEUED (used by the host entry point to overlap the
+// device-to-host copy of chunk i with the computation of chunk i+1).
+template <typename Hook>
+static int knn_run(const float *x_dev, int64_t n, int d, int k, int64_t q0, int64_t nq, int use, int64_t *idx_dev,
+                   float *dist_dev, void *ws, size_t ws_bytes, cudaStream_t st, vvb_knn_stats *stats, Hook after_chunk) {
+  const int64_t chunk = knn_tensor_chunk_rows(nq);
+  std::vector<char> session(knn_tensor_session_bytes() + 64);
+  void *sess = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(session.data()) + 63) & ~uintptr_t(63));
+  int rc;
+  if (use == VVB_KNN_TENSOR) {
+    rc = knn_tensor_begin(sess, x_dev, n, d, k, chunk, ws, ws_bytes, st, stats);
+    if (rc) return rc;
+  }
+  for (int64_t c0 = 0; c0 < nq; c0 += chunk) {
+    const int64_t rows = std::min(chunk, nq - c0);
+    int64_t *oi = idx_dev + c0 * (k + 1);
+    float *od = dist_dev + c0 * (k + 1);
+    if (use == VVB_KNN_TENSOR) {
+      rc = knn_tensor_chunk(sess, q0 + c0, rows, oi, od, st, stats, false);
+    } else {
+      EventTimer tm(st);
+      if (stats) tm.start();
+      rc = launch_knn_brute(x_dev, n, d, k, nullptr, q0 + c0, rows, oi, od, q0 + c0, ws, ws_bytes, st);
+      if (!rc && stats) {
+        tm.stop();
+        stats->ms_fallback += tm.ms();
+        stats->rows_fallback += rows;
+      }
+    }
+    if (rc) return rc;
+    rc = after_chunk(c0, rows);
+    if (rc) return rc;
+  }
+  return VVB_OK;
+}
+
+static size_t knn_ws_bytes(int use, int64_t n, int d, int k, int64_t nq) {
+  return (use == VVB_KNN_BRUTE) ? brute_workspace_bytes(knn_tensor_chunk_rows(nq), k)
+                                : knn_tensor_workspace_bytes(n, d, k, nq);
+}
+
+extern "C" {
 
 int vvb_make_knn_device(const float *x_dev, int64_t n, int d, int k, int64_t q0, int64_t nq, int algo,
                         int64_t *idx_out_dev, float *dist_out_dev, void *workspace_dev, size_t workspace_bytes,
@@ -147,6 +316,7 @@ int vvb_make_knn_device(const float *x_dev, int64_t n, int d, int k, int64_t q0,
   int use = 0;
   rc = resolve_algo(algo, n, d, k, &use);
   if (rc) return rc;
+  VVB_REQUIRE(workspace_bytes >= knn_ws_bytes(use, n, d, k, nq), "make_knn: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t launches0 = g_launches.load();
   if (stats) {
@@ -154,22 +324,9 @@ int vvb_make_knn_device(const float *x_dev, int64_t n, int d, int k, int64_t q0,
     stats->rows = nq;
     stats->algo_used = use;
   }
-  if (use == VVB_KNN_BRUTE) {
-    EventTimer tm(st);
-    if (stats) tm.start();
-    rc = launch_knn_brute(x_dev, n, d, k, nullptr, q0, nq, idx_out_dev, dist_out_dev, q0, workspace_dev,
-                          workspace_bytes, st);
-    if (rc) return rc;
-    if (stats) {
-      tm.stop();
-      stats->ms_fallback = tm.ms();
-      stats->rows_fallback = nq;
-    }
-  } else {
-    rc = launch_knn_tensor(x_dev, n, d, k, q0, nq, idx_out_dev, dist_out_dev, workspace_dev, workspace_bytes, st,
-                           stats);
-    if (rc) return rc;
-  }
+  rc = knn_run(x_dev, n, d, k, q0, nq, use, idx_out_dev, dist_out_dev, workspace_dev, workspace_bytes, st, stats,
+               [](int64_t, int64_t) { return VVB_OK; });
+  if (rc) return rc;
   if (stats) {
     VVB_CUDA(cudaStreamSynchronize(st));
     stats->kernel_launches = g_launches.load() - launches0;
@@ -181,24 +338,81 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
                       int64_t *idx_out_host, float *dist_out_host, vvb_knn_stats *stats) {
   int rc = knn_check_args(x_host, n, d, k, q0, nq, idx_out_host, dist_out_host);
   if (rc) return rc;
-  size_t ws_bytes = 0;
-  rc = vvb_make_knn_workspace_bytes(n, d, k, nq, algo, &ws_bytes);
+  int use = 0;
+  rc = resolve_algo(algo, n, d, k, &use);
   if (rc) return rc;
-  DevBuf x, idx, dist, ws;
-  if ((rc = x.alloc(static_cast<size_t>(n) * d * sizeof(float)))) return rc;
-  if ((rc = idx.alloc(static_cast<size_t>(nq) * (k + 1) * sizeof(int64_t)))) return rc;
-  if ((rc = dist.alloc(static_cast<size_t>(nq) * (k + 1) * sizeof(float)))) return rc;
-  if ((rc = ws.alloc(ws_bytes))) return rc;
-  cudaStream_t st = nullptr;
-  VVB_CUDA(cudaMemcpyAsync(x.p, x_host, static_cast<size_t>(n) * d * sizeof(float), cudaMemcpyHostToDevice, st));
-  rc = vvb_make_knn_device(static_cast<const float *>(x.p), n, d, k, q0, nq, algo, static_cast<int64_t *>(idx.p),
-                           static_cast<float *>(dist.p), ws.p, ws_bytes, st, stats);
+  const size_t ws_bytes = knn_ws_bytes(use, n, d, k, nq);
+  const size_t idx_bytes = static_cast<size_t>(nq) * (k + 1) * sizeof(int64_t);
+  const size_t dist_bytes = static_cast<size_t>(nq) * (k + 1) * sizeof(float);
+  // the output arrays are usually freshly allocated: fault their pages in on helper threads while
+  // the GPU works (a D2H copy into untouched pageable memory runs 8x slower than into touched pages)
+  HostPrefault pf;
+  pf.add(idx_out_host, idx_bytes);
+  pf.add(dist_out_host, dist_bytes);
+  pf.start();
+  DeviceCache &dc = DeviceCache::get();
+  std::lock_guard<std::mutex> lock(dc.mu);
+  float *x_dev = static_cast<float *>(dc.slot(0, static_cast<size_t>(n) * d * sizeof(float)));
+  int64_t *idx_dev = static_cast<int64_t *>(dc.slot(1, idx_bytes));
+  float *dist_dev = static_cast<float *>(dc.slot(2, dist_bytes));
+  void *ws = dc.slot(3, ws_bytes);
+  if (!x_dev || !idx_dev || !dist_dev || !ws) return dc.last_rc;
+  cudaStream_t st = dc.compute_stream(), cp = dc.copy_stream();
+  if (!st || !cp) return VVB_ECUDA;
+  const int64_t launches0 = g_launches.load();
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->rows = nq;
+    stats->algo_used = use;
+  }
+  VVB_CUDA(cudaMemcpyAsync(x_dev, x_host, static_cast<size_t>(n) * d * sizeof(float), cudaMemcpyHostToDevice, st));
+  // D2H of chunk i is issued after chunk i+1 has been enqueued: the (host-blocking, pageable) copy
+  // then overlaps the next chunk's kernels
+  int64_t pend_c0 = -1, pend_rows = 0;
+  cudaEvent_t pend_ev = nullptr, next_ev = nullptr;
+  VVB_CUDA(cudaEventCreateWithFlags(&pend_ev, cudaEventDisableTiming));
+  VVB_CUDA(cudaEventCreateWithFlags(&next_ev, cudaEventDisableTiming));
+  bool joined = false;
+  auto flush = [&](int64_t c0, int64_t rows, cudaEvent_t ev) -> int {
+    if (!joined) {
+      pf.join();
+      joined = true;
+    }
+    VVB_CUDA(cudaStreamWaitEvent(cp, ev, 0));
+    VVB_CUDA(cudaMemcpyAsync(idx_out_host + c0 * (k + 1), idx_dev + c0 * (k + 1),
+                             static_cast<size_t>(rows) * (k + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, cp));
+    VVB_CUDA(cudaMemcpyAsync(dist_out_host + c0 * (k + 1), dist_dev + c0 * (k + 1),
+                             static_cast<size_t>(rows) * (k + 1) * sizeof(float), cudaMemcpyDeviceToHost, cp));
+    return VVB_OK;
+  };
+  rc = knn_run(x_dev, n, d, k, q0, nq, use, idx_dev, dist_dev, ws, ws_bytes, st, stats,
+               [&](int64_t c0, int64_t rows) -> int {
+                 VVB_CUDA(cudaEventRecord(next_ev, st));
+                 int r2 = VVB_OK;
+                 if (pend_c0 >= 0) r2 = flush(pend_c0, pend_rows, pend_ev);
+                 std::swap(pend_ev, next_ev);
+                 pend_c0 = c0;
+                 pend_rows = rows;
+                 return r2;
+               });
+  if (!rc && pend_c0 >= 0) rc = flush(pend_c0, pend_rows, pend_ev);
+  if (!joined) pf.join();
+  cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(cp);
+  cudaEventDestroy(pend_ev);
+  cudaEventDestroy(next_ev);
   if (rc) return rc;
-  VVB_CUDA(cudaMemcpyAsync(idx_out_host, idx.p, static_cast<size_t>(nq) * (k + 1) * sizeof(int64_t),
-                           cudaMemcpyDeviceToHost, st));
-  VVB_CUDA(cudaMemcpyAsync(dist_out_host, dist.p, static_cast<size_t>(nq) * (k + 1) * sizeof(float),
-                           cudaMemcpyDeviceToHost, st));
-  VVB_CUDA(cudaStreamSynchronize(st));
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    set_error("make_knn: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return VVB_ECUDA;
+  }
+  if (stats) stats->kernel_launches = g_launches.load() - launches0;
+  return VVB_OK;
+}
+
+int vvb_release_cached_memory(void) {
+  DeviceCache &dc = DeviceCache::get();
+  std::lock_guard<std::mutex> lock(dc.mu);
+  dc.release();
   return VVB_OK;
 }
 
@@ -241,22 +455,29 @@ int vvb_smooth_host(const void *x_host, int elem_size, int64_t n, int d, const i
   if (rc) return rc;
   VVB_REQUIRE(ld_idx >= k && k >= 1, "smooth: neighbour matrix has fewer than k columns");
   const size_t xb = static_cast<size_t>(n) * d * elem_size;
-  DevBuf x, out, idx, ws;
-  if ((rc = x.alloc(xb))) return rc;
-  if ((rc = out.alloc(xb))) return rc;
-  // only the first k columns are consumed: ship a compact (n, k) copy
-  if ((rc = idx.alloc(static_cast<size_t>(n) * k * sizeof(int64_t)))) return rc;
-  if ((rc = ws.alloc(ws_bytes))) return rc;
-  cudaStream_t st = nullptr;
-  VVB_CUDA(cudaMemcpyAsync(x.p, x_host, xb, cudaMemcpyHostToDevice, st));
-  VVB_CUDA(cudaMemcpy2DAsync(idx.p, static_cast<size_t>(k) * sizeof(int64_t), idx_host,
-                             static_cast<size_t>(ld_idx) * sizeof(int64_t), static_cast<size_t>(k) * sizeof(int64_t),
-                             static_cast<size_t>(n), cudaMemcpyHostToDevice, st));
-  rc = vvb_smooth_device(x.p, elem_size, n, d, static_cast<const int64_t *>(idx.p), k, k, coef, n_iter, mode, out.p,
-                         ws.p, ws_bytes, st);
+  const size_t ib = static_cast<size_t>(n) * ld_idx * sizeof(int64_t);
+  HostPrefault pf;
+  pf.add(out_host, xb);
+  pf.start();
+  DeviceCache &dc = DeviceCache::get();
+  std::lock_guard<std::mutex> lock(dc.mu);
+  void *x = dc.slot(0, xb), *out = dc.slot(4, xb), *idx = dc.slot(1, ib), *ws = dc.slot(3, ws_bytes);
+  if (!x || !out || !idx || !ws) return dc.last_rc;
+  cudaStream_t st = dc.compute_stream();
+  if (!st) return VVB_ECUDA;
+  // the whole index matrix goes over as ONE contiguous copy (a pitched copy of the first k columns
+  // moves fewer bytes but runs far slower from pageable memory); the kernel strides by ld_idx
+  VVB_CUDA(cudaMemcpyAsync(x, x_host, xb, cudaMemcpyHostToDevice, st));
+  VVB_CUDA(cudaMemcpyAsync(idx, idx_host, ib, cudaMemcpyHostToDevice, st));
+  rc = vvb_smooth_device(x, elem_size, n, d, static_cast<const int64_t *>(idx), ld_idx, k, coef, n_iter, mode, out, ws,
+                         ws_bytes, st);
   if (rc) return rc;
-  VVB_CUDA(cudaMemcpyAsync(out_host, out.p, xb, cudaMemcpyDeviceToHost, st));
+  int bad = 0;
+  VVB_CUDA(cudaMemcpyAsync(&bad, ws, sizeof(int), cudaMemcpyDeviceToHost, st));
+  pf.join();
+  VVB_CUDA(cudaMemcpyAsync(out_host, out, xb, cudaMemcpyDeviceToHost, st));
   VVB_CUDA(cudaStreamSynchronize(st));
+  VVB_REQUIRE(bad == 0, "Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed");
   return VVB_OK;
 }
 

@@ -32,6 +32,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <new>
+
 #include "common.cuh"
 
 namespace vvb {
@@ -643,8 +645,10 @@ static int make_operand_map(CUtensorMap *map, void *ptr, int64_t rows) {
   return VVB_OK;
 }
 
+// Workspace of one "session": the database operand (built once per call) plus the per-chunk
+// query operand, candidate lists and fallback list (sized for `chunk` query rows).
 struct TcLayout {
-  int64_t n_pad, nq_pad;
+  int64_t n_pad, chunk_pad;
   __half *opB, *opA;
   double *partial;
   float *mu;
@@ -662,29 +666,29 @@ struct TcLayout {
   size_t total;
 };
 
-static TcLayout tc_layout(void *ws, int64_t n, int k, int64_t nq) {
+static TcLayout tc_layout(void *ws, int64_t n, int k, int64_t chunk) {
   TcLayout L;
   L.n_pad = (n + TC_N - 1) / TC_N * TC_N;
-  L.nq_pad = (nq + TC_M - 1) / TC_M * TC_M;
-  if (L.nq_pad == 0) L.nq_pad = TC_M;
+  L.chunk_pad = (chunk + TC_M - 1) / TC_M * TC_M;
+  if (L.chunk_pad == 0) L.chunk_pad = TC_M;
   Carver cv(ws);
   L.opB = cv.take<__half>(static_cast<size_t>(L.n_pad) * TC_OP_COLS);
-  L.opA = cv.take<__half>(static_cast<size_t>(L.nq_pad) * TC_OP_COLS);
+  L.opA = cv.take<__half>(static_cast<size_t>(L.chunk_pad) * TC_OP_COLS);
   L.partial = cv.take<double>(PREP_BLOCKS * 64);
   L.mu = cv.take<float>(64);
   L.maxn2 = cv.take<unsigned int>(1);
   L.scalars = cv.take<PrepScalars>(1);
-  L.xnorm = cv.take<float>(static_cast<size_t>(L.nq_pad));
-  L.cand_cnt = cv.take<int>(static_cast<size_t>(L.nq_pad));
-  L.cand_thr = cv.take<float>(static_cast<size_t>(L.nq_pad));
+  L.xnorm = cv.take<float>(static_cast<size_t>(L.chunk_pad));
+  L.cand_cnt = cv.take<int>(static_cast<size_t>(L.chunk_pad));
+  L.cand_thr = cv.take<float>(static_cast<size_t>(L.chunk_pad));
   L.fb_count = cv.take<int>(1);
-  L.fb_rows = cv.take<int64_t>(static_cast<size_t>(L.nq_pad));
-  L.cand_key = cv.take<float>(static_cast<size_t>(L.nq_pad) * TC_CAP);
-  L.cand_idx = cv.take<uint32_t>(static_cast<size_t>(L.nq_pad) * TC_CAP);
+  L.fb_rows = cv.take<int64_t>(static_cast<size_t>(L.chunk_pad));
+  L.cand_key = cv.take<float>(static_cast<size_t>(L.chunk_pad) * TC_CAP);
+  L.cand_idx = cv.take<uint32_t>(static_cast<size_t>(L.chunk_pad) * TC_CAP);
   // the fallback's candidate lists reuse the screening lists (dead after the re-rank)
   L.brute_ws = L.cand_key;
-  L.brute_ws_bytes = static_cast<size_t>(L.nq_pad) * TC_CAP * 8;
-  const size_t need_brute = brute_workspace_bytes(nq, k);
+  L.brute_ws_bytes = static_cast<size_t>(L.chunk_pad) * TC_CAP * 8;
+  const size_t need_brute = brute_workspace_bytes(chunk, k);
   if (need_brute > L.brute_ws_bytes) {  // never for the supported k, kept for safety
     L.brute_ws = cv.take<char>(need_brute);
     L.brute_ws_bytes = need_brute;
@@ -693,31 +697,51 @@ static TcLayout tc_layout(void *ws, int64_t n, int k, int64_t nq) {
   return L;
 }
 
-size_t knn_tensor_workspace_bytes(int64_t n, int d, int k, int64_t nq) {
-  (void)d;
-  return tc_layout(nullptr, n, k, nq).total;
+// query rows processed per pass of the tensor path: bounds the workspace (2 KB of candidate list
+// per row) and is the granularity at which the host entry point overlaps D2H with compute
+int64_t knn_tensor_chunk_rows(int64_t nq) {
+  const int64_t cap = 262144;
+  return nq < cap ? nq : cap;
 }
 
-int launch_knn_tensor(const float *x_dev, int64_t n, int d, int k, int64_t q0, int64_t nq, int64_t *out_idx,
-                      float *out_dist, void *workspace, size_t workspace_bytes, cudaStream_t st,
-                      vvb_knn_stats *stats) {
-  VVB_REQUIRE(knn_tensor_supported(n, d, k), "tensor kNN: unsupported shape n=%lld d=%d k=%d", (long long)n, d, k);
-  if (nq == 0) return VVB_OK;
-  TcLayout L = tc_layout(workspace, n, k, nq);
-  VVB_REQUIRE(workspace_bytes >= L.total, "tensor kNN: workspace too small (%zu < %zu)", workspace_bytes, L.total);
-  const int keep = tc_candidates(k);
+size_t knn_tensor_workspace_bytes(int64_t n, int d, int k, int64_t nq) {
+  (void)d;
+  return tc_layout(nullptr, n, k, knn_tensor_chunk_rows(nq)).total;
+}
 
+// ---- session API used by api.cu ----------------------------------------------------------
+struct TcSession {
+  const float *x;
+  int64_t n;
+  int d, k, keep;
+  TcLayout L;
+  CUtensorMap map_a, map_b;
+};
+
+size_t knn_tensor_session_bytes() { return sizeof(TcSession); }
+
+// Build the database operand (column means, largest centred norm, FP16 hi/lo split) once.
+int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, int k, int64_t chunk_rows,
+                     void *workspace, size_t workspace_bytes, cudaStream_t st, vvb_knn_stats *stats) {
+  VVB_REQUIRE(knn_tensor_supported(n, d, k), "tensor kNN: unsupported shape n=%lld d=%d k=%d", (long long)n, d, k);
+  TcSession *S = new (session_mem) TcSession();
+  S->x = x_dev;
+  S->n = n;
+  S->d = d;
+  S->k = k;
+  S->keep = tc_candidates(k);
+  S->L = tc_layout(workspace, n, k, chunk_rows);
+  VVB_REQUIRE(workspace_bytes >= S->L.total, "tensor kNN: workspace too small (%zu < %zu)", workspace_bytes,
+              S->L.total);
   VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(TC_SMEM_BYTES)));
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  if (stats)
-    for (auto &e : ev) VVB_CUDA(cudaEventCreate(&e));
-  auto mark = [&](int i) {
-    if (stats) cudaEventRecord(ev[i], st);
-  };
-
-  // ---- prepare: means, max centred norm, operands
-  mark(0);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (stats) {
+    VVB_CUDA(cudaEventCreate(&e0));
+    VVB_CUDA(cudaEventCreate(&e1));
+    cudaEventRecord(e0, st);
+  }
+  TcLayout &L = S->L;
   colsum_partial_kernel<<<PREP_BLOCKS, 256, 0, st>>>(x_dev, n, d, L.partial);
   VVB_CHECK_LAUNCH();
   colsum_final_kernel<<<1, 64, 0, st>>>(L.partial, PREP_BLOCKS, n, d, L.mu, L.maxn2);
@@ -725,67 +749,91 @@ int launch_knn_tensor(const float *x_dev, int64_t n, int d, int k, int64_t q0, i
   const int prep_grid = sm_count() * 8;
   maxnorm_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.mu, L.maxn2);
   VVB_CHECK_LAUNCH();
-  build_operands_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.mu, L.maxn2, L.n_pad, L.opB, q0, nq, L.nq_pad,
-                                                   L.opA, L.xnorm, L.scalars);
+  build_operands_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.mu, L.maxn2, L.n_pad, L.opB, 0, 0, 0, L.opA,
+                                                   L.xnorm, L.scalars);
+  VVB_CHECK_LAUNCH();
+  int rc = make_operand_map(&S->map_a, L.opA, L.chunk_pad);
+  if (rc) return rc;
+  rc = make_operand_map(&S->map_b, L.opB, L.n_pad);
+  if (rc) return rc;
+  if (stats) {
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    stats->ms_prepare += ms;
+    stats->candidates = S->keep;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  return VVB_OK;
+}
+
+// Query rows [q0, q0+nq) (nq <= the session's chunk size): operand, screen, re-rank, fallback.
+// out_idx / out_dist point at the first output row of this chunk.
+int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx, float *out_dist, cudaStream_t st,
+                     vvb_knn_stats *stats, bool screen_only) {
+  TcSession *S = static_cast<TcSession *>(session_mem);
+  TcLayout &L = S->L;
+  if (nq == 0) return VVB_OK;
+  VVB_REQUIRE(nq <= L.chunk_pad, "tensor kNN: chunk of %lld rows exceeds the session's %lld", (long long)nq,
+              (long long)L.chunk_pad);
+  const int64_t nq_pad = (nq + TC_M - 1) / TC_M * TC_M;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (stats)
+    for (auto &e : ev) VVB_CUDA(cudaEventCreate(&e));
+  auto mark = [&](int i) {
+    if (stats) cudaEventRecord(ev[i], st);
+  };
+  mark(0);
+  // query operand of this chunk (the database part of the kernel's row range is empty here)
+  build_operands_kernel<<<sm_count() * 4, 256, 0, st>>>(S->x, S->n, S->d, L.mu, L.maxn2, 0, L.opB, q0, nq, nq_pad,
+                                                       L.opA, L.xnorm, L.scalars);
   VVB_CHECK_LAUNCH();
   VVB_CUDA(cudaMemsetAsync(L.fb_count, 0, sizeof(int), st));
-
-  // ---- screen
-  CUtensorMap map_a, map_b;
-  int rc = make_operand_map(&map_a, L.opA, L.nq_pad);
-  if (rc) return rc;
-  rc = make_operand_map(&map_b, L.opB, L.n_pad);
-  if (rc) return rc;
   TcParams p;
-  p.n = n;
+  p.n = S->n;
   p.nq = nq;
   p.n_tiles = static_cast<int>(L.n_pad / TC_N);
-  p.ks_hi = (d + 3 + 15) / 16;
-  p.ks_lo = (d + 15) / 16;
-  p.keep = keep;
+  p.ks_hi = (S->d + 3 + 15) / 16;
+  p.ks_lo = (S->d + 15) / 16;
+  p.keep = S->keep;
   p.cand_key = L.cand_key;
   p.cand_idx = L.cand_idx;
   p.cand_cnt = L.cand_cnt;
   p.cand_thr = L.cand_thr;
-  mark(1);
-  knn_screen_kernel<<<static_cast<unsigned>(L.nq_pad / TC_M), TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, p);
+  knn_screen_kernel<<<static_cast<unsigned>(nq_pad / TC_M), TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, p);
   VVB_CHECK_LAUNCH();
-
-  // ---- re-rank + certificate
-  mark(2);
+  if (screen_only) return VVB_OK;
+  mark(1);
   const unsigned rr_grid = static_cast<unsigned>((nq + 7) / 8);
-  const int e_need = (keep + 31) / 32;
-#define VVB_RR(EE)                                                                                               \
-  knn_rerank_kernel<EE><<<rr_grid, 256, 0, st>>>(x_dev, n, d, q0, nq, k, L.cand_idx, L.cand_cnt, L.cand_thr,    \
+  const int e_need = (S->keep + 31) / 32;
+#define VVB_RR(EE)                                                                                                  \
+  knn_rerank_kernel<EE><<<rr_grid, 256, 0, st>>>(S->x, S->n, S->d, q0, nq, S->k, L.cand_idx, L.cand_cnt, L.cand_thr, \
                                                  L.xnorm, L.scalars, out_idx, out_dist, L.fb_count, L.fb_rows)
   if (e_need <= 2) VVB_RR(2);
   else if (e_need <= 4) VVB_RR(4);
   else VVB_RR(8);
 #undef VVB_RR
   VVB_CHECK_LAUNCH();
-
-  // ---- fallback: rows the certificate rejected, exact FP32 brute force (device-side count)
-  mark(3);
-  rc = launch_knn_brute_list(x_dev, n, d, k, L.fb_rows, L.fb_count, nq, out_idx, out_dist, q0, L.brute_ws,
-                             L.brute_ws_bytes, st);
+  mark(2);
+  // rows the certificate rejected: exact FP32 brute force, count consumed on the device
+  int rc = launch_knn_brute_list(S->x, S->n, S->d, S->k, L.fb_rows, L.fb_count, nq, out_idx, out_dist, q0, L.brute_ws,
+                                 L.brute_ws_bytes, st);
   if (rc) return rc;
-  mark(4);
-
+  mark(3);
   if (stats) {
     int fb = 0;
     VVB_CUDA(cudaMemcpyAsync(&fb, L.fb_count, sizeof(int), cudaMemcpyDeviceToHost, st));
     VVB_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev[0], ev[1]);
-    stats->ms_prepare = ms;
+    stats->ms_screen += ms;
     cudaEventElapsedTime(&ms, ev[1], ev[2]);
-    stats->ms_screen = ms;
+    stats->ms_rerank += ms;
     cudaEventElapsedTime(&ms, ev[2], ev[3]);
-    stats->ms_rerank = ms;
-    cudaEventElapsedTime(&ms, ev[3], ev[4]);
-    stats->ms_fallback = ms;
-    stats->rows_fallback = fb;
-    stats->candidates = keep;
+    stats->ms_fallback += ms;
+    stats->rows_fallback += fb;
     for (auto &e : ev) cudaEventDestroy(e);
   }
   return VVB_OK;
@@ -797,40 +845,21 @@ int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, i
                      float *cand_key_out, int *cand_cnt_out, float *cand_thr_out, float *xnorm_out,
                      float *scale_ymax_out, float *mu_out) {
   VVB_REQUIRE(knn_tensor_supported(n, d, k) && nq >= 1 && q0 >= 0 && q0 + nq <= n, "screen debug: unsupported shape");
+  VVB_REQUIRE(nq <= knn_tensor_chunk_rows(nq), "screen debug: at most %lld query rows", (long long)knn_tensor_chunk_rows(nq));
   const size_t ws_bytes = knn_tensor_workspace_bytes(n, d, k, nq);
-  void *ws = nullptr, *xd = nullptr;
+  void *ws = nullptr, *xd = nullptr, *oi = nullptr, *od = nullptr;
   VVB_CUDA(cudaMalloc(&ws, ws_bytes));
   VVB_CUDA(cudaMalloc(&xd, static_cast<size_t>(n) * d * sizeof(float)));
+  VVB_CUDA(cudaMalloc(&oi, static_cast<size_t>(nq) * (k + 1) * sizeof(int64_t)));
+  VVB_CUDA(cudaMalloc(&od, static_cast<size_t>(nq) * (k + 1) * sizeof(float)));
   VVB_CUDA(cudaMemcpy(xd, x_host, static_cast<size_t>(n) * d * sizeof(float), cudaMemcpyHostToDevice));
-  TcLayout L = tc_layout(ws, n, k, nq);
+  alignas(64) char session[sizeof(TcSession)];
   cudaStream_t st = nullptr;
-  const float *x_dev = static_cast<const float *>(xd);
-  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(TC_SMEM_BYTES)));
-  colsum_partial_kernel<<<PREP_BLOCKS, 256, 0, st>>>(x_dev, n, d, L.partial);
-  colsum_final_kernel<<<1, 64, 0, st>>>(L.partial, PREP_BLOCKS, n, d, L.mu, L.maxn2);
-  const int prep_grid = sm_count() * 8;
-  maxnorm_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.mu, L.maxn2);
-  build_operands_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.mu, L.maxn2, L.n_pad, L.opB, q0, nq, L.nq_pad,
-                                                   L.opA, L.xnorm, L.scalars);
-  count_launch(4);
-  CUtensorMap map_a, map_b;
-  int rc = make_operand_map(&map_a, L.opA, L.nq_pad);
-  if (!rc) rc = make_operand_map(&map_b, L.opB, L.n_pad);
+  int rc = knn_tensor_begin(session, static_cast<const float *>(xd), n, d, k, nq, ws, ws_bytes, st, nullptr);
+  if (!rc)
+    rc = knn_tensor_chunk(session, q0, nq, static_cast<int64_t *>(oi), static_cast<float *>(od), st, nullptr,
+                          /*screen_only=*/true);
   if (!rc) {
-    TcParams p;
-    p.n = n;
-    p.nq = nq;
-    p.n_tiles = static_cast<int>(L.n_pad / TC_N);
-    p.ks_hi = (d + 3 + 15) / 16;
-    p.ks_lo = (d + 15) / 16;
-    p.keep = tc_candidates(k);
-    p.cand_key = L.cand_key;
-    p.cand_idx = L.cand_idx;
-    p.cand_cnt = L.cand_cnt;
-    p.cand_thr = L.cand_thr;
-    knn_screen_kernel<<<static_cast<unsigned>(L.nq_pad / TC_M), TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, p);
-    count_launch();
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
       set_error("screen debug: %s", cudaGetErrorString(e));
@@ -838,6 +867,7 @@ int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, i
     }
   }
   if (!rc) {
+    TcLayout &L = reinterpret_cast<TcSession *>(session)->L;
     cudaMemcpy(cand_idx_out, L.cand_idx, static_cast<size_t>(nq) * TC_CAP * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(cand_key_out, L.cand_key, static_cast<size_t>(nq) * TC_CAP * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(cand_cnt_out, L.cand_cnt, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
@@ -848,6 +878,8 @@ int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, i
   }
   cudaFree(ws);
   cudaFree(xd);
+  cudaFree(oi);
+  cudaFree(od);
   return rc;
 }
 

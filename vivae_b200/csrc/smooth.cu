@@ -40,7 +40,7 @@ template <> struct Arith<double> {
 template <typename T, int DPL, int KPL, bool GS>
 __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
     const T *__restrict__ prev, T *next, const int64_t *__restrict__ idx, int64_t ld_idx, int64_t n,
-    int d, int k, T coef, int *flags, int epoch, unsigned long long *ticket) {
+    int d, int k, T coef, int *flags, int epoch, unsigned long long *ticket, int *bad_index) {
   const int lane = threadIdx.x & 31;
   const T kk = static_cast<T>(k);
   for (;;) {
@@ -56,7 +56,12 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
 #pragma unroll
       for (int q = 0; q < KPL; ++q) {
         const int jj = q * 32 + lane;
-        mine[q] = (jj < k) ? __ldg(nb + jj) : i;
+        int64_t j = (jj < k) ? __ldg(nb + jj) : i;
+        if (static_cast<uint64_t>(j) >= static_cast<uint64_t>(n)) {  // never dereference a bad index
+          *bad_index = 1;
+          j = i;
+        }
+        mine[q] = j;
       }
       if (GS) {
         // wait until every lower-indexed neighbour has been published in this sweep;
@@ -133,11 +138,13 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
 template <typename T, int DPL, int KPL>
 static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
                          double coef, int n_iter, int mode, T *out, void *workspace, cudaStream_t st) {
-  // workspace: [scratch (n*d) T][flags n int][tickets n_iter u64]
+  // workspace: [bad-index flag][scratch (n*d) T][flags n int][tickets n_iter u64]
   Carver cv(workspace);
+  int *bad = cv.take<int>(1);
   T *scratch = cv.take<T>(static_cast<size_t>(n) * d);
   int *flags = cv.take<int>(static_cast<size_t>(n));
   unsigned long long *tickets = cv.take<unsigned long long>(static_cast<size_t>(n_iter));
+  VVB_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
   VVB_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(n) * sizeof(int), st));
   VVB_CUDA(cudaMemsetAsync(tickets, 0, static_cast<size_t>(n_iter) * sizeof(unsigned long long), st));
 
@@ -166,10 +173,10 @@ static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64
     T *dst = to_out ? out : scratch;
     if (mode == VVB_SMOOTH_JACOBI)
       kern_ja<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k,
-                                                                 static_cast<T>(coef), flags, it + 1, tickets + it);
+                                                                 static_cast<T>(coef), flags, it + 1, tickets + it, bad);
     else
       kern_gs<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k,
-                                                                 static_cast<T>(coef), flags, it + 1, tickets + it);
+                                                                 static_cast<T>(coef), flags, it + 1, tickets + it, bad);
     VVB_CHECK_LAUNCH();
     src = dst;
   }
@@ -177,7 +184,7 @@ static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64
 }
 
 size_t smooth_workspace_bytes(int elem_size, int64_t n, int d, int n_iter) {
-  return align_up(static_cast<size_t>(n) * d * elem_size, 256) + align_up(static_cast<size_t>(n) * sizeof(int), 256) +
+  return 256 + align_up(static_cast<size_t>(n) * d * elem_size, 256) + align_up(static_cast<size_t>(n) * sizeof(int), 256) +
          align_up(static_cast<size_t>(n_iter) * sizeof(unsigned long long), 256) + 256;
 }
 

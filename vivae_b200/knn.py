@@ -177,10 +177,7 @@ def smooth(
 
     xin = x if x.dtype in (np.float32, np.float64) else x.astype(np.float64)
     xin = np.ascontiguousarray(xin)
-    idx = np.ascontiguousarray(knn[0], dtype=np.int64)
-    used = idx[:, :k]  # only these columns are dereferenced on the device
-    if used.min() < 0 or used.max() >= x.shape[0]:
-        raise ValueError("Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed")
+    idx = np.ascontiguousarray(knn[0], dtype=np.int64)  # index range is validated on the device
     out = np.empty_like(xin)
     lib = _lib.load()
     _lib.check(lib.vvb_smooth_host(_ptr(xin), xin.dtype.itemsize, xin.shape[0], xin.shape[1], _ptr(idx),

@@ -98,9 +98,14 @@ class KLDivLoss:
 
     def __init__(self):
         self.eps_sq = 1e-2 ** 2
+        self._cache = {}  # (device, dtype) -> (eps^2, log eps^2): no host-to-device copy per call
 
     def __call__(self, mu: torch.Tensor, logvar: torch.Tensor) -> torch.Tensor:
-        eps_sq = torch.tensor([self.eps_sq], dtype=mu.dtype, device=mu.device)
+        key = (mu.device, mu.dtype)
+        if key not in self._cache:
+            e = torch.tensor([self.eps_sq], dtype=mu.dtype, device=mu.device)
+            self._cache[key] = e
+        eps_sq = self._cache[key]
         inner = logvar + torch.log(eps_sq) - mu.square() - eps_sq * logvar.exp()
         return -0.5 * inner.mean() / mu.shape[0]
 

@@ -9,7 +9,10 @@ What is re-plumbed for the GPU:
     instead of the DataLoader's per-sample indexing + stack (model.py:249-254);
   * per-term loss sums are accumulated on the device and read back once per epoch,
     instead of three `.item()` host syncs per batch (model.py:151,157,169);
-  * the quartet term runs as one fused kernel (see `losses.MDSLoss`).
+  * the quartet term runs as one fused kernel (see `losses.MDSLoss`);
+  * full-size batches replay ONE captured CUDA graph of the whole step (forward, backward, Adam,
+    loss bookkeeping): the step is ~100 tiny kernels and was launch-bound.  Disable with
+    `VIVAE_CUDA_GRAPH=0` or `model.use_cuda_graph = False`.
 RNG call order is the reference's: the loader permutation comes from a dedicated
 generator seeded with `random_state` (model.py:246-248), `randn_like` and the quartet
 re-sampling permutations from the global generator.
@@ -17,6 +20,8 @@ re-sampling permutations from the global generator.
 
 from __future__ import annotations
 
+import copy
+import os
 import random
 from collections.abc import Callable
 from typing import Optional
@@ -24,6 +29,7 @@ from typing import Optional
 import numpy as np
 import torch
 
+from . import _lib
 from .network import Autoencoder
 
 __all__ = ["ViVAE", "DeviceBatchLoader"]
@@ -97,6 +103,8 @@ class ViVAE:
         self.optimizer = None
         self.trained = False
         self.decoder_active = False
+        self.use_cuda_graph = os.environ.get("VIVAE_CUDA_GRAPH", "1") != "0"
+        self._graph = None  # (key, CUDAGraph, static batch, static loss sums)
 
     def __repr__(self):
         return f"ViVAE(input_dim={self.net.input_dim}, latent_dim={self.net.latent_dim}, device={self.device_name})"
@@ -113,32 +121,105 @@ class ViVAE:
         if self.data_loader is None:
             raise ValueError("No data to train on: use the `fit` or `fit_transform` method")
         dev = next(self.net.parameters()).device
+        cfg = dict(lam_recon=lam_recon, lam_kldiv=lam_kldiv, lam_geom=lam_geom, lam_egeom=lam_egeom, lam_mds=lam_mds,
+                   mds_distf_hd=mds_distf_hd, mds_distf_ld=mds_distf_ld, mds_nsamp=mds_nsamp, lam_imit=lam_imit,
+                   ref_model=ref_model)
         sums = torch.zeros(len(_TERMS), dtype=torch.float32, device=dev)
+        graph_ok = (self.use_cuda_graph and dev.type == "cuda" and lam_geom == 0.0 and lam_egeom == 0.0
+                    and mds_nsamp == 1 and (lam_imit == 0.0 or ref_model is None)
+                    and isinstance(self.data_loader, DeviceBatchLoader))
+        full = getattr(self.data_loader, "batch_size", None)
         for batch in self.data_loader:
             x = batch[0]
-            self.optimizer.zero_grad()
-            terms = self.net(x, lam_recon=lam_recon, lam_kldiv=lam_kldiv, lam_geom=lam_geom, lam_egeom=lam_egeom,
-                             lam_mds=lam_mds, mds_distf_hd=mds_distf_hd, mds_distf_ld=mds_distf_ld,
-                             mds_nsamp=mds_nsamp, lam_imit=lam_imit, ref_model=ref_model)
-            loss = None
-            vals = []
-            for name in _TERMS:  # same summation order as model.py:149-174
-                t = terms[name]
-                if name == "kldiv" and not self.net.variational:
-                    t = None
-                if t is None:
-                    vals.append(None)
+            if graph_ok and x.shape[0] == full and full >= 4:
+                g = self._graphed_step(x, cfg)
+                if g is not None:
+                    _, graph, static_x, static_sums, n_kernels = g
+                    static_x.copy_(x)
+                    static_sums.zero_()
+                    graph.replay()
+                    _lib.note_graph_replay(n_kernels)
+                    sums += static_sums
                     continue
-                vals.append(t.detach().reshape(()))
-                loss = t if loss is None else loss + t
-            with torch.no_grad():
-                present = [i for i, v in enumerate(vals) if v is not None]
-                if present:
-                    sums[present] += torch.stack([vals[i] for i in present])
-            loss.backward()
-            self.optimizer.step()
+            self._eager_step(x, cfg, sums)
         host = sums.tolist()  # the only host sync of the epoch
         return dict(zip(_TERMS, host))
+
+    # one optimisation step on batch x; adds the batch's loss terms into `sums` (device tensor)
+    def _eager_step(self, x: torch.Tensor, cfg: dict, sums: torch.Tensor) -> None:
+        self.optimizer.zero_grad()
+        terms = self.net(x, **cfg)
+        loss = None
+        vals = []
+        for name in _TERMS:  # same summation order as model.py:149-174
+            t = terms[name]
+            if name == "kldiv" and not self.net.variational:
+                t = None
+            if t is None:
+                vals.append(None)
+                continue
+            vals.append(t.detach().reshape(()))
+            loss = t if loss is None else loss + t
+        with torch.no_grad():  # graph-capture safe: no host-side index tensors
+            zero = torch.zeros((), dtype=torch.float32, device=sums.device)
+            sums += torch.stack([zero if v is None else v.to(torch.float32) for v in vals])
+        loss.backward()
+        self.optimizer.step()
+
+    def _graphed_step(self, x: torch.Tensor, cfg: dict):
+        """Capture (once per configuration) the whole step as a CUDA graph.  Warm-up steps run on a
+        side stream first (lazy cuBLAS / optimiser state initialisation); parameters, optimiser
+        state and the RNG are restored afterwards so training is unaffected by the warm-up."""
+        key = (tuple(x.shape), id(self.optimizer), tuple(sorted((k, str(v)) for k, v in cfg.items())))
+        if self._graph is not None and self._graph[0] == key:
+            return self._graph
+        if self._graph is not None and self._graph[0] == ("failed",) + key:
+            return None
+        dev = x.device
+        try:
+            static_x = x.clone()
+            static_sums = torch.zeros(len(_TERMS), dtype=torch.float32, device=dev)
+            params = [p.detach().clone() for p in self.net.parameters()]
+            opt_state = copy.deepcopy(self.optimizer.state_dict())
+            rng = torch.cuda.get_rng_state(dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self._eager_step(static_x, cfg, static_sums)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            # undo the warm-up: same tensors, original contents
+            with torch.no_grad():
+                for p, saved in zip(self.net.parameters(), params):
+                    p.copy_(saved)
+                for st in self.optimizer.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+            for grp, saved in zip(self.optimizer.param_groups, opt_state["param_groups"]):
+                for k_, v_ in saved.items():
+                    if k_ != "params":
+                        grp[k_] = v_
+            if opt_state["state"]:
+                self.optimizer.load_state_dict(opt_state)
+            torch.cuda.set_rng_state(rng, dev)
+            self.optimizer.zero_grad(set_to_none=True)
+            static_sums.zero_()
+            graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                self._eager_step(static_x, cfg, static_sums)
+            n_kernels = _lib.launch_count() - before  # this library's kernel nodes in the graph
+            _lib.note_graph_replay(-n_kernels)         # capture records, it does not execute
+            self._graph = (key, graph, static_x, static_sums, n_kernels)
+        except Exception as exc:  # capture unsupported for this configuration: stay eager, loudly
+            import warnings
+
+            warnings.warn(f"vivae_b200: CUDA-graph capture of the training step failed ({exc!r}); running eagerly")
+            torch.cuda.synchronize(dev)
+            self._graph = (("failed",) + key, None, None, None, 0)
+            return None
+        return self._graph
 
     def fit(self, X: np.ndarray, n_epochs: int = 50, batch_size: int = 256, learning_rate: float = 1e-3,
             weight_decay: float = 1e-4, lam_recon: float = 1.0, lam_kldiv: float = 1.0, lam_geom: float = 0.0,
@@ -164,7 +245,10 @@ class ViVAE:
         # would raise a dtype mismatch inside nn.Linear)
         data = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32)).to(dev)
         self.data_loader = DeviceBatchLoader(data, batch_size=batch_size, generator=g, shuffle=True)
-        self.optimizer = torch.optim.Adam(self.net.parameters(), lr=learning_rate, weight_decay=weight_decay)
+        graphs = self.use_cuda_graph and dev.type == "cuda"
+        self.optimizer = torch.optim.Adam(self.net.parameters(), lr=learning_rate, weight_decay=weight_decay,
+                                          capturable=graphs)
+        self._graph = None
         self.net.train()
 
         for epoch in range(1, n_epochs + 1):
