@@ -55,6 +55,8 @@ constexpr int TC_CAP = 32 * TC_CAP_E;
 constexpr int TC_MAX_D = 61;         // d + 3 norm slots must fit one 64-column atom
 constexpr float TC_PAD_NORM = 60000.0f;
 constexpr float TC_EPS = 1.0f / 32768.0f;  // 2^-15
+constexpr int TC_PREPASS_STRIDE = 16;      // threshold pre-pass: every 16th database tile ...
+constexpr int TC_PREPASS_MIN_TILES = 512;  // ... when the database has at least 65,536 rows
 
 constexpr size_t TC_SMEM_A = 4 * TC_ATOM_BYTES;                       // [mb][atom]
 constexpr size_t TC_SMEM_B = TC_STAGES * 2 * TC_ATOM_BYTES;           // [stage][atom]
@@ -63,6 +65,14 @@ constexpr size_t TC_SMEM_BYTES = TC_SMEM_A + TC_SMEM_B + 1024 /*align*/ + 256 /*
 static inline int tc_candidates(int k) {
   const int slack = k / 4 > 16 ? k / 4 : 16;
   return k + 1 + slack;
+}
+// List length that triggers a compaction.  Measured on B200 (1M x 50, k=50; screening kernel time):
+// trigger 224 of capacity 256: 380 ms; trigger 96 (fresher thresholds, 3x the compactions): 445 ms;
+// capacity 512 / trigger 480: 433 ms.  A compaction stalls the whole warp (32 rows) and, through the
+// accumulator hand-off, the MMA issuer, so it is done as late as the capacity allows.
+static inline int tc_trigger(int keep) {
+  (void)keep;
+  return TC_CAP - 32;
 }
 
 bool knn_tensor_supported(int64_t n, int d, int k) {
@@ -300,9 +310,9 @@ __global__ void __launch_bounds__(256) build_operands_kernel(
 // Out-of-line list maintenance, so that the hot screening loop stays small in the instruction
 // cache.  In-sweep compaction uses the cheap threshold selection; the full sort runs once per
 // row at the end of the sweep.
-__device__ __noinline__ float tc_select_truncate(float *keys, uint32_t *idxs, int cnt, int keep, int lane,
-                                                 int *new_cnt) {
-  return warp_select_truncate<TC_CAP_E>(keys, idxs, cnt, keep, TC_CAP - 64, lane, new_cnt);
+__device__ __noinline__ float tc_select_truncate(float *keys, uint32_t *idxs, int cnt, int keep, int keep_max,
+                                                 int lane, int *new_cnt) {
+  return warp_select_truncate<TC_CAP_E>(keys, idxs, cnt, keep, keep_max, lane, new_cnt);
 }
 __device__ __noinline__ float tc_sort_truncate(float *keys, uint32_t *idxs, int cnt, int keep, int lane, int *new_cnt) {
   return warp_sort_truncate<TC_CAP_E>(keys, idxs, cnt, keep, lane, new_cnt);
@@ -316,6 +326,9 @@ struct TcParams {
   int ks_hi;        // k-steps (of 16) covering d + 3 columns
   int ks_lo;        // k-steps covering d columns
   int keep;         // m: candidates kept per row
+  int trigger;      // a list longer than this is compacted before the next 32-column chunk
+  int tile_stride;  // visit database tiles 0, s, 2s, ... (s = 1: all; s = 16: the threshold pre-pass)
+  int use_tau_init; // start each row at cand_thr[row] (from the pre-pass) instead of +inf
   float *cand_key;  // (nq_pad, TC_CAP)
   uint32_t *cand_idx;
   int *cand_cnt;    // (nq_pad)
@@ -384,7 +397,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_b_full + 8 * s, 2 * TC_ATOM_BYTES);
         for (int atom = 0; atom < 2; ++atom)
-          tma_load_2d(smem_b + (s * 2 + atom) * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, atom * 64, t * TC_N);
+          tma_load_2d(smem_b + (s * 2 + atom) * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, atom * 64,
+                      t * p.tile_stride * TC_N);
       }
     }
   } else if (warp == 1) {
@@ -428,20 +442,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     const bool active = t_row < p.nq;
     float *ck = p.cand_key + t_row * TC_CAP;
     uint32_t *ci = p.cand_idx + t_row * TC_CAP;
-    float tau = active ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
+    float tau = -__int_as_float(0x7f800000);
+    if (active) tau = p.use_tau_init ? p.cand_thr[t_row] : __int_as_float(0x7f800000);
     int cnt = 0;
 
     // One 32-column chunk: make room, then screen.  The chunk is reduced to four group minima
     // (8 columns each) with 3-input min instructions; only groups that beat tau are expanded.
     auto process = [&](const uint32_t(&r)[32], int64_t j0) {
-      unsigned need = __ballot_sync(FULL, cnt > TC_CAP - 32);
+      unsigned need = __ballot_sync(FULL, cnt > p.trigger);
       while (need) {
         const int src = __ffs(need) - 1;
         need &= need - 1;
         const int64_t tt = __shfl_sync(FULL, t_row, src);
         const int c = __shfl_sync(FULL, cnt, src);
         int nc;
-        const float thr = tc_select_truncate(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, lane, &nc);
+        const float thr =
+            tc_select_truncate(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, p.trigger, lane, &nc);
         if (lane == src) {
           cnt = nc;
           tau = thr;
@@ -483,7 +499,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>((buf * 2 + mb) * TC_N);
-      const int64_t jt = static_cast<int64_t>(t) * TC_N;
+      const int64_t jt = static_cast<int64_t>(t) * p.tile_stride * TC_N;
       // software pipeline over the four chunks: the TMEM load of chunk c+1 is in flight while
       // chunk c is screened
       uint32_t ra[32], rb[32];
@@ -509,9 +525,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     for (int src = 0; src < 32; ++src) {
       const int64_t tt = __shfl_sync(FULL, t_row, src);
       const int c = __shfl_sync(FULL, cnt, src);
+      const float tau_src = __shfl_sync(FULL, tau, src);
       if (tt >= p.nq) continue;  // warp-uniform
       int nc;
-      const float thr = tc_sort_truncate(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, lane, &nc);
+      float thr = tc_sort_truncate(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, lane, &nc);
+      // every rejected entry has key >= the threshold in force when it was rejected >= tau_src;
+      // with fewer than `keep` entries the sort has no keep-th key and tau_src is the bound
+      thr = fminf(thr, tau_src);
       if (lane == 0) {
         p.cand_cnt[tt] = nc;
         p.cand_thr[tt] = thr;
@@ -798,11 +818,30 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   p.ks_hi = (S->d + 3 + 15) / 16;
   p.ks_lo = (S->d + 15) / 16;
   p.keep = S->keep;
+  p.trigger = tc_trigger(S->keep);
+  p.tile_stride = 1;
+  p.use_tau_init = 0;
   p.cand_key = L.cand_key;
   p.cand_idx = L.cand_idx;
   p.cand_cnt = L.cand_cnt;
   p.cand_thr = L.cand_thr;
-  knn_screen_kernel<<<static_cast<unsigned>(nq_pad / TC_M), TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, p);
+  const unsigned sgrid = static_cast<unsigned>(nq_pad / TC_M);
+  if (p.n_tiles >= TC_PREPASS_MIN_TILES) {
+    // Threshold pre-pass over every 16th database tile: the r-th smallest key of the sample,
+    // r = m/16 + 7 sqrt(m/16) + 2, is with overwhelming probability above the row's m-th smallest
+    // key over the whole database, yet close to it.  Starting the full sweep there removes the long
+    // warm-up in which almost every chunk has admissions (1400 -> ~350 admissions per row at 1M).
+    // Exactness never depends on it: a row left with too few candidates fails the certificate.
+    TcParams q = p;
+    q.tile_stride = TC_PREPASS_STRIDE;
+    q.n_tiles = (p.n_tiles + TC_PREPASS_STRIDE - 1) / TC_PREPASS_STRIDE;
+    const float mf = static_cast<float>(S->keep) / TC_PREPASS_STRIDE;
+    q.keep = static_cast<int>(ceilf(mf + 7.0f * sqrtf(mf) + 2.0f));
+    knn_screen_kernel<<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, q);
+    VVB_CHECK_LAUNCH();
+    p.use_tau_init = 1;
+  }
+  knn_screen_kernel<<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, p);
   VVB_CHECK_LAUNCH();
   if (screen_only) return VVB_OK;
   mark(1);
