@@ -419,7 +419,21 @@ def test_tensor_path_is_used_and_fallback_is_rare():
         wi, wd = orc.knn(x, 50, q0, q0 + 500)
         assert np.array_equal(idx[q0:q0 + 500], wi) and np.array_equal(dist[q0:q0 + 500], wd)
     with pytest.raises(NotImplementedError):
-        vv.make_knn(clustered(500, 100, 3, seed=2), k=10, verbose=False, algo="tensor")  # d > 61: brute only
+        vv.make_knn(clustered(300, 4200, 3, seed=2), k=10, verbose=False, algo="tensor")  # d + 3 > 4096: brute only
+    with pytest.raises(NotImplementedError):
+        vv.make_knn(clustered(2000, 20, 3, seed=2), k=400, verbose=False, algo="tensor")  # k too large: brute only
+
+
+@pytest.mark.parametrize("n,d,k", [(6000, 100, 50), (4000, 500, 30), (3000, 2000, 50), (2500, 62, 100), (1000, 129, 5)])
+def test_knn_wide_rows_use_the_k_loop_tensor_kernel(n, d, k):
+    """d + 3 > 64: the K-loop variant (query and database atoms streamed together); PCA-100 and the
+    2000-gene dense configuration of BASELINE.json are in this regime."""
+    x = clustered(n, d, 7, seed=d)
+    st = {}
+    got = vv.make_knn(x, k=k, verbose=False, algo="tensor", stats=st)
+    assert st["algo_used"] == 2
+    assert_knn_equal(got, orc.knn(x, k))
+    assert st["rows_fallback"] <= 0.02 * n, st
 
 
 def test_certificate_rejects_adversarial_rows_and_fallback_repairs_them():

@@ -32,6 +32,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <new>
 
 #include "common.cuh"
@@ -49,18 +50,22 @@ constexpr int TC_N = 128;            // database rows per tile
 constexpr int TC_STAGES = 3;         // database-tile ring
 constexpr int TC_THREADS = 384;      // 4 control warps + 8 epilogue warps
 constexpr int TC_ATOM_BYTES = 128 * 128;  // 128 rows x 64 fp16 (one 128B-swizzle K atom)
-constexpr int TC_OP_COLS = 128;      // operand row: [hi atom | lo atom] fp16
 constexpr int TC_CAP_E = 8;          // candidate list capacity = 32 * 8 = 256
 constexpr int TC_CAP = 32 * TC_CAP_E;
-constexpr int TC_MAX_D = 61;         // d + 3 norm slots must fit one 64-column atom
+constexpr int TC_MAX_KA = 64;        // K atoms (64 columns each) per operand half: d + 3 <= 4096
+constexpr int TC_KSTAGES = 2;        // K-loop variant: (query + database) atom stages
 constexpr float TC_PAD_NORM = 60000.0f;
 constexpr float TC_EPS = 1.0f / 32768.0f;  // 2^-15
 constexpr int TC_PREPASS_STRIDE = 16;      // threshold pre-pass: every 16th database tile ...
-constexpr int TC_PREPASS_MIN_TILES = 512;  // ... when the database has at least 65,536 rows
+constexpr int TC_PREPASS_MIN_TILES = 512;  // ... when the database has at least 65,536 rows (opt-in: VVB_TC_PREPASS=1)
 
 constexpr size_t TC_SMEM_A = 4 * TC_ATOM_BYTES;                       // [mb][atom]
 constexpr size_t TC_SMEM_B = TC_STAGES * 2 * TC_ATOM_BYTES;           // [stage][atom]
 constexpr size_t TC_SMEM_BYTES = TC_SMEM_A + TC_SMEM_B + 1024 /*align*/ + 256 /*barriers*/;
+// K-loop variant: every stage holds one K atom of everything: query hi/lo for both M blocks + database hi/lo
+constexpr size_t TC_SMEM_K = TC_KSTAGES * 6 * TC_ATOM_BYTES;
+constexpr size_t TC_SMEM_BYTES_K = TC_SMEM_K + 1024 + 256;
+static inline int tc_atoms(int d) { return (d + 3 + 63) / 64; }
 
 static inline int tc_candidates(int k) {
   const int slack = k / 4 > 16 ? k / 4 : 16;
@@ -76,7 +81,7 @@ static inline int tc_trigger(int keep) {
 }
 
 bool knn_tensor_supported(int64_t n, int d, int k) {
-  return d <= TC_MAX_D && tc_candidates(k) <= TC_CAP - 64 && n >= 2 && n <= 0x7fffffffLL;
+  return d >= 1 && tc_atoms(d) <= TC_MAX_KA && tc_candidates(k) <= TC_CAP - 64 && n >= 2 && n <= 0x7fffffffLL;
 }
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -175,11 +180,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int n_cols) {
 // ------------------------------------------------------------------ preparation kernels
 constexpr int PREP_BLOCKS = 256;
 
-// stage 1 of the column means: per-block partial sums in double
+// stage 1 of the column means: per-block partial sums in double; blockIdx.y = 64-column block
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float *__restrict__ x, int64_t n, int d,
                                                             double *__restrict__ partial) {
-  // thread (c = threadIdx.x % 64, sub = threadIdx.x / 64) sums rows sub, sub+4*gridDim.x ... of column c
-  const int c = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  // thread (c = threadIdx.x % 64, sub = threadIdx.x / 64) sums rows sub, sub+4*gridDim.x ... of its column
+  const int cl = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  const int c = blockIdx.y * 64 + cl;
   double acc = 0.0;
   if (c < d)
     for (int64_t r = static_cast<int64_t>(blockIdx.x) * 4 + sub; r < n; r += static_cast<int64_t>(gridDim.x) * 4)
@@ -187,16 +193,17 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float *__rest
   __shared__ double sh[256];
   sh[threadIdx.x] = acc;
   __syncthreads();
-  if (sub == 0) partial[blockIdx.x * 64 + c] = sh[c] + sh[64 + c] + sh[128 + c] + sh[192 + c];
+  if (sub == 0)
+    partial[(static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y) * 64 + cl] =
+        sh[cl] + sh[64 + cl] + sh[128 + cl] + sh[192 + cl];
 }
 __global__ void colsum_final_kernel(const double *__restrict__ partial, int nblocks, int64_t n, int d,
                                     float *__restrict__ mu, unsigned int *__restrict__ maxn2_bits) {
-  const int c = threadIdx.x;
-  if (c < 64) {
-    double acc = 0.0;
-    for (int b = 0; b < nblocks; ++b) acc += partial[b * 64 + c];
-    mu[c] = (c < d) ? static_cast<float>(acc / static_cast<double>(n)) : 0.0f;
-  }
+  const int cl = threadIdx.x;  // 64 threads; blockIdx.x = 64-column block
+  const int c = blockIdx.x * 64 + cl;
+  double acc = 0.0;
+  for (int b = 0; b < nblocks; ++b) acc += partial[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * 64 + cl];
+  mu[c] = (c < d) ? static_cast<float>(acc / static_cast<double>(n)) : 0.0f;
   if (c == 0) *maxn2_bits = 0u;
 }
 // largest squared centred norm (order-independent: atomicMax on the bits of a non-negative float)
@@ -235,8 +242,10 @@ __device__ __forceinline__ float pick_scale(float maxn2) {
 
 // One warp per row: centre, scale, split into FP16 hi/lo, write the database operand row
 // (and, for rows of the query shard, the query operand row and |x^|^2).
+// Operand row layout (fp16): [hi part: ka atoms of 64 columns | lo part: ka atoms]; the hi part carries
+// the data in columns 0..d-1 and, in columns d..d+2, the norm terms (database) or ones (query).
 __global__ void __launch_bounds__(256) build_operands_kernel(
-    const float *__restrict__ x, int64_t n, int d, const float *__restrict__ mu,
+    const float *__restrict__ x, int64_t n, int d, int ka, const float *__restrict__ mu,
     const unsigned int *__restrict__ maxn2_bits, int64_t n_pad, __half *__restrict__ opB, int64_t q0, int64_t nq,
     int64_t nq_pad, __half *__restrict__ opA, float *__restrict__ xnorm, PrepScalars *__restrict__ scalars) {
   const int lane = threadIdx.x & 31;
@@ -248,61 +257,42 @@ __global__ void __launch_bounds__(256) build_operands_kernel(
     scalars->scale = s;
     scalars->ymax = sqrtf(maxn2) * s * 1.0001f;
   }
-  const __half zero = __float2half_rn(0.0f);
+  const int half_cols = ka * 64;
+  const int64_t op_cols = 2 * half_cols;
   // rows [0, n_pad) -> database operand; rows [n_pad, n_pad + nq_pad) -> query operand of row q0 + (r - n_pad)
   for (int64_t w = warp; w < n_pad + nq_pad; w += nwarps) {
     const bool is_q = w >= n_pad;
     const int64_t local = is_q ? w - n_pad : w;
     const int64_t src = is_q ? q0 + local : local;
     const bool valid = is_q ? (local < nq) : (local < n);
-    __half hi[2], lo[2];
+    __half *row = (is_q ? opA : opB) + local * op_cols;
+    const float fac = is_q ? -2.0f : 1.0f;  // power of two: exact in FP16
     float nrm = 0.0f;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int c = q * 32 + lane;
+    for (int c = lane; c < half_cols; c += 32) {
       float v = 0.0f;
       if (valid && c < d) v = (__ldg(x + src * d + c) - __ldg(mu + c)) * s;
-      hi[q] = __float2half_rn(v);
-      const float hf = __half2float(hi[q]);
-      lo[q] = __float2half_rn(v - hf);
-      const float rep = hf + __half2float(lo[q]);
+      const __half hi = __float2half_rn(v);
+      const float hf = __half2float(hi);
+      const __half lo = __float2half_rn(v - hf);
+      const float rep = hf + __half2float(lo);
       nrm = fmaf(rep, rep, nrm);
+      row[c] = __float2half_rn(fac * hf);
+      row[half_cols + c] = __float2half_rn(fac * __half2float(lo));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(FULL, nrm, o);
-    __half *row = (is_q ? opA : opB) + local * TC_OP_COLS;
+    __syncwarp();
     if (is_q) {
       if (lane == 0) xnorm[local] = nrm;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int c = q * 32 + lane;
-        __half h = __float2half_rn(-2.0f * __half2float(hi[q]));  // exact (power-of-two factor)
-        __half l = __float2half_rn(-2.0f * __half2float(lo[q]));
-        if (c >= d) {
-          h = (c < d + 3 && valid) ? __float2half_rn(1.0f) : zero;
-          l = zero;
-        }
-        row[c] = h;
-        row[64 + c] = l;
-      }
+      if (lane < 3) row[d + lane] = __float2half_rn(valid ? 1.0f : 0.0f);
     } else {
-      // squared norm as a three-term FP16 sum (33 significant bits)
+      // squared norm as a three-term FP16 sum (33 significant bits); padding rows get a huge norm
       const float base = valid ? nrm : TC_PAD_NORM;
       const __half n0 = __float2half_rn(base);
       const float r1 = base - __half2float(n0);
       const __half n1 = __float2half_rn(r1);
       const __half n2 = __float2half_rn(r1 - __half2float(n1));
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int c = q * 32 + lane;
-        __half h = hi[q], l = lo[q];
-        if (c >= d) {
-          h = (c == d) ? n0 : (c == d + 1) ? n1 : (c == d + 2) ? n2 : zero;
-          l = zero;
-        }
-        row[c] = h;
-        row[64 + c] = l;
-      }
+      if (lane < 3) row[d + lane] = (lane == 0) ? n0 : (lane == 1) ? n1 : n2;
     }
   }
 }
@@ -329,21 +319,32 @@ struct TcParams {
   int trigger;      // a list longer than this is compacted before the next 32-column chunk
   int tile_stride;  // visit database tiles 0, s, 2s, ... (s = 1: all; s = 16: the threshold pre-pass)
   int use_tau_init; // start each row at cand_thr[row] (from the pre-pass) instead of +inf
+  int ka;           // K atoms per operand half (1: query operand resident; >1: K-loop variant)
+  int debug_mode;   // profiling only (env VVB_TC_DEBUG): 1 = drain TMEM but skip the screening,
+                    // 2 = screening minima only, no admissions.  Results are garbage in both.
   float *cand_key;  // (nq_pad, TC_CAP)
   uint32_t *cand_idx;
   int *cand_cnt;    // (nq_pad)
   float *cand_thr;  // (nq_pad) final admission threshold tau
 };
 
+// KLOOP = false: d + 3 <= 64, the query operand (2 atoms per M block) stays in shared memory for the
+//                 whole sweep and only database tiles stream (3-stage ring).
+// KLOOP = true : any d; every database tile is accumulated over `ka` K atoms, query and database atoms
+//                stream together through a 2-stage ring (6 atoms = 96 KB per stage).  The epilogue is
+//                identical; with ka >= 2 the MMA time per tile exceeds the TMEM read-out and the kernel
+//                becomes tensor bound.
+template <bool KLOOP>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
                                                                    const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 128B swizzle needs 1024-byte aligned atoms
-  const uint32_t smem_a = base;                                 // [mb 2][atom 2] x 16 KB
-  const uint32_t smem_b = base + TC_SMEM_A;                     // [stage][atom 2] x 16 KB
-  const uint32_t bars = base + TC_SMEM_A + TC_SMEM_B;           // mbarriers (8 B each)
+  const uint32_t smem_a = base;                                 // [mb 2][atom 2] x 16 KB   (resident variant)
+  const uint32_t smem_b = base + TC_SMEM_A;                     // [stage][atom 2] x 16 KB  (resident variant)
+  const uint32_t smem_k = base;                                 // [stage][6 atoms]         (K-loop variant)
+  const uint32_t bars = base + (KLOOP ? TC_SMEM_K : TC_SMEM_A + TC_SMEM_B);  // mbarriers (8 B each)
   const uint32_t bar_a_full = bars;
   const uint32_t bar_b_full = bars + 8;                         // [TC_STAGES]
   const uint32_t bar_b_empty = bar_b_full + 8 * TC_STAGES;      // [TC_STAGES]
@@ -386,51 +387,107 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      mbar_expect_tx(bar_a_full, 4 * TC_ATOM_BYTES);
-      for (int mb = 0; mb < 2; ++mb)
-        for (int atom = 0; atom < 2; ++atom)
-          tma_load_2d(smem_a + (mb * 2 + atom) * TC_ATOM_BYTES, &map_a, bar_a_full, atom * 64,
-                      static_cast<int>(q_base + mb * 128));
-      for (int t = 0; t < p.n_tiles; ++t) {
-        const int s = t % TC_STAGES;
-        const uint32_t ph = (t / TC_STAGES) & 1;
-        mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
-        mbar_expect_tx(bar_b_full + 8 * s, 2 * TC_ATOM_BYTES);
-        for (int atom = 0; atom < 2; ++atom)
-          tma_load_2d(smem_b + (s * 2 + atom) * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, atom * 64,
-                      t * p.tile_stride * TC_N);
+      if constexpr (!KLOOP) {
+        mbar_expect_tx(bar_a_full, 4 * TC_ATOM_BYTES);
+        for (int mb = 0; mb < 2; ++mb)
+          for (int atom = 0; atom < 2; ++atom)
+            tma_load_2d(smem_a + (mb * 2 + atom) * TC_ATOM_BYTES, &map_a, bar_a_full, atom * 64,
+                        static_cast<int>(q_base + mb * 128));
+        for (int t = 0; t < p.n_tiles; ++t) {
+          const int s = t % TC_STAGES;
+          const uint32_t ph = (t / TC_STAGES) & 1;
+          mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
+          mbar_expect_tx(bar_b_full + 8 * s, 2 * TC_ATOM_BYTES);
+          for (int atom = 0; atom < 2; ++atom)
+            tma_load_2d(smem_b + (s * 2 + atom) * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, atom * 64,
+                        t * p.tile_stride * TC_N);
+        }
+      } else {
+        int it = 0;
+        for (int t = 0; t < p.n_tiles; ++t) {
+          const int row_b = t * p.tile_stride * TC_N;
+          for (int a = 0; a < p.ka; ++a, ++it) {
+            const int s = it % TC_KSTAGES;
+            const uint32_t ph = (it / TC_KSTAGES) & 1;
+            const uint32_t st = smem_k + s * 6 * TC_ATOM_BYTES;
+            const int c_hi = a * 64, c_lo = (p.ka + a) * 64;
+            mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
+            mbar_expect_tx(bar_b_full + 8 * s, 6 * TC_ATOM_BYTES);
+            // stage layout: [A.hi mb0][A.lo mb0][A.hi mb1][A.lo mb1][B.hi][B.lo]
+            tma_load_2d(st + 0 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_hi, static_cast<int>(q_base));
+            tma_load_2d(st + 1 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_lo, static_cast<int>(q_base));
+            tma_load_2d(st + 2 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_hi, static_cast<int>(q_base + 128));
+            tma_load_2d(st + 3 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_lo, static_cast<int>(q_base + 128));
+            tma_load_2d(st + 4 * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, c_hi, row_b);
+            tma_load_2d(st + 5 * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, c_lo, row_b);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(TC_N);
-      mbar_wait(bar_a_full, 0);
-      for (int t = 0; t < p.n_tiles; ++t) {
-        const int s = t % TC_STAGES;
-        const uint32_t ph = (t / TC_STAGES) & 1;
-        const int buf = t & 1;
-        const uint32_t aph = (t >> 1) & 1;
-        mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
-        mbar_wait(bar_b_full + 8 * s, ph);
-        tc_fence_after();
-        const uint64_t b_hi = make_desc(smem_b + (s * 2 + 0) * TC_ATOM_BYTES);
-        const uint64_t b_lo = make_desc(smem_b + (s * 2 + 1) * TC_ATOM_BYTES);
+      if constexpr (!KLOOP) {
+        mbar_wait(bar_a_full, 0);
+        for (int t = 0; t < p.n_tiles; ++t) {
+          const int s = t % TC_STAGES;
+          const uint32_t ph = (t / TC_STAGES) & 1;
+          const int buf = t & 1;
+          const uint32_t aph = (t >> 1) & 1;
+          mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
+          mbar_wait(bar_b_full + 8 * s, ph);
+          tc_fence_after();
+          const uint64_t b_hi = make_desc(smem_b + (s * 2 + 0) * TC_ATOM_BYTES);
+          const uint64_t b_lo = make_desc(smem_b + (s * 2 + 1) * TC_ATOM_BYTES);
 #pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((buf * 2 + mb) * TC_N);
-          const uint64_t a_hi = make_desc(smem_a + (mb * 2 + 0) * TC_ATOM_BYTES);
-          const uint64_t a_lo = make_desc(smem_a + (mb * 2 + 1) * TC_ATOM_BYTES);
-          uint32_t acc = 0;
-          for (int ks = 0; ks < p.ks_hi; ++ks) {  // [-2xh | 1 1 1] . [yh | norm]
-            tc_mma_f16(d_tmem, a_hi + 2 * ks, b_hi + 2 * ks, idesc, acc);
-            acc = 1;
+          for (int mb = 0; mb < 2; ++mb) {
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((buf * 2 + mb) * TC_N);
+            const uint64_t a_hi = make_desc(smem_a + (mb * 2 + 0) * TC_ATOM_BYTES);
+            const uint64_t a_lo = make_desc(smem_a + (mb * 2 + 1) * TC_ATOM_BYTES);
+            uint32_t acc = 0;
+            for (int ks = 0; ks < p.ks_hi; ++ks) {  // [-2xh | 1 1 1] . [yh | norm]
+              tc_mma_f16(d_tmem, a_hi + 2 * ks, b_hi + 2 * ks, idesc, acc);
+              acc = 1;
+            }
+            for (int ks = 0; ks < p.ks_lo; ++ks) tc_mma_f16(d_tmem, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1);  // xh.yl
+            for (int ks = 0; ks < p.ks_lo; ++ks) tc_mma_f16(d_tmem, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1);  // xl.yh
           }
-          for (int ks = 0; ks < p.ks_lo; ++ks) tc_mma_f16(d_tmem, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1);  // xh.yl
-          for (int ks = 0; ks < p.ks_lo; ++ks) tc_mma_f16(d_tmem, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1);  // xl.yh
+          tc_commit(bar_b_empty + 8 * s);       // smem stage reusable once these MMAs retire
+          tc_commit(bar_acc_full + 8 * buf);    // accumulators ready for the epilogue
         }
-        tc_commit(bar_b_empty + 8 * s);       // smem stage reusable once these MMAs retire
-        tc_commit(bar_acc_full + 8 * buf);    // accumulators ready for the epilogue
+      } else {
+        int it = 0;
+        for (int t = 0; t < p.n_tiles; ++t) {
+          const int buf = t & 1;
+          const uint32_t aph = (t >> 1) & 1;
+          mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
+          for (int a = 0; a < p.ka; ++a, ++it) {
+            const int s = it % TC_KSTAGES;
+            const uint32_t ph = (it / TC_KSTAGES) & 1;
+            const uint32_t st = smem_k + s * 6 * TC_ATOM_BYTES;
+            mbar_wait(bar_b_full + 8 * s, ph);
+            tc_fence_after();
+            const uint64_t b_hi = make_desc(st + 4 * TC_ATOM_BYTES);
+            const uint64_t b_lo = make_desc(st + 5 * TC_ATOM_BYTES);
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((buf * 2 + mb) * TC_N);
+              const uint64_t a_hi = make_desc(st + (mb * 2 + 0) * TC_ATOM_BYTES);
+              const uint64_t a_lo = make_desc(st + (mb * 2 + 1) * TC_ATOM_BYTES);
+              // zero-padded columns contribute exactly 0, so every atom runs its 4 k-steps
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                tc_mma_f16(d_tmem, a_hi + 2 * ks, b_hi + 2 * ks, idesc, (a > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1);
+            }
+            tc_commit(bar_b_empty + 8 * s);
+          }
+          tc_commit(bar_acc_full + 8 * buf);
+        }
       }
     }
   } else if (warp >= 4) {
@@ -449,6 +506,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     // One 32-column chunk: make room, then screen.  The chunk is reduced to four group minima
     // (8 columns each) with 3-input min instructions; only groups that beat tau are expanded.
     auto process = [&](const uint32_t(&r)[32], int64_t j0) {
+      if (p.debug_mode == 1) {
+        if (__uint_as_float(r[0]) == 123.456f && __uint_as_float(r[31]) == 1.5f) tau = 0.f;  // keep the load alive
+        return;
+      }
       unsigned need = __ballot_sync(FULL, cnt > p.trigger);
       while (need) {
         const int src = __ffs(need) - 1;
@@ -473,7 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         g[q] = fminf(fminf(a, b), fminf(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
       }
       const float mn = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
-      if (mn < tau) {
+      if (mn < tau && p.debug_mode != 2) {
         const int lim = static_cast<int>(min(static_cast<int64_t>(32), p.n - j0));  // columns that are real rows
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -644,15 +705,15 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// operand matrix (rows, 128) fp16 row-major; box = 64 columns x 128 rows, 128B swizzle
-static int make_operand_map(CUtensorMap *map, void *ptr, int64_t rows) {
+// operand matrix (rows, op_cols) fp16 row-major; box = 64 columns x 128 rows, 128B swizzle
+static int make_operand_map(CUtensorMap *map, void *ptr, int64_t rows, int64_t op_cols) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return VVB_ECUDA;
   }
-  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(TC_OP_COLS), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(TC_OP_COLS) * sizeof(__half)};
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(op_cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(op_cols) * sizeof(__half)};
   const cuuint32_t box[2] = {64, 128};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, dims, strides, box, estr,
@@ -669,6 +730,8 @@ static int make_operand_map(CUtensorMap *map, void *ptr, int64_t rows) {
 // query operand, candidate lists and fallback list (sized for `chunk` query rows).
 struct TcLayout {
   int64_t n_pad, chunk_pad;
+  int ka;           // K atoms per operand half
+  int64_t op_cols;  // fp16 columns per operand row = 2 * ka * 64
   __half *opB, *opA;
   double *partial;
   float *mu;
@@ -686,16 +749,18 @@ struct TcLayout {
   size_t total;
 };
 
-static TcLayout tc_layout(void *ws, int64_t n, int k, int64_t chunk) {
+static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
   TcLayout L;
+  L.ka = tc_atoms(d);
+  L.op_cols = 2 * static_cast<int64_t>(L.ka) * 64;
   L.n_pad = (n + TC_N - 1) / TC_N * TC_N;
   L.chunk_pad = (chunk + TC_M - 1) / TC_M * TC_M;
   if (L.chunk_pad == 0) L.chunk_pad = TC_M;
   Carver cv(ws);
-  L.opB = cv.take<__half>(static_cast<size_t>(L.n_pad) * TC_OP_COLS);
-  L.opA = cv.take<__half>(static_cast<size_t>(L.chunk_pad) * TC_OP_COLS);
-  L.partial = cv.take<double>(PREP_BLOCKS * 64);
-  L.mu = cv.take<float>(64);
+  L.opB = cv.take<__half>(static_cast<size_t>(L.n_pad) * L.op_cols);
+  L.opA = cv.take<__half>(static_cast<size_t>(L.chunk_pad) * L.op_cols);
+  L.partial = cv.take<double>(static_cast<size_t>(PREP_BLOCKS) * L.ka * 64);
+  L.mu = cv.take<float>(static_cast<size_t>(L.ka) * 64);
   L.maxn2 = cv.take<unsigned int>(1);
   L.scalars = cv.take<PrepScalars>(1);
   L.xnorm = cv.take<float>(static_cast<size_t>(L.chunk_pad));
@@ -725,8 +790,7 @@ int64_t knn_tensor_chunk_rows(int64_t nq) {
 }
 
 size_t knn_tensor_workspace_bytes(int64_t n, int d, int k, int64_t nq) {
-  (void)d;
-  return tc_layout(nullptr, n, k, knn_tensor_chunk_rows(nq)).total;
+  return tc_layout(nullptr, n, d, k, knn_tensor_chunk_rows(nq)).total;
 }
 
 // ---- session API used by api.cu ----------------------------------------------------------
@@ -750,11 +814,13 @@ int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, in
   S->d = d;
   S->k = k;
   S->keep = tc_candidates(k);
-  S->L = tc_layout(workspace, n, k, chunk_rows);
+  S->L = tc_layout(workspace, n, d, k, chunk_rows);
   VVB_REQUIRE(workspace_bytes >= S->L.total, "tensor kNN: workspace too small (%zu < %zu)", workspace_bytes,
               S->L.total);
-  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(TC_SMEM_BYTES)));
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(TC_SMEM_BYTES_K)));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (stats) {
     VVB_CUDA(cudaEventCreate(&e0));
@@ -762,19 +828,19 @@ int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, in
     cudaEventRecord(e0, st);
   }
   TcLayout &L = S->L;
-  colsum_partial_kernel<<<PREP_BLOCKS, 256, 0, st>>>(x_dev, n, d, L.partial);
+  colsum_partial_kernel<<<dim3(PREP_BLOCKS, L.ka), 256, 0, st>>>(x_dev, n, d, L.partial);
   VVB_CHECK_LAUNCH();
-  colsum_final_kernel<<<1, 64, 0, st>>>(L.partial, PREP_BLOCKS, n, d, L.mu, L.maxn2);
+  colsum_final_kernel<<<L.ka, 64, 0, st>>>(L.partial, PREP_BLOCKS, n, d, L.mu, L.maxn2);
   VVB_CHECK_LAUNCH();
   const int prep_grid = sm_count() * 8;
   maxnorm_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.mu, L.maxn2);
   VVB_CHECK_LAUNCH();
-  build_operands_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.mu, L.maxn2, L.n_pad, L.opB, 0, 0, 0, L.opA,
+  build_operands_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.ka, L.mu, L.maxn2, L.n_pad, L.opB, 0, 0, 0, L.opA,
                                                    L.xnorm, L.scalars);
   VVB_CHECK_LAUNCH();
-  int rc = make_operand_map(&S->map_a, L.opA, L.chunk_pad);
+  int rc = make_operand_map(&S->map_a, L.opA, L.chunk_pad, L.op_cols);
   if (rc) return rc;
-  rc = make_operand_map(&S->map_b, L.opB, L.n_pad);
+  rc = make_operand_map(&S->map_b, L.opB, L.n_pad, L.op_cols);
   if (rc) return rc;
   if (stats) {
     cudaEventRecord(e1, st);
@@ -807,8 +873,8 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   };
   mark(0);
   // query operand of this chunk (the database part of the kernel's row range is empty here)
-  build_operands_kernel<<<sm_count() * 4, 256, 0, st>>>(S->x, S->n, S->d, L.mu, L.maxn2, 0, L.opB, q0, nq, nq_pad,
-                                                       L.opA, L.xnorm, L.scalars);
+  build_operands_kernel<<<sm_count() * 4, 256, 0, st>>>(S->x, S->n, S->d, L.ka, L.mu, L.maxn2, 0, L.opB, q0, nq,
+                                                       nq_pad, L.opA, L.xnorm, L.scalars);
   VVB_CHECK_LAUNCH();
   VVB_CUDA(cudaMemsetAsync(L.fb_count, 0, sizeof(int), st));
   TcParams p;
@@ -821,12 +887,20 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   p.trigger = tc_trigger(S->keep);
   p.tile_stride = 1;
   p.use_tau_init = 0;
+  p.ka = L.ka;
+  {
+    const char *dbg = getenv("VVB_TC_DEBUG");
+    p.debug_mode = dbg ? atoi(dbg) : 0;
+  }
   p.cand_key = L.cand_key;
   p.cand_idx = L.cand_idx;
   p.cand_cnt = L.cand_cnt;
   p.cand_thr = L.cand_thr;
   const unsigned sgrid = static_cast<unsigned>(nq_pad / TC_M);
-  if (p.n_tiles >= TC_PREPASS_MIN_TILES) {
+  const char *pre = getenv("VVB_TC_PREPASS");
+  if (pre && atoi(pre) == 1 && p.n_tiles >= TC_PREPASS_MIN_TILES) {
+    // OPT-IN (measured neutral on B200: 376 ms vs 380 ms at 1M x 50 -- the full sweep gets 15 %
+    // faster, the pre-pass costs as much; the kernel is bound by the TMEM read-out, not by admissions).
     // Threshold pre-pass over every 16th database tile: the r-th smallest key of the sample,
     // r = m/16 + 7 sqrt(m/16) + 2, is with overwhelming probability above the row's m-th smallest
     // key over the whole database, yet close to it.  Starting the full sweep there removes the long
@@ -837,11 +911,13 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     q.n_tiles = (p.n_tiles + TC_PREPASS_STRIDE - 1) / TC_PREPASS_STRIDE;
     const float mf = static_cast<float>(S->keep) / TC_PREPASS_STRIDE;
     q.keep = static_cast<int>(ceilf(mf + 7.0f * sqrtf(mf) + 2.0f));
-    knn_screen_kernel<<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, q);
+    if (L.ka == 1) knn_screen_kernel<false><<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, q);
+    else knn_screen_kernel<true><<<sgrid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, q);
     VVB_CHECK_LAUNCH();
     p.use_tau_init = 1;
   }
-  knn_screen_kernel<<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, p);
+  if (L.ka == 1) knn_screen_kernel<false><<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, p);
+  else knn_screen_kernel<true><<<sgrid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, p);
   VVB_CHECK_LAUNCH();
   if (screen_only) return VVB_OK;
   mark(1);
@@ -913,7 +989,7 @@ int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, i
     cudaMemcpy(cand_thr_out, L.cand_thr, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(xnorm_out, L.xnorm, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(scale_ymax_out, L.scalars, 2 * sizeof(float), cudaMemcpyDeviceToHost);
-    cudaMemcpy(mu_out, L.mu, 64 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaMemcpy(mu_out, L.mu, static_cast<size_t>(d < 64 ? d : 64) * sizeof(float), cudaMemcpyDeviceToHost);
   }
   cudaFree(ws);
   cudaFree(xd);
