@@ -256,6 +256,16 @@ def run_ours(args) -> None:
                 "bound": "tensor", "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf"], "traffic": None, "peak_source": peaks["source"],
                 "ms": dom_ms, "algorithmic_flops": flops}
+    # at small d the screening kernel is bound by the accumulator read-out (4 B per pair through
+    # tcgen05.ld at 64 B/clk/SM), not by the MMA: report that roofline next to the tensor one
+    tmem_roof = None
+    if st.get("algo_used") == 2:
+        clk = 1.83e9
+        peak_pairs = 148 * 16 * clk  # pairs/s: 16 FP32 accumulators per clock per SM
+        ach_pairs = float(nq) * n / (dom_ms / 1e3)
+        tmem_roof = {"kernel": "knn_screen_tcgen05", "bound": "tmem-read", "achieved": ach_pairs * 4 / 1e12,
+                     "peak": peak_pairs * 4 / 1e12, "unit": "TB/s", "frac": ach_pairs / peak_pairs,
+                     "note": "64 B/clk/SM TMEM read rate (B300_MICROARCH.md) at 1.83 GHz; see profiles/r01_knn_screen_ncu.md"}
     smooth_roof = None
     if ms_smooth:
         sbytes = float(n) * (k * d * 4 + k * 4 + d * 4)
@@ -289,12 +299,36 @@ def run_ours(args) -> None:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        h2d = n * d * 4 + (n * d * 4 + n * k * 8 if world == 1 else 0)
+        h2d = n * d * 4 + (n * d * 4 + n * (k + 1) * 8 if world == 1 else 0)
         d2h = nq * (k + 1) * 12 + (n * d * 4 if world == 1 else 0)
         e2e = {"value": n / dt, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "path": "vv.make_knn + vv.smooth (host NumPy in/out)" if world == 1 else
                        "vvb_make_knn_host per rank on its query shard (host in/out); smooth not included at N>1"}
+
+    # ---- quartet loss at a bandwidth-sized batch (rank 0): achieved GB/s of fwd+bwd
+    quartet = None
+    if rank == 0 and not args.skip_fit:
+        Bq = min(n, 1 << 20)
+        xq_ = x_dev[:Bq].contiguous()
+        zq_ = torch.randn(Bq, 2, device=dev, requires_grad=True)
+        for _ in range(3):
+            l_ = vv.MDSLoss()(xq_, zq_)
+            l_.backward()
+        torch.cuda.synchronize()
+        q0e, q1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0e.record()
+        for _ in range(10):
+            zq_.grad = None
+            l_ = vv.MDSLoss()(xq_, zq_)
+            l_.backward()
+        q1e.record()
+        torch.cuda.synchronize()
+        msq = q0e.elapsed_time(q1e) / 10
+        qbytes = float(Bq) * (4 * (d + 2) + 4 * (2 + 2 * 2))  # fwd reads x,z; writes unit grad; bwd reads it, writes dz
+        quartet = {"batch": Bq, "ms_fwd_bwd": msq, "achieved_gbs": qbytes / (msq / 1e3) / 1e9,
+                   "peak_gbs": peaks["hbm_gbs"], "frac": qbytes / (msq / 1e3) / 1e9 / peaks["hbm_gbs"],
+                   "algorithmic_bytes": qbytes}
 
     # ---- fit (secondary metric: s/epoch), rank 0 only
     fit = None
@@ -323,7 +357,7 @@ def run_ours(args) -> None:
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 (screening operands f16 hi/lo, f32 accumulate; re-rank f32)",
             "data": "synthetic", "config": workload_config(args, world), "clocks": clocks.summary(),
-            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_smooth": smooth_roof,
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_tmem": tmem_roof, "roofline_smooth": smooth_roof, "quartet": quartet,
             "knn_stats": st, "ms_knn": ms_knn, "ms_smooth": ms_smooth, "cpu_baseline": base, "fit": fit,
             "parity": {"knn": "bit-exact vs FP32 brute-force oracle (tests/test_gpu_parity.py)",
                        "smooth": "bit-exact vs reference smooth()", "quartet": "1e-4 relative"},

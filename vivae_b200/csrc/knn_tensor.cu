@@ -56,8 +56,7 @@ constexpr int TC_MAX_KA = 64;        // K atoms (64 columns each) per operand ha
 constexpr int TC_KSTAGES = 2;        // K-loop variant: (query + database) atom stages
 constexpr float TC_PAD_NORM = 60000.0f;
 constexpr float TC_EPS = 1.0f / 32768.0f;  // 2^-15
-constexpr int TC_PREPASS_STRIDE = 16;      // threshold pre-pass: every 16th database tile ...
-constexpr int TC_PREPASS_MIN_TILES = 512;  // ... when the database has at least 65,536 rows (opt-in: VVB_TC_PREPASS=1)
+constexpr int TC_PREPASS_MIN_TILES = 512;  // ... when the database has at least 65,536 rows (opt-in: VVB_TC_PREPASS=<tile stride>)
 
 constexpr size_t TC_SMEM_A = 4 * TC_ATOM_BYTES;                       // [mb][atom]
 constexpr size_t TC_SMEM_B = TC_STAGES * 2 * TC_ATOM_BYTES;           // [stage][atom]
@@ -898,7 +897,8 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   p.cand_thr = L.cand_thr;
   const unsigned sgrid = static_cast<unsigned>(nq_pad / TC_M);
   const char *pre = getenv("VVB_TC_PREPASS");
-  if (pre && atoi(pre) == 1 && p.n_tiles >= TC_PREPASS_MIN_TILES) {
+  const int pre_stride = pre ? atoi(pre) : 0;  // VVB_TC_PREPASS=<stride>, e.g. 16 or 64; 0/unset = off
+  if (pre_stride >= 2 && p.n_tiles >= TC_PREPASS_MIN_TILES) {
     // OPT-IN (measured neutral on B200: 376 ms vs 380 ms at 1M x 50 -- the full sweep gets 15 %
     // faster, the pre-pass costs as much; the kernel is bound by the TMEM read-out, not by admissions).
     // Threshold pre-pass over every 16th database tile: the r-th smallest key of the sample,
@@ -907,9 +907,9 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     // warm-up in which almost every chunk has admissions (1400 -> ~350 admissions per row at 1M).
     // Exactness never depends on it: a row left with too few candidates fails the certificate.
     TcParams q = p;
-    q.tile_stride = TC_PREPASS_STRIDE;
-    q.n_tiles = (p.n_tiles + TC_PREPASS_STRIDE - 1) / TC_PREPASS_STRIDE;
-    const float mf = static_cast<float>(S->keep) / TC_PREPASS_STRIDE;
+    q.tile_stride = pre_stride;
+    q.n_tiles = (p.n_tiles + pre_stride - 1) / pre_stride;
+    const float mf = static_cast<float>(S->keep) / pre_stride;
     q.keep = static_cast<int>(ceilf(mf + 7.0f * sqrtf(mf) + 2.0f));
     if (L.ka == 1) knn_screen_kernel<false><<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, q);
     else knn_screen_kernel<true><<<sgrid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, q);

@@ -13,12 +13,14 @@
 // neighbour order (starting from the first row, not from zero), true division by k,
 // then r + (target - r) * coef as three separately rounded operations (no FMA).
 // VVB_SMOOTH_JACOBI (every row reads `prev`) is the documented non-parity variant.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vvb {
 
 constexpr int SM_THREADS = 256;
-constexpr int SM_ROWS_PER_TICKET = 4;
+constexpr int SM_ROWS_PER_TICKET_DEFAULT = 1;  // rows a warp claims per atomic ticket (env VVB_SMOOTH_RPT overrides)
 constexpr int SM_UNROLL = 16;  // neighbour rows in flight per warp
 
 template <typename T> struct Arith;
@@ -40,15 +42,15 @@ template <> struct Arith<double> {
 template <typename T, int DPL, int KPL, bool GS>
 __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
     const T *__restrict__ prev, T *next, const int64_t *__restrict__ idx, int64_t ld_idx, int64_t n,
-    int d, int k, T coef, int *flags, int epoch, unsigned long long *ticket, int *bad_index) {
+    int d, int k, T coef, int *flags, int epoch, unsigned long long *ticket, int *bad_index, int rows_per_ticket) {
   const int lane = threadIdx.x & 31;
   const T kk = static_cast<T>(k);
   for (;;) {
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(ticket, 1ull) * SM_ROWS_PER_TICKET;
+    if (lane == 0) base = atomicAdd(ticket, 1ull) * rows_per_ticket;
     base = __shfl_sync(FULL, base, 0);
     if (base >= static_cast<unsigned long long>(n)) break;
-    const int64_t row_end = min(static_cast<int64_t>(base) + SM_ROWS_PER_TICKET, n);
+    const int64_t row_end = min(static_cast<int64_t>(base) + rows_per_ticket, n);
     for (int64_t i = static_cast<int64_t>(base); i < row_end; ++i) {
       // the row's neighbour list, coalesced, into registers: lane l holds entries l, l+32, ...
       const int64_t *nb = idx + i * ld_idx;
@@ -154,14 +156,16 @@ static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64
   VVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, mode == VVB_SMOOTH_JACOBI ? kern_ja : kern_gs,
                                                          SM_THREADS, 0));
   if (blocks_per_sm < 1) blocks_per_sm = 1;
-  const int64_t warps_needed = (n + SM_ROWS_PER_TICKET - 1) / SM_ROWS_PER_TICKET;
+  int rpt = SM_ROWS_PER_TICKET_DEFAULT;
+  if (const char *e = getenv("VVB_SMOOTH_RPT")) rpt = atoi(e) > 0 ? atoi(e) : rpt;
+  const int64_t warps_needed = (n + rpt - 1) / rpt;
   int64_t grid = static_cast<int64_t>(sm_count()) * blocks_per_sm;
   const int64_t max_useful = (warps_needed + SM_THREADS / 32 - 1) / (SM_THREADS / 32);
   if (grid > max_useful) grid = max_useful;
   if (mode != VVB_SMOOTH_JACOBI) {
     // Gauss-Seidel: rows in flight wait on each other, so keep the in-flight window a small
     // fraction of n (waiting warps only burn issue slots and L2 polls)
-    const int64_t cap = n / (16 * SM_ROWS_PER_TICKET * (SM_THREADS / 32)) + 1;
+    const int64_t cap = n / (16 * rpt * (SM_THREADS / 32)) + 1;
     if (grid > cap) grid = cap;
   }
   if (grid < 1) grid = 1;
@@ -173,10 +177,10 @@ static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64
     T *dst = to_out ? out : scratch;
     if (mode == VVB_SMOOTH_JACOBI)
       kern_ja<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k,
-                                                                 static_cast<T>(coef), flags, it + 1, tickets + it, bad);
+                                                                 static_cast<T>(coef), flags, it + 1, tickets + it, bad, rpt);
     else
       kern_gs<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k,
-                                                                 static_cast<T>(coef), flags, it + 1, tickets + it, bad);
+                                                                 static_cast<T>(coef), flags, it + 1, tickets + it, bad, rpt);
     VVB_CHECK_LAUNCH();
     src = dst;
   }
