@@ -374,9 +374,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
-    ap.add_argument("--d", type=int, default=50)
-    ap.add_argument("--k", type=int, default=50)
+    ap.add_argument("--cells", "--n", dest="n", type=int, default=1_000_000)  # use --cells under torchrun
+    ap.add_argument("--dims", "--d", dest="d", type=int, default=50)
+    ap.add_argument("--neighbours", "--k", dest="k", type=int, default=50)
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--skip-e2e", action="store_true")

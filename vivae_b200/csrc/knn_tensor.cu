@@ -609,13 +609,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
 
 // ------------------------------------------------------------------ re-rank + certificate
 // One warp per query row.  E = ceil(m / 32).
-template <int E>
+// WIDE = false: each lane walks its candidate's row directly (fine for d ~ 50).
+// WIDE = true : for wide rows the 32 candidate rows of a group are staged through shared memory in
+//               32-column chunks (coalesced 128 B loads, conflict-free transposed reads); every lane
+//               still evaluates ITS candidate's chain strictly left to right, so the result is bit-identical.
+template <int E, bool WIDE>
 __global__ void __launch_bounds__(256) knn_rerank_kernel(
     const float *__restrict__ x, int64_t n, int d, int64_t q0, int64_t nq, int k,
     const uint32_t *__restrict__ cand_idx, const int *__restrict__ cand_cnt, const float *__restrict__ cand_thr,
     const float *__restrict__ xnorm, const PrepScalars *__restrict__ scalars, int64_t *__restrict__ out_idx,
     float *__restrict__ out_dist, int *__restrict__ fb_count, int64_t *__restrict__ fb_rows) {
+  __shared__ float stage[WIDE ? 8 : 1][WIDE ? 32 : 1][WIDE ? 33 : 1];
   const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
   const int64_t t = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (t >= nq) return;  // warp-uniform
   const int64_t g = q0 + t;
@@ -627,14 +633,40 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
   for (int e = 0; e < E; ++e) {
     const int pos = e * 32 + lane;
     key[e] = ~0ull;
-    if (pos < cnt) {
-      const uint32_t j = cand_idx[t * TC_CAP + pos];
-      const float *y = x + static_cast<int64_t>(j) * d;
-      float acc = 0.0f;
-      for (int c = 0; c < d; ++c) {  // the contract's chain: left to right, one rounding per fmaf
-        const float df = __fsub_rn(__ldg(xq + c), __ldg(y + c));
-        acc = __fmaf_rn(df, df, acc);
+    uint32_t j = 0;
+    float acc = 0.0f;
+    if (!WIDE) {
+      if (pos < cnt) {
+        j = cand_idx[t * TC_CAP + pos];
+        const float *y = x + static_cast<int64_t>(j) * d;
+        for (int c = 0; c < d; ++c) {  // the contract's chain: left to right, one rounding per fmaf
+          const float df = __fsub_rn(__ldg(xq + c), __ldg(y + c));
+          acc = __fmaf_rn(df, df, acc);
+        }
       }
+    } else {
+      if (e * 32 < cnt) {  // warp-uniform: this group of 32 candidates is not empty
+        if (pos < cnt) j = cand_idx[t * TC_CAP + pos];
+        const int in_group = min(32, cnt - e * 32);
+        for (int c0 = 0; c0 < d; c0 += 32) {
+          const float xv = (c0 + lane < d) ? __ldg(xq + c0 + lane) : 0.0f;
+          for (int cc = 0; cc < in_group; ++cc) {
+            const uint32_t jc = __shfl_sync(FULL, j, cc);
+            stage[wib][cc][lane] = (c0 + lane < d) ? __ldg(x + static_cast<int64_t>(jc) * d + c0 + lane) : 0.0f;
+          }
+          __syncwarp();
+          // every lane runs the chain (lanes beyond the group compute on stale tiles and are ignored):
+          // the shuffles must be executed by the full warp
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {  // zero-padded tail: fmaf(0, 0, acc) == acc exactly
+            const float df = __fsub_rn(__shfl_sync(FULL, xv, c), stage[wib][lane][c]);
+            acc = __fmaf_rn(df, df, acc);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (pos < cnt) {
       if (static_cast<int64_t>(j) == g) {
         key[e] = 0ull;  // self sorts first
         self_here = true;
@@ -923,9 +955,17 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   mark(1);
   const unsigned rr_grid = static_cast<unsigned>((nq + 7) / 8);
   const int e_need = (S->keep + 31) / 32;
-#define VVB_RR(EE)                                                                                                  \
-  knn_rerank_kernel<EE><<<rr_grid, 256, 0, st>>>(S->x, S->n, S->d, q0, nq, S->k, L.cand_idx, L.cand_cnt, L.cand_thr, \
-                                                 L.xnorm, L.scalars, out_idx, out_dist, L.fb_count, L.fb_rows)
+#define VVB_RR(EE)                                                                                                    \
+  do {                                                                                                                \
+    if (S->d >= 128)                                                                                                  \
+      knn_rerank_kernel<EE, true><<<rr_grid, 256, 0, st>>>(S->x, S->n, S->d, q0, nq, S->k, L.cand_idx, L.cand_cnt,   \
+                                                           L.cand_thr, L.xnorm, L.scalars, out_idx, out_dist,       \
+                                                           L.fb_count, L.fb_rows);                                   \
+    else                                                                                                              \
+      knn_rerank_kernel<EE, false><<<rr_grid, 256, 0, st>>>(S->x, S->n, S->d, q0, nq, S->k, L.cand_idx, L.cand_cnt,  \
+                                                            L.cand_thr, L.xnorm, L.scalars, out_idx, out_dist,      \
+                                                            L.fb_count, L.fb_rows);                                  \
+  } while (0)
   if (e_need <= 2) VVB_RR(2);
   else if (e_need <= 4) VVB_RR(4);
   else VVB_RR(8);
