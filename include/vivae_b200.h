@@ -88,8 +88,10 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
 /* bytes of device workspace vvb_make_knn_device needs for these sizes */
 int vvb_make_knn_workspace_bytes(int64_t n, int d, int k, int64_t nq, int algo, size_t *bytes);
 
-/* same contract with device-resident buffers; synchronises `stream` before
- * returning only if `stats` is non-NULL (the timings need it). */
+/* same contract with device-resident buffers.  The tensor path reads the number of rows its
+ * certificate rejected back to the host once per 262,144-row chunk (a stream synchronisation), so
+ * the call is not capturable in a CUDA graph; on return all work is enqueued (and, with `stats`
+ * non-NULL, finished). */
 int vvb_make_knn_device(const float *x_dev, int64_t n, int d, int k, int64_t q0, int64_t nq,
                         int algo, int64_t *idx_out_dev, float *dist_out_dev, void *workspace_dev,
                         size_t workspace_bytes, void *stream, vvb_knn_stats *stats);

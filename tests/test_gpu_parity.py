@@ -475,3 +475,21 @@ def test_make_knn_host_chunked_path_matches_oracle_samples():
     idx2, dist2 = vv.make_knn(x, k=k, verbose=False)  # second call reuses the cached device buffers
     assert np.array_equal(idx, idx2) and np.array_equal(dist, dist2)
     assert vv._lib.load().vvb_release_cached_memory() == 0
+
+
+def test_few_row_fallback_slices_the_database():
+    """A tight knot of 90 nearly coincident points inside 60k cells: their neighbour order is below the
+    screening resolution, so exactly those rows fail the certificate and take the few-row fallback
+    (one CTA per row and database slice + merge).  The answer must still be the oracle's."""
+    x = clustered(60_000, 50, 10, seed=17)
+    rng = np.random.default_rng(1)
+    knot = np.arange(1000, 1090)
+    x[knot] = x[1000] + (rng.standard_normal((90, 50)) * 2e-6).astype(np.float32)
+    st = {}
+    idx, dist = vv.make_knn(x, k=50, verbose=False, algo="tensor", stats=st)
+    assert 1 <= st["rows_fallback"] <= 2048, st
+    wi, wd = orc.knn(x, 50, 900, 1200)
+    assert np.array_equal(idx[900:1200], wi) and np.array_equal(dist[900:1200], wd)
+    wi, wd = orc.knn(x, 50, 30_000, 30_200)
+    assert np.array_equal(idx[30_000:30_200], wi) and np.array_equal(dist[30_000:30_200], wd)
+    print("few-row fallback:", st["rows_fallback"], "rows,", f"{st['ms_fallback']:.2f} ms")

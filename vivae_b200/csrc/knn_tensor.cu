@@ -43,6 +43,11 @@ int launch_knn_brute_list(const float *x_dev, int64_t n, int d, int k, const int
                           const int *count_dev, int64_t max_rows, int64_t *out_idx, float *out_dist,
                           int64_t out_row0, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t brute_workspace_bytes(int64_t nq, int k);
+int knn_brute_few_max_rows();
+size_t knn_brute_few_workspace_bytes(int k);
+int launch_knn_brute_few(const float *x_dev, int64_t n, int d, int k, const int64_t *qrows_dev, int count,
+                         int64_t *out_idx, float *out_dist, int64_t out_row0, void *workspace, size_t workspace_bytes,
+                         cudaStream_t stream);
 
 // ------------------------------------------------------------------ compile-time shape
 constexpr int TC_M = 256;            // query rows per CTA
@@ -55,7 +60,7 @@ constexpr int TC_CAP = 32 * TC_CAP_E;
 constexpr int TC_MAX_KA = 64;        // K atoms (64 columns each) per operand half: d + 3 <= 4096
 constexpr int TC_KSTAGES = 2;        // K-loop variant: (query + database) atom stages
 constexpr float TC_PAD_NORM = 60000.0f;
-constexpr float TC_EPS = 1.0f / 32768.0f;  // 2^-15
+constexpr float TC_EPS = 1.0f / 131072.0f;  // 2^-17: 26x the measured screening error (2^-21.7), ~5x its analytic bound
 constexpr int TC_PREPASS_MIN_TILES = 512;  // ... when the database has at least 65,536 rows (opt-in: VVB_TC_PREPASS=<tile stride>)
 
 constexpr size_t TC_SMEM_A = 4 * TC_ATOM_BYTES;                       // [mb][atom]
@@ -804,7 +809,8 @@ static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
   // the fallback's candidate lists reuse the screening lists (dead after the re-rank)
   L.brute_ws = L.cand_key;
   L.brute_ws_bytes = static_cast<size_t>(L.chunk_pad) * TC_CAP * 8;
-  const size_t need_brute = brute_workspace_bytes(chunk, k);
+  size_t need_brute = brute_workspace_bytes(chunk, k);
+  if (knn_brute_few_workspace_bytes(k) > need_brute) need_brute = knn_brute_few_workspace_bytes(k);
   if (need_brute > L.brute_ws_bytes) {  // never for the supported k, kept for safety
     L.brute_ws = cv.take<char>(need_brute);
     L.brute_ws_bytes = need_brute;
@@ -972,14 +978,22 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
 #undef VVB_RR
   VVB_CHECK_LAUNCH();
   mark(2);
-  // rows the certificate rejected: exact FP32 brute force, count consumed on the device
-  int rc = launch_knn_brute_list(S->x, S->n, S->d, S->k, L.fb_rows, L.fb_count, nq, out_idx, out_dist, q0, L.brute_ws,
-                                 L.brute_ws_bytes, st);
+  // rows the certificate rejected: exact FP32 brute force.  The count comes back to the host (one
+  // 4-byte copy + stream sync per chunk) so that a handful of rows can be spread over the whole GPU
+  // (database slices) instead of leaving one CTA to sweep the database alone.
+  int fb = 0;
+  VVB_CUDA(cudaMemcpyAsync(&fb, L.fb_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+  VVB_CUDA(cudaStreamSynchronize(st));
+  int rc = VVB_OK;
+  if (fb > 0 && fb <= knn_brute_few_max_rows())
+    rc = launch_knn_brute_few(S->x, S->n, S->d, S->k, L.fb_rows, fb, out_idx, out_dist, q0, L.brute_ws,
+                              L.brute_ws_bytes, st);
+  else if (fb > 0)
+    rc = launch_knn_brute_list(S->x, S->n, S->d, S->k, L.fb_rows, L.fb_count, nq, out_idx, out_dist, q0, L.brute_ws,
+                               L.brute_ws_bytes, st);
   if (rc) return rc;
   mark(3);
   if (stats) {
-    int fb = 0;
-    VVB_CUDA(cudaMemcpyAsync(&fb, L.fb_count, sizeof(int), cudaMemcpyDeviceToHost, st));
     VVB_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev[0], ev[1]);
