@@ -13,8 +13,15 @@
 //
 // Kernel shape (one CTA per SM, persistent over the database):
 //   CTA = 256 query rows (two M=128 MMAs share every database tile), database tile N=128,
-//   warp 0 lane 0 : TMA producer  (query operand once, database tiles through a 3-stage ring)
-//   warp 1 lane 0 : tcgen05.mma issuer, accumulators double-buffered in TMEM (4 x 128 columns)
+//   warp 0 lane 0 : TMA producer  (database tiles through a 4-stage ring)
+//   warp 1 lane 0 : tcgen05.mma issuer.  For d + 3 <= 64 the query operand lives in TENSOR MEMORY
+//                   (128 columns, written once with tcgen05.st) and is the MMA's A operand from there:
+//                   an M=128,N=128,K=16 MMA with both operands in shared memory reads 8 KB per 64
+//                   cycles = the whole 128 B/clk shared-memory bandwidth of the SM (measured: the
+//                   all-shared-memory version ran at 63 % of the tensor rate even with the epilogue
+//                   switched off); with A in TMEM it reads 4 KB.  The remaining 384 columns hold THREE
+//                   accumulator slots used round-robin by the (tile, M block) sequence, which gives each
+//                   epilogue group the same 2 x MMA time to drain a slot as full double buffering.
 //   warp 2        : TMEM allocator
 //   warps 4..11   : epilogue -- tcgen05.ld 32x32b, ONE THREAD OWNS ONE QUERY ROW, so the
 //                   running threshold tau and the candidate count are registers; a 32-column
@@ -52,7 +59,7 @@ int launch_knn_brute_few(const float *x_dev, int64_t n, int d, int k, const int6
 // ------------------------------------------------------------------ compile-time shape
 constexpr int TC_M = 256;            // query rows per CTA
 constexpr int TC_N = 128;            // database rows per tile
-constexpr int TC_STAGES = 3;         // database-tile ring
+constexpr int TC_STAGES = 4;         // database-tile ring
 constexpr int TC_THREADS = 384;      // 4 control warps + 8 epilogue warps
 constexpr int TC_ATOM_BYTES = 128 * 128;  // 128 rows x 64 fp16 (one 128B-swizzle K atom)
 constexpr int TC_CAP_E = 8;          // candidate list capacity = 32 * 8 = 256
@@ -63,9 +70,9 @@ constexpr float TC_PAD_NORM = 60000.0f;
 constexpr float TC_EPS = 1.0f / 131072.0f;  // 2^-17: 26x the measured screening error (2^-21.7), ~5x its analytic bound
 constexpr int TC_PREPASS_MIN_TILES = 512;  // ... when the database has at least 65,536 rows (opt-in: VVB_TC_PREPASS=<tile stride>)
 
-constexpr size_t TC_SMEM_A = 4 * TC_ATOM_BYTES;                       // [mb][atom]
 constexpr size_t TC_SMEM_B = TC_STAGES * 2 * TC_ATOM_BYTES;           // [stage][atom]
-constexpr size_t TC_SMEM_BYTES = TC_SMEM_A + TC_SMEM_B + 1024 /*align*/ + 256 /*barriers*/;
+constexpr size_t TC_SMEM_BYTES = TC_SMEM_B + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_TMEM_A = 384;       // resident variant: first TMEM column of the query operand (2 x 64 columns)
 // K-loop variant: every stage holds one K atom of everything: query hi/lo for both M blocks + database hi/lo
 constexpr size_t TC_SMEM_K = TC_KSTAGES * 6 * TC_ATOM_BYTES;
 constexpr size_t TC_SMEM_BYTES_K = TC_SMEM_K + 1024 + 256;
@@ -134,6 +141,29 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// A operand in tensor memory (128 lanes x 8 columns of packed fp16 pairs per K=16 step), B in shared memory
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
 // tcgen05.ld is asynchronous: tc_ld32_issue starts the load of 32 consecutive columns of this
@@ -325,36 +355,40 @@ struct TcParams {
   int use_tau_init; // start each row at cand_thr[row] (from the pre-pass) instead of +inf
   int ka;           // K atoms per operand half (1: query operand resident; >1: K-loop variant)
   int debug_mode;   // profiling only (env VVB_TC_DEBUG): 1 = drain TMEM but skip the screening,
-                    // 2 = screening minima only, no admissions.  Results are garbage in both.
+                    // 2 = screening minima only, no admissions, 3 = no TMEM drain at all.  Results are garbage.
+  const uint32_t *op_a;  // query operand rows as 32-bit words (64 per row), resident variant only
   float *cand_key;  // (nq_pad, TC_CAP)
   uint32_t *cand_idx;
   int *cand_cnt;    // (nq_pad)
   float *cand_thr;  // (nq_pad) final admission threshold tau
 };
 
-// KLOOP = false: d + 3 <= 64, the query operand (2 atoms per M block) stays in shared memory for the
-//                 whole sweep and only database tiles stream (3-stage ring).
+// KLOOP = false: d + 3 <= 64.  The query operand (256 rows x [hi 64 | lo 64] fp16) is copied once into
+//                 tensor memory (columns 384..511) and feeds the MMAs from there; only database tiles
+//                 stream through shared memory (4-stage ring).  Three accumulator slots (columns 0..383).
 // KLOOP = true : any d; every database tile is accumulated over `ka` K atoms, query and database atoms
-//                stream together through a 2-stage ring (6 atoms = 96 KB per stage).  The epilogue is
-//                identical; with ka >= 2 the MMA time per tile exceeds the TMEM read-out and the kernel
-//                becomes tensor bound.
+//                stream together through a 2-stage ring (6 atoms = 96 KB per stage); four accumulator
+//                slots.  The epilogue is identical.
+// Accumulator slots: the sequence it = 2 t + mb (tile t, M block mb) uses slot it % NSLOT for the
+// (it / NSLOT)-th time; acc_full[slot] is committed by the MMA issuer, acc_empty[slot] is released by
+// the four epilogue warps of that M block.
 template <bool KLOOP>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
                                                                    const TcParams p) {
+  constexpr int NSLOT = KLOOP ? 4 : 3;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 128B swizzle needs 1024-byte aligned atoms
-  const uint32_t smem_a = base;                                 // [mb 2][atom 2] x 16 KB   (resident variant)
-  const uint32_t smem_b = base + TC_SMEM_A;                     // [stage][atom 2] x 16 KB  (resident variant)
+  const uint32_t smem_b = base;                                 // [stage][atom 2] x 16 KB  (resident variant)
   const uint32_t smem_k = base;                                 // [stage][6 atoms]         (K-loop variant)
-  const uint32_t bars = base + (KLOOP ? TC_SMEM_K : TC_SMEM_A + TC_SMEM_B);  // mbarriers (8 B each)
+  const uint32_t bars = base + (KLOOP ? TC_SMEM_K : TC_SMEM_B);  // mbarriers (8 B each)
   const uint32_t bar_a_full = bars;
   const uint32_t bar_b_full = bars + 8;                         // [TC_STAGES]
   const uint32_t bar_b_empty = bar_b_full + 8 * TC_STAGES;      // [TC_STAGES]
-  const uint32_t bar_acc_full = bar_b_empty + 8 * TC_STAGES;    // [2]
-  const uint32_t bar_acc_empty = bar_acc_full + 16;             // [2]
-  const uint32_t tmem_slot = bar_acc_empty + 16;                // u32 written by tcgen05.alloc
+  const uint32_t bar_acc_full = bar_b_empty + 8 * TC_STAGES;    // [4]
+  const uint32_t bar_acc_empty = bar_acc_full + 32;             // [4]
+  const uint32_t tmem_slot = bar_acc_empty + 32;                // u32 written by tcgen05.alloc
   volatile uint32_t *tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
 
@@ -363,18 +397,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   const int64_t q_base = static_cast<int64_t>(blockIdx.x) * TC_M;  // first (local) query row of this CTA
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    if constexpr (KLOOP) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar_a_full, 1);
+    mbar_init(bar_a_full, 8);  // resident variant: one arrival per epilogue warp once its rows are in TMEM
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_b_full + 8 * s, 1);
       mbar_init(bar_b_empty + 8 * s, 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(bar_acc_full + 8 * b, 1);
-      mbar_init(bar_acc_empty + 8 * b, 8);  // one arrival per epilogue warp
+      mbar_init(bar_acc_empty + 8 * b, 4);  // one arrival per epilogue warp of the M block
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -392,11 +426,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     // =========================== TMA producer ===========================
     if (lane == 0) {
       if constexpr (!KLOOP) {
-        mbar_expect_tx(bar_a_full, 4 * TC_ATOM_BYTES);
-        for (int mb = 0; mb < 2; ++mb)
-          for (int atom = 0; atom < 2; ++atom)
-            tma_load_2d(smem_a + (mb * 2 + atom) * TC_ATOM_BYTES, &map_a, bar_a_full, atom * 64,
-                        static_cast<int>(q_base + mb * 128));
         for (int t = 0; t < p.n_tiles; ++t) {
           const int s = t % TC_STAGES;
           const uint32_t ph = (t / TC_STAGES) & 1;
@@ -433,39 +462,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(TC_N);
       if constexpr (!KLOOP) {
-        mbar_wait(bar_a_full, 0);
+        mbar_wait(bar_a_full, 0);  // query operand is in tensor memory
+        tc_fence_after();
+        int slot = 0;
+        uint32_t use_par = 0;  // parity of (it / NSLOT)
         for (int t = 0; t < p.n_tiles; ++t) {
           const int s = t % TC_STAGES;
           const uint32_t ph = (t / TC_STAGES) & 1;
-          const int buf = t & 1;
-          const uint32_t aph = (t >> 1) & 1;
-          mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
           mbar_wait(bar_b_full + 8 * s, ph);
-          tc_fence_after();
           const uint64_t b_hi = make_desc(smem_b + (s * 2 + 0) * TC_ATOM_BYTES);
           const uint64_t b_lo = make_desc(smem_b + (s * 2 + 1) * TC_ATOM_BYTES);
 #pragma unroll
           for (int mb = 0; mb < 2; ++mb) {
-            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((buf * 2 + mb) * TC_N);
-            const uint64_t a_hi = make_desc(smem_a + (mb * 2 + 0) * TC_ATOM_BYTES);
-            const uint64_t a_lo = make_desc(smem_a + (mb * 2 + 1) * TC_ATOM_BYTES);
+            mbar_wait(bar_acc_empty + 8 * slot, use_par ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(slot * TC_N);
+            const uint32_t a_hi = tmem_base + static_cast<uint32_t>(TC_TMEM_A + mb * 64);  // 8 columns per k-step
+            const uint32_t a_lo = a_hi + 32;
             uint32_t acc = 0;
             for (int ks = 0; ks < p.ks_hi; ++ks) {  // [-2xh | 1 1 1] . [yh | norm]
-              tc_mma_f16(d_tmem, a_hi + 2 * ks, b_hi + 2 * ks, idesc, acc);
+              tc_mma_f16_ts(d_tmem, a_hi + 8 * ks, b_hi + 2 * ks, idesc, acc);
               acc = 1;
             }
-            for (int ks = 0; ks < p.ks_lo; ++ks) tc_mma_f16(d_tmem, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1);  // xh.yl
-            for (int ks = 0; ks < p.ks_lo; ++ks) tc_mma_f16(d_tmem, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1);  // xl.yh
+            for (int ks = 0; ks < p.ks_lo; ++ks) tc_mma_f16_ts(d_tmem, a_hi + 8 * ks, b_lo + 2 * ks, idesc, 1);  // xh.yl
+            for (int ks = 0; ks < p.ks_lo; ++ks) tc_mma_f16_ts(d_tmem, a_lo + 8 * ks, b_hi + 2 * ks, idesc, 1);  // xl.yh
+            tc_commit(bar_acc_full + 8 * slot);  // accumulator ready for the epilogue
+            if (++slot == NSLOT) {
+              slot = 0;
+              use_par ^= 1;
+            }
           }
-          tc_commit(bar_b_empty + 8 * s);       // smem stage reusable once these MMAs retire
-          tc_commit(bar_acc_full + 8 * buf);    // accumulators ready for the epilogue
+          tc_commit(bar_b_empty + 8 * s);  // smem stage reusable once these MMAs retire
         }
       } else {
         int it = 0;
         for (int t = 0; t < p.n_tiles; ++t) {
           const int buf = t & 1;
           const uint32_t aph = (t >> 1) & 1;
-          mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
+          mbar_wait(bar_acc_empty + 8 * (buf * 2 + 0), aph ^ 1);
+          mbar_wait(bar_acc_empty + 8 * (buf * 2 + 1), aph ^ 1);
           for (int a = 0; a < p.ka; ++a, ++it) {
             const int s = it % TC_KSTAGES;
             const uint32_t ph = (it / TC_KSTAGES) & 1;
@@ -490,7 +525,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
             }
             tc_commit(bar_b_empty + 8 * s);
           }
-          tc_commit(bar_acc_full + 8 * buf);
+          tc_commit(bar_acc_full + 8 * (buf * 2 + 0));
+          tc_commit(bar_acc_full + 8 * (buf * 2 + 1));
         }
       }
     }
@@ -501,6 +537,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     const int mb = ew >> 2;           // which M=128 block
     const int64_t t_row = q_base + mb * 128 + quad * 32 + lane;  // local query row owned by this thread
     const bool active = t_row < p.nq;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    if constexpr (!KLOOP) {
+      // this thread's query operand row -> tensor memory: 64 words = [hi: 32 columns | lo: 32 columns],
+      // two fp16 per 32-bit column (K index 2c in the low half), which is the A-operand layout of kind::f16
+      const uint4 *src = reinterpret_cast<const uint4 *>(p.op_a + t_row * 64);
+      uint32_t w[32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const uint4 q4 = __ldg(src + h * 8 + v);
+          w[4 * v + 0] = q4.x;
+          w[4 * v + 1] = q4.y;
+          w[4 * v + 2] = q4.z;
+          w[4 * v + 3] = q4.w;
+        }
+        tc_st32(t_lane + static_cast<uint32_t>(TC_TMEM_A + mb * 64 + h * 32), w);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a_full);
+    }
     float *ck = p.cand_key + t_row * TC_CAP;
     uint32_t *ci = p.cand_idx + t_row * TC_CAP;
     float tau = -__int_as_float(0x7f800000);
@@ -557,33 +616,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       }
     };
 
+    int slot = mb % NSLOT;
+    uint32_t use_par = 0;  // parity of (it / NSLOT), it = 2 t + mb
     for (int t = 0; t < p.n_tiles; ++t) {
-      const int buf = t & 1;
-      const uint32_t aph = (t >> 1) & 1;
-      mbar_wait(bar_acc_full + 8 * buf, aph);
+      mbar_wait(bar_acc_full + 8 * slot, use_par);
       tc_fence_after();
-      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                             static_cast<uint32_t>((buf * 2 + mb) * TC_N);
+      const uint32_t t_acc = t_lane + static_cast<uint32_t>(slot * TC_N);
       const int64_t jt = static_cast<int64_t>(t) * p.tile_stride * TC_N;
-      // software pipeline over the four chunks: the TMEM load of chunk c+1 is in flight while
-      // chunk c is screened
-      uint32_t ra[32], rb[32];
-      tc_ld32_issue(t_acc, ra);
+      if (p.debug_mode == 3) {  // profiling only: hand the accumulator straight back (MMA/TMA rate alone)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
+      } else {
+        // software pipeline over the four chunks: the TMEM load of chunk c+1 is in flight while
+        // chunk c is screened
+        uint32_t ra[32], rb[32];
+        tc_ld32_issue(t_acc, ra);
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        tc_ld32_wait(ra);
-        tc_ld32_issue(t_acc + half * 64 + 32, rb);
-        process(ra, jt + half * 64);
-        tc_ld32_wait(rb);
-        if (half == 0) {
-          tc_ld32_issue(t_acc + 64, ra);
-        } else {
-          // accumulator fully drained into registers: hand it back to the MMA issuer
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+        for (int half = 0; half < 2; ++half) {
+          tc_ld32_wait(ra);
+          tc_ld32_issue(t_acc + half * 64 + 32, rb);
+          process(ra, jt + half * 64);
+          tc_ld32_wait(rb);
+          if (half == 0) {
+            tc_ld32_issue(t_acc + 64, ra);
+          } else {
+            // accumulator fully drained into registers: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
+          }
+          process(rb, jt + half * 64 + 32);
         }
-        process(rb, jt + half * 64 + 32);
+      }
+      // it += 2
+      slot += 2;
+      if (slot >= NSLOT) {
+        slot -= NSLOT;
+        use_par ^= 1;
       }
     }
     // final: sort every row's list, keep the best m, publish count and threshold
@@ -929,6 +999,7 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     const char *dbg = getenv("VVB_TC_DEBUG");
     p.debug_mode = dbg ? atoi(dbg) : 0;
   }
+  p.op_a = reinterpret_cast<const uint32_t *>(L.opA);
   p.cand_key = L.cand_key;
   p.cand_idx = L.cand_idx;
   p.cand_cnt = L.cand_cnt;
