@@ -58,6 +58,12 @@ typedef struct vvb_knn_stats {
   float ms_rerank;         /* device time, FP32 re-rank + certify                   */
   float ms_fallback;       /* device time, brute-force fallback                     */
   int64_t kernel_launches; /* kernels launched by this call                         */
+  int64_t tiles_swept;     /* (256 query rows x 128 database rows) tiles the screening
+                              kernel actually computed                              */
+  int64_t tiles_dense;     /* tiles of the full cross product (what a sweep without
+                              the cell bounds would compute)                        */
+  int32_t cells;           /* spatial cells of the partition (1 = none)             */
+  int32_t reserved;
 } vvb_knn_stats;
 
 int vvb_version(void);

@@ -493,3 +493,43 @@ def test_few_row_fallback_slices_the_database():
     wi, wd = orc.knn(x, 50, 30_000, 30_200)
     assert np.array_equal(idx[30_000:30_200], wi) and np.array_equal(dist[30_000:30_200], wd)
     print("few-row fallback:", st["rows_fallback"], "rows,", f"{st['ms_fallback']:.2f} ms")
+
+
+# ===================================================== cell-ordered sweep (exact pruning)
+@pytest.mark.parametrize("cells", [1, 7, 64])
+@pytest.mark.parametrize("kind,n,d,k", [("clustered", 20_000, 50, 50), ("iid", 6000, 20, 30), ("ties", 5000, 6, 20),
+                                        ("clustered", 5000, 100, 20), ("line", 8000, 3, 10)])
+def test_cell_sweep_is_exact_for_any_partition(monkeypatch, cells, kind, n, d, k):
+    """The cell bounds only decide which database tiles a query block skips; whatever the partition
+    (forced here through VVB_TC_CELLS, including cell counts that are not powers of two and cells far
+    smaller than a tile) the result must be the brute-force contract bit for bit."""
+    monkeypatch.setenv("VVB_TC_CELLS", str(cells))
+    if kind == "clustered":
+        x = clustered(n, d, 12, seed=cells)
+    elif kind == "iid":
+        x = np.random.default_rng(cells).standard_normal((n, d)).astype(np.float32)
+    elif kind == "ties":
+        x = tie_data(n, d, seed=cells)
+    else:  # points along a line, sorted: long thin cells, many empty pivots are impossible but tiny ones are not
+        t = np.sort(np.random.default_rng(cells).uniform(0, 1000, n)).astype(np.float32)
+        x = np.stack([t, 0.5 * t, np.zeros_like(t)], axis=1).astype(np.float32)
+    st = {}
+    got = vv.make_knn(x, k=k, verbose=False, algo="tensor", stats=st)
+    assert st["cells"] == cells
+    assert_knn_equal(got, orc.knn(x, k))
+    if kind in ("clustered", "iid"):
+        assert st["rows_fallback"] <= 0.02 * n, st
+
+
+def test_cell_sweep_skips_far_clusters_and_stays_exact(monkeypatch):
+    """Well-separated clusters: most database tiles are skipped, the graph is still exact, and a
+    query-row shard (rows of an arbitrary range, not a whole cell) sees the same answers."""
+    monkeypatch.setenv("VVB_TC_CELLS", "128")
+    x = clustered(60_000, 50, 20, seed=5)
+    st = {}
+    idx, dist = vv.make_knn(x, k=50, verbose=False, algo="tensor", stats=st)
+    assert st["tiles_swept"] < 0.5 * st["tiles_dense"], st
+    for q0 in (0, 31_000, 59_000):
+        wi, wd = orc.knn(x, 50, q0, q0 + 400)
+        assert np.array_equal(idx[q0:q0 + 400], wi) and np.array_equal(dist[q0:q0 + 400], wd)
+    print("tiles swept / dense:", st["tiles_swept"], st["tiles_dense"], "fallback rows:", st["rows_fallback"])

@@ -33,6 +33,10 @@ class KnnStats(ctypes.Structure):
         ("ms_rerank", ctypes.c_float),
         ("ms_fallback", ctypes.c_float),
         ("kernel_launches", ctypes.c_int64),
+        ("tiles_swept", ctypes.c_int64),
+        ("tiles_dense", ctypes.c_int64),
+        ("cells", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
     def as_dict(self) -> dict:

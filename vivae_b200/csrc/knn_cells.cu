@@ -1,0 +1,413 @@
+// Spatial cells for the exact kNN screening sweep.
+//
+// The screening kernel (knn_tensor.cu) is bound by the tensor pipe: every (query, database row)
+// pair it touches costs 192 fp16 MACs at d = 50.  The only way below that floor is to touch
+// fewer pairs -- exactly.  The rows are therefore partitioned into P cells (nearest of P pivot
+// rows), sorted by cell, and for every ordered pair of cells (a, b) a LOWER BOUND of the
+// distance between any row of a and any row of b is computed:
+//
+//   * discriminant bound: u_ab = normalise((c_b - c_a) / var) with `var` the pooled within-cell
+//     variance per coordinate (the data is PCA-like: a diagonal metric is the natural one).
+//     For any unit vector u, |x - y| >= u.(y - x), hence
+//         |x - y| >= u_ab.(c_b - c_a) - max_{x in a} u_ab.(x - c_a) - max_{y in b} u_ba.(y - c_b)
+//     Elongated clusters that the ball bound cannot separate are separated by this one.
+//   * ball bound: |c_b - c_a| - r_a - r_b.
+//
+// All geometry uses the first min(d, 64) coordinates (a projection never increases a distance,
+// so the bounds stay valid for the full rows) and is carried out on centred FP32 values with an
+// explicit safety margin.  A query block sweeps the cells in increasing order of its bound and
+// stops at the first cell whose bound exceeds every row's current k-th candidate distance; the
+// certificate of the re-rank kernel covers the skipped rows (knn_tensor.cu).  Exactness never
+// depends on the quality of the partition: bad cells only mean a longer sweep.
+#include "knn_cells.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace vvb {
+
+int cells_choose_count(int64_t n) {
+  if (const char *e = getenv("VVB_TC_CELLS")) {
+    const int v = atoi(e);
+    if (v >= 1) return v > CELL_MAX ? CELL_MAX : v;
+  }
+  if (n < 32768) return 1;
+  int p = 1;
+  while (static_cast<int64_t>(p) * 4096 < n && p < CELL_MAX) p *= 2;
+  return p;
+}
+
+int64_t cells_perm_capacity(int64_t n, int P) {
+  return (n + CELL_GROUP - 1) / CELL_GROUP * CELL_GROUP + static_cast<int64_t>(P) * CELL_GROUP;
+}
+
+size_t cells_carve(CellPlan *plan, void *ws, int64_t n, int d, int P) {
+  CellPlan L;
+  L.P = P;
+  L.dsub = d < CELL_DIMS ? d : CELL_DIMS;
+  L.n = n;
+  L.n_perm_cap = cells_perm_capacity(n, P);
+  Carver cv(ws);
+  const size_t PP = static_cast<size_t>(P) * P;
+  L.cell_of = cv.take<int>(static_cast<size_t>(n));
+  L.cnt = cv.take<int>(P);
+  L.off = cv.take<int>(P + 1);
+  L.cursor = cv.take<int>(P);
+  L.perm = cv.take<int>(static_cast<size_t>(L.n_perm_cap));
+  L.sums = cv.take<double>(static_cast<size_t>(P) * CELL_DIMS);
+  L.sqs = cv.take<double>(static_cast<size_t>(P) * CELL_DIMS);
+  L.cen = cv.take<float>(static_cast<size_t>(P) * CELL_DIMS);
+  L.var = cv.take<float>(CELL_DIMS);
+  L.cw = cv.take<float>(static_cast<size_t>(P) * CELL_DIMS);
+  L.inv_norm = cv.take<float>(PP);
+  L.gap = cv.take<float>(PP);
+  L.cdist = cv.take<float>(PP);
+  L.ext = cv.take<unsigned int>(PP);
+  L.rad2 = cv.take<unsigned int>(P);
+  L.lb = cv.take<float>(PP);
+  L.qcnt = cv.take<int>(P);
+  L.qoff = cv.take<int>(P + 1);
+  L.qcursor = cv.take<int>(P);
+  if (plan) *plan = L;
+  return cv.used();
+}
+
+// ------------------------------------------------------------------ partition
+// Thread per row: nearest pivot in the first dsub centred coordinates (ties -> lowest pivot).
+// Pivot p is row floor((p + 0.5) n / P).
+__global__ void __launch_bounds__(128) cell_assign_kernel(const float *__restrict__ x, int64_t n, int d, int dsub,
+                                                         const float *__restrict__ mu, int P,
+                                                         int *__restrict__ cell_of, int *__restrict__ cnt) {
+  __shared__ __align__(16) float piv[128][CELL_DIMS];
+  __shared__ float pn[128];
+  __shared__ int hist[CELL_MAX];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < P; i += 128) hist[i] = 0;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 128 + tid;
+  float xr[CELL_DIMS];
+#pragma unroll
+  for (int c = 0; c < CELL_DIMS; ++c) xr[c] = (row < n && c < dsub) ? __ldg(x + row * d + c) - __ldg(mu + c) : 0.0f;
+  float best = __int_as_float(0x7f800000);
+  int best_p = 0;
+  for (int p0 = 0; p0 < P; p0 += 128) {
+    __syncthreads();
+    const int np = min(128, P - p0);
+    for (int i = tid; i < np * CELL_DIMS; i += 128) {
+      const int pl = i / CELL_DIMS, c = i % CELL_DIMS;
+      const int64_t pr = static_cast<int64_t>((static_cast<double>(p0 + pl) + 0.5) * static_cast<double>(n) / P);
+      piv[pl][c] = (c < dsub) ? __ldg(x + pr * d + c) - __ldg(mu + c) : 0.0f;
+    }
+    __syncthreads();
+    if (tid < np) {
+      float s = 0.0f;
+      for (int c = 0; c < CELL_DIMS; ++c) s = fmaf(piv[tid][c], piv[tid][c], s);
+      pn[tid] = s;
+    }
+    __syncthreads();
+    for (int pl = 0; pl < np; ++pl) {
+      float dot = 0.0f;
+      const float4 *pv = reinterpret_cast<const float4 *>(piv[pl]);
+#pragma unroll
+      for (int c4 = 0; c4 < CELL_DIMS / 4; ++c4) {
+        const float4 q = pv[c4];
+        dot = fmaf(xr[4 * c4 + 0], q.x, dot);
+        dot = fmaf(xr[4 * c4 + 1], q.y, dot);
+        dot = fmaf(xr[4 * c4 + 2], q.z, dot);
+        dot = fmaf(xr[4 * c4 + 3], q.w, dot);
+      }
+      const float score = fmaf(-2.0f, dot, pn[pl]);
+      if (score < best) {
+        best = score;
+        best_p = p0 + pl;
+      }
+    }
+  }
+  if (row < n) {
+    cell_of[row] = best_p;
+    atomicAdd(&hist[best_p], 1);
+  }
+  __syncthreads();
+  for (int i = tid; i < P; i += 128)
+    if (hist[i]) atomicAdd(cnt + i, hist[i]);
+}
+
+// exclusive scan of the cell sizes (rounded up to `granule` rows) by one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) cell_scan_kernel(const int *__restrict__ cnt, int P, int granule,
+                                                        int *__restrict__ off, int *__restrict__ cursor) {
+  __shared__ int sh[CELL_MAX];
+  const int tid = threadIdx.x;
+  const int mine = (tid < P) ? (cnt[tid] + granule - 1) / granule * granule : 0;
+  sh[tid] = mine;
+  __syncthreads();
+  for (int o = 1; o < CELL_MAX; o <<= 1) {
+    const int v = (tid >= o) ? sh[tid - o] : 0;
+    __syncthreads();
+    sh[tid] += v;
+    __syncthreads();
+  }
+  if (tid < P) {
+    off[tid] = sh[tid] - mine;
+    cursor[tid] = sh[tid] - mine;
+  }
+  if (tid == P - 1) off[P] = sh[tid];
+}
+
+__global__ void __launch_bounds__(256) cell_scatter_kernel(const int *__restrict__ cell_of, int64_t row0, int64_t rows,
+                                                          int *__restrict__ cursor, int *__restrict__ list,
+                                                          int64_t list_len) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < rows) {
+    const int pos = atomicAdd(cursor + cell_of[row0 + i], 1);
+    list[pos] = static_cast<int>(row0 + i);
+  } else if (i < list_len) {
+    list[i] = -1;  // tail of a query list (database lists are pre-filled with -1 by a memset: list_len = -1)
+  }
+}
+
+__global__ void __launch_bounds__(256) cell_hist_kernel(const int *__restrict__ cell_of, int64_t row0, int64_t rows, int P,
+                                                       int *__restrict__ cnt) {
+  __shared__ int hist[CELL_MAX];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    atomicAdd(&hist[cell_of[row0 + i]], 1);
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x)
+    if (hist[i]) atomicAdd(cnt + i, hist[i]);
+}
+
+// ------------------------------------------------------------------ cell geometry
+// one CTA per group of 128 permuted rows (a group never straddles cells): coordinate sums and sums of squares
+__global__ void __launch_bounds__(256) cell_moments_kernel(const float *__restrict__ x, int d, int dsub,
+                                                          const float *__restrict__ mu, const int *__restrict__ perm,
+                                                          const int *__restrict__ off, int P,
+                                                          const int *__restrict__ cell_of, double *__restrict__ sums,
+                                                          double *__restrict__ sqs) {
+  __shared__ double sh_s[4][CELL_DIMS], sh_q[4][CELL_DIMS];
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * CELL_GROUP;
+  if (p0 >= off[P]) return;
+  const int a = cell_of[perm[p0]];
+  const int c = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  double s = 0.0, q = 0.0;
+  if (c < dsub) {
+    const float m = __ldg(mu + c);
+    for (int i = rl; i < CELL_GROUP; i += 4) {
+      const int r = perm[p0 + i];
+      if (r >= 0) {
+        const double v = static_cast<double>(__ldg(x + static_cast<int64_t>(r) * d + c) - m);
+        s += v;
+        q += v * v;
+      }
+    }
+  }
+  sh_s[rl][c] = s;
+  sh_q[rl][c] = q;
+  __syncthreads();
+  if (rl == 0 && c < dsub) {
+    atomicAdd(sums + a * CELL_DIMS + c, sh_s[0][c] + sh_s[1][c] + sh_s[2][c] + sh_s[3][c]);
+    atomicAdd(sqs + a * CELL_DIMS + c, sh_q[0][c] + sh_q[1][c] + sh_q[2][c] + sh_q[3][c]);
+  }
+}
+
+__global__ void cell_centres_kernel(const double *__restrict__ sums, const int *__restrict__ cnt,
+                                    float *__restrict__ cen) {
+  const int a = blockIdx.x, c = threadIdx.x;  // 64 threads
+  cen[a * CELL_DIMS + c] = cnt[a] > 0 ? static_cast<float>(sums[a * CELL_DIMS + c] / cnt[a]) : 0.0f;
+}
+
+// pooled within-cell variance per coordinate = (total sum of squares - between-cell part) / n, floored
+__global__ void cell_var_kernel(const double *__restrict__ sqs, const float *__restrict__ cen,
+                                const int *__restrict__ cnt, int P, int dsub, int64_t n, float *__restrict__ var) {
+  __shared__ float sh[CELL_DIMS];
+  const int c = threadIdx.x;  // 64 threads
+  double tot = 0.0;
+  for (int a = 0; a < P; ++a) {
+    const double m = cen[a * CELL_DIMS + c];
+    tot += sqs[a * CELL_DIMS + c] - static_cast<double>(cnt[a]) * m * m;
+  }
+  float v = (c < dsub) ? static_cast<float>(fmax(tot, 0.0) / static_cast<double>(n)) : 0.0f;
+  sh[c] = v;
+  __syncthreads();
+  float vmax = 0.0f;
+  for (int i = 0; i < CELL_DIMS; ++i) vmax = fmaxf(vmax, sh[i]);
+  if (!(vmax > 0.0f)) vmax = 1.0f;
+  v = fmaxf(v, 1e-6f * vmax);
+  var[c] = (c < dsub) ? v : 1.0f;
+}
+
+__global__ void cell_cw_kernel(const float *__restrict__ cen, const float *__restrict__ var, float *__restrict__ cw) {
+  const int a = blockIdx.x, c = threadIdx.x;  // 64 threads
+  cw[a * CELL_DIMS + c] = cen[a * CELL_DIMS + c] / var[c];
+}
+
+// per ordered pair (a, b): the direction w_ab = cw_b - cw_a (bitwise the negative of w_ba; the extent kernel
+// forms it the same way, so gap and extents refer to exactly the same vector, whatever it was rounded to),
+// 1 / |w_ab|, the centre gap along it, the centre distance; resets the extents
+__global__ void __launch_bounds__(128) cell_pairs_kernel(const float *__restrict__ cen, const float *__restrict__ cw,
+                                                        int P, float *__restrict__ inv_norm, float *__restrict__ gap,
+                                                        float *__restrict__ cdist, unsigned int *__restrict__ ext,
+                                                        unsigned int *__restrict__ rad2) {
+  __shared__ float ca[CELL_DIMS], wa[CELL_DIMS];
+  const int a = blockIdx.x;
+  if (threadIdx.x < CELL_DIMS) {
+    ca[threadIdx.x] = cen[a * CELL_DIMS + threadIdx.x];
+    wa[threadIdx.x] = cw[a * CELL_DIMS + threadIdx.x];
+  }
+  if (threadIdx.x == 0) rad2[a] = f2ord(0.0f);
+  __syncthreads();
+  for (int b = threadIdx.x; b < P; b += blockDim.x) {
+    float nn = 0.0f, g = 0.0f, dd = 0.0f;
+    for (int c = 0; c < CELL_DIMS; ++c) {
+      const float dl = cen[b * CELL_DIMS + c] - ca[c];
+      const float w = cw[b * CELL_DIMS + c] - wa[c];
+      nn = fmaf(w, w, nn);
+      g = fmaf(dl, w, g);
+      dd = fmaf(dl, dl, dd);
+    }
+    const float nrm = sqrtf(nn);
+    const size_t o = static_cast<size_t>(a) * P + b;
+    inv_norm[o] = nrm > 0.0f ? 1.0f / nrm : 0.0f;
+    gap[o] = nrm > 0.0f ? g / nrm : 0.0f;
+    cdist[o] = sqrtf(dd);
+    ext[o] = f2ord(-__int_as_float(0x7f800000));
+  }
+}
+
+// one CTA per group of 128 permuted rows of cell a (thread per row): for every other cell b the largest
+// projection of (x - c_a) on the direction a -> b, and the largest squared distance to the centre
+__global__ void __launch_bounds__(128) cell_extent_kernel(const float *__restrict__ x, int d, int dsub,
+                                                         const float *__restrict__ mu, const int *__restrict__ perm,
+                                                         const int *__restrict__ off, int P,
+                                                         const int *__restrict__ cell_of, const float *__restrict__ cen,
+                                                         const float *__restrict__ cw,
+                                                         const float *__restrict__ inv_norm,
+                                                         unsigned int *__restrict__ ext,
+                                                         unsigned int *__restrict__ rad2) {
+  __shared__ __align__(16) float cwb[128][CELL_DIMS];
+  __shared__ unsigned int emax[128];
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * CELL_GROUP;
+  if (p0 >= off[P]) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int a = cell_of[perm[p0]];
+  const int r = perm[p0 + tid];
+  float xr[CELL_DIMS];
+  float r2 = 0.0f;
+#pragma unroll
+  for (int c = 0; c < CELL_DIMS; ++c) {
+    xr[c] = (r >= 0 && c < dsub)
+                ? (__ldg(x + static_cast<int64_t>(r) * d + c) - __ldg(mu + c)) - __ldg(cen + a * CELL_DIMS + c)
+                : 0.0f;
+    r2 = fmaf(xr[c], xr[c], r2);
+  }
+  {
+    unsigned int m = __reduce_max_sync(FULL, f2ord(r2));
+    if (lane == 0) atomicMax(rad2 + a, m);
+  }
+  const unsigned int neg_inf = f2ord(-__int_as_float(0x7f800000));
+  for (int b0 = 0; b0 < P; b0 += 128) {
+    __syncthreads();
+    const int nb = min(128, P - b0);
+    for (int i = tid; i < nb * CELL_DIMS; i += 128)
+      cwb[i / CELL_DIMS][i % CELL_DIMS] = cw[b0 * CELL_DIMS + i] - __ldg(cw + a * CELL_DIMS + i % CELL_DIMS);  // w_ab
+    emax[tid] = neg_inf;
+    __syncthreads();
+    for (int bl = 0; bl < nb; ++bl) {
+      float tb = 0.0f;
+      const float4 *pv = reinterpret_cast<const float4 *>(cwb[bl]);
+#pragma unroll
+      for (int c4 = 0; c4 < CELL_DIMS / 4; ++c4) {
+        const float4 q = pv[c4];
+        tb = fmaf(xr[4 * c4 + 0], q.x, tb);
+        tb = fmaf(xr[4 * c4 + 1], q.y, tb);
+        tb = fmaf(xr[4 * c4 + 2], q.z, tb);
+        tb = fmaf(xr[4 * c4 + 3], q.w, tb);
+      }
+      const float proj = tb * __ldg(inv_norm + static_cast<size_t>(a) * P + b0 + bl);
+      const unsigned int o = (r >= 0) ? f2ord(proj) : neg_inf;
+      const unsigned int m = __reduce_max_sync(FULL, o);
+      if (lane == 0) atomicMax(&emax[bl], m);
+    }
+    __syncthreads();
+    if (tid < nb && emax[tid] != neg_inf) atomicMax(ext + static_cast<size_t>(a) * P + b0 + tid, emax[tid]);
+  }
+}
+
+// lb(a, b) = scale * max(discriminant bound, ball bound) - margin; +inf for empty b, -inf on the diagonal
+__global__ void __launch_bounds__(128) cell_lb_kernel(const int *__restrict__ cnt, int P, const float *__restrict__ gap,
+                                                     const float *__restrict__ cdist,
+                                                     const unsigned int *__restrict__ ext,
+                                                     const unsigned int *__restrict__ rad2,
+                                                     const float *__restrict__ scale_ymax, float *__restrict__ lb) {
+  const int a = blockIdx.x;
+  const float s = scale_ymax[0], ymax = scale_ymax[1];
+  const float inf = __int_as_float(0x7f800000);
+  const float ra = sqrtf(ord2f(rad2[a])) * 1.00001f;
+  for (int b = threadIdx.x; b < P; b += blockDim.x) {
+    const size_t o = static_cast<size_t>(a) * P + b, ot = static_cast<size_t>(b) * P + a;
+    float v;
+    if (cnt[b] == 0) {
+      v = inf;
+    } else if (a == b || cnt[a] == 0) {
+      v = -inf;
+    } else {
+      const float rb = sqrtf(ord2f(rad2[b])) * 1.00001f;
+      const float fisher = gap[o] - ord2f(ext[o]) - ord2f(ext[ot]);
+      const float ball = cdist[o] - ra - rb;
+      // FP32 evaluation error: ~64 x 2^-24 relative to (centre distance + radii) for the dot products and
+      // norms, ~2^-23 of the largest centred norm for the centring subtractions; both covered ~50x
+      const float margin = 2e-4f * (cdist[o] + ra + rb) * s + 2e-5f * ymax;
+      v = fmaxf(fisher, ball) * s - margin;
+    }
+    lb[o] = v;
+  }
+}
+
+int cells_build(const CellPlan &L, const float *x, int d, const float *mu, const float *scale_dev, cudaStream_t st) {
+  const int P = L.P;
+  const int64_t n = L.n;
+  VVB_CUDA(cudaMemsetAsync(L.cnt, 0, sizeof(int) * P, st));
+  VVB_CUDA(cudaMemsetAsync(L.perm, 0xFF, sizeof(int) * static_cast<size_t>(L.n_perm_cap), st));
+  VVB_CUDA(cudaMemsetAsync(L.sums, 0, sizeof(double) * static_cast<size_t>(P) * CELL_DIMS, st));
+  VVB_CUDA(cudaMemsetAsync(L.sqs, 0, sizeof(double) * static_cast<size_t>(P) * CELL_DIMS, st));
+  cell_assign_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(x, n, d, L.dsub, mu, P, L.cell_of, L.cnt);
+  VVB_CHECK_LAUNCH();
+  cell_scan_kernel<<<1, 1024, 0, st>>>(L.cnt, P, CELL_GROUP, L.off, L.cursor);
+  VVB_CHECK_LAUNCH();
+  cell_scatter_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(L.cell_of, 0, n, L.cursor, L.perm, -1);
+  VVB_CHECK_LAUNCH();
+  const unsigned groups = static_cast<unsigned>(L.n_perm_cap / CELL_GROUP);
+  cell_moments_kernel<<<groups, 256, 0, st>>>(x, d, L.dsub, mu, L.perm, L.off, P, L.cell_of, L.sums, L.sqs);
+  VVB_CHECK_LAUNCH();
+  cell_centres_kernel<<<P, CELL_DIMS, 0, st>>>(L.sums, L.cnt, L.cen);
+  VVB_CHECK_LAUNCH();
+  cell_var_kernel<<<1, CELL_DIMS, 0, st>>>(L.sqs, L.cen, L.cnt, P, L.dsub, n, L.var);
+  VVB_CHECK_LAUNCH();
+  cell_cw_kernel<<<P, CELL_DIMS, 0, st>>>(L.cen, L.var, L.cw);
+  VVB_CHECK_LAUNCH();
+  cell_pairs_kernel<<<P, 128, 0, st>>>(L.cen, L.cw, P, L.inv_norm, L.gap, L.cdist, L.ext, L.rad2);
+  VVB_CHECK_LAUNCH();
+  cell_extent_kernel<<<groups, 128, 0, st>>>(x, d, L.dsub, mu, L.perm, L.off, P, L.cell_of, L.cen, L.cw, L.inv_norm,
+                                             L.ext, L.rad2);
+  VVB_CHECK_LAUNCH();
+  cell_lb_kernel<<<P, 128, 0, st>>>(L.cnt, P, L.gap, L.cdist, L.ext, L.rad2, scale_dev, L.lb);
+  VVB_CHECK_LAUNCH();
+  return VVB_OK;
+}
+
+int cells_query_list(const CellPlan &L, int64_t q0, int64_t nq, int64_t nq_pad, int *qlist, cudaStream_t st) {
+  VVB_CUDA(cudaMemsetAsync(L.qcnt, 0, sizeof(int) * L.P, st));
+  cell_hist_kernel<<<static_cast<unsigned>(std::min<int64_t>((nq + 255) / 256, 1184)), 256, 0, st>>>(L.cell_of, q0, nq,
+                                                                                                      L.P, L.qcnt);
+  VVB_CHECK_LAUNCH();
+  cell_scan_kernel<<<1, 1024, 0, st>>>(L.qcnt, L.P, 1, L.qoff, L.qcursor);
+  VVB_CHECK_LAUNCH();
+  cell_scatter_kernel<<<static_cast<unsigned>((nq_pad + 255) / 256), 256, 0, st>>>(L.cell_of, q0, nq, L.qcursor, qlist,
+                                                                                   nq_pad);
+  VVB_CHECK_LAUNCH();
+  return VVB_OK;
+}
+
+}  // namespace vvb

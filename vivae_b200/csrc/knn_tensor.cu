@@ -41,8 +41,10 @@
 
 #include <cstdlib>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
+#include "knn_cells.cuh"
 
 namespace vvb {
 
@@ -66,16 +68,18 @@ constexpr int TC_CAP_E = 8;          // candidate list capacity = 32 * 8 = 256
 constexpr int TC_CAP = 32 * TC_CAP_E;
 constexpr int TC_MAX_KA = 64;        // K atoms (64 columns each) per operand half: d + 3 <= 4096
 constexpr int TC_KSTAGES = 2;        // K-loop variant: (query + database) atom stages
-constexpr float TC_PAD_NORM = 60000.0f;
+constexpr float TC_PAD_NORM = 60000.0f;  // squared "norm" of padding rows: their keys stay above TC_PAD_CUT
+constexpr float TC_PAD_CUT = 30000.0f;   // real keys are below 64^2 + 2 * 64 * 64
+constexpr int TC_RING = 16;              // tile-sequence ring (producer runs at most stages + slots tiles ahead)
 constexpr float TC_EPS = 1.0f / 131072.0f;  // 2^-17: 26x the measured screening error (2^-21.7), ~5x its analytic bound
-constexpr int TC_PREPASS_MIN_TILES = 512;  // ... when the database has at least 65,536 rows (opt-in: VVB_TC_PREPASS=<tile stride>)
 
 constexpr size_t TC_SMEM_B = TC_STAGES * 2 * TC_ATOM_BYTES;           // [stage][atom]
-constexpr size_t TC_SMEM_BYTES = TC_SMEM_B + 1024 /*align*/ + 256 /*barriers*/;
+constexpr size_t TC_SMEM_TAIL = 256 /*barriers*/ + 8 * CELL_MAX /*cell order*/ + 4 * TC_RING + 64 /*tau*/;
+constexpr size_t TC_SMEM_BYTES = TC_SMEM_B + 1024 /*align*/ + TC_SMEM_TAIL;
 constexpr int TC_TMEM_A = 384;       // resident variant: first TMEM column of the query operand (2 x 64 columns)
 // K-loop variant: every stage holds one K atom of everything: query hi/lo for both M blocks + database hi/lo
 constexpr size_t TC_SMEM_K = TC_KSTAGES * 6 * TC_ATOM_BYTES;
-constexpr size_t TC_SMEM_BYTES_K = TC_SMEM_K + 1024 + 256;
+constexpr size_t TC_SMEM_BYTES_K = TC_SMEM_K + 1024 + TC_SMEM_TAIL;
 static inline int tc_atoms(int d) { return (d + 3 + 63) / 64; }
 
 static inline int tc_candidates(int k) {
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(256) maxnorm_kernel(const float *__restrict__ 
   if (lane == 0 && best > 0.0f) atomicMax(maxn2_bits, __float_as_uint(best));
 }
 
-struct PrepScalars {  // written by build_operands_kernel (block 0), read by the re-rank kernel
+struct PrepScalars {  // written by scalars_kernel, read by the operand, bound and re-rank kernels
   float scale;        // power of two
   float ymax;         // largest scaled centred norm (<= 64 before rounding slack)
 };
@@ -274,33 +278,35 @@ __device__ __forceinline__ float pick_scale(float maxn2) {
   return ldexpf(1.0f, e - 1);  // largest power of two <= target
 }
 
-// One warp per row: centre, scale, split into FP16 hi/lo, write the database operand row
-// (and, for rows of the query shard, the query operand row and |x^|^2).
+__global__ void scalars_kernel(const unsigned int *__restrict__ maxn2_bits, PrepScalars *__restrict__ scalars) {
+  const float maxn2 = __uint_as_float(*maxn2_bits);
+  const float s = pick_scale(maxn2);
+  scalars->scale = s;
+  scalars->ymax = sqrtf(maxn2) * s * 1.0001f;
+}
+
+// One warp per operand row: row w of the operand is original row list[w] (-1 = padding): centre, scale,
+// split into FP16 hi/lo.  IS_QUERY: the query role ([-2 xh | 1 1 1], [-2 xl], and |x^|^2 to xnorm);
+// otherwise the database role ([yh | nh nl nl2], [yl]).
 // Operand row layout (fp16): [hi part: ka atoms of 64 columns | lo part: ka atoms]; the hi part carries
 // the data in columns 0..d-1 and, in columns d..d+2, the norm terms (database) or ones (query).
-__global__ void __launch_bounds__(256) build_operands_kernel(
-    const float *__restrict__ x, int64_t n, int d, int ka, const float *__restrict__ mu,
-    const unsigned int *__restrict__ maxn2_bits, int64_t n_pad, __half *__restrict__ opB, int64_t q0, int64_t nq,
-    int64_t nq_pad, __half *__restrict__ opA, float *__restrict__ xnorm, PrepScalars *__restrict__ scalars) {
+template <bool IS_QUERY>
+__global__ void __launch_bounds__(256) build_operands_kernel(const float *__restrict__ x, int d, int ka,
+                                                            const float *__restrict__ mu,
+                                                            const PrepScalars *__restrict__ scalars,
+                                                            const int *__restrict__ list, int64_t rows,
+                                                            __half *__restrict__ op, float *__restrict__ xnorm) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  const float maxn2 = __uint_as_float(*maxn2_bits);
-  const float s = pick_scale(maxn2);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    scalars->scale = s;
-    scalars->ymax = sqrtf(maxn2) * s * 1.0001f;
-  }
+  const float s = scalars->scale;
   const int half_cols = ka * 64;
   const int64_t op_cols = 2 * half_cols;
-  // rows [0, n_pad) -> database operand; rows [n_pad, n_pad + nq_pad) -> query operand of row q0 + (r - n_pad)
-  for (int64_t w = warp; w < n_pad + nq_pad; w += nwarps) {
-    const bool is_q = w >= n_pad;
-    const int64_t local = is_q ? w - n_pad : w;
-    const int64_t src = is_q ? q0 + local : local;
-    const bool valid = is_q ? (local < nq) : (local < n);
-    __half *row = (is_q ? opA : opB) + local * op_cols;
-    const float fac = is_q ? -2.0f : 1.0f;  // power of two: exact in FP16
+  for (int64_t w = warp; w < rows; w += nwarps) {
+    const int64_t src = list[w];
+    const bool valid = src >= 0;
+    __half *row = op + w * op_cols;
+    const float fac = IS_QUERY ? -2.0f : 1.0f;  // power of two: exact in FP16
     float nrm = 0.0f;
     for (int c = lane; c < half_cols; c += 32) {
       float v = 0.0f;
@@ -316,8 +322,8 @@ __global__ void __launch_bounds__(256) build_operands_kernel(
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(FULL, nrm, o);
     __syncwarp();
-    if (is_q) {
-      if (lane == 0) xnorm[local] = nrm;
+    if (IS_QUERY) {
+      if (lane == 0) xnorm[w] = nrm;
       if (lane < 3) row[d + lane] = __float2half_rn(valid ? 1.0f : 0.0f);
     } else {
       // squared norm as a three-term FP16 sum (33 significant bits); padding rows get a huge norm
@@ -344,21 +350,25 @@ __device__ __noinline__ float tc_sort_truncate(float *keys, uint32_t *idxs, int 
 
 // ------------------------------------------------------------------ the screening kernel
 struct TcParams {
-  int64_t n;        // database rows
-  int64_t nq;       // query rows of this launch
-  int n_tiles;      // ceil(n / TC_N)
+  int64_t nq;       // query rows of this launch (entries of qlist)
   int ks_hi;        // k-steps (of 16) covering d + 3 columns
   int ks_lo;        // k-steps covering d columns
   int keep;         // m: candidates kept per row
   int trigger;      // a list longer than this is compacted before the next 32-column chunk
-  int tile_stride;  // visit database tiles 0, s, 2s, ... (s = 1: all; s = 16: the threshold pre-pass)
-  int use_tau_init; // start each row at cand_thr[row] (from the pre-pass) instead of +inf
   int ka;           // K atoms per operand half (1: query operand resident; >1: K-loop variant)
   int debug_mode;   // profiling only (env VVB_TC_DEBUG): 1 = drain TMEM but skip the screening,
                     // 2 = screening minima only, no admissions, 3 = no TMEM drain at all.  Results are garbage.
+  int n_cells;      // P
   const uint32_t *op_a;  // query operand rows as 32-bit words (64 per row), resident variant only
+  const int *qlist;      // (nq_pad) original row of every query-list entry, -1 = padding
+  const int *cell_of;    // (n) cell of every original row
+  const int *cell_off;   // (P + 1) first permuted database row of every cell (multiples of TC_N)
+  const float *cell_lb;  // (P, P) lower bound of the scaled distance between rows of two cells
+  const float *xnorm;    // (nq_pad) |x^|^2 of the query rows
+  const PrepScalars *scalars;
+  unsigned long long *tiles_done;  // database tiles actually swept, summed over CTAs
   float *cand_key;  // (nq_pad, TC_CAP)
-  uint32_t *cand_idx;
+  uint32_t *cand_idx;   // PERMUTED database row ids
   int *cand_cnt;    // (nq_pad)
   float *cand_thr;  // (nq_pad) final admission threshold tau
 };
@@ -372,6 +382,14 @@ struct TcParams {
 // Accumulator slots: the sequence it = 2 t + mb (tile t, M block mb) uses slot it % NSLOT for the
 // (it / NSLOT)-th time; acc_full[slot] is committed by the MMA issuer, acc_empty[slot] is released by
 // the four epilogue warps of that M block.
+//
+// Sweep order.  The query rows of a CTA are consecutive entries of the cell-sorted query list, the
+// database is stored cell by cell (knn_cells.cu).  The CTA sorts the cells by its lower bound of the
+// distance to them and the producer walks that order, publishing the first database row of every tile
+// it loads in `tile_seq` (-1 = end of sweep).  Before entering a cell with a positive bound it reads
+// the largest "k-th candidate distance" the epilogue warps currently hold (tau_i + |x^_i|^2, refreshed
+// at every list compaction): once bound^2 exceeds it (plus the screening error), no row of this or
+// any later cell can enter any list and the sweep ends.
 template <bool KLOOP>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
@@ -389,12 +407,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   const uint32_t bar_acc_full = bar_b_empty + 8 * TC_STAGES;    // [4]
   const uint32_t bar_acc_empty = bar_acc_full + 32;             // [4]
   const uint32_t tmem_slot = bar_acc_empty + 32;                // u32 written by tcgen05.alloc
-  volatile uint32_t *tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
+  uint8_t *tail = smem_raw + (bars - raw) + 256;
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
+  unsigned long long *order = reinterpret_cast<unsigned long long *>(tail);             // [CELL_MAX] (bound, cell)
+  volatile int *tile_seq = reinterpret_cast<volatile int *>(tail + 8 * CELL_MAX);       // [TC_RING]
+  volatile float *tau_pub = reinterpret_cast<volatile float *>(tail + 8 * CELL_MAX + 4 * TC_RING);  // [8]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t q_base = static_cast<int64_t>(blockIdx.x) * TC_M;  // first (local) query row of this CTA
+  const int64_t q_base = static_cast<int64_t>(blockIdx.x) * TC_M;  // first query-list entry of this CTA
 
   if (warp == 0 && lane == 0) {
     if constexpr (KLOOP) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -417,6 +438,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (threadIdx.x < 8) tau_pub[threadIdx.x] = __int_as_float(0x7f800000);
+
+  // ---- cell order of this CTA: bound(b) = min over the cells a of its rows of lb(a, b), sorted ascending
+  const int P = p.n_cells;
+  int P2 = 1;
+  while (P2 < P) P2 <<= 1;
+  {
+    const int64_t last = min(q_base + TC_M, p.nq) - 1;
+    const int a0 = p.cell_of[p.qlist[q_base]], a1 = p.cell_of[p.qlist[last]];  // the list is sorted by cell
+    for (int b = threadIdx.x; b < P2; b += TC_THREADS) {
+      float v = __int_as_float(0x7f800000);
+      if (b < P)
+        for (int a = a0; a <= a1; ++a) v = fminf(v, __ldg(p.cell_lb + static_cast<size_t>(a) * P + b));
+      order[b] = (static_cast<unsigned long long>(f2ord(v)) << 32) | static_cast<unsigned>(b);
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= P2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (P2 >> 1); i += TC_THREADS) {
+        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+        const int hi = lo | stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long x0 = order[lo], x1 = order[hi];
+        if ((x0 > x1) == up) {
+          order[lo] = x1;
+          order[hi] = x0;
+        }
+      }
+      __syncthreads();
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -425,37 +478,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      if constexpr (!KLOOP) {
-        for (int t = 0; t < p.n_tiles; ++t) {
-          const int s = t % TC_STAGES;
-          const uint32_t ph = (t / TC_STAGES) & 1;
-          mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
-          mbar_expect_tx(bar_b_full + 8 * s, 2 * TC_ATOM_BYTES);
-          for (int atom = 0; atom < 2; ++atom)
-            tma_load_2d(smem_b + (s * 2 + atom) * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, atom * 64,
-                        t * p.tile_stride * TC_N);
+      const float ymax2 = 2.0f * p.scalars->ymax;
+      const float eps_max = TC_EPS * ymax2 * ymax2;  // the certificate's margin for the longest query row
+      int t = 0;    // tiles issued
+      int it = 0;   // K-loop variant: stage uses
+      for (int ci = 0; ci < P; ++ci) {
+        const unsigned long long e = order[ci];
+        const float bound = ord2f(static_cast<uint32_t>(e >> 32));
+        const int b = static_cast<int>(static_cast<uint32_t>(e));
+        if (bound == __int_as_float(0x7f800000)) break;  // empty cells sort last
+        if (bound > 0.0f) {
+          float tmax = tau_pub[0];
+#pragma unroll
+          for (int w = 1; w < 8; ++w) tmax = fmaxf(tmax, tau_pub[w]);
+          if (bound * bound >= tmax + eps_max) break;  // ascending order: every later cell is at least as far
         }
-      } else {
-        int it = 0;
-        for (int t = 0; t < p.n_tiles; ++t) {
-          const int row_b = t * p.tile_stride * TC_N;
-          for (int a = 0; a < p.ka; ++a, ++it) {
-            const int s = it % TC_KSTAGES;
-            const uint32_t ph = (it / TC_KSTAGES) & 1;
-            const uint32_t st = smem_k + s * 6 * TC_ATOM_BYTES;
-            const int c_hi = a * 64, c_lo = (p.ka + a) * 64;
+        const int row_end = p.cell_off[b + 1];
+        for (int row_b = p.cell_off[b]; row_b < row_end; row_b += TC_N, ++t) {
+          if constexpr (!KLOOP) {
+            const int s = t % TC_STAGES;
+            const uint32_t ph = (t / TC_STAGES) & 1;
             mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
-            mbar_expect_tx(bar_b_full + 8 * s, 6 * TC_ATOM_BYTES);
-            // stage layout: [A.hi mb0][A.lo mb0][A.hi mb1][A.lo mb1][B.hi][B.lo]
-            tma_load_2d(st + 0 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_hi, static_cast<int>(q_base));
-            tma_load_2d(st + 1 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_lo, static_cast<int>(q_base));
-            tma_load_2d(st + 2 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_hi, static_cast<int>(q_base + 128));
-            tma_load_2d(st + 3 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_lo, static_cast<int>(q_base + 128));
-            tma_load_2d(st + 4 * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, c_hi, row_b);
-            tma_load_2d(st + 5 * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, c_lo, row_b);
+            tile_seq[t % TC_RING] = row_b;
+            mbar_expect_tx(bar_b_full + 8 * s, 2 * TC_ATOM_BYTES);
+            for (int atom = 0; atom < 2; ++atom)
+              tma_load_2d(smem_b + (s * 2 + atom) * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, atom * 64, row_b);
+          } else {
+            for (int a = 0; a < p.ka; ++a, ++it) {
+              const int s = it % TC_KSTAGES;
+              const uint32_t ph = (it / TC_KSTAGES) & 1;
+              const uint32_t st = smem_k + s * 6 * TC_ATOM_BYTES;
+              const int c_hi = a * 64, c_lo = (p.ka + a) * 64;
+              mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
+              if (a == 0) tile_seq[t % TC_RING] = row_b;
+              mbar_expect_tx(bar_b_full + 8 * s, 6 * TC_ATOM_BYTES);
+              // stage layout: [A.hi mb0][A.lo mb0][A.hi mb1][A.lo mb1][B.hi][B.lo]
+              tma_load_2d(st + 0 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_hi, static_cast<int>(q_base));
+              tma_load_2d(st + 1 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_lo, static_cast<int>(q_base));
+              tma_load_2d(st + 2 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_hi, static_cast<int>(q_base + 128));
+              tma_load_2d(st + 3 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_lo, static_cast<int>(q_base + 128));
+              tma_load_2d(st + 4 * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, c_hi, row_b);
+              tma_load_2d(st + 5 * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, c_lo, row_b);
+            }
           }
         }
       }
+      // end of sweep: a stage carrying no data, marked in the tile sequence
+      {
+        const int u = KLOOP ? it : t;
+        const int ns = KLOOP ? TC_KSTAGES : TC_STAGES;
+        const int s = u % ns;
+        const uint32_t ph = (u / ns) & 1;
+        mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
+        tile_seq[t % TC_RING] = -1;
+        mbar_arrive(bar_b_full + 8 * s);
+      }
+      atomicAdd(p.tiles_done, static_cast<unsigned long long>(t));
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
@@ -464,14 +542,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       if constexpr (!KLOOP) {
         mbar_wait(bar_a_full, 0);  // query operand is in tensor memory
         tc_fence_after();
-        int slot = 0;
-        uint32_t use_par = 0;  // parity of (it / NSLOT)
-        for (int t = 0; t < p.n_tiles; ++t) {
-          const int s = t % TC_STAGES;
-          const uint32_t ph = (t / TC_STAGES) & 1;
-          mbar_wait(bar_b_full + 8 * s, ph);
-          const uint64_t b_hi = make_desc(smem_b + (s * 2 + 0) * TC_ATOM_BYTES);
-          const uint64_t b_lo = make_desc(smem_b + (s * 2 + 1) * TC_ATOM_BYTES);
+      }
+      int slot = 0;
+      uint32_t use_par = 0;  // parity of (it / NSLOT)
+      int it = 0;            // K-loop variant: stage uses
+      for (int t = 0;; ++t) {
+        const int s0 = KLOOP ? it % TC_KSTAGES : t % TC_STAGES;
+        const uint32_t ph0 = KLOOP ? (it / TC_KSTAGES) & 1 : (t / TC_STAGES) & 1;
+        mbar_wait(bar_b_full + 8 * s0, ph0);
+        const bool last = tile_seq[t % TC_RING] < 0;
+        if (last) {
+          // pass the end marker on: the epilogue reads tile_seq after its acc_full wait
+          for (int mb = 0; mb < 2; ++mb) {
+            mbar_wait(bar_acc_empty + 8 * slot, use_par ^ 1);
+            mbar_arrive(bar_acc_full + 8 * slot);
+            if (++slot == NSLOT) {
+              slot = 0;
+              use_par ^= 1;
+            }
+          }
+          break;
+        }
+        if constexpr (!KLOOP) {
+          const uint64_t b_hi = make_desc(smem_b + (s0 * 2 + 0) * TC_ATOM_BYTES);
+          const uint64_t b_lo = make_desc(smem_b + (s0 * 2 + 1) * TC_ATOM_BYTES);
 #pragma unroll
           for (int mb = 0; mb < 2; ++mb) {
             mbar_wait(bar_acc_empty + 8 * slot, use_par ^ 1);
@@ -492,26 +586,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
               use_par ^= 1;
             }
           }
-          tc_commit(bar_b_empty + 8 * s);  // smem stage reusable once these MMAs retire
-        }
-      } else {
-        int it = 0;
-        for (int t = 0; t < p.n_tiles; ++t) {
-          const int buf = t & 1;
-          const uint32_t aph = (t >> 1) & 1;
-          mbar_wait(bar_acc_empty + 8 * (buf * 2 + 0), aph ^ 1);
-          mbar_wait(bar_acc_empty + 8 * (buf * 2 + 1), aph ^ 1);
+          tc_commit(bar_b_empty + 8 * s0);  // smem stage reusable once these MMAs retire
+        } else {
+          // slots of this tile: slot (mb 0) and slot + 1 (mb 1); NSLOT = 4 keeps the pair aligned
+          mbar_wait(bar_acc_empty + 8 * slot, use_par ^ 1);
+          mbar_wait(bar_acc_empty + 8 * (slot + 1), use_par ^ 1);
           for (int a = 0; a < p.ka; ++a, ++it) {
             const int s = it % TC_KSTAGES;
             const uint32_t ph = (it / TC_KSTAGES) & 1;
             const uint32_t st = smem_k + s * 6 * TC_ATOM_BYTES;
-            mbar_wait(bar_b_full + 8 * s, ph);
+            if (a > 0) mbar_wait(bar_b_full + 8 * s, ph);
             tc_fence_after();
             const uint64_t b_hi = make_desc(st + 4 * TC_ATOM_BYTES);
             const uint64_t b_lo = make_desc(st + 5 * TC_ATOM_BYTES);
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
-              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((buf * 2 + mb) * TC_N);
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((slot + mb) * TC_N);
               const uint64_t a_hi = make_desc(st + (mb * 2 + 0) * TC_ATOM_BYTES);
               const uint64_t a_lo = make_desc(st + (mb * 2 + 1) * TC_ATOM_BYTES);
               // zero-padded columns contribute exactly 0, so every atom runs its 4 k-steps
@@ -525,8 +615,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
             }
             tc_commit(bar_b_empty + 8 * s);
           }
-          tc_commit(bar_acc_full + 8 * (buf * 2 + 0));
-          tc_commit(bar_acc_full + 8 * (buf * 2 + 1));
+          tc_commit(bar_acc_full + 8 * slot);
+          tc_commit(bar_acc_full + 8 * (slot + 1));
+          slot += 2;
+          if (slot == NSLOT) {
+            slot = 0;
+            use_par ^= 1;
+          }
         }
       }
     }
@@ -535,7 +630,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     const int ew = warp - 4;          // 0..7
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access
     const int mb = ew >> 2;           // which M=128 block
-    const int64_t t_row = q_base + mb * 128 + quad * 32 + lane;  // local query row owned by this thread
+    const int64_t t_row = q_base + mb * 128 + quad * 32 + lane;  // query-list entry owned by this thread
     const bool active = t_row < p.nq;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     if constexpr (!KLOOP) {
@@ -562,30 +657,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     }
     float *ck = p.cand_key + t_row * TC_CAP;
     uint32_t *ci = p.cand_idx + t_row * TC_CAP;
-    float tau = -__int_as_float(0x7f800000);
-    if (active) tau = p.use_tau_init ? p.cand_thr[t_row] : __int_as_float(0x7f800000);
+    const float inf = __int_as_float(0x7f800000);
+    float tau = active ? inf : -inf;
+    const float xn = active ? p.xnorm[t_row] : 0.0f;
     int cnt = 0;
+    {  // a warp without query rows must not hold the sweep open
+      const unsigned m0 = __reduce_max_sync(FULL, f2ord(tau));
+      if (lane == 0) tau_pub[ew] = ord2f(m0);
+    }
 
     // One 32-column chunk: make room, then screen.  The chunk is reduced to four group minima
     // (8 columns each) with 3-input min instructions; only groups that beat tau are expanded.
-    auto process = [&](const uint32_t(&r)[32], int64_t j0) {
+    auto process = [&](const uint32_t(&r)[32], int j0) {
       if (p.debug_mode == 1) {
         if (__uint_as_float(r[0]) == 123.456f && __uint_as_float(r[31]) == 1.5f) tau = 0.f;  // keep the load alive
         return;
       }
       unsigned need = __ballot_sync(FULL, cnt > p.trigger);
-      while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const int64_t tt = __shfl_sync(FULL, t_row, src);
-        const int c = __shfl_sync(FULL, cnt, src);
-        int nc;
-        const float thr =
-            tc_select_truncate(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, p.trigger, lane, &nc);
-        if (lane == src) {
-          cnt = nc;
-          tau = thr;
+      if (need) {
+        while (need) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          const int64_t tt = __shfl_sync(FULL, t_row, src);
+          const int c = __shfl_sync(FULL, cnt, src);
+          int nc;
+          const float thr =
+              tc_select_truncate(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, p.trigger, lane, &nc);
+          if (lane == src) {
+            cnt = nc;
+            tau = thr;
+          }
         }
+        // publish the largest k-th candidate distance of the warp's rows (the producer's stopping rule)
+        const unsigned m = __reduce_max_sync(FULL, f2ord(tau + xn));  // inactive rows: -inf
+        if (lane == 0) tau_pub[ew] = ord2f(m);
       }
       float g[4];
 #pragma unroll
@@ -597,15 +702,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         g[q] = fminf(fminf(a, b), fminf(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
       }
       const float mn = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
-      if (mn < tau && p.debug_mode != 2) {
-        const int lim = static_cast<int>(min(static_cast<int64_t>(32), p.n - j0));  // columns that are real rows
+      const float cut = fminf(tau, TC_PAD_CUT);  // padding rows of the database carry a huge norm
+      if (mn < cut && p.debug_mode != 2) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          if (g[q] < tau) {
+          if (g[q] < cut) {
 #pragma unroll
             for (int c = 8 * q; c < 8 * q + 8; ++c) {
               const float v = __uint_as_float(r[c]);
-              if (v < tau && c < lim) {
+              if (v < cut) {
                 ck[cnt] = v;
                 ci[cnt] = static_cast<uint32_t>(j0 + c);
                 ++cnt;
@@ -618,11 +723,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
 
     int slot = mb % NSLOT;
     uint32_t use_par = 0;  // parity of (it / NSLOT), it = 2 t + mb
-    for (int t = 0; t < p.n_tiles; ++t) {
+    for (int t = 0;; ++t) {
       mbar_wait(bar_acc_full + 8 * slot, use_par);
+      const int jt = tile_seq[t % TC_RING];  // first (permuted) database row of the tile
+      if (jt < 0) break;
       tc_fence_after();
       const uint32_t t_acc = t_lane + static_cast<uint32_t>(slot * TC_N);
-      const int64_t jt = static_cast<int64_t>(t) * p.tile_stride * TC_N;
       if (p.debug_mode == 3) {  // profiling only: hand the accumulator straight back (MMA/TMA rate alone)
         tc_fence_before();
         __syncwarp();
@@ -664,7 +770,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       if (tt >= p.nq) continue;  // warp-uniform
       int nc;
       float thr = tc_sort_truncate(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, lane, &nc);
-      // every rejected entry has key >= the threshold in force when it was rejected >= tau_src;
+      // every rejected entry has key >= the threshold in force when it was rejected >= tau_src, and every
+      // row of a cell the sweep skipped has key >= the row's tau at that moment >= tau_src;
       // with fewer than `keep` entries the sort has no keep-th key and tau_src is the bound
       thr = fminf(thr, tau_src);
       if (lane == 0) {
@@ -690,8 +797,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
 //               still evaluates ITS candidate's chain strictly left to right, so the result is bit-identical.
 template <int E, bool WIDE>
 __global__ void __launch_bounds__(256) knn_rerank_kernel(
-    const float *__restrict__ x, int64_t n, int d, int64_t q0, int64_t nq, int k,
-    const uint32_t *__restrict__ cand_idx, const int *__restrict__ cand_cnt, const float *__restrict__ cand_thr,
+    const float *__restrict__ x, int64_t n, int d, int64_t q0, int64_t nq, int k, const int *__restrict__ qlist,
+    const int *__restrict__ perm, const uint32_t *__restrict__ cand_idx, const int *__restrict__ cand_cnt,
+    const float *__restrict__ cand_thr,
     const float *__restrict__ xnorm, const PrepScalars *__restrict__ scalars, int64_t *__restrict__ out_idx,
     float *__restrict__ out_dist, int *__restrict__ fb_count, int64_t *__restrict__ fb_rows) {
   __shared__ float stage[WIDE ? 8 : 1][WIDE ? 32 : 1][WIDE ? 33 : 1];
@@ -699,7 +807,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
   const int wib = threadIdx.x >> 5;
   const int64_t t = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (t >= nq) return;  // warp-uniform
-  const int64_t g = q0 + t;
+  const int64_t g = qlist[t];  // original row of this query-list entry; candidates are permuted row ids
   const int cnt = cand_cnt[t];
   const float *xq = x + g * d;
   uint64_t key[E];
@@ -712,7 +820,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
     float acc = 0.0f;
     if (!WIDE) {
       if (pos < cnt) {
-        j = cand_idx[t * TC_CAP + pos];
+        j = static_cast<uint32_t>(perm[cand_idx[t * TC_CAP + pos]]);
         const float *y = x + static_cast<int64_t>(j) * d;
         for (int c = 0; c < d; ++c) {  // the contract's chain: left to right, one rounding per fmaf
           const float df = __fsub_rn(__ldg(xq + c), __ldg(y + c));
@@ -721,7 +829,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
       }
     } else {
       if (e * 32 < cnt) {  // warp-uniform: this group of 32 candidates is not empty
-        if (pos < cnt) j = cand_idx[t * TC_CAP + pos];
+        if (pos < cnt) j = static_cast<uint32_t>(perm[cand_idx[t * TC_CAP + pos]]);
         const int in_group = min(32, cnt - e * 32);
         for (int c0 = 0; c0 < d; c0 += 32) {
           const float xv = (c0 + lane < d) ? __ldg(xq + c0 + lane) : 0.0f;
@@ -753,8 +861,8 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
   const bool has_self = __any_sync(FULL, self_here);
   warp_bitonic_sort<E>(key, lane);
   const int shift = has_self ? 0 : 1;  // self absent from the list (more than m duplicates): still column 0
-  int64_t *oi = out_idx + t * (k + 1);
-  float *od = out_dist + t * (k + 1);
+  int64_t *oi = out_idx + (g - q0) * (k + 1);
+  float *od = out_dist + (g - q0) * (k + 1);
   if (lane == 0) {
     oi[0] = g;
     od[0] = 0.0f;
@@ -832,17 +940,21 @@ static int make_operand_map(CUtensorMap *map, void *ptr, int64_t rows, int64_t o
   return VVB_OK;
 }
 
-// Workspace of one "session": the database operand (built once per call) plus the per-chunk
-// query operand, candidate lists and fallback list (sized for `chunk` query rows).
+// Workspace of one "session": the cell plan and the database operand (built once per call) plus the
+// per-chunk query list, query operand, candidate lists and fallback list (sized for `chunk` query rows).
 struct TcLayout {
-  int64_t n_pad, chunk_pad;
+  int64_t n_rows_b;  // rows of the database operand = capacity of the permuted order
+  int64_t chunk_pad;
   int ka;           // K atoms per operand half
   int64_t op_cols;  // fp16 columns per operand row = 2 * ka * 64
+  CellPlan cells;
   __half *opB, *opA;
   double *partial;
   float *mu;
   unsigned int *maxn2;
   PrepScalars *scalars;
+  unsigned long long *tiles_done;
+  int *qlist;
   float *xnorm;
   float *cand_key;
   uint32_t *cand_idx;
@@ -859,16 +971,24 @@ static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
   TcLayout L;
   L.ka = tc_atoms(d);
   L.op_cols = 2 * static_cast<int64_t>(L.ka) * 64;
-  L.n_pad = (n + TC_N - 1) / TC_N * TC_N;
+  const int P = cells_choose_count(n);
+  L.n_rows_b = cells_perm_capacity(n, P);
   L.chunk_pad = (chunk + TC_M - 1) / TC_M * TC_M;
   if (L.chunk_pad == 0) L.chunk_pad = TC_M;
   Carver cv(ws);
-  L.opB = cv.take<__half>(static_cast<size_t>(L.n_pad) * L.op_cols);
+  {
+    const size_t cb = cells_carve(nullptr, nullptr, n, d, P);
+    char *cbase = cv.take<char>(cb);
+    cells_carve(&L.cells, cbase, n, d, P);
+  }
+  L.opB = cv.take<__half>(static_cast<size_t>(L.n_rows_b) * L.op_cols);
   L.opA = cv.take<__half>(static_cast<size_t>(L.chunk_pad) * L.op_cols);
   L.partial = cv.take<double>(static_cast<size_t>(PREP_BLOCKS) * L.ka * 64);
   L.mu = cv.take<float>(static_cast<size_t>(L.ka) * 64);
   L.maxn2 = cv.take<unsigned int>(1);
   L.scalars = cv.take<PrepScalars>(1);
+  L.tiles_done = cv.take<unsigned long long>(1);
+  L.qlist = cv.take<int>(static_cast<size_t>(L.chunk_pad));
   L.xnorm = cv.take<float>(static_cast<size_t>(L.chunk_pad));
   L.cand_cnt = cv.take<int>(static_cast<size_t>(L.chunk_pad));
   L.cand_thr = cv.take<float>(static_cast<size_t>(L.chunk_pad));
@@ -911,7 +1031,8 @@ struct TcSession {
 
 size_t knn_tensor_session_bytes() { return sizeof(TcSession); }
 
-// Build the database operand (column means, largest centred norm, FP16 hi/lo split) once.
+// Once per call: column means, largest centred norm, the cell partition with its pairwise bounds, and
+// the database operand (FP16 hi/lo split) in cell order.
 int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, int k, int64_t chunk_rows,
                      void *workspace, size_t workspace_bytes, cudaStream_t st, vvb_knn_stats *stats) {
   VVB_REQUIRE(knn_tensor_supported(n, d, k), "tensor kNN: unsupported shape n=%lld d=%d k=%d", (long long)n, d, k);
@@ -942,12 +1063,17 @@ int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, in
   const int prep_grid = sm_count() * 8;
   maxnorm_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.mu, L.maxn2);
   VVB_CHECK_LAUNCH();
-  build_operands_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.ka, L.mu, L.maxn2, L.n_pad, L.opB, 0, 0, 0, L.opA,
-                                                   L.xnorm, L.scalars);
+  scalars_kernel<<<1, 1, 0, st>>>(L.maxn2, L.scalars);
   VVB_CHECK_LAUNCH();
-  int rc = make_operand_map(&S->map_a, L.opA, L.chunk_pad, L.op_cols);
+  int rc = cells_build(L.cells, x_dev, d, L.mu, reinterpret_cast<const float *>(L.scalars), st);
   if (rc) return rc;
-  rc = make_operand_map(&S->map_b, L.opB, L.n_pad, L.op_cols);
+  build_operands_kernel<false><<<prep_grid, 256, 0, st>>>(x_dev, d, L.ka, L.mu, L.scalars, L.cells.perm, L.n_rows_b,
+                                                          L.opB, nullptr);
+  VVB_CHECK_LAUNCH();
+  VVB_CUDA(cudaMemsetAsync(L.tiles_done, 0, sizeof(unsigned long long), st));
+  rc = make_operand_map(&S->map_a, L.opA, L.chunk_pad, L.op_cols);
+  if (rc) return rc;
+  rc = make_operand_map(&S->map_b, L.opB, L.n_rows_b, L.op_cols);
   if (rc) return rc;
   if (stats) {
     cudaEventRecord(e1, st);
@@ -956,14 +1082,15 @@ int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, in
     cudaEventElapsedTime(&ms, e0, e1);
     stats->ms_prepare += ms;
     stats->candidates = S->keep;
+    stats->cells = L.cells.P;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
   }
   return VVB_OK;
 }
 
-// Query rows [q0, q0+nq) (nq <= the session's chunk size): operand, screen, re-rank, fallback.
-// out_idx / out_dist point at the first output row of this chunk.
+// Query rows [q0, q0+nq) (nq <= the session's chunk size): cell-sorted query list, operand, screen,
+// re-rank, fallback.  out_idx / out_dist point at the output row of query row q0.
 int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx, float *out_dist, cudaStream_t st,
                      vvb_knn_stats *stats, bool screen_only) {
   TcSession *S = static_cast<TcSession *>(session_mem);
@@ -979,52 +1106,37 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     if (stats) cudaEventRecord(ev[i], st);
   };
   mark(0);
-  // query operand of this chunk (the database part of the kernel's row range is empty here)
-  build_operands_kernel<<<sm_count() * 4, 256, 0, st>>>(S->x, S->n, S->d, L.ka, L.mu, L.maxn2, 0, L.opB, q0, nq,
-                                                       nq_pad, L.opA, L.xnorm, L.scalars);
+  int rc = cells_query_list(L.cells, q0, nq, nq_pad, L.qlist, st);
+  if (rc) return rc;
+  build_operands_kernel<true><<<sm_count() * 4, 256, 0, st>>>(S->x, S->d, L.ka, L.mu, L.scalars, L.qlist, nq_pad, L.opA,
+                                                              L.xnorm);
   VVB_CHECK_LAUNCH();
   VVB_CUDA(cudaMemsetAsync(L.fb_count, 0, sizeof(int), st));
   TcParams p;
-  p.n = S->n;
   p.nq = nq;
-  p.n_tiles = static_cast<int>(L.n_pad / TC_N);
   p.ks_hi = (S->d + 3 + 15) / 16;
   p.ks_lo = (S->d + 15) / 16;
   p.keep = S->keep;
   p.trigger = tc_trigger(S->keep);
-  p.tile_stride = 1;
-  p.use_tau_init = 0;
   p.ka = L.ka;
   {
     const char *dbg = getenv("VVB_TC_DEBUG");
     p.debug_mode = dbg ? atoi(dbg) : 0;
   }
+  p.n_cells = L.cells.P;
   p.op_a = reinterpret_cast<const uint32_t *>(L.opA);
+  p.qlist = L.qlist;
+  p.cell_of = L.cells.cell_of;
+  p.cell_off = L.cells.off;
+  p.cell_lb = L.cells.lb;
+  p.xnorm = L.xnorm;
+  p.scalars = L.scalars;
+  p.tiles_done = L.tiles_done;
   p.cand_key = L.cand_key;
   p.cand_idx = L.cand_idx;
   p.cand_cnt = L.cand_cnt;
   p.cand_thr = L.cand_thr;
   const unsigned sgrid = static_cast<unsigned>(nq_pad / TC_M);
-  const char *pre = getenv("VVB_TC_PREPASS");
-  const int pre_stride = pre ? atoi(pre) : 0;  // VVB_TC_PREPASS=<stride>, e.g. 16 or 64; 0/unset = off
-  if (pre_stride >= 2 && p.n_tiles >= TC_PREPASS_MIN_TILES) {
-    // OPT-IN (measured neutral on B200: 376 ms vs 380 ms at 1M x 50 -- the full sweep gets 15 %
-    // faster, the pre-pass costs as much; the kernel is bound by the TMEM read-out, not by admissions).
-    // Threshold pre-pass over every 16th database tile: the r-th smallest key of the sample,
-    // r = m/16 + 7 sqrt(m/16) + 2, is with overwhelming probability above the row's m-th smallest
-    // key over the whole database, yet close to it.  Starting the full sweep there removes the long
-    // warm-up in which almost every chunk has admissions (1400 -> ~350 admissions per row at 1M).
-    // Exactness never depends on it: a row left with too few candidates fails the certificate.
-    TcParams q = p;
-    q.tile_stride = pre_stride;
-    q.n_tiles = (p.n_tiles + pre_stride - 1) / pre_stride;
-    const float mf = static_cast<float>(S->keep) / pre_stride;
-    q.keep = static_cast<int>(ceilf(mf + 7.0f * sqrtf(mf) + 2.0f));
-    if (L.ka == 1) knn_screen_kernel<false><<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, q);
-    else knn_screen_kernel<true><<<sgrid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, q);
-    VVB_CHECK_LAUNCH();
-    p.use_tau_init = 1;
-  }
   if (L.ka == 1) knn_screen_kernel<false><<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, p);
   else knn_screen_kernel<true><<<sgrid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, p);
   VVB_CHECK_LAUNCH();
@@ -1035,13 +1147,13 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
 #define VVB_RR(EE)                                                                                                    \
   do {                                                                                                                \
     if (S->d >= 128)                                                                                                  \
-      knn_rerank_kernel<EE, true><<<rr_grid, 256, 0, st>>>(S->x, S->n, S->d, q0, nq, S->k, L.cand_idx, L.cand_cnt,   \
-                                                           L.cand_thr, L.xnorm, L.scalars, out_idx, out_dist,       \
-                                                           L.fb_count, L.fb_rows);                                   \
+      knn_rerank_kernel<EE, true><<<rr_grid, 256, 0, st>>>(S->x, S->n, S->d, q0, nq, S->k, L.qlist, L.cells.perm,    \
+                                                           L.cand_idx, L.cand_cnt, L.cand_thr, L.xnorm, L.scalars,   \
+                                                           out_idx, out_dist, L.fb_count, L.fb_rows);               \
     else                                                                                                              \
-      knn_rerank_kernel<EE, false><<<rr_grid, 256, 0, st>>>(S->x, S->n, S->d, q0, nq, S->k, L.cand_idx, L.cand_cnt,  \
-                                                            L.cand_thr, L.xnorm, L.scalars, out_idx, out_dist,      \
-                                                            L.fb_count, L.fb_rows);                                  \
+      knn_rerank_kernel<EE, false><<<rr_grid, 256, 0, st>>>(S->x, S->n, S->d, q0, nq, S->k, L.qlist, L.cells.perm,   \
+                                                            L.cand_idx, L.cand_cnt, L.cand_thr, L.xnorm, L.scalars,  \
+                                                            out_idx, out_dist, L.fb_count, L.fb_rows);              \
   } while (0)
   if (e_need <= 2) VVB_RR(2);
   else if (e_need <= 4) VVB_RR(4);
@@ -1055,7 +1167,7 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   int fb = 0;
   VVB_CUDA(cudaMemcpyAsync(&fb, L.fb_count, sizeof(int), cudaMemcpyDeviceToHost, st));
   VVB_CUDA(cudaStreamSynchronize(st));
-  int rc = VVB_OK;
+  rc = VVB_OK;
   if (fb > 0 && fb <= knn_brute_few_max_rows())
     rc = launch_knn_brute_few(S->x, S->n, S->d, S->k, L.fb_rows, fb, out_idx, out_dist, q0, L.brute_ws,
                               L.brute_ws_bytes, st);
@@ -1074,13 +1186,20 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     cudaEventElapsedTime(&ms, ev[2], ev[3]);
     stats->ms_fallback += ms;
     stats->rows_fallback += fb;
+    unsigned long long done = 0;
+    int used = 0;
+    VVB_CUDA(cudaMemcpy(&done, L.tiles_done, sizeof(done), cudaMemcpyDeviceToHost));
+    VVB_CUDA(cudaMemcpy(&used, L.cells.off + L.cells.P, sizeof(int), cudaMemcpyDeviceToHost));
+    stats->tiles_swept = static_cast<int64_t>(done);  // cumulative over the chunks of this call
+    stats->tiles_dense += static_cast<int64_t>(sgrid) * (used / TC_N);
     for (auto &e : ev) cudaEventDestroy(e);
   }
   return VVB_OK;
 }
 
 // Diagnostics: run preparation + screening only and hand the raw candidate lists back to the
-// host (tests use this to measure the screening error against FP64 and to check the lists).
+// host (tests use this to measure the screening error against FP64 and to check the lists).  The
+// lists are returned per ORIGINAL query row with ORIGINAL database row ids.
 int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, int64_t nq, uint32_t *cand_idx_out,
                      float *cand_key_out, int *cand_cnt_out, float *cand_thr_out, float *xnorm_out,
                      float *scale_ymax_out, float *mu_out) {
@@ -1108,11 +1227,26 @@ int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, i
   }
   if (!rc) {
     TcLayout &L = reinterpret_cast<TcSession *>(session)->L;
-    cudaMemcpy(cand_idx_out, L.cand_idx, static_cast<size_t>(nq) * TC_CAP * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(cand_key_out, L.cand_key, static_cast<size_t>(nq) * TC_CAP * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(cand_cnt_out, L.cand_cnt, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(cand_thr_out, L.cand_thr, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(xnorm_out, L.xnorm, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
+    std::vector<uint32_t> ci(static_cast<size_t>(nq) * TC_CAP);
+    std::vector<float> ck(static_cast<size_t>(nq) * TC_CAP), ct(nq), xn(nq);
+    std::vector<int> cc(nq), ql(nq), perm(static_cast<size_t>(L.n_rows_b));
+    cudaMemcpy(ci.data(), L.cand_idx, ci.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(ck.data(), L.cand_key, ck.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(cc.data(), L.cand_cnt, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(ct.data(), L.cand_thr, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(xn.data(), L.xnorm, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(ql.data(), L.qlist, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(perm.data(), L.cells.perm, perm.size() * 4, cudaMemcpyDeviceToHost);
+    for (int64_t t = 0; t < nq; ++t) {
+      const int64_t o = ql[t] - q0;
+      cand_cnt_out[o] = cc[t];
+      cand_thr_out[o] = ct[t];
+      xnorm_out[o] = xn[t];
+      for (int e = 0; e < TC_CAP; ++e) {
+        cand_key_out[o * TC_CAP + e] = ck[t * TC_CAP + e];
+        cand_idx_out[o * TC_CAP + e] = e < cc[t] ? static_cast<uint32_t>(perm[ci[t * TC_CAP + e]]) : 0u;
+      }
+    }
     cudaMemcpy(scale_ymax_out, L.scalars, 2 * sizeof(float), cudaMemcpyDeviceToHost);
     cudaMemcpy(mu_out, L.mu, static_cast<size_t>(d < 64 ? d : 64) * sizeof(float), cudaMemcpyDeviceToHost);
   }
