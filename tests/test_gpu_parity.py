@@ -390,15 +390,17 @@ def test_screening_error_is_far_below_the_certificate_margin(kind):
     nq = 1024
     ci, ck, cc, ct, xn, s, ymax, mu = _screen_debug(x, k, 500, nq)
     m = k + 1 + max(16, k // 4)
-    assert np.all(cc == m) and s > 0 and 16.0 < ymax <= 64.1
-    assert np.all(np.diff(ck[:, :m], axis=1) >= 0)
+    # the kept list holds the m smallest keys and at most a whole number of 32-entry groups, unsorted
+    assert np.all(cc >= m) and np.all(cc <= (m + 31) // 32 * 32) and s > 0 and 16.0 < ymax <= 64.1
+    for t in range(0, nq, 13):
+        assert np.all(ck[t, :cc[t]] <= ct[t])
     xc = (x.astype(np.float64) - mu.astype(np.float64)) * s
     worst = 0.0
     for t in range(0, nq, 7):
         g = 500 + t
-        j = ci[t, :m].astype(np.int64)
+        j = ci[t, :cc[t]].astype(np.int64)
         d2 = ((xc[g][None, :] - xc[j]) ** 2).sum(1)
-        err = np.abs(ck[t, :m].astype(np.float64) + float(xn[t]) - d2)
+        err = np.abs(ck[t, :cc[t]].astype(np.float64) + float(xn[t]) - d2)
         bound = (np.sqrt(float(xn[t])) + ymax) ** 2
         worst = max(worst, float((err / bound).max()))
     print(f"screening error / (|x|+Ymax)^2 = 2^{np.log2(max(worst, 1e-30)):.1f}")
@@ -406,7 +408,7 @@ def test_screening_error_is_far_below_the_certificate_margin(kind):
     # every true neighbour is among the candidates, self included
     oi, _ = orc.knn(x, k, 500, 500 + nq)
     for t in range(0, nq, 11):
-        assert set(oi[t].tolist()) <= set(ci[t, :m].astype(np.int64).tolist())
+        assert set(oi[t].tolist()) <= set(ci[t, :cc[t]].astype(np.int64).tolist())
 
 
 def test_tensor_path_is_used_and_fallback_is_rare():
@@ -525,11 +527,11 @@ def test_cell_sweep_skips_far_clusters_and_stays_exact(monkeypatch):
     """Well-separated clusters: most database tiles are skipped, the graph is still exact, and a
     query-row shard (rows of an arbitrary range, not a whole cell) sees the same answers."""
     monkeypatch.setenv("VVB_TC_CELLS", "128")
-    x = clustered(60_000, 50, 20, seed=5)
+    x = clustered(160_000, 50, 20, seed=5)
     st = {}
     idx, dist = vv.make_knn(x, k=50, verbose=False, algo="tensor", stats=st)
-    assert st["tiles_swept"] < 0.5 * st["tiles_dense"], st
-    for q0 in (0, 31_000, 59_000):
+    assert st["tiles_swept"] < 0.5 * st["tiles_dense"], st  # includes the threshold pre-pass (256 tiles per block)
+    for q0 in (0, 31_000, 159_000):
         wi, wd = orc.knn(x, 50, q0, q0 + 400)
         assert np.array_equal(idx[q0:q0 + 400], wi) and np.array_equal(dist[q0:q0 + 400], wd)
     print("tiles swept / dense:", st["tiles_swept"], st["tiles_dense"], "fallback rows:", st["rows_fallback"])

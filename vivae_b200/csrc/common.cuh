@@ -241,6 +241,88 @@ __device__ __forceinline__ float warp_select_truncate(float *keys, uint32_t *idx
   *new_cnt = base;
   return ord2f(cut);
 }
+
+// ---- the same selection on a list of interleaved (key bits, index) pairs -----------------
+// (the tensor-core screening kernel appends candidates with ONE 8-byte store)
+template <int E>
+__device__ __forceinline__ float warp_select_truncate_pairs(uint2 *list, int cnt, int m, int keep_max, int lane,
+                                                            int *new_cnt) {
+  uint32_t u[E], id[E];
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int p = e * 32 + lane;
+    u[e] = 0xffffffffu;
+    id[e] = 0;
+    if (p < cnt) {
+      const uint2 v = list[p];
+      u[e] = f2ord(__uint_as_float(v.x));
+      id[e] = v.y;
+    }
+  }
+  // the keys of a row share their leading bits: start the bitwise search below the common prefix
+  uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const bool valid = e * 32 + lane < cnt;
+    lo = valid ? min(lo, u[e]) : lo;
+    hi = valid ? max(hi, u[e]) : hi;
+  }
+  lo = __reduce_min_sync(FULL, lo);
+  hi = __reduce_max_sync(FULL, hi);
+  const int top = 31 - __clz(static_cast<int>((lo ^ hi) | 1u));  // highest bit in which two keys differ
+  const int slack = (keep_max - m) < 24 ? (keep_max - m) : 24;
+  uint32_t T = (top >= 31) ? 0u : (lo & ~((2u << top) - 1u));  // invariant: count(u < T) < m   (count(u < lo) = 0)
+  uint32_t cut = 0;     // entries with u < cut are kept
+  bool exact = true;    // loop ran to the end: T is the m-th smallest key itself
+  for (int b = top; b >= 0; --b) {
+    const uint32_t trial = T | (1u << b);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c += (u[e] < trial) ? 1 : 0;
+    c = __reduce_add_sync(FULL, c);
+    if (c < m) {
+      T = trial;
+    } else if (c <= m + slack) {
+      cut = trial;
+      exact = false;
+      break;
+    }
+  }
+  int ties_allowed = 0;
+  if (exact) {
+    // count(u < T) < m <= count(u <= T): keep everything below T plus the first ties
+    int c_less = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c_less += (u[e] < T) ? 1 : 0;
+    c_less = __reduce_add_sync(FULL, c_less);
+    cut = T;
+    ties_allowed = keep_max - c_less;
+  }
+  __syncwarp();
+  int base = 0, ties_seen = 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int p = e * 32 + lane;
+    const bool valid = p < cnt;
+    const bool below = valid && (u[e] < cut);
+    const bool tie = exact && valid && (u[e] == cut);
+    const unsigned tb = __ballot_sync(FULL, tie);
+    const bool tie_kept = tie && (ties_seen + __popc(tb & lt_mask) < ties_allowed);
+    ties_seen += __popc(tb);
+    const bool keep = below || tie_kept;
+    const unsigned kb = __ballot_sync(FULL, keep);
+    if (keep) {
+      const int dst = base + __popc(kb & lt_mask);
+      list[dst] = make_uint2(__float_as_uint(ord2f(u[e])), id[e]);
+    }
+    base += __popc(kb);
+  }
+  __syncwarp();
+  *new_cnt = base;
+  return ord2f(cut);
+}
 #endif  // __CUDACC__
 
 }  // namespace vvb

@@ -40,6 +40,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <new>
 #include <vector>
 
@@ -71,6 +72,10 @@ constexpr int TC_KSTAGES = 2;        // K-loop variant: (query + database) atom 
 constexpr float TC_PAD_NORM = 60000.0f;  // squared "norm" of padding rows: their keys stay above TC_PAD_CUT
 constexpr float TC_PAD_CUT = 30000.0f;   // real keys are below 64^2 + 2 * 64 * 64
 constexpr int TC_RING = 16;              // tile-sequence ring (producer runs at most stages + slots tiles ahead)
+constexpr int TC_PRE_TILES = TC_CAP;     // threshold pre-pass: tiles whose minima seed the admission thresholds
+constexpr int TC_PRE_MIN_TOTAL = 512;    // ... run only when the database has at least this many tiles
+constexpr int TC_SEQ_END = -1;           // tile_seq markers
+constexpr int TC_SEQ_PRE_END = -2;
 constexpr float TC_EPS = 1.0f / 131072.0f;  // 2^-17: 26x the measured screening error (2^-21.7), ~5x its analytic bound
 
 constexpr size_t TC_SMEM_B = TC_STAGES * 2 * TC_ATOM_BYTES;           // [stage][atom]
@@ -169,6 +174,17 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
       "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 // tcgen05.ld is asynchronous: tc_ld32_issue starts the load of 32 consecutive columns of this
 // thread's TMEM lane, tc_ld32_wait makes them usable.  The wait lists the registers as in/out
@@ -340,12 +356,8 @@ __global__ void __launch_bounds__(256) build_operands_kernel(const float *__rest
 // Out-of-line list maintenance, so that the hot screening loop stays small in the instruction
 // cache.  In-sweep compaction uses the cheap threshold selection; the full sort runs once per
 // row at the end of the sweep.
-__device__ __noinline__ float tc_select_truncate(float *keys, uint32_t *idxs, int cnt, int keep, int keep_max,
-                                                 int lane, int *new_cnt) {
-  return warp_select_truncate<TC_CAP_E>(keys, idxs, cnt, keep, keep_max, lane, new_cnt);
-}
-__device__ __noinline__ float tc_sort_truncate(float *keys, uint32_t *idxs, int cnt, int keep, int lane, int *new_cnt) {
-  return warp_sort_truncate<TC_CAP_E>(keys, idxs, cnt, keep, lane, new_cnt);
+__device__ __noinline__ float tc_select_truncate(uint2 *list, int cnt, int keep, int keep_max, int lane, int *new_cnt) {
+  return warp_select_truncate_pairs<TC_CAP_E>(list, cnt, keep, keep_max, lane, new_cnt);
 }
 
 // ------------------------------------------------------------------ the screening kernel
@@ -367,8 +379,8 @@ struct TcParams {
   const float *xnorm;    // (nq_pad) |x^|^2 of the query rows
   const PrepScalars *scalars;
   unsigned long long *tiles_done;  // database tiles actually swept, summed over CTAs
-  float *cand_key;  // (nq_pad, TC_CAP)
-  uint32_t *cand_idx;   // PERMUTED database row ids
+  long long *times;      // profiling only (env VVB_TC_TIMES): 8 clock64 stamps per CTA, or nullptr
+  uint2 *cand;      // (nq_pad, TC_CAP) candidate lists: (key bits, PERMUTED database row id)
   int *cand_cnt;    // (nq_pad)
   float *cand_thr;  // (nq_pad) final admission threshold tau
 };
@@ -390,6 +402,16 @@ struct TcParams {
 // the largest "k-th candidate distance" the epilogue warps currently hold (tau_i + |x^_i|^2, refreshed
 // at every list compaction): once bound^2 exceeds it (plus the screening error), no row of this or
 // any later cell can enter any list and the sweep ends.
+//
+// Threshold pre-pass.  With the far cells skipped, what a CTA sweeps is its own neighbourhood, where
+// admissions are dense: starting every row at tau = +inf costs ~900 list insertions and ~5 compactions
+// per row before tau has decayed to the k-th neighbour distance, and that list handling, not the MMA,
+// then bounds the kernel.  So the first TC_PRE_TILES tiles of the order are swept TWICE: the first time
+// the epilogue only records each tile's minimum key per row (four 3-input-min trees per tile, no
+// lists).  The m-th smallest of those minima is a valid starting threshold -- m different tiles each
+// hold a key at or below it -- and a tight one, because the m nearest rows of a query are spread over
+// almost as many tiles.  The real sweep then starts at that threshold: ~100 insertions per row, rarely a
+// compaction.  Exactness never depends on it (a threshold is only ever an upper bound of the m-th key).
 template <bool KLOOP>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
@@ -416,6 +438,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t q_base = static_cast<int64_t>(blockIdx.x) * TC_M;  // first query-list entry of this CTA
+  auto stamp = [&](int i) {
+    if (p.times && warp == 4 && lane == 0) p.times[blockIdx.x * 8 + i] = clock64();
+  };
+  stamp(0);
 
   if (warp == 0 && lane == 0) {
     if constexpr (KLOOP) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -474,27 +500,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  stamp(1);
+  const bool pre_pass = p.debug_mode == 0 && p.cell_off[P] >= TC_PRE_MIN_TOTAL * TC_N;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       const float ymax2 = 2.0f * p.scalars->ymax;
       const float eps_max = TC_EPS * ymax2 * ymax2;  // the certificate's margin for the longest query row
-      int t = 0;    // tiles issued
+      int t = 0;    // tile_seq entries issued (tiles and markers)
       int it = 0;   // K-loop variant: stage uses
+      int swept = 0;
+      // a marker: a stage carrying no data, flagged in the tile sequence
+      auto issue_marker = [&](int marker) {
+        const int u = KLOOP ? it : t;
+        const int ns = KLOOP ? TC_KSTAGES : TC_STAGES;
+        const int s = u % ns;
+        const uint32_t ph = (u / ns) & 1;
+        mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
+        tile_seq[t % TC_RING] = marker;
+        mbar_arrive(bar_b_full + 8 * s);
+        ++t;
+        ++it;
+      };
+      for (int pass = pre_pass ? 0 : 1; pass < 2; ++pass) {
+      int pass_tiles = 0;
       for (int ci = 0; ci < P; ++ci) {
         const unsigned long long e = order[ci];
         const float bound = ord2f(static_cast<uint32_t>(e >> 32));
         const int b = static_cast<int>(static_cast<uint32_t>(e));
         if (bound == __int_as_float(0x7f800000)) break;  // empty cells sort last
-        if (bound > 0.0f) {
+        if (pass == 0 && pass_tiles >= TC_PRE_TILES) break;
+        if (pass == 1 && bound > 0.0f) {
           float tmax = tau_pub[0];
 #pragma unroll
           for (int w = 1; w < 8; ++w) tmax = fmaxf(tmax, tau_pub[w]);
           if (bound * bound >= tmax + eps_max) break;  // ascending order: every later cell is at least as far
         }
         const int row_end = p.cell_off[b + 1];
-        for (int row_b = p.cell_off[b]; row_b < row_end; row_b += TC_N, ++t) {
+        for (int row_b = p.cell_off[b]; row_b < row_end; row_b += TC_N, ++t, ++pass_tiles) {
+          if (pass == 0 && pass_tiles >= TC_PRE_TILES) break;
           if constexpr (!KLOOP) {
             const int s = t % TC_STAGES;
             const uint32_t ph = (t / TC_STAGES) & 1;
@@ -523,26 +568,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
           }
         }
       }
-      // end of sweep: a stage carrying no data, marked in the tile sequence
-      {
-        const int u = KLOOP ? it : t;
-        const int ns = KLOOP ? TC_KSTAGES : TC_STAGES;
-        const int s = u % ns;
-        const uint32_t ph = (u / ns) & 1;
-        mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
-        tile_seq[t % TC_RING] = -1;
-        mbar_arrive(bar_b_full + 8 * s);
+      swept += pass_tiles;
+      issue_marker(pass == 0 ? TC_SEQ_PRE_END : TC_SEQ_END);
       }
-      atomicAdd(p.tiles_done, static_cast<unsigned long long>(t));
+      atomicAdd(p.tiles_done, static_cast<unsigned long long>(swept));
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // One ELECTED lane runs the loop (elect.sync, not a lane-id test: ptxas then keeps descriptors and
+    // addresses on the uniform datapath and emits back-to-back UTCHMMAs; with `lane == 0` it wrapped
+    // every MMA in a per-thread serialisation loop that cost ~100 cycles per MMA and bounded the kernel).
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(TC_N);
       if constexpr (!KLOOP) {
         mbar_wait(bar_a_full, 0);  // query operand is in tensor memory
         tc_fence_after();
       }
+      const uint64_t desc_b0 = make_desc(KLOOP ? smem_k : smem_b);  // + (byte offset >> 4) moves the start address
       int slot = 0;
       uint32_t use_par = 0;  // parity of (it / NSLOT)
       int it = 0;            // K-loop variant: stage uses
@@ -550,9 +592,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         const int s0 = KLOOP ? it % TC_KSTAGES : t % TC_STAGES;
         const uint32_t ph0 = KLOOP ? (it / TC_KSTAGES) & 1 : (t / TC_STAGES) & 1;
         mbar_wait(bar_b_full + 8 * s0, ph0);
-        const bool last = tile_seq[t % TC_RING] < 0;
-        if (last) {
-          // pass the end marker on: the epilogue reads tile_seq after its acc_full wait
+        const int marker = tile_seq[t % TC_RING];
+        if (marker < 0) {
+          // pass the marker on (the epilogue reads tile_seq after its acc_full wait) and free the stage
           for (int mb = 0; mb < 2; ++mb) {
             mbar_wait(bar_acc_empty + 8 * slot, use_par ^ 1);
             mbar_arrive(bar_acc_full + 8 * slot);
@@ -561,11 +603,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
               use_par ^= 1;
             }
           }
-          break;
+          if (marker == TC_SEQ_END) break;
+          mbar_arrive(bar_b_empty + 8 * s0);
+          ++it;
+          continue;
         }
         if constexpr (!KLOOP) {
-          const uint64_t b_hi = make_desc(smem_b + (s0 * 2 + 0) * TC_ATOM_BYTES);
-          const uint64_t b_lo = make_desc(smem_b + (s0 * 2 + 1) * TC_ATOM_BYTES);
+          const uint64_t b_hi = desc_b0 + static_cast<uint64_t>(s0 * (2 * TC_ATOM_BYTES >> 4));
+          const uint64_t b_lo = b_hi + (TC_ATOM_BYTES >> 4);
 #pragma unroll
           for (int mb = 0; mb < 2; ++mb) {
             mbar_wait(bar_acc_empty + 8 * slot, use_par ^ 1);
@@ -573,13 +618,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(slot * TC_N);
             const uint32_t a_hi = tmem_base + static_cast<uint32_t>(TC_TMEM_A + mb * 64);  // 8 columns per k-step
             const uint32_t a_lo = a_hi + 32;
-            uint32_t acc = 0;
-            for (int ks = 0; ks < p.ks_hi; ++ks) {  // [-2xh | 1 1 1] . [yh | norm]
-              tc_mma_f16_ts(d_tmem, a_hi + 8 * ks, b_hi + 2 * ks, idesc, acc);
-              acc = 1;
-            }
-            for (int ks = 0; ks < p.ks_lo; ++ks) tc_mma_f16_ts(d_tmem, a_hi + 8 * ks, b_lo + 2 * ks, idesc, 1);  // xh.yl
-            for (int ks = 0; ks < p.ks_lo; ++ks) tc_mma_f16_ts(d_tmem, a_lo + 8 * ks, b_hi + 2 * ks, idesc, 1);  // xl.yh
+            // [-2xh | 1 1 1] . [yh | norm],  xh . yl,  xl . yh   (k-steps beyond the data are skipped)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (ks < p.ks_hi) tc_mma_f16_ts(d_tmem, a_hi + 8 * ks, b_hi + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (ks < p.ks_lo) tc_mma_f16_ts(d_tmem, a_hi + 8 * ks, b_lo + 2 * ks, idesc, 1u);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (ks < p.ks_lo) tc_mma_f16_ts(d_tmem, a_lo + 8 * ks, b_hi + 2 * ks, idesc, 1u);
             tc_commit(bar_acc_full + 8 * slot);  // accumulator ready for the epilogue
             if (++slot == NSLOT) {
               slot = 0;
@@ -594,24 +642,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
           for (int a = 0; a < p.ka; ++a, ++it) {
             const int s = it % TC_KSTAGES;
             const uint32_t ph = (it / TC_KSTAGES) & 1;
-            const uint32_t st = smem_k + s * 6 * TC_ATOM_BYTES;
             if (a > 0) mbar_wait(bar_b_full + 8 * s, ph);
             tc_fence_after();
-            const uint64_t b_hi = make_desc(st + 4 * TC_ATOM_BYTES);
-            const uint64_t b_lo = make_desc(st + 5 * TC_ATOM_BYTES);
+            const uint64_t st = desc_b0 + static_cast<uint64_t>(s * (6 * TC_ATOM_BYTES >> 4));
+            const uint64_t b_hi = st + 4 * (TC_ATOM_BYTES >> 4);
+            const uint64_t b_lo = st + 5 * (TC_ATOM_BYTES >> 4);
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
               const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((slot + mb) * TC_N);
-              const uint64_t a_hi = make_desc(st + (mb * 2 + 0) * TC_ATOM_BYTES);
-              const uint64_t a_lo = make_desc(st + (mb * 2 + 1) * TC_ATOM_BYTES);
+              const uint64_t a_hi = st + (mb * 2 + 0) * (TC_ATOM_BYTES >> 4);
+              const uint64_t a_lo = st + (mb * 2 + 1) * (TC_ATOM_BYTES >> 4);
               // zero-padded columns contribute exactly 0, so every atom runs its 4 k-steps
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
                 tc_mma_f16(d_tmem, a_hi + 2 * ks, b_hi + 2 * ks, idesc, (a > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1);
+              for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1);
+              for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
             }
             tc_commit(bar_b_empty + 8 * s);
           }
@@ -655,8 +703,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a_full);
     }
-    float *ck = p.cand_key + t_row * TC_CAP;
-    uint32_t *ci = p.cand_idx + t_row * TC_CAP;
+    uint2 *cl = p.cand + t_row * TC_CAP;  // this row's candidate list
     const float inf = __int_as_float(0x7f800000);
     float tau = active ? inf : -inf;
     const float xn = active ? p.xnorm[t_row] : 0.0f;
@@ -682,7 +729,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
           const int c = __shfl_sync(FULL, cnt, src);
           int nc;
           const float thr =
-              tc_select_truncate(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, p.trigger, lane, &nc);
+              tc_select_truncate(p.cand + tt * TC_CAP, c, p.keep, p.trigger, lane, &nc);
           if (lane == src) {
             cnt = nc;
             tau = thr;
@@ -692,29 +739,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         const unsigned m = __reduce_max_sync(FULL, f2ord(tau + xn));  // inactive rows: -inf
         if (lane == 0) tau_pub[ew] = ord2f(m);
       }
-      float g[4];
+      // minima of 3 + 3 + 2 columns, of the groups of 8 and of the chunk; a hit is then located by
+      // descending that tree, so that one insertion costs ~20 instructions of divergent code, not ~60
+      float sa[4], sb[4], sc[4], g[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float a = fminf(fminf(__uint_as_float(r[8 * q + 0]), __uint_as_float(r[8 * q + 1])),
-                              __uint_as_float(r[8 * q + 2]));
-        const float b = fminf(fminf(__uint_as_float(r[8 * q + 3]), __uint_as_float(r[8 * q + 4])),
-                              __uint_as_float(r[8 * q + 5]));
-        g[q] = fminf(fminf(a, b), fminf(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
+        sa[q] = fminf(fminf(__uint_as_float(r[8 * q + 0]), __uint_as_float(r[8 * q + 1])), __uint_as_float(r[8 * q + 2]));
+        sb[q] = fminf(fminf(__uint_as_float(r[8 * q + 3]), __uint_as_float(r[8 * q + 4])), __uint_as_float(r[8 * q + 5]));
+        sc[q] = fminf(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7]));
+        g[q] = fminf(fminf(sa[q], sb[q]), sc[q]);
       }
       const float mn = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
       const float cut = fminf(tau, TC_PAD_CUT);  // padding rows of the database carry a huge norm
       if (mn < cut && p.debug_mode != 2) {
+        auto ins = [&](int c) {
+          if (__uint_as_float(r[c]) < cut) {
+            cl[cnt] = make_uint2(r[c], static_cast<uint32_t>(j0 + c));  // one 8-byte store
+            ++cnt;
+          }
+        };
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (g[q] < cut) {
-#pragma unroll
-            for (int c = 8 * q; c < 8 * q + 8; ++c) {
-              const float v = __uint_as_float(r[c]);
-              if (v < cut) {
-                ck[cnt] = v;
-                ci[cnt] = static_cast<uint32_t>(j0 + c);
-                ++cnt;
-              }
+            if (sa[q] < cut) {
+              ins(8 * q + 0);
+              ins(8 * q + 1);
+              ins(8 * q + 2);
+            }
+            if (sb[q] < cut) {
+              ins(8 * q + 3);
+              ins(8 * q + 4);
+              ins(8 * q + 5);
+            }
+            if (sc[q] < cut) {
+              ins(8 * q + 6);
+              ins(8 * q + 7);
             }
           }
         }
@@ -723,13 +782,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
 
     int slot = mb % NSLOT;
     uint32_t use_par = 0;  // parity of (it / NSLOT), it = 2 t + mb
+    bool in_pre = pre_pass;
+    int n_pre = 0;  // tile minima recorded by the pre-pass (row-major in this row's list buffer)
     for (int t = 0;; ++t) {
       mbar_wait(bar_acc_full + 8 * slot, use_par);
-      const int jt = tile_seq[t % TC_RING];  // first (permuted) database row of the tile
-      if (jt < 0) break;
+      const int jt = tile_seq[t % TC_RING];  // first (permuted) database row of the tile, or a marker
+      if (jt == TC_SEQ_END) break;
+      if (t == 0) stamp(2);
       tc_fence_after();
       const uint32_t t_acc = t_lane + static_cast<uint32_t>(slot * TC_N);
-      if (p.debug_mode == 3) {  // profiling only: hand the accumulator straight back (MMA/TMA rate alone)
+      if (jt == TC_SEQ_PRE_END) {
+        stamp(3);
+        // end of the pre-pass: starting threshold = m-th smallest tile minimum (just above it, so that
+        // the strict admission test cannot lose a tie)
+        if (n_pre >= p.keep) {
+          for (int src = 0; src < 32; ++src) {
+            const int64_t tt = __shfl_sync(FULL, t_row, src);
+            if (tt >= p.nq) continue;  // warp-uniform
+            int nc;
+            const int km = (p.keep + 24 < n_pre) ? p.keep + 24 : n_pre;
+            const float thr =
+                tc_select_truncate(p.cand + tt * TC_CAP, n_pre, p.keep, km, lane, &nc);
+            if (lane == src) tau = (thr < inf) ? ord2f(f2ord(thr) + 1u) : inf;
+          }
+          const unsigned m = __reduce_max_sync(FULL, f2ord(tau + xn));
+          if (lane == 0) tau_pub[ew] = ord2f(m);
+        }
+        in_pre = false;
+        stamp(4);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
+      } else if (in_pre) {
+        // pre-pass tile: minimum key of the tile for this row, nothing else
+        uint32_t ra[32], rb[32];
+        tc_ld32_issue(t_acc, ra);
+        tc_ld32_issue(t_acc + 32, rb);
+        float tmin = inf;
+        auto fold = [&](const uint32_t(&r)[32]) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 2)
+            tmin = fminf(fminf(__uint_as_float(r[q]), __uint_as_float(r[q + 1])), tmin);
+        };
+        tc_ld32_wait(ra);
+        tc_ld32_wait(rb);
+        fold(ra);
+        tc_ld32_issue(t_acc + 64, ra);
+        fold(rb);
+        tc_ld32_issue(t_acc + 96, rb);
+        tc_ld32_wait(ra);
+        tc_ld32_wait(rb);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
+        fold(ra);
+        fold(rb);
+        if (active) cl[n_pre] = make_uint2(__float_as_uint(tmin), 0u);
+        ++n_pre;
+      } else if (p.debug_mode == 3) {  // profiling only: hand the accumulator straight back (MMA/TMA rate alone)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
@@ -762,14 +871,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         use_par ^= 1;
       }
     }
-    // final: sort every row's list, keep the best m, publish count and threshold
+    // final: keep the best m of every row's list, publish count and threshold
+    stamp(5);
     for (int src = 0; src < 32; ++src) {
       const int64_t tt = __shfl_sync(FULL, t_row, src);
       const int c = __shfl_sync(FULL, cnt, src);
       const float tau_src = __shfl_sync(FULL, tau, src);
       if (tt >= p.nq) continue;  // warp-uniform
-      int nc;
-      float thr = tc_sort_truncate(p.cand_key + tt * TC_CAP, p.cand_idx + tt * TC_CAP, c, p.keep, lane, &nc);
+      // keep the m smallest (up to a whole number of 32-entry groups: the re-rank kernel sorts by the exact
+      // distance anyway, so a cheap threshold selection replaces the full sort of the list)
+      const int keep_max = (p.keep + 31) & ~31;
+      int nc = c;
+      float thr = inf;
+      if (c > keep_max) thr = tc_select_truncate(p.cand + tt * TC_CAP, c, p.keep, keep_max, lane, &nc);
       // every rejected entry has key >= the threshold in force when it was rejected >= tau_src, and every
       // row of a cell the sweep skipped has key >= the row's tau at that moment >= tau_src;
       // with fewer than `keep` entries the sort has no keep-th key and tau_src is the bound
@@ -781,8 +895,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     }
   }
 
+  stamp(6);
   tc_fence_before();
   __syncthreads();
+  stamp(7);
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -798,7 +914,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
 template <int E, bool WIDE>
 __global__ void __launch_bounds__(256) knn_rerank_kernel(
     const float *__restrict__ x, int64_t n, int d, int64_t q0, int64_t nq, int k, const int *__restrict__ qlist,
-    const int *__restrict__ perm, const uint32_t *__restrict__ cand_idx, const int *__restrict__ cand_cnt,
+    const int *__restrict__ perm, const uint2 *__restrict__ cand, const int *__restrict__ cand_cnt,
     const float *__restrict__ cand_thr,
     const float *__restrict__ xnorm, const PrepScalars *__restrict__ scalars, int64_t *__restrict__ out_idx,
     float *__restrict__ out_dist, int *__restrict__ fb_count, int64_t *__restrict__ fb_rows) {
@@ -820,7 +936,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
     float acc = 0.0f;
     if (!WIDE) {
       if (pos < cnt) {
-        j = static_cast<uint32_t>(perm[cand_idx[t * TC_CAP + pos]]);
+        j = static_cast<uint32_t>(perm[cand[t * TC_CAP + pos].y]);
         const float *y = x + static_cast<int64_t>(j) * d;
         for (int c = 0; c < d; ++c) {  // the contract's chain: left to right, one rounding per fmaf
           const float df = __fsub_rn(__ldg(xq + c), __ldg(y + c));
@@ -829,7 +945,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
       }
     } else {
       if (e * 32 < cnt) {  // warp-uniform: this group of 32 candidates is not empty
-        if (pos < cnt) j = static_cast<uint32_t>(perm[cand_idx[t * TC_CAP + pos]]);
+        if (pos < cnt) j = static_cast<uint32_t>(perm[cand[t * TC_CAP + pos].y]);
         const int in_group = min(32, cnt - e * 32);
         for (int c0 = 0; c0 < d; c0 += 32) {
           const float xv = (c0 + lane < d) ? __ldg(xq + c0 + lane) : 0.0f;
@@ -956,8 +1072,7 @@ struct TcLayout {
   unsigned long long *tiles_done;
   int *qlist;
   float *xnorm;
-  float *cand_key;
-  uint32_t *cand_idx;
+  uint2 *cand;
   int *cand_cnt;
   float *cand_thr;
   int *fb_count;
@@ -987,17 +1102,16 @@ static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
   L.mu = cv.take<float>(static_cast<size_t>(L.ka) * 64);
   L.maxn2 = cv.take<unsigned int>(1);
   L.scalars = cv.take<PrepScalars>(1);
-  L.tiles_done = cv.take<unsigned long long>(1);
+  L.tiles_done = cv.take<unsigned long long>(2);
   L.qlist = cv.take<int>(static_cast<size_t>(L.chunk_pad));
   L.xnorm = cv.take<float>(static_cast<size_t>(L.chunk_pad));
   L.cand_cnt = cv.take<int>(static_cast<size_t>(L.chunk_pad));
   L.cand_thr = cv.take<float>(static_cast<size_t>(L.chunk_pad));
   L.fb_count = cv.take<int>(1);
   L.fb_rows = cv.take<int64_t>(static_cast<size_t>(L.chunk_pad));
-  L.cand_key = cv.take<float>(static_cast<size_t>(L.chunk_pad) * TC_CAP);
-  L.cand_idx = cv.take<uint32_t>(static_cast<size_t>(L.chunk_pad) * TC_CAP);
+  L.cand = cv.take<uint2>(static_cast<size_t>(L.chunk_pad) * TC_CAP);
   // the fallback's candidate lists reuse the screening lists (dead after the re-rank)
-  L.brute_ws = L.cand_key;
+  L.brute_ws = L.cand;
   L.brute_ws_bytes = static_cast<size_t>(L.chunk_pad) * TC_CAP * 8;
   size_t need_brute = brute_workspace_bytes(chunk, k);
   if (knn_brute_few_workspace_bytes(k) > need_brute) need_brute = knn_brute_few_workspace_bytes(k);
@@ -1070,7 +1184,7 @@ int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, in
   build_operands_kernel<false><<<prep_grid, 256, 0, st>>>(x_dev, d, L.ka, L.mu, L.scalars, L.cells.perm, L.n_rows_b,
                                                           L.opB, nullptr);
   VVB_CHECK_LAUNCH();
-  VVB_CUDA(cudaMemsetAsync(L.tiles_done, 0, sizeof(unsigned long long), st));
+  VVB_CUDA(cudaMemsetAsync(L.tiles_done, 0, 2 * sizeof(unsigned long long), st));
   rc = make_operand_map(&S->map_a, L.opA, L.chunk_pad, L.op_cols);
   if (rc) return rc;
   rc = make_operand_map(&S->map_b, L.opB, L.n_rows_b, L.op_cols);
@@ -1132,14 +1246,34 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   p.xnorm = L.xnorm;
   p.scalars = L.scalars;
   p.tiles_done = L.tiles_done;
-  p.cand_key = L.cand_key;
-  p.cand_idx = L.cand_idx;
+  p.times = nullptr;
+  const bool want_times = getenv("VVB_TC_TIMES") != nullptr;
+  if (want_times) {
+    VVB_CUDA(cudaMalloc(&p.times, static_cast<size_t>(nq_pad / TC_M) * 8 * sizeof(long long)));
+    VVB_CUDA(cudaMemsetAsync(p.times, 0, static_cast<size_t>(nq_pad / TC_M) * 8 * sizeof(long long), st));
+  }
+  p.cand = L.cand;
   p.cand_cnt = L.cand_cnt;
   p.cand_thr = L.cand_thr;
   const unsigned sgrid = static_cast<unsigned>(nq_pad / TC_M);
   if (L.ka == 1) knn_screen_kernel<false><<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, p);
   else knn_screen_kernel<true><<<sgrid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, p);
   VVB_CHECK_LAUNCH();
+  if (want_times) {  // profiling only: mean duration of the phases of a CTA, in SM clocks
+    const size_t nc = static_cast<size_t>(nq_pad / TC_M);
+    std::vector<long long> h(nc * 8);
+    VVB_CUDA(cudaStreamSynchronize(st));
+    VVB_CUDA(cudaMemcpy(h.data(), p.times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.times);
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (size_t c = 0; c < nc; ++c)
+      for (int i = 0; i < 7; ++i)
+        if (h[c * 8 + i + 1] && h[c * 8 + i]) acc[i] += static_cast<double>(h[c * 8 + i + 1] - h[c * 8 + i]);
+    fprintf(stderr,
+            "[vvb times] CTAs %zu: prologue %.0f | first accumulator %.0f | pre-pass %.0f | pre select %.0f | main sweep "
+            "%.0f | final select %.0f | exit barrier %.0f  (mean SM clocks per CTA)\n",
+            nc, acc[0] / nc, acc[1] / nc, acc[2] / nc, acc[3] / nc, acc[4] / nc, acc[5] / nc, acc[6] / nc);
+  }
   if (screen_only) return VVB_OK;
   mark(1);
   const unsigned rr_grid = static_cast<unsigned>((nq + 7) / 8);
@@ -1148,11 +1282,11 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   do {                                                                                                                \
     if (S->d >= 128)                                                                                                  \
       knn_rerank_kernel<EE, true><<<rr_grid, 256, 0, st>>>(S->x, S->n, S->d, q0, nq, S->k, L.qlist, L.cells.perm,    \
-                                                           L.cand_idx, L.cand_cnt, L.cand_thr, L.xnorm, L.scalars,   \
+                                                           L.cand, L.cand_cnt, L.cand_thr, L.xnorm, L.scalars,   \
                                                            out_idx, out_dist, L.fb_count, L.fb_rows);               \
     else                                                                                                              \
       knn_rerank_kernel<EE, false><<<rr_grid, 256, 0, st>>>(S->x, S->n, S->d, q0, nq, S->k, L.qlist, L.cells.perm,   \
-                                                            L.cand_idx, L.cand_cnt, L.cand_thr, L.xnorm, L.scalars,  \
+                                                            L.cand, L.cand_cnt, L.cand_thr, L.xnorm, L.scalars,  \
                                                             out_idx, out_dist, L.fb_count, L.fb_rows);              \
   } while (0)
   if (e_need <= 2) VVB_RR(2);
@@ -1227,11 +1361,10 @@ int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, i
   }
   if (!rc) {
     TcLayout &L = reinterpret_cast<TcSession *>(session)->L;
-    std::vector<uint32_t> ci(static_cast<size_t>(nq) * TC_CAP);
-    std::vector<float> ck(static_cast<size_t>(nq) * TC_CAP), ct(nq), xn(nq);
+    std::vector<uint2> cl(static_cast<size_t>(nq) * TC_CAP);
+    std::vector<float> ct(nq), xn(nq);
     std::vector<int> cc(nq), ql(nq), perm(static_cast<size_t>(L.n_rows_b));
-    cudaMemcpy(ci.data(), L.cand_idx, ci.size() * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(ck.data(), L.cand_key, ck.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(cl.data(), L.cand, cl.size() * sizeof(uint2), cudaMemcpyDeviceToHost);
     cudaMemcpy(cc.data(), L.cand_cnt, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(ct.data(), L.cand_thr, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(xn.data(), L.xnorm, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost);
@@ -1243,8 +1376,10 @@ int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, i
       cand_thr_out[o] = ct[t];
       xnorm_out[o] = xn[t];
       for (int e = 0; e < TC_CAP; ++e) {
-        cand_key_out[o * TC_CAP + e] = ck[t * TC_CAP + e];
-        cand_idx_out[o * TC_CAP + e] = e < cc[t] ? static_cast<uint32_t>(perm[ci[t * TC_CAP + e]]) : 0u;
+        float key;
+        memcpy(&key, &cl[t * TC_CAP + e].x, sizeof(float));
+        cand_key_out[o * TC_CAP + e] = key;
+        cand_idx_out[o * TC_CAP + e] = e < cc[t] ? static_cast<uint32_t>(perm[cl[t * TC_CAP + e].y]) : 0u;
       }
     }
     cudaMemcpy(scale_ymax_out, L.scalars, 2 * sizeof(float), cudaMemcpyDeviceToHost);
