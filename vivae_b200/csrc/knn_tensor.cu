@@ -73,7 +73,7 @@ constexpr float TC_PAD_NORM = 60000.0f;  // squared "norm" of padding rows: thei
 constexpr float TC_PAD_CUT = 30000.0f;   // real keys are below 64^2 + 2 * 64 * 64
 constexpr int TC_RING = 16;              // tile-sequence ring (producer runs at most stages + slots tiles ahead)
 constexpr int TC_PRE_TILES = TC_CAP;     // threshold pre-pass: tiles whose minima seed the admission thresholds
-constexpr int TC_PRE_MIN_TOTAL = 512;    // ... run only when the database has at least this many tiles
+constexpr int TC_PRE_MAX_KA = 2;         // ... only where the epilogue, not the MMA, bounds the sweep (d + 3 <= 128)
 constexpr int TC_SEQ_END = -1;           // tile_seq markers
 constexpr int TC_SEQ_PRE_END = -2;
 constexpr float TC_EPS = 1.0f / 131072.0f;  // 2^-17: 26x the measured screening error (2^-21.7), ~5x its analytic bound
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   stamp(1);
-  const bool pre_pass = p.debug_mode == 0 && p.cell_off[P] >= TC_PRE_MIN_TOTAL * TC_N;
+  const bool pre_pass = p.debug_mode == 0 && p.ka <= TC_PRE_MAX_KA;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -523,6 +523,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         ++t;
         ++it;
       };
+      // the pre-pass covers the block's own neighbourhood: the cells its bound cannot separate from it
+      // (bound <= 0), at most TC_PRE_TILES tiles; with too few tiles for m distinct minima it is skipped
+      int pre_tiles = 0;
+      if (pre_pass) {
+        for (int ci = 0; ci < P && pre_tiles < TC_PRE_TILES; ++ci) {
+          const unsigned long long e = order[ci];
+          if (ord2f(static_cast<uint32_t>(e >> 32)) > 0.0f) break;
+          const int b = static_cast<int>(static_cast<uint32_t>(e));
+          pre_tiles += (p.cell_off[b + 1] - p.cell_off[b]) / TC_N;
+        }
+        pre_tiles = min(pre_tiles, TC_PRE_TILES);
+        if (pre_tiles < p.keep + 16) pre_tiles = 0;
+      }
       for (int pass = pre_pass ? 0 : 1; pass < 2; ++pass) {
       int pass_tiles = 0;
       for (int ci = 0; ci < P; ++ci) {
@@ -530,7 +543,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         const float bound = ord2f(static_cast<uint32_t>(e >> 32));
         const int b = static_cast<int>(static_cast<uint32_t>(e));
         if (bound == __int_as_float(0x7f800000)) break;  // empty cells sort last
-        if (pass == 0 && pass_tiles >= TC_PRE_TILES) break;
+        if (pass == 0 && pass_tiles >= pre_tiles) break;
         if (pass == 1 && bound > 0.0f) {
           float tmax = tau_pub[0];
 #pragma unroll
@@ -539,7 +552,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         }
         const int row_end = p.cell_off[b + 1];
         for (int row_b = p.cell_off[b]; row_b < row_end; row_b += TC_N, ++t, ++pass_tiles) {
-          if (pass == 0 && pass_tiles >= TC_PRE_TILES) break;
+          if (pass == 0 && pass_tiles >= pre_tiles) break;
           if constexpr (!KLOOP) {
             const int s = t % TC_STAGES;
             const uint32_t ph = (t / TC_STAGES) & 1;
