@@ -53,6 +53,26 @@ def synth_cells(n: int, d: int, seed: int = 1, n_clusters: int = 30) -> np.ndarr
     return out
 
 
+def synth_cells_device(n: int, d: int, dev, seed: int = 4, n_clusters: int = 40):
+    """C5-syn of SURVEY.md section 8(d), generated on the device (a 2M x 2000 float32 matrix is 16 GB per rank:
+    too large to draw on the host of every rank): non-negative log1p-transformed counts, ~65 % zeros, 40 clusters
+    with Gamma-distributed expression programmes."""
+    import torch
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    shape = torch.full((n_clusters, d), 0.35, device=dev)
+    centres = torch._standard_gamma(shape, generator=g) * 1.5  # many near-silent genes, a few strong ones
+    out = torch.empty((n, d), dtype=torch.float32, device=dev)
+    chunk = 1 << 16
+    for s0 in range(0, n, chunk):
+        e0 = min(n, s0 + chunk)
+        lab = torch.randint(0, n_clusters, (e0 - s0,), device=dev, generator=g)
+        depth = torch.exp(0.3 * torch.randn(e0 - s0, 1, device=dev, generator=g))
+        out[s0:e0] = torch.log1p(torch.poisson(centres[lab] * depth, generator=g))
+    return out
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -165,7 +185,8 @@ def run_reference(args) -> None:
 def workload_config(args, n_gpus: int) -> dict:
     return {"workload": f"synthetic {args.n} cells x {args.d} PCs, exact kNN k={args.k} + smooth(k={args.k}, coef=1, n_iter=1)",
             "n": args.n, "d": args.d, "k": args.k, "parallelism": f"query-row shards x{n_gpus}, smooth replicated",
-            "l2": "inputs larger than L2 (matrix 200 MB, graph 612 MB vs 126 MB L2)"}
+            "l2": f"inputs larger than L2 (matrix {args.n * args.d * 4 / 1e6:.0f} MB, graph "
+                  f"{args.n * (args.k + 1) * 12 / 1e6:.0f} MB vs 126 MB L2)"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -187,8 +208,14 @@ def run_ours(args) -> None:
         dist.init_process_group("nccl", device_id=dev)
 
     n, d, k = args.n, args.d, args.k
-    x_host = synth_cells(n, d)
-    x_dev = torch.from_numpy(x_host).to(dev)
+    device_data = args.device_data or n * d > 1_000_000_000
+    if device_data:
+        x_host = None
+        x_dev = synth_cells_device(n, d, dev)
+        args.skip_e2e = args.skip_cpu = args.skip_fit = True  # these legs need the host matrix
+    else:
+        x_host = synth_cells(n, d)
+        x_dev = torch.from_numpy(x_host).to(dev)
     q0, nq = shard_bounds(n, world, rank)
 
     def step_device(stats=None):
@@ -261,6 +288,17 @@ def run_ours(args) -> None:
         # three fp16 products of the hi/lo split, K padded to the MMA's k-step (16) or to the 64-column atom
         return 16 * ((dd + 3 + 15) // 16 + 2 * ((dd + 15) // 16)) if dd + 3 <= 64 else 3 * 64 * ((dd + 3 + 63) // 64)
 
+    cap = os.path.join(ROOT, "profiles", "r01_screen_cells_raw.csv")
+    if st.get("algo_used") == 2 and (n, d, k) == (1_000_000, 50, 50) and os.path.isfile(cap):
+        import csv
+        with open(cap) as f:
+            rows_ = list(csv.reader(f))
+        col = {h: i for i, h in enumerate(rows_[0])}
+        gb = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        tr = sum(float(rows_[2][col[m]]) * gb[rows_[1][col[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        roofline["traffic"] = tr
+        roofline["traffic_note"] = ("dram__bytes_read + dram__bytes_write of ONE launch (262,144 query rows; a 1M step is 4 launches) "
+                                    "from the committed ncu --set full capture profiles/r01_screen_cells_raw.csv")
     dense_roof = None
     if st.get("algo_used") == 2:
         # The sweep is exact but not dense: cells whose distance lower bound exceeds every row's k-th candidate
@@ -385,7 +423,8 @@ def run_ours(args) -> None:
             "metric": "cells/sec exact kNN(k=50)+smooth", "value": value, "unit": "cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 (screening operands f16 hi/lo, f32 accumulate; re-rank f32)",
-            "data": "synthetic", "config": workload_config(args, world), "clocks": clocks.summary(),
+            "data": "synthetic (generated on the device)" if device_data else "synthetic",
+            "config": workload_config(args, world), "clocks": clocks.summary(),
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_dense": dense_roof, "roofline_smooth": smooth_roof, "quartet": quartet,
             "knn_stats": st, "ms_knn": ms_knn, "ms_smooth": ms_smooth, "cpu_baseline": base, "fit": fit,
             "parity": {"knn": "bit-exact vs FP32 brute-force oracle (tests/test_gpu_parity.py)",
@@ -412,6 +451,7 @@ def main():
     ap.add_argument("--skip-fit", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-dense", action="store_true")
+    ap.add_argument("--device-data", action="store_true")
     ap.add_argument("--fit-rows", type=int, default=200_000)
     ap.add_argument("--fit-batch", type=int, default=512)
     ap.add_argument("--fit-epochs", type=int, default=1)

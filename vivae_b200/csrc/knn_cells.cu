@@ -13,8 +13,9 @@
 //     Elongated clusters that the ball bound cannot separate are separated by this one.
 //   * ball bound: |c_b - c_a| - r_a - r_b.
 //
-// All geometry uses the first min(d, 64) coordinates (a projection never increases a distance,
-// so the bounds stay valid for the full rows) and is carried out on centred FP32 values with an
+// All geometry uses min(d, 64) coordinates -- for d > 64 the 64 columns of largest variance (for PCA
+// input these are the leading components, for gene-expression input the most variable genes); a
+// projection never increases a distance, so the bounds stay valid for the full rows -- and is carried out on centred FP32 values with an
 // explicit safety margin.  A query block sweeps the cells in increasing order of its bound and
 // stops at the first cell whose bound exceeds every row's current k-th candidate distance; the
 // certificate of the re-rank kernel covers the skipped rows (knn_tensor.cu).  Exactness never
@@ -74,10 +75,97 @@ size_t cells_carve(CellPlan *plan, void *ws, int64_t n, int d, int P) {
   return cv.used();
 }
 
+// ------------------------------------------------------------------ coordinates used by the geometry
+// per-column sum of squared centred values, partial sums in double (same tiling as the column means)
+__global__ void __launch_bounds__(256) colvar_partial_kernel(const float *__restrict__ x, int64_t n, int d,
+                                                            const float *__restrict__ mu, double *__restrict__ partial) {
+  const int cl = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  const int c = blockIdx.y * 64 + cl;
+  double acc = 0.0;
+  if (c < d) {
+    const float m = __ldg(mu + c);
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * 4 + sub; r < n; r += static_cast<int64_t>(gridDim.x) * 4) {
+      const double v = static_cast<double>(__ldg(x + r * d + c) - m);
+      acc += v * v;
+    }
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (sub == 0)
+    partial[(static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y) * 64 + cl] =
+        sh[cl] + sh[64 + cl] + sh[128 + cl] + sh[192 + cl];
+}
+// one CTA: total per column, then the CELL_DIMS columns of largest variance (ties -> lowest column), ascending
+__global__ void __launch_bounds__(1024) select_dims_kernel(const double *__restrict__ partial, int nblocks, int nyb,
+                                                          int d, int *__restrict__ dims) {
+  __shared__ float var[4096];
+  __shared__ unsigned long long best[32];
+  __shared__ int chosen[CELL_DIMS];
+  for (int c = threadIdx.x; c < 4096; c += blockDim.x) {
+    double acc = -1.0;
+    if (c < d) {
+      acc = 0.0;
+      for (int b = 0; b < nblocks; ++b) acc += partial[(static_cast<size_t>(b) * nyb + c / 64) * 64 + (c & 63)];
+    }
+    var[c] = static_cast<float>(acc);
+  }
+  __syncthreads();
+  for (int it = 0; it < CELL_DIMS; ++it) {
+    unsigned long long mine = 0ull;
+    for (int c = threadIdx.x; c < 4096; c += blockDim.x)
+      if (var[c] >= 0.0f) {
+        const unsigned long long k = (static_cast<unsigned long long>(__float_as_uint(var[c])) << 32) |
+                                     static_cast<unsigned>(4095 - c);
+        mine = k > mine ? k : mine;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(FULL, mine, o);
+      mine = other > mine ? other : mine;
+    }
+    if ((threadIdx.x & 31) == 0) best[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long m = 0ull;
+      for (int w = 0; w < 32; ++w) m = best[w] > m ? best[w] : m;
+      const int c = 4095 - static_cast<int>(static_cast<unsigned>(m));
+      chosen[it] = c;
+      var[c] = -1.0f;
+    }
+    __syncthreads();
+  }
+  // ascending column order (keeps the gathers of a row as local as they can be)
+  if (threadIdx.x < CELL_DIMS) {
+    const int mine = chosen[threadIdx.x];
+    int rank = 0;
+    for (int j = 0; j < CELL_DIMS; ++j) rank += (chosen[j] < mine) ? 1 : 0;
+    dims[rank] = mine;
+  }
+}
+__global__ void identity_dims_kernel(int *__restrict__ dims) { dims[threadIdx.x] = threadIdx.x; }
+
+// dims[0 .. CELL_DIMS): the coordinates the cell geometry uses.  `partial` needs gridDim.x * ceil(d/64) * 64 doubles.
+int cells_select_dims(const float *x, int64_t n, int d, const float *mu, double *partial, int nblocks, int *dims,
+                      cudaStream_t st) {
+  if (d <= CELL_DIMS) {
+    identity_dims_kernel<<<1, CELL_DIMS, 0, st>>>(dims);
+    VVB_CHECK_LAUNCH();
+    return VVB_OK;
+  }
+  const int nyb = (d + 63) / 64;
+  colvar_partial_kernel<<<dim3(nblocks, nyb), 256, 0, st>>>(x, n, d, mu, partial);
+  VVB_CHECK_LAUNCH();
+  select_dims_kernel<<<1, 1024, 0, st>>>(partial, nblocks, nyb, d, dims);
+  VVB_CHECK_LAUNCH();
+  return VVB_OK;
+}
+
 // ------------------------------------------------------------------ partition
 // Thread per row: nearest pivot in the first dsub centred coordinates (ties -> lowest pivot).
 // Pivot p is row floor((p + 0.5) n / P).
 __global__ void __launch_bounds__(128) cell_assign_kernel(const float *__restrict__ x, int64_t n, int d, int dsub,
+                                                         const int *__restrict__ dims,
                                                          const float *__restrict__ mu, int P,
                                                          int *__restrict__ cell_of, int *__restrict__ cnt) {
   __shared__ __align__(16) float piv[128][CELL_DIMS];
@@ -88,7 +176,8 @@ __global__ void __launch_bounds__(128) cell_assign_kernel(const float *__restric
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 128 + tid;
   float xr[CELL_DIMS];
 #pragma unroll
-  for (int c = 0; c < CELL_DIMS; ++c) xr[c] = (row < n && c < dsub) ? __ldg(x + row * d + c) - __ldg(mu + c) : 0.0f;
+  for (int c = 0; c < CELL_DIMS; ++c)
+    xr[c] = (row < n && c < dsub) ? __ldg(x + row * d + __ldg(dims + c)) - __ldg(mu + __ldg(dims + c)) : 0.0f;
   float best = __int_as_float(0x7f800000);
   int best_p = 0;
   for (int p0 = 0; p0 < P; p0 += 128) {
@@ -97,7 +186,7 @@ __global__ void __launch_bounds__(128) cell_assign_kernel(const float *__restric
     for (int i = tid; i < np * CELL_DIMS; i += 128) {
       const int pl = i / CELL_DIMS, c = i % CELL_DIMS;
       const int64_t pr = static_cast<int64_t>((static_cast<double>(p0 + pl) + 0.5) * static_cast<double>(n) / P);
-      piv[pl][c] = (c < dsub) ? __ldg(x + pr * d + c) - __ldg(mu + c) : 0.0f;
+      piv[pl][c] = (c < dsub) ? __ldg(x + pr * d + __ldg(dims + c)) - __ldg(mu + __ldg(dims + c)) : 0.0f;
     }
     __syncthreads();
     if (tid < np) {
@@ -182,6 +271,7 @@ __global__ void __launch_bounds__(256) cell_hist_kernel(const int *__restrict__ 
 // ------------------------------------------------------------------ cell geometry
 // one CTA per group of 128 permuted rows (a group never straddles cells): coordinate sums and sums of squares
 __global__ void __launch_bounds__(256) cell_moments_kernel(const float *__restrict__ x, int d, int dsub,
+                                                          const int *__restrict__ dims,
                                                           const float *__restrict__ mu, const int *__restrict__ perm,
                                                           const int *__restrict__ off, int P,
                                                           const int *__restrict__ cell_of, double *__restrict__ sums,
@@ -193,11 +283,12 @@ __global__ void __launch_bounds__(256) cell_moments_kernel(const float *__restri
   const int c = threadIdx.x & 63, rl = threadIdx.x >> 6;
   double s = 0.0, q = 0.0;
   if (c < dsub) {
-    const float m = __ldg(mu + c);
+    const int col = __ldg(dims + c);
+    const float m = __ldg(mu + col);
     for (int i = rl; i < CELL_GROUP; i += 4) {
       const int r = perm[p0 + i];
       if (r >= 0) {
-        const double v = static_cast<double>(__ldg(x + static_cast<int64_t>(r) * d + c) - m);
+        const double v = static_cast<double>(__ldg(x + static_cast<int64_t>(r) * d + col) - m);
         s += v;
         q += v * v;
       }
@@ -279,6 +370,7 @@ __global__ void __launch_bounds__(128) cell_pairs_kernel(const float *__restrict
 // one CTA per group of 128 permuted rows of cell a (thread per row): for every other cell b the largest
 // projection of (x - c_a) on the direction a -> b, and the largest squared distance to the centre
 __global__ void __launch_bounds__(128) cell_extent_kernel(const float *__restrict__ x, int d, int dsub,
+                                                         const int *__restrict__ dims,
                                                          const float *__restrict__ mu, const int *__restrict__ perm,
                                                          const int *__restrict__ off, int P,
                                                          const int *__restrict__ cell_of, const float *__restrict__ cen,
@@ -298,7 +390,8 @@ __global__ void __launch_bounds__(128) cell_extent_kernel(const float *__restric
 #pragma unroll
   for (int c = 0; c < CELL_DIMS; ++c) {
     xr[c] = (r >= 0 && c < dsub)
-                ? (__ldg(x + static_cast<int64_t>(r) * d + c) - __ldg(mu + c)) - __ldg(cen + a * CELL_DIMS + c)
+                ? (__ldg(x + static_cast<int64_t>(r) * d + __ldg(dims + c)) - __ldg(mu + __ldg(dims + c))) -
+                      __ldg(cen + a * CELL_DIMS + c)
                 : 0.0f;
     r2 = fmaf(xr[c], xr[c], r2);
   }
@@ -365,21 +458,23 @@ __global__ void __launch_bounds__(128) cell_lb_kernel(const int *__restrict__ cn
   }
 }
 
-int cells_build(const CellPlan &L, const float *x, int d, const float *mu, const float *scale_dev, cudaStream_t st) {
+int cells_build(const CellPlan &L, const float *x, int d, const float *mu, const int *dims, const float *scale_dev,
+                cudaStream_t st) {
   const int P = L.P;
   const int64_t n = L.n;
   VVB_CUDA(cudaMemsetAsync(L.cnt, 0, sizeof(int) * P, st));
   VVB_CUDA(cudaMemsetAsync(L.perm, 0xFF, sizeof(int) * static_cast<size_t>(L.n_perm_cap), st));
   VVB_CUDA(cudaMemsetAsync(L.sums, 0, sizeof(double) * static_cast<size_t>(P) * CELL_DIMS, st));
   VVB_CUDA(cudaMemsetAsync(L.sqs, 0, sizeof(double) * static_cast<size_t>(P) * CELL_DIMS, st));
-  cell_assign_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(x, n, d, L.dsub, mu, P, L.cell_of, L.cnt);
+  cell_assign_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(x, n, d, L.dsub, dims, mu, P, L.cell_of,
+                                                                             L.cnt);
   VVB_CHECK_LAUNCH();
   cell_scan_kernel<<<1, 1024, 0, st>>>(L.cnt, P, CELL_GROUP, L.off, L.cursor);
   VVB_CHECK_LAUNCH();
   cell_scatter_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(L.cell_of, 0, n, L.cursor, L.perm, -1);
   VVB_CHECK_LAUNCH();
   const unsigned groups = static_cast<unsigned>(L.n_perm_cap / CELL_GROUP);
-  cell_moments_kernel<<<groups, 256, 0, st>>>(x, d, L.dsub, mu, L.perm, L.off, P, L.cell_of, L.sums, L.sqs);
+  cell_moments_kernel<<<groups, 256, 0, st>>>(x, d, L.dsub, dims, mu, L.perm, L.off, P, L.cell_of, L.sums, L.sqs);
   VVB_CHECK_LAUNCH();
   cell_centres_kernel<<<P, CELL_DIMS, 0, st>>>(L.sums, L.cnt, L.cen);
   VVB_CHECK_LAUNCH();
@@ -389,7 +484,7 @@ int cells_build(const CellPlan &L, const float *x, int d, const float *mu, const
   VVB_CHECK_LAUNCH();
   cell_pairs_kernel<<<P, 128, 0, st>>>(L.cen, L.cw, P, L.inv_norm, L.gap, L.cdist, L.ext, L.rad2);
   VVB_CHECK_LAUNCH();
-  cell_extent_kernel<<<groups, 128, 0, st>>>(x, d, L.dsub, mu, L.perm, L.off, P, L.cell_of, L.cen, L.cw, L.inv_norm,
+  cell_extent_kernel<<<groups, 128, 0, st>>>(x, d, L.dsub, dims, mu, L.perm, L.off, P, L.cell_of, L.cen, L.cw, L.inv_norm,
                                              L.ext, L.rad2);
   VVB_CHECK_LAUNCH();
   cell_lb_kernel<<<P, 128, 0, st>>>(L.cnt, P, L.gap, L.cdist, L.ext, L.rad2, scale_dev, L.lb);

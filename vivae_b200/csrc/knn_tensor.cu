@@ -1083,6 +1083,7 @@ struct TcLayout {
   unsigned int *maxn2;
   PrepScalars *scalars;
   unsigned long long *tiles_done;
+  int *dims;
   int *qlist;
   float *xnorm;
   uint2 *cand;
@@ -1116,6 +1117,7 @@ static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
   L.maxn2 = cv.take<unsigned int>(1);
   L.scalars = cv.take<PrepScalars>(1);
   L.tiles_done = cv.take<unsigned long long>(2);
+  L.dims = cv.take<int>(CELL_DIMS);
   L.qlist = cv.take<int>(static_cast<size_t>(L.chunk_pad));
   L.xnorm = cv.take<float>(static_cast<size_t>(L.chunk_pad));
   L.cand_cnt = cv.take<int>(static_cast<size_t>(L.chunk_pad));
@@ -1192,7 +1194,9 @@ int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, in
   VVB_CHECK_LAUNCH();
   scalars_kernel<<<1, 1, 0, st>>>(L.maxn2, L.scalars);
   VVB_CHECK_LAUNCH();
-  int rc = cells_build(L.cells, x_dev, d, L.mu, reinterpret_cast<const float *>(L.scalars), st);
+  int rc = cells_select_dims(x_dev, n, d, L.mu, L.partial, PREP_BLOCKS, L.dims, st);
+  if (rc) return rc;
+  rc = cells_build(L.cells, x_dev, d, L.mu, L.dims, reinterpret_cast<const float *>(L.scalars), st);
   if (rc) return rc;
   build_operands_kernel<false><<<prep_grid, 256, 0, st>>>(x_dev, d, L.ka, L.mu, L.scalars, L.cells.perm, L.n_rows_b,
                                                           L.opB, nullptr);
