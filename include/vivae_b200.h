@@ -95,7 +95,7 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
 int vvb_make_knn_workspace_bytes(int64_t n, int d, int k, int64_t nq, int algo, size_t *bytes);
 
 /* same contract with device-resident buffers.  The tensor path reads the number of rows its
- * certificate rejected back to the host once per 262,144-row chunk (a stream synchronisation), so
+ * certificate rejected back to the host once per chunk of up to 1,048,576 rows (a stream synchronisation), so
  * the call is not capturable in a CUDA graph; on return all work is enqueued (and, with `stats`
  * non-NULL, finished). */
 int vvb_make_knn_device(const float *x_dev, int64_t n, int d, int k, int64_t q0, int64_t nq,

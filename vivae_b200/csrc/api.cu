@@ -44,9 +44,9 @@ size_t brute_workspace_bytes(int64_t nq, int k);
 int launch_knn_brute(const float *x_dev, int64_t n, int d, int k, const int64_t *qrows_dev, int64_t q0,
                      int64_t nq, int64_t *out_idx, float *out_dist, int64_t out_row0, void *workspace,
                      size_t workspace_bytes, cudaStream_t stream);
-size_t knn_tensor_workspace_bytes(int64_t n, int d, int k, int64_t nq);
+size_t knn_tensor_workspace_bytes(int64_t n, int d, int k, int64_t nq, bool host_path);
 bool knn_tensor_supported(int64_t n, int d, int k);
-int64_t knn_tensor_chunk_rows(int64_t nq);
+int64_t knn_tensor_chunk_rows(int64_t nq, bool host_path);
 size_t knn_tensor_session_bytes();
 int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, int k, int64_t chunk_rows,
                      void *workspace, size_t workspace_bytes, cudaStream_t st, vvb_knn_stats *stats);
@@ -257,8 +257,8 @@ int vvb_make_knn_workspace_bytes(int64_t n, int d, int k, int64_t nq, int algo, 
   int use = 0;
   int rc = resolve_algo(algo, n, d, k, &use);
   if (rc) return rc;
-  *bytes = (use == VVB_KNN_BRUTE) ? brute_workspace_bytes(knn_tensor_chunk_rows(nq), k)
-                                   : knn_tensor_workspace_bytes(n, d, k, nq);
+  *bytes = (use == VVB_KNN_BRUTE) ? brute_workspace_bytes(knn_tensor_chunk_rows(nq, false), k)
+                                   : knn_tensor_workspace_bytes(n, d, k, nq, false);
   return VVB_OK;
 }
 
@@ -269,8 +269,9 @@ int vvb_make_knn_workspace_bytes(int64_t n, int d, int k, int64_t nq, int algo, 
 // device-to-host copy of chunk i with the computation of chunk i+1).
 template <typename Hook>
 static int knn_run(const float *x_dev, int64_t n, int d, int k, int64_t q0, int64_t nq, int use, int64_t *idx_dev,
-                   float *dist_dev, void *ws, size_t ws_bytes, cudaStream_t st, vvb_knn_stats *stats, Hook after_chunk) {
-  const int64_t chunk = knn_tensor_chunk_rows(nq);
+                   float *dist_dev, void *ws, size_t ws_bytes, cudaStream_t st, vvb_knn_stats *stats, bool host_path,
+                   Hook after_chunk) {
+  const int64_t chunk = knn_tensor_chunk_rows(nq, host_path);
   std::vector<char> session(knn_tensor_session_bytes() + 64);
   void *sess = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(session.data()) + 63) & ~uintptr_t(63));
   int rc;
@@ -301,9 +302,9 @@ static int knn_run(const float *x_dev, int64_t n, int d, int k, int64_t q0, int6
   return VVB_OK;
 }
 
-static size_t knn_ws_bytes(int use, int64_t n, int d, int k, int64_t nq) {
-  return (use == VVB_KNN_BRUTE) ? brute_workspace_bytes(knn_tensor_chunk_rows(nq), k)
-                                : knn_tensor_workspace_bytes(n, d, k, nq);
+static size_t knn_ws_bytes(int use, int64_t n, int d, int k, int64_t nq, bool host_path) {
+  return (use == VVB_KNN_BRUTE) ? brute_workspace_bytes(knn_tensor_chunk_rows(nq, host_path), k)
+                                : knn_tensor_workspace_bytes(n, d, k, nq, host_path);
 }
 
 extern "C" {
@@ -316,7 +317,7 @@ int vvb_make_knn_device(const float *x_dev, int64_t n, int d, int k, int64_t q0,
   int use = 0;
   rc = resolve_algo(algo, n, d, k, &use);
   if (rc) return rc;
-  VVB_REQUIRE(workspace_bytes >= knn_ws_bytes(use, n, d, k, nq), "make_knn: workspace too small");
+  VVB_REQUIRE(workspace_bytes >= knn_ws_bytes(use, n, d, k, nq, false), "make_knn: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t launches0 = g_launches.load();
   if (stats) {
@@ -325,7 +326,7 @@ int vvb_make_knn_device(const float *x_dev, int64_t n, int d, int k, int64_t q0,
     stats->algo_used = use;
   }
   rc = knn_run(x_dev, n, d, k, q0, nq, use, idx_out_dev, dist_out_dev, workspace_dev, workspace_bytes, st, stats,
-               [](int64_t, int64_t) { return VVB_OK; });
+               /*host_path=*/false, [](int64_t, int64_t) { return VVB_OK; });
   if (rc) return rc;
   if (stats) {
     VVB_CUDA(cudaStreamSynchronize(st));
@@ -341,7 +342,7 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
   int use = 0;
   rc = resolve_algo(algo, n, d, k, &use);
   if (rc) return rc;
-  const size_t ws_bytes = knn_ws_bytes(use, n, d, k, nq);
+  const size_t ws_bytes = knn_ws_bytes(use, n, d, k, nq, true);
   const size_t idx_bytes = static_cast<size_t>(nq) * (k + 1) * sizeof(int64_t);
   const size_t dist_bytes = static_cast<size_t>(nq) * (k + 1) * sizeof(float);
   // the output arrays are usually freshly allocated: fault their pages in on helper threads while
@@ -385,7 +386,7 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
                              static_cast<size_t>(rows) * (k + 1) * sizeof(float), cudaMemcpyDeviceToHost, cp));
     return VVB_OK;
   };
-  rc = knn_run(x_dev, n, d, k, q0, nq, use, idx_dev, dist_dev, ws, ws_bytes, st, stats,
+  rc = knn_run(x_dev, n, d, k, q0, nq, use, idx_dev, dist_dev, ws, ws_bytes, st, stats, /*host_path=*/true,
                [&](int64_t c0, int64_t rows) -> int {
                  VVB_CUDA(cudaEventRecord(next_ev, st));
                  int r2 = VVB_OK;

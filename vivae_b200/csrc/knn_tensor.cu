@@ -1138,15 +1138,18 @@ static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
   return L;
 }
 
-// query rows processed per pass of the tensor path: bounds the workspace (2 KB of candidate list
-// per row) and is the granularity at which the host entry point overlaps D2H with compute
-int64_t knn_tensor_chunk_rows(int64_t nq) {
-  const int64_t cap = 262144;
+// Query rows processed per launch of the screening kernel.  The candidate lists cost 2 KB per row, and the
+// host entry point overlaps the D2H copy of one chunk with the kernels of the next, so it uses 262,144-row
+// chunks; the device entry point takes up to 1,048,576 rows at once (2 GB of lists): CTAs differ in length
+// (their neighbourhoods differ in size), and one launch of 4096 CTAs has one tail where four launches of 1024
+// have four (17 % of the SM time at 1M rows).
+int64_t knn_tensor_chunk_rows(int64_t nq, bool host_path) {
+  const int64_t cap = host_path ? 262144 : 1048576;
   return nq < cap ? nq : cap;
 }
 
-size_t knn_tensor_workspace_bytes(int64_t n, int d, int k, int64_t nq) {
-  return tc_layout(nullptr, n, d, k, knn_tensor_chunk_rows(nq)).total;
+size_t knn_tensor_workspace_bytes(int64_t n, int d, int k, int64_t nq, bool host_path) {
+  return tc_layout(nullptr, n, d, k, knn_tensor_chunk_rows(nq, host_path)).total;
 }
 
 // ---- session API used by api.cu ----------------------------------------------------------
@@ -1355,8 +1358,9 @@ int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, i
                      float *cand_key_out, int *cand_cnt_out, float *cand_thr_out, float *xnorm_out,
                      float *scale_ymax_out, float *mu_out) {
   VVB_REQUIRE(knn_tensor_supported(n, d, k) && nq >= 1 && q0 >= 0 && q0 + nq <= n, "screen debug: unsupported shape");
-  VVB_REQUIRE(nq <= knn_tensor_chunk_rows(nq), "screen debug: at most %lld query rows", (long long)knn_tensor_chunk_rows(nq));
-  const size_t ws_bytes = knn_tensor_workspace_bytes(n, d, k, nq);
+  VVB_REQUIRE(nq <= knn_tensor_chunk_rows(nq, true), "screen debug: at most %lld query rows",
+              (long long)knn_tensor_chunk_rows(nq, true));
+  const size_t ws_bytes = knn_tensor_workspace_bytes(n, d, k, nq, true);
   void *ws = nullptr, *xd = nullptr, *oi = nullptr, *od = nullptr;
   VVB_CUDA(cudaMalloc(&ws, ws_bytes));
   VVB_CUDA(cudaMalloc(&xd, static_cast<size_t>(n) * d * sizeof(float)));
