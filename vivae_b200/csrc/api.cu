@@ -143,6 +143,99 @@ struct HostPrefault {
   ~HostPrefault() { join(); }
 };
 
+// Host <-> device copies of large PAGEABLE arrays (the drop-in API takes and returns NumPy arrays).
+// A plain cudaMemcpy from pageable memory is staged by the driver through one bounce buffer by one thread
+// (~10 GB/s measured on the bench host).  Here T worker threads each own a slice of the array, two pinned
+// bounce buffers and a stream: memcpy into pinned memory and DMA out of it overlap, and the T memcpys run in
+// parallel.  Blocking: returns when the data has arrived.
+struct StagedCopier {
+  static constexpr int T = 6;
+  static constexpr size_t CH = 4u << 20;
+  char *pin[T][2] = {};
+  cudaStream_t st[T] = {};
+  cudaEvent_t ev[T][2] = {};
+  bool ready = false;
+  int init() {
+    if (ready) return VVB_OK;
+    for (int t = 0; t < T; ++t) {
+      VVB_CUDA(cudaStreamCreateWithFlags(&st[t], cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b) {
+        VVB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&pin[t][b]), CH, cudaHostAllocDefault));
+        VVB_CUDA(cudaEventCreateWithFlags(&ev[t][b], cudaEventDisableTiming));
+      }
+    }
+    ready = true;
+    return VVB_OK;
+  }
+  void release() {
+    if (!ready) return;
+    for (int t = 0; t < T; ++t) {
+      for (int b = 0; b < 2; ++b) {
+        cudaFreeHost(pin[t][b]);
+        cudaEventDestroy(ev[t][b]);
+        pin[t][b] = nullptr;
+      }
+      cudaStreamDestroy(st[t]);
+    }
+    ready = false;
+  }
+  // dir = cudaMemcpyHostToDevice: dst device, src host;  cudaMemcpyDeviceToHost: dst host, src device.
+  // `after`: event the device side must wait for before it is read (D2H) or overwritten (H2D); may be null.
+  int copy(void *dst, const void *src, size_t bytes, cudaMemcpyKind dir, cudaEvent_t after) {
+    if (bytes == 0) return VVB_OK;
+    int rc = init();
+    if (rc) return rc;
+    int dev = 0;
+    VVB_CUDA(cudaGetDevice(&dev));
+    const size_t nch = (bytes + CH - 1) / CH;
+    const int nt = static_cast<int>(nch < static_cast<size_t>(T) ? nch : T);
+    std::atomic<int> failed{0};
+    auto work = [&](int t) {
+      cudaSetDevice(dev);
+      if (after) cudaStreamWaitEvent(st[t], after, 0);
+      const size_t c0 = nch * t / nt, c1 = nch * (t + 1) / nt;
+      char *d = static_cast<char *>(dst);
+      const char *s = static_cast<const char *>(src);
+      if (dir == cudaMemcpyHostToDevice) {
+        for (size_t c = c0; c < c1; ++c) {
+          const int b = static_cast<int>((c - c0) & 1);
+          const size_t off = c * CH, len = (off + CH <= bytes) ? CH : bytes - off;
+          if (c - c0 >= 2 && cudaEventSynchronize(ev[t][b]) != cudaSuccess) failed = 1;  // bounce buffer free again
+          memcpy(pin[t][b], s + off, len);
+          if (cudaMemcpyAsync(d + off, pin[t][b], len, cudaMemcpyHostToDevice, st[t]) != cudaSuccess) failed = 1;
+          cudaEventRecord(ev[t][b], st[t]);
+        }
+      } else {
+        // DMA of chunk c overlaps the memcpy of chunk c-1 out of the other bounce buffer
+        for (size_t c = c0; c <= c1; ++c) {
+          if (c < c1) {
+            const int b = static_cast<int>((c - c0) & 1);
+            const size_t off = c * CH, len = (off + CH <= bytes) ? CH : bytes - off;
+            if (cudaMemcpyAsync(pin[t][b], s + off, len, cudaMemcpyDeviceToHost, st[t]) != cudaSuccess) failed = 1;
+            cudaEventRecord(ev[t][b], st[t]);
+          }
+          if (c > c0) {
+            const int b = static_cast<int>((c - 1 - c0) & 1);
+            const size_t off = (c - 1) * CH, len = (off + CH <= bytes) ? CH : bytes - off;
+            if (cudaEventSynchronize(ev[t][b]) != cudaSuccess) failed = 1;
+            memcpy(d + off, pin[t][b], len);
+          }
+        }
+      }
+      if (cudaStreamSynchronize(st[t]) != cudaSuccess) failed = 1;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    if (failed) {
+      set_error("staged host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return VVB_ECUDA;
+    }
+    return VVB_OK;
+  }
+};
+
 // Grow-only device buffers and two streams kept between *_host calls (a 2 GB cudaMalloc/cudaFree
 // pair costs ~27 ms per call otherwise).  Released by vvb_release_cached_memory().
 struct DeviceCache {
@@ -151,6 +244,7 @@ struct DeviceCache {
   void *ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  StagedCopier copier;
   int last_rc = VVB_OK;
   static DeviceCache &get() {
     static DeviceCache c;
@@ -165,6 +259,7 @@ struct DeviceCache {
     if (s_compute) cudaStreamDestroy(s_compute);
     if (s_copy) cudaStreamDestroy(s_copy);
     s_compute = s_copy = nullptr;
+    copier.release();
   }
   void check_device() {
     int dev = 0;
@@ -358,52 +453,69 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
   float *dist_dev = static_cast<float *>(dc.slot(2, dist_bytes));
   void *ws = dc.slot(3, ws_bytes);
   if (!x_dev || !idx_dev || !dist_dev || !ws) return dc.last_rc;
-  cudaStream_t st = dc.compute_stream(), cp = dc.copy_stream();
-  if (!st || !cp) return VVB_ECUDA;
+  cudaStream_t st = dc.compute_stream();
+  if (!st) return VVB_ECUDA;
   const int64_t launches0 = g_launches.load();
   if (stats) {
     memset(stats, 0, sizeof(*stats));
     stats->rows = nq;
     stats->algo_used = use;
   }
-  VVB_CUDA(cudaMemcpyAsync(x_dev, x_host, static_cast<size_t>(n) * d * sizeof(float), cudaMemcpyHostToDevice, st));
-  // D2H of chunk i is issued after chunk i+1 has been enqueued: the (host-blocking, pageable) copy
-  // then overlaps the next chunk's kernels
-  int64_t pend_c0 = -1, pend_rows = 0;
-  cudaEvent_t pend_ev = nullptr, next_ev = nullptr;
-  VVB_CUDA(cudaEventCreateWithFlags(&pend_ev, cudaEventDisableTiming));
-  VVB_CUDA(cudaEventCreateWithFlags(&next_ev, cudaEventDisableTiming));
+  rc = dc.copier.copy(x_dev, x_host, static_cast<size_t>(n) * d * sizeof(float), cudaMemcpyHostToDevice, nullptr);
+  if (rc) return rc;
+  // The D2H copy of chunk i runs on a helper thread (multi-threaded pinned staging) while the kernels of
+  // chunk i+1 execute; one copy at a time.
+  int dev = 0;
+  VVB_CUDA(cudaGetDevice(&dev));
+  std::thread bg;
+  int bg_rc = VVB_OK;
+  std::vector<cudaEvent_t> events;
   bool joined = false;
   auto flush = [&](int64_t c0, int64_t rows, cudaEvent_t ev) -> int {
+    if (bg.joinable()) bg.join();
+    if (bg_rc) return bg_rc;
     if (!joined) {
       pf.join();
       joined = true;
     }
-    VVB_CUDA(cudaStreamWaitEvent(cp, ev, 0));
-    VVB_CUDA(cudaMemcpyAsync(idx_out_host + c0 * (k + 1), idx_dev + c0 * (k + 1),
-                             static_cast<size_t>(rows) * (k + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, cp));
-    VVB_CUDA(cudaMemcpyAsync(dist_out_host + c0 * (k + 1), dist_dev + c0 * (k + 1),
-                             static_cast<size_t>(rows) * (k + 1) * sizeof(float), cudaMemcpyDeviceToHost, cp));
+    bg = std::thread([&dc, &bg_rc, dev, c0, rows, ev, k, idx_out_host, dist_out_host, idx_dev, dist_dev]() {
+      cudaSetDevice(dev);
+      int r = dc.copier.copy(idx_out_host + c0 * (k + 1), idx_dev + c0 * (k + 1),
+                             static_cast<size_t>(rows) * (k + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ev);
+      if (!r)
+        r = dc.copier.copy(dist_out_host + c0 * (k + 1), dist_dev + c0 * (k + 1),
+                           static_cast<size_t>(rows) * (k + 1) * sizeof(float), cudaMemcpyDeviceToHost, ev);
+      bg_rc = r;
+    });
     return VVB_OK;
   };
+  int64_t pend_c0 = -1, pend_rows = 0;
+  cudaEvent_t pend_ev = nullptr;
   rc = knn_run(x_dev, n, d, k, q0, nq, use, idx_dev, dist_dev, ws, ws_bytes, st, stats, /*host_path=*/true,
                [&](int64_t c0, int64_t rows) -> int {
-                 VVB_CUDA(cudaEventRecord(next_ev, st));
+                 cudaEvent_t e = nullptr;
+                 VVB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                 events.push_back(e);
+                 VVB_CUDA(cudaEventRecord(e, st));
                  int r2 = VVB_OK;
                  if (pend_c0 >= 0) r2 = flush(pend_c0, pend_rows, pend_ev);
-                 std::swap(pend_ev, next_ev);
+                 pend_ev = e;
                  pend_c0 = c0;
                  pend_rows = rows;
                  return r2;
                });
   if (!rc && pend_c0 >= 0) rc = flush(pend_c0, pend_rows, pend_ev);
+  if (bg.joinable()) bg.join();
+  if (!rc) rc = bg_rc;
   if (!joined) pf.join();
-  cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(cp);
-  cudaEventDestroy(pend_ev);
-  cudaEventDestroy(next_ev);
-  if (rc) return rc;
-  if (e1 != cudaSuccess || e2 != cudaSuccess) {
-    set_error("make_knn: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  cudaError_t e1 = cudaStreamSynchronize(st);
+  for (cudaEvent_t e : events) cudaEventDestroy(e);
+  if (rc) {
+    if (rc == bg_rc) set_error("make_knn: staged device-to-host copy failed");
+    return rc;
+  }
+  if (e1 != cudaSuccess) {
+    set_error("make_knn: %s", cudaGetErrorString(e1));
     return VVB_ECUDA;
   }
   if (stats) stats->kernel_launches = g_launches.load() - launches0;
@@ -468,15 +580,21 @@ int vvb_smooth_host(const void *x_host, int elem_size, int64_t n, int d, const i
   if (!st) return VVB_ECUDA;
   // the whole index matrix goes over as ONE contiguous copy (a pitched copy of the first k columns
   // moves fewer bytes but runs far slower from pageable memory); the kernel strides by ld_idx
-  VVB_CUDA(cudaMemcpyAsync(x, x_host, xb, cudaMemcpyHostToDevice, st));
-  VVB_CUDA(cudaMemcpyAsync(idx, idx_host, ib, cudaMemcpyHostToDevice, st));
+  rc = dc.copier.copy(x, x_host, xb, cudaMemcpyHostToDevice, nullptr);
+  if (!rc) rc = dc.copier.copy(idx, idx_host, ib, cudaMemcpyHostToDevice, nullptr);
+  if (rc) return rc;
   rc = vvb_smooth_device(x, elem_size, n, d, static_cast<const int64_t *>(idx), ld_idx, k, coef, n_iter, mode, out, ws,
                          ws_bytes, st);
   if (rc) return rc;
   int bad = 0;
   VVB_CUDA(cudaMemcpyAsync(&bad, ws, sizeof(int), cudaMemcpyDeviceToHost, st));
+  cudaEvent_t done = nullptr;
+  VVB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+  VVB_CUDA(cudaEventRecord(done, st));
   pf.join();
-  VVB_CUDA(cudaMemcpyAsync(out_host, out, xb, cudaMemcpyDeviceToHost, st));
+  rc = dc.copier.copy(out_host, out, xb, cudaMemcpyDeviceToHost, done);
+  cudaEventDestroy(done);
+  if (rc) return rc;
   VVB_CUDA(cudaStreamSynchronize(st));
   VVB_REQUIRE(bad == 0, "Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed");
   return VVB_OK;
