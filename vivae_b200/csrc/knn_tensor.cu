@@ -893,7 +893,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       if (tt >= p.nq) continue;  // warp-uniform
       // keep the m smallest (up to a whole number of 32-entry groups: the re-rank kernel sorts by the exact
       // distance anyway, so a cheap threshold selection replaces the full sort of the list)
-      const int keep_max = (p.keep + 31) & ~31;
+      const int keep_max = min((p.keep + 31) & ~31, p.keep + 8);  // every extra candidate is a 200-byte gather in the re-rank
       int nc = c;
       float thr = inf;
       if (c > keep_max) thr = tc_select_truncate(p.cand + tt * TC_CAP, c, p.keep, keep_max, lane, &nc);
@@ -1144,7 +1144,7 @@ static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
 // (their neighbourhoods differ in size), and one launch of 4096 CTAs has one tail where four launches of 1024
 // have four (17 % of the SM time at 1M rows).
 int64_t knn_tensor_chunk_rows(int64_t nq, bool host_path) {
-  const int64_t cap = host_path ? 262144 : 1048576;
+  const int64_t cap = host_path ? 524288 : 1048576;
   return nq < cap ? nq : cap;
 }
 
