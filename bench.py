@@ -403,14 +403,16 @@ def run_ours(args) -> None:
         rows = min(n, args.fit_rows)
         model = vv.ViVAE(input_dim=d, random_state=1)
         xf = x_host[:rows]
-        model.fit(xf, n_epochs=1, batch_size=args.fit_batch, lam_mds=100.0, verbose=False)  # warm-up epoch
+        model.fit(xf, n_epochs=1, batch_size=args.fit_batch, lam_mds=100.0, verbose=False)  # upload, capture, warm-up
         torch.cuda.synchronize()
         l0 = _lib.launch_count()
         t0 = time.perf_counter()
-        model.fit(xf, n_epochs=args.fit_epochs, batch_size=args.fit_batch, lam_mds=100.0, verbose=False)
+        for _ in range(args.fit_epochs):  # the epochs fit() runs after its one-off set-up (reference: model.py:258-270)
+            model.train_epoch(lam_mds=100.0)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / args.fit_epochs
         fit = {"rows": rows, "batch_size": args.fit_batch, "s_per_epoch": dt, "cells_per_s": rows / dt,
+               "epochs_timed": args.fit_epochs,
                "quartet_kernel_launches_per_epoch": (_lib.launch_count() - l0) / args.fit_epochs}
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
@@ -454,7 +456,7 @@ def main():
     ap.add_argument("--device-data", action="store_true")
     ap.add_argument("--fit-rows", type=int, default=200_000)
     ap.add_argument("--fit-batch", type=int, default=512)
-    ap.add_argument("--fit-epochs", type=int, default=1)
+    ap.add_argument("--fit-epochs", type=int, default=3)
     ap.add_argument("--cpu-knn-queries", type=int, default=4096)
     ap.add_argument("--cpu-smooth-rows", type=int, default=200_000)
     args = ap.parse_args()

@@ -535,3 +535,9 @@ def test_cell_sweep_skips_far_clusters_and_stays_exact(monkeypatch):
         wi, wd = orc.knn(x, 50, q0, q0 + 400)
         assert np.array_equal(idx[q0:q0 + 400], wi) and np.array_equal(dist[q0:q0 + 400], wd)
     print("tiles swept / dense:", st["tiles_swept"], st["tiles_dense"], "fallback rows:", st["rows_fallback"])
+    # a query-row shard that starts and ends in the middle of cells (C ABI: q0, nq)
+    from vivae_b200.knn import _knn_host
+
+    q0, nq = 77_777, 3_001
+    si, sd = _knn_host(x, 50, q0, nq, "tensor", None)
+    assert np.array_equal(si, idx[q0:q0 + nq]) and np.array_equal(sd, dist[q0:q0 + nq])

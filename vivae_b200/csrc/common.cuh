@@ -323,6 +323,43 @@ __device__ __forceinline__ float warp_select_truncate_pairs(uint2 *list, int cnt
   *new_cnt = base;
   return ord2f(cut);
 }
+
+// ---- m-th smallest of a list of floats: threshold only ------------------------------------
+// Returns a value tau with  count(keys < tau) >= m  (and at most m + slack such keys when the search
+// stops early, exactly the m-th smallest key's successor otherwise).  Requires cnt >= m.  No list is
+// rewritten: this serves the threshold pre-pass of the screening kernel, where only the value matters.
+template <int E>
+__device__ __forceinline__ float warp_select_threshold(const float *keys, int cnt, int m, int slack, int lane) {
+  uint32_t u[E];
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int p = e * 32 + lane;
+    u[e] = (p < cnt) ? f2ord(keys[p]) : 0xffffffffu;
+  }
+  uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const bool valid = e * 32 + lane < cnt;
+    lo = valid ? min(lo, u[e]) : lo;
+    hi = valid ? max(hi, u[e]) : hi;
+  }
+  lo = __reduce_min_sync(FULL, lo);
+  hi = __reduce_max_sync(FULL, hi);
+  const int top = 31 - __clz(static_cast<int>((lo ^ hi) | 1u));
+  uint32_t T = (top >= 31) ? 0u : (lo & ~((2u << top) - 1u));  // invariant: count(u < T) < m
+  for (int b = top; b >= 0; --b) {
+    const uint32_t trial = T | (1u << b);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c += (u[e] < trial) ? 1 : 0;
+    c = __reduce_add_sync(FULL, c);
+    if (c < m) T = trial;
+    else if (c <= m + slack) return ord2f(trial);
+  }
+  // T is the m-th smallest key itself: count(u < T) < m <= count(u <= T)
+  return (T < 0xff800000u) ? ord2f(T + 1u) : ord2f(T);
+}
 #endif  // __CUDACC__
 
 }  // namespace vvb

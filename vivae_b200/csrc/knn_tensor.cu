@@ -72,7 +72,8 @@ constexpr int TC_KSTAGES = 2;        // K-loop variant: (query + database) atom 
 constexpr float TC_PAD_NORM = 60000.0f;  // squared "norm" of padding rows: their keys stay above TC_PAD_CUT
 constexpr float TC_PAD_CUT = 30000.0f;   // real keys are below 64^2 + 2 * 64 * 64
 constexpr int TC_RING = 16;              // tile-sequence ring (producer runs at most stages + slots tiles ahead)
-constexpr int TC_PRE_TILES = TC_CAP;     // threshold pre-pass: tiles whose minima seed the admission thresholds
+constexpr int TC_PRE_TILES = 2 * TC_CAP;  // threshold pre-pass: at most this many tiles (their minima, one float each,
+                                          // are kept in the row's 2 KB list buffer)
 constexpr int TC_PRE_MAX_KA = 2;         // ... only where the epilogue, not the MMA, bounds the sweep (d + 3 <= 128)
 constexpr int TC_SEQ_END = -1;           // tile_seq markers
 constexpr int TC_SEQ_PRE_END = -2;
@@ -356,6 +357,9 @@ __global__ void __launch_bounds__(256) build_operands_kernel(const float *__rest
 // Out-of-line list maintenance, so that the hot screening loop stays small in the instruction
 // cache.  In-sweep compaction uses the cheap threshold selection; the full sort runs once per
 // row at the end of the sweep.
+__device__ __noinline__ float tc_select_threshold(const float *keys, int cnt, int m, int lane) {
+  return warp_select_threshold<2 * TC_CAP_E>(keys, cnt, m, 3, lane);
+}
 __device__ __noinline__ float tc_select_truncate(uint2 *list, int cnt, int keep, int keep_max, int lane, int *new_cnt) {
   return warp_select_truncate_pairs<TC_CAP_E>(list, cnt, keep, keep_max, lane, new_cnt);
 }
@@ -812,11 +816,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
           for (int src = 0; src < 32; ++src) {
             const int64_t tt = __shfl_sync(FULL, t_row, src);
             if (tt >= p.nq) continue;  // warp-uniform
-            int nc;
-            const int km = (p.keep + 24 < n_pre) ? p.keep + 24 : n_pre;
             const float thr =
-                tc_select_truncate(p.cand + tt * TC_CAP, n_pre, p.keep, km, lane, &nc);
-            if (lane == src) tau = (thr < inf) ? ord2f(f2ord(thr) + 1u) : inf;
+                tc_select_threshold(reinterpret_cast<const float *>(p.cand + tt * TC_CAP), n_pre, p.keep, lane);
+            if (lane == src) tau = thr;  // at least m of the recorded minima are strictly below it
           }
           const unsigned m = __reduce_max_sync(FULL, f2ord(tau + xn));
           if (lane == 0) tau_pub[ew] = ord2f(m);
@@ -849,7 +851,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
         fold(ra);
         fold(rb);
-        if (active) cl[n_pre] = make_uint2(__float_as_uint(tmin), 0u);
+        if (active) reinterpret_cast<float *>(cl)[n_pre] = tmin;
         ++n_pre;
       } else if (p.debug_mode == 3) {  // profiling only: hand the accumulator straight back (MMA/TMA rate alone)
         tc_fence_before();
@@ -1298,9 +1300,11 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   mark(1);
   const unsigned rr_grid = static_cast<unsigned>((nq + 7) / 8);
   const int e_need = (S->keep + 31) / 32;
+  const char *rrw = getenv("VVB_RR_WIDE_MIN");
+  const int rr_wide_min = rrw ? atoi(rrw) : 32;  // measured at d = 50: 5.8 ms staged vs 6.3 ms direct per 1M rows
 #define VVB_RR(EE)                                                                                                    \
   do {                                                                                                                \
-    if (S->d >= 128)                                                                                                  \
+    if (S->d >= rr_wide_min)                                                                                                \
       knn_rerank_kernel<EE, true><<<rr_grid, 256, 0, st>>>(S->x, S->n, S->d, q0, nq, S->k, L.qlist, L.cells.perm,    \
                                                            L.cand, L.cand_cnt, L.cand_thr, L.xnorm, L.scalars,   \
                                                            out_idx, out_dist, L.fb_count, L.fb_rows);               \
