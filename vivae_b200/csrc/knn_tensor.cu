@@ -416,11 +416,12 @@ struct TcParams {
 // hold a key at or below it -- and a tight one, because the m nearest rows of a query are spread over
 // almost as many tiles.  The real sweep then starts at that threshold: ~100 insertions per row, rarely a
 // compaction.  Exactness never depends on it (a threshold is only ever an upper bound of the m-th key).
-template <bool KLOOP>
+template <bool KLOOP, bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
                                                                    const TcParams p) {
   constexpr int NSLOT = KLOOP ? 4 : 3;
+  const int dbg_mode = DBG ? p.debug_mode : 0;  // the profiling modes live in their own instantiation
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 128B swizzle needs 1024-byte aligned atoms
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   const int lane = threadIdx.x & 31;
   const int64_t q_base = static_cast<int64_t>(blockIdx.x) * TC_M;  // first query-list entry of this CTA
   auto stamp = [&](int i) {
-    if (p.times && warp == 4 && lane == 0) p.times[blockIdx.x * 8 + i] = clock64();
+    if (DBG && p.times && warp == 4 && lane == 0) p.times[blockIdx.x * 8 + i] = clock64();
   };
   stamp(0);
 
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   stamp(1);
-  const bool pre_pass = p.debug_mode == 0 && p.ka <= TC_PRE_MAX_KA;
+  const bool pre_pass = dbg_mode == 0 && p.ka <= TC_PRE_MAX_KA;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -733,7 +734,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     // One 32-column chunk: make room, then screen.  The chunk is reduced to four group minima
     // (8 columns each) with 3-input min instructions; only groups that beat tau are expanded.
     auto process = [&](const uint32_t(&r)[32], int j0) {
-      if (p.debug_mode == 1) {
+      if (dbg_mode == 1) {
         if (__uint_as_float(r[0]) == 123.456f && __uint_as_float(r[31]) == 1.5f) tau = 0.f;  // keep the load alive
         return;
       }
@@ -768,7 +769,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       }
       const float mn = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
       const float cut = fminf(tau, TC_PAD_CUT);  // padding rows of the database carry a huge norm
-      if (mn < cut && p.debug_mode != 2) {
+      if (mn < cut && dbg_mode != 2) {
         auto ins = [&](int c) {
           if (__uint_as_float(r[c]) < cut) {
             cl[cnt] = make_uint2(r[c], static_cast<uint32_t>(j0 + c));  // one 8-byte store
@@ -853,7 +854,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         fold(rb);
         if (active) reinterpret_cast<float *>(cl)[n_pre] = tmin;
         ++n_pre;
-      } else if (p.debug_mode == 3) {  // profiling only: hand the accumulator straight back (MMA/TMA rate alone)
+      } else if (dbg_mode == 3) {  // profiling only: hand the accumulator straight back (MMA/TMA rate alone)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
@@ -1179,9 +1180,13 @@ int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, in
   S->L = tc_layout(workspace, n, d, k, chunk_rows);
   VVB_REQUIRE(workspace_bytes >= S->L.total, "tensor kNN: workspace too small (%zu < %zu)", workspace_bytes,
               S->L.total);
-  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(TC_SMEM_BYTES)));
-  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(TC_SMEM_BYTES_K)));
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(TC_SMEM_BYTES)));
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(TC_SMEM_BYTES_K)));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (stats) {
@@ -1278,8 +1283,11 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   p.cand_cnt = L.cand_cnt;
   p.cand_thr = L.cand_thr;
   const unsigned sgrid = static_cast<unsigned>(nq_pad / TC_M);
-  if (L.ka == 1) knn_screen_kernel<false><<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, p);
-  else knn_screen_kernel<true><<<sgrid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, p);
+  const bool dbg = p.debug_mode != 0 || p.times != nullptr;
+  if (L.ka == 1 && !dbg) knn_screen_kernel<false, false><<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, p);
+  else if (L.ka == 1) knn_screen_kernel<false, true><<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, p);
+  else if (!dbg) knn_screen_kernel<true, false><<<sgrid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, p);
+  else knn_screen_kernel<true, true><<<sgrid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, p);
   VVB_CHECK_LAUNCH();
   if (want_times) {  // profiling only: mean duration of the phases of a CTA, in SM clocks
     const size_t nc = static_cast<size_t>(nq_pad / TC_M);
