@@ -360,6 +360,59 @@ __device__ __forceinline__ float warp_select_threshold(const float *keys, int cn
   // T is the m-th smallest key itself: count(u < T) < m <= count(u <= T)
   return (T < 0xff800000u) ? ord2f(T + 1u) : ord2f(T);
 }
+
+// ---- the same for several rows in a row: the keys of row r+1 are fetched while row r is searched ----------
+// keys of row r: base + r * stride (floats), `cnt` of them (cnt >= m); out[r] = threshold, r in [r0, r1).
+template <int E>
+__device__ __forceinline__ void warp_select_threshold_rows(const float *base, size_t stride, int r0, int r1, int cnt,
+                                                           int m, int slack, int lane, float *out) {
+  if (r0 >= r1) return;
+  uint32_t u[E], un[E];
+  auto fetch = [&](int r, uint32_t(&dst)[E]) {
+    const float *keys = base + static_cast<size_t>(r) * stride;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int p = e * 32 + lane;
+      dst[e] = (p < cnt) ? f2ord(keys[p]) : 0xffffffffu;
+    }
+  };
+  fetch(r0, un);
+  for (int r = r0; r < r1; ++r) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) u[e] = un[e];
+    if (r + 1 < r1) fetch(r + 1, un);
+    uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const bool valid = e * 32 + lane < cnt;
+      lo = valid ? min(lo, u[e]) : lo;
+      hi = valid ? max(hi, u[e]) : hi;
+    }
+    lo = __reduce_min_sync(FULL, lo);
+    hi = __reduce_max_sync(FULL, hi);
+    const int top = 31 - __clz(static_cast<int>((lo ^ hi) | 1u));
+    uint32_t T = (top >= 31) ? 0u : (lo & ~((2u << top) - 1u));  // invariant: count(u < T) < m
+    uint32_t res = 0u;
+    bool found = false;
+    for (int b = top; b >= 0; --b) {
+      const uint32_t trial = T | (1u << b);
+      int c = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) c += (u[e] < trial) ? 1 : 0;
+      c = __reduce_add_sync(FULL, c);
+      if (c < m) {
+        T = trial;
+      } else if (c <= m + slack) {
+        res = trial;
+        found = true;
+        break;
+      }
+    }
+    if (!found) res = (T < 0xff800000u) ? T + 1u : T;  // T is the m-th smallest key itself
+    if (lane == 0) out[r] = ord2f(res);
+  }
+  __syncwarp();
+}
 #endif  // __CUDACC__
 
 }  // namespace vvb

@@ -63,7 +63,7 @@ int launch_knn_brute_few(const float *x_dev, int64_t n, int d, int k, const int6
 constexpr int TC_M = 256;            // query rows per CTA
 constexpr int TC_N = 128;            // database rows per tile
 constexpr int TC_STAGES = 4;         // database-tile ring
-constexpr int TC_THREADS = 384;      // 4 control warps + 8 epilogue warps
+constexpr int TC_THREADS = 640;      // 4 control warps + 16 epilogue warps
 constexpr int TC_ATOM_BYTES = 128 * 128;  // 128 rows x 64 fp16 (one 128B-swizzle K atom)
 constexpr int TC_CAP_E = 8;          // candidate list capacity = 32 * 8 = 256
 constexpr int TC_CAP = 32 * TC_CAP_E;
@@ -72,15 +72,16 @@ constexpr int TC_KSTAGES = 2;        // K-loop variant: (query + database) atom 
 constexpr float TC_PAD_NORM = 60000.0f;  // squared "norm" of padding rows: their keys stay above TC_PAD_CUT
 constexpr float TC_PAD_CUT = 30000.0f;   // real keys are below 64^2 + 2 * 64 * 64
 constexpr int TC_RING = 16;              // tile-sequence ring (producer runs at most stages + slots tiles ahead)
-constexpr int TC_PRE_TILES = 2 * TC_CAP;  // threshold pre-pass: at most this many tiles (their minima, one float each,
-                                          // are kept in the row's 2 KB list buffer)
+constexpr int TC_PRE_TILES = TC_CAP;     // threshold pre-pass: at most this many tiles (two half-tile minima each, one
+                                         // float per minimum, kept in the row's first 2 KB list buffer)
 constexpr int TC_PRE_MAX_KA = 2;         // ... only where the epilogue, not the MMA, bounds the sweep (d + 3 <= 128)
 constexpr int TC_SEQ_END = -1;           // tile_seq markers
 constexpr int TC_SEQ_PRE_END = -2;
 constexpr float TC_EPS = 1.0f / 131072.0f;  // 2^-17: 26x the measured screening error (2^-21.7), ~5x its analytic bound
 
 constexpr size_t TC_SMEM_B = TC_STAGES * 2 * TC_ATOM_BYTES;           // [stage][atom]
-constexpr size_t TC_SMEM_TAIL = 256 /*barriers*/ + 8 * CELL_MAX /*cell order*/ + 4 * TC_RING + 64 /*tau*/;
+constexpr size_t TC_SMEM_TAIL = 256 /*barriers*/ + 8 * CELL_MAX /*cell order*/ + 4 * TC_RING + 64 /*tau*/ +
+                                5 * TC_M * 4 /*per-row hand-over between the two warps of a row*/;
 constexpr size_t TC_SMEM_BYTES = TC_SMEM_B + 1024 /*align*/ + TC_SMEM_TAIL;
 constexpr int TC_TMEM_A = 384;       // resident variant: first TMEM column of the query operand (2 x 64 columns)
 // K-loop variant: every stage holds one K atom of everything: query hi/lo for both M blocks + database hi/lo
@@ -357,8 +358,13 @@ __global__ void __launch_bounds__(256) build_operands_kernel(const float *__rest
 // Out-of-line list maintenance, so that the hot screening loop stays small in the instruction
 // cache.  In-sweep compaction uses the cheap threshold selection; the full sort runs once per
 // row at the end of the sweep.
-__device__ __noinline__ float tc_select_threshold(const float *keys, int cnt, int m, int lane) {
-  return warp_select_threshold<2 * TC_CAP_E>(keys, cnt, m, 3, lane);
+__device__ __noinline__ void tc_select_threshold_rows(const float *base, int r0, int r1, int cnt, int m, int lane,
+                                                      float *out) {
+  warp_select_threshold_rows<2 * TC_CAP_E>(base, 2 * TC_CAP * 2, r0, r1, cnt, m, 3, lane, out);
+}
+__device__ __noinline__ float tc_select_truncate_wide(uint2 *list, int cnt, int keep, int keep_max, int lane,
+                                                      int *new_cnt) {  // up to 2 * TC_CAP entries
+  return warp_select_truncate_pairs<2 * TC_CAP_E>(list, cnt, keep, keep_max, lane, new_cnt);
 }
 __device__ __noinline__ float tc_select_truncate(uint2 *list, int cnt, int keep, int keep_max, int lane, int *new_cnt) {
   return warp_select_truncate_pairs<TC_CAP_E>(list, cnt, keep, keep_max, lane, new_cnt);
@@ -438,7 +444,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
   unsigned long long *order = reinterpret_cast<unsigned long long *>(tail);             // [CELL_MAX] (bound, cell)
   volatile int *tile_seq = reinterpret_cast<volatile int *>(tail + 8 * CELL_MAX);       // [TC_RING]
-  volatile float *tau_pub = reinterpret_cast<volatile float *>(tail + 8 * CELL_MAX + 4 * TC_RING);  // [8]
+  volatile float *tau_pub = reinterpret_cast<volatile float *>(tail + 8 * CELL_MAX + 4 * TC_RING);  // [16]
+  float *row_tau = reinterpret_cast<float *>(tail + 8 * CELL_MAX + 4 * TC_RING + 64);  // [TC_M] pre-pass threshold
+  int *half_cnt = reinterpret_cast<int *>(row_tau + TC_M);                            // [2][TC_M] final list lengths
+  float *half_tau = reinterpret_cast<float *>(half_cnt + 2 * TC_M);                   // [2][TC_M] final thresholds
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -460,7 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     }
     for (int b = 0; b < 4; ++b) {
       mbar_init(bar_acc_full + 8 * b, 1);
-      mbar_init(bar_acc_empty + 8 * b, 4);  // one arrival per epilogue warp of the M block
+      mbar_init(bar_acc_empty + 8 * b, 8);  // one arrival per epilogue warp of the M block
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -469,7 +478,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x < 8) tau_pub[threadIdx.x] = __int_as_float(0x7f800000);
+  if (threadIdx.x < 16) tau_pub[threadIdx.x] = __int_as_float(0x7f800000);
 
   // ---- cell order of this CTA: bound(b) = min over the cells a of its rows of lb(a, b), sorted ascending
   const int P = p.n_cells;
@@ -552,7 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         if (pass == 1 && bound > 0.0f) {
           float tmax = tau_pub[0];
 #pragma unroll
-          for (int w = 1; w < 8; ++w) tmax = fmaxf(tmax, tau_pub[w]);
+          for (int w = 1; w < 16; ++w) tmax = fmaxf(tmax, tau_pub[w]);
           if (bound * bound >= tmax + eps_max) break;  // ascending order: every later cell is at least as far
         }
         const int row_end = p.cell_off[b + 1];
@@ -693,35 +702,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     }
   } else if (warp >= 4) {
     // =========================== epilogue: fused per-row top-m ===========================
-    const int ew = warp - 4;          // 0..7
-    const int quad = warp & 3;        // TMEM lane quadrant this warp may access
-    const int mb = ew >> 2;           // which M=128 block
-    const int64_t t_row = q_base + mb * 128 + quad * 32 + lane;  // query-list entry owned by this thread
+    // 16 warps: a query row is owned by TWO threads (same lane of two warps of the same TMEM quadrant), one per
+    // 64-column half of every database tile, each with its own candidate list, list length and threshold
+    // (four epilogue warps per scheduler hide the dependent-issue latency of the list handling better than
+    // two).  The halves meet twice: at the end of the pre-pass (one common threshold per row) and at the end of
+    // the sweep (the second list is appended to the first); each warp of a pair serves 16 of the 32 rows there.
+    const int ew = warp - 4;           // 0..15
+    const int quad = warp & 3;         // TMEM lane quadrant this warp may access
+    const int mb = (ew >> 2) & 1;      // which M=128 block
+    const int half = ew >> 3;          // which 64 columns of every tile
+    const int prow = mb * 128 + quad * 32 + lane;  // row within the CTA
+    const int64_t t_row = q_base + prow;           // query-list entry owned by this thread
     const bool active = t_row < p.nq;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int pair_bar = 1 + (ew & 7);  // named barrier of the two warps that own the same 32 rows
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
     if constexpr (!KLOOP) {
-      // this thread's query operand row -> tensor memory: 64 words = [hi: 32 columns | lo: 32 columns],
-      // two fp16 per 32-bit column (K index 2c in the low half), which is the A-operand layout of kind::f16
-      const uint4 *src = reinterpret_cast<const uint4 *>(p.op_a + t_row * 64);
-      uint32_t w[32];
+      if (half == 0) {
+        // this thread's query operand row -> tensor memory: 64 words = [hi: 32 columns | lo: 32 columns],
+        // two fp16 per 32-bit column (K index 2c in the low half), which is the A-operand layout of kind::f16
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.op_a + t_row * 64);
+        uint32_t w[32];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          const uint4 q4 = __ldg(src + h * 8 + v);
-          w[4 * v + 0] = q4.x;
-          w[4 * v + 1] = q4.y;
-          w[4 * v + 2] = q4.z;
-          w[4 * v + 3] = q4.w;
+          for (int v = 0; v < 8; ++v) {
+            const uint4 q4 = __ldg(src + h * 8 + v);
+            w[4 * v + 0] = q4.x;
+            w[4 * v + 1] = q4.y;
+            w[4 * v + 2] = q4.z;
+            w[4 * v + 3] = q4.w;
+          }
+          tc_st32(t_lane + static_cast<uint32_t>(TC_TMEM_A + mb * 64 + h * 32), w);
         }
-        tc_st32(t_lane + static_cast<uint32_t>(TC_TMEM_A + mb * 64 + h * 32), w);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a_full);
       }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_a_full);
     }
-    uint2 *cl = p.cand + t_row * TC_CAP;  // this row's candidate list
+    uint2 *cl = p.cand + (t_row * 2 + half) * TC_CAP;  // this thread's candidate list
+    uint2 *warp_lists = p.cand + ((q_base + mb * 128 + quad * 32) * 2 + half) * TC_CAP;  // + 2 * TC_CAP per lane
     const float inf = __int_as_float(0x7f800000);
     float tau = active ? inf : -inf;
     const float xn = active ? p.xnorm[t_row] : 0.0f;
@@ -731,8 +752,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       if (lane == 0) tau_pub[ew] = ord2f(m0);
     }
 
-    // One 32-column chunk: make room, then screen.  The chunk is reduced to four group minima
-    // (8 columns each) with 3-input min instructions; only groups that beat tau are expanded.
+    // One 32-column chunk: make room, then screen.
     auto process = [&](const uint32_t(&r)[32], int j0) {
       if (dbg_mode == 1) {
         if (__uint_as_float(r[0]) == 123.456f && __uint_as_float(r[31]) == 1.5f) tau = 0.f;  // keep the load alive
@@ -743,11 +763,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         while (need) {
           const int src = __ffs(need) - 1;
           need &= need - 1;
-          const int64_t tt = __shfl_sync(FULL, t_row, src);
           const int c = __shfl_sync(FULL, cnt, src);
           int nc;
-          const float thr =
-              tc_select_truncate(p.cand + tt * TC_CAP, c, p.keep, p.trigger, lane, &nc);
+          const float thr = tc_select_truncate(warp_lists + src * 2 * TC_CAP, c, p.keep, p.trigger, lane, &nc);
           if (lane == src) {
             cnt = nc;
             tau = thr;
@@ -757,18 +775,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         const unsigned m = __reduce_max_sync(FULL, f2ord(tau + xn));  // inactive rows: -inf
         if (lane == 0) tau_pub[ew] = ord2f(m);
       }
-      // minima of 3 + 3 + 2 columns, of the groups of 8 and of the chunk; a hit is then located by
-      // descending that tree, so that one insertion costs ~20 instructions of divergent code, not ~60
-      float sa[4], sb[4], sc[4], g[4];
+      // minima of 3 + 3 + 2 columns, of the groups of 8 and of the chunk; a hit is located by descending that tree
+      const float cut = fminf(tau, TC_PAD_CUT);  // padding rows of the database carry a huge norm
+      float g[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        sa[q] = fminf(fminf(__uint_as_float(r[8 * q + 0]), __uint_as_float(r[8 * q + 1])), __uint_as_float(r[8 * q + 2]));
-        sb[q] = fminf(fminf(__uint_as_float(r[8 * q + 3]), __uint_as_float(r[8 * q + 4])), __uint_as_float(r[8 * q + 5]));
-        sc[q] = fminf(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7]));
-        g[q] = fminf(fminf(sa[q], sb[q]), sc[q]);
+        const float a = fminf(fminf(__uint_as_float(r[8 * q + 0]), __uint_as_float(r[8 * q + 1])), __uint_as_float(r[8 * q + 2]));
+        const float b = fminf(fminf(__uint_as_float(r[8 * q + 3]), __uint_as_float(r[8 * q + 4])), __uint_as_float(r[8 * q + 5]));
+        g[q] = fminf(fminf(a, b), fminf(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
       }
       const float mn = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
-      const float cut = fminf(tau, TC_PAD_CUT);  // padding rows of the database carry a huge norm
       if (mn < cut && dbg_mode != 2) {
         auto ins = [&](int c) {
           if (__uint_as_float(r[c]) < cut) {
@@ -779,20 +795,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (g[q] < cut) {
-            if (sa[q] < cut) {
+            if (fminf(fminf(__uint_as_float(r[8 * q + 0]), __uint_as_float(r[8 * q + 1])), __uint_as_float(r[8 * q + 2])) < cut) {
               ins(8 * q + 0);
               ins(8 * q + 1);
               ins(8 * q + 2);
             }
-            if (sb[q] < cut) {
+            if (fminf(fminf(__uint_as_float(r[8 * q + 3]), __uint_as_float(r[8 * q + 4])), __uint_as_float(r[8 * q + 5])) < cut) {
               ins(8 * q + 3);
               ins(8 * q + 4);
               ins(8 * q + 5);
             }
-            if (sc[q] < cut) {
-              ins(8 * q + 6);
-              ins(8 * q + 7);
-            }
+            ins(8 * q + 6);
+            ins(8 * q + 7);
           }
         }
       }
@@ -801,26 +815,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     int slot = mb % NSLOT;
     uint32_t use_par = 0;  // parity of (it / NSLOT), it = 2 t + mb
     bool in_pre = pre_pass;
-    int n_pre = 0;  // tile minima recorded by the pre-pass (row-major in this row's list buffer)
+    int n_pre = 0;  // tiles recorded by the pre-pass: half-tile minima at [2 n + half] of the row's first list buffer
+    float *pre_buf = reinterpret_cast<float *>(p.cand + t_row * 2 * TC_CAP);
     for (int t = 0;; ++t) {
       mbar_wait(bar_acc_full + 8 * slot, use_par);
       const int jt = tile_seq[t % TC_RING];  // first (permuted) database row of the tile, or a marker
       if (jt == TC_SEQ_END) break;
       if (t == 0) stamp(2);
       tc_fence_after();
-      const uint32_t t_acc = t_lane + static_cast<uint32_t>(slot * TC_N);
+      const uint32_t t_acc = t_lane + static_cast<uint32_t>(slot * TC_N + half * 64);
+      uint32_t ra[32];
       if (jt == TC_SEQ_PRE_END) {
         stamp(3);
-        // end of the pre-pass: starting threshold = m-th smallest tile minimum (just above it, so that
-        // the strict admission test cannot lose a tie)
-        if (n_pre >= p.keep) {
-          for (int src = 0; src < 32; ++src) {
-            const int64_t tt = __shfl_sync(FULL, t_row, src);
-            if (tt >= p.nq) continue;  // warp-uniform
-            const float thr =
-                tc_select_threshold(reinterpret_cast<const float *>(p.cand + tt * TC_CAP), n_pre, p.keep, lane);
-            if (lane == src) tau = thr;  // at least m of the recorded minima are strictly below it
-          }
+        // end of the pre-pass: one starting threshold per row from the 2 n_pre half-tile minima both warps
+        // recorded; each warp of the pair selects for 16 of the 32 rows
+        if (half == 0) row_tau[prow] = tau;
+        pair_sync();
+        if (2 * n_pre >= p.keep) {
+          // rows of this warp pair that exist: the query list is padded at its end only
+          const int64_t first = q_base + mb * 128 + quad * 32;
+          const int nv = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(32), p.nq - first)));
+          // (at least m of a row's recorded minima are strictly below the threshold written for it)
+          tc_select_threshold_rows(reinterpret_cast<const float *>(p.cand + first * 2 * TC_CAP), half * 16,
+                                   min(half * 16 + 16, nv), 2 * n_pre, p.keep, lane,
+                                   row_tau + mb * 128 + quad * 32);
+        }
+        pair_sync();
+        tau = row_tau[prow];
+        {
           const unsigned m = __reduce_max_sync(FULL, f2ord(tau + xn));
           if (lane == 0) tau_pub[ew] = ord2f(m);
         }
@@ -829,56 +851,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
       } else if (in_pre) {
-        // pre-pass tile: minimum key of the tile for this row, nothing else
-        uint32_t ra[32], rb[32];
-        tc_ld32_issue(t_acc, ra);
-        tc_ld32_issue(t_acc + 32, rb);
+        // pre-pass tile: minimum key of this thread's 64 columns, nothing else
         float tmin = inf;
         auto fold = [&](const uint32_t(&r)[32]) {
 #pragma unroll
           for (int q = 0; q < 32; q += 2)
             tmin = fminf(fminf(__uint_as_float(r[q]), __uint_as_float(r[q + 1])), tmin);
         };
+        tc_ld32_issue(t_acc, ra);
         tc_ld32_wait(ra);
-        tc_ld32_wait(rb);
         fold(ra);
-        tc_ld32_issue(t_acc + 64, ra);
-        fold(rb);
-        tc_ld32_issue(t_acc + 96, rb);
+        tc_ld32_issue(t_acc + 32, ra);
         tc_ld32_wait(ra);
-        tc_ld32_wait(rb);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
         fold(ra);
-        fold(rb);
-        if (active) reinterpret_cast<float *>(cl)[n_pre] = tmin;
+        if (active) pre_buf[2 * n_pre + half] = tmin;
         ++n_pre;
       } else if (dbg_mode == 3) {  // profiling only: hand the accumulator straight back (MMA/TMA rate alone)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
       } else {
-        // software pipeline over the four chunks: the TMEM load of chunk c+1 is in flight while
-        // chunk c is screened
-        uint32_t ra[32], rb[32];
         tc_ld32_issue(t_acc, ra);
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          tc_ld32_wait(ra);
-          tc_ld32_issue(t_acc + half * 64 + 32, rb);
-          process(ra, jt + half * 64);
-          tc_ld32_wait(rb);
-          if (half == 0) {
-            tc_ld32_issue(t_acc + 64, ra);
-          } else {
-            // accumulator fully drained into registers: hand it back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
-          }
-          process(rb, jt + half * 64 + 32);
-        }
+        tc_ld32_wait(ra);
+        process(ra, jt + half * 64);
+        tc_ld32_issue(t_acc + 32, ra);
+        tc_ld32_wait(ra);
+        // accumulator half fully drained into registers: hand it back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
+        process(ra, jt + half * 64 + 32);
       }
       // it += 2
       slot += 2;
@@ -887,23 +892,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         use_par ^= 1;
       }
     }
-    // final: keep the best m of every row's list, publish count and threshold
+    // final: the second half's list is appended to the first, the best m are kept, count and threshold published
     stamp(5);
-    for (int src = 0; src < 32; ++src) {
+    half_cnt[half * TC_M + prow] = cnt;
+    half_tau[half * TC_M + prow] = tau;
+    pair_sync();
+    for (int src = half * 16; src < half * 16 + 16; ++src) {
       const int64_t tt = __shfl_sync(FULL, t_row, src);
-      const int c = __shfl_sync(FULL, cnt, src);
-      const float tau_src = __shfl_sync(FULL, tau, src);
       if (tt >= p.nq) continue;  // warp-uniform
-      // keep the m smallest (up to a whole number of 32-entry groups: the re-rank kernel sorts by the exact
-      // distance anyway, so a cheap threshold selection replaces the full sort of the list)
-      const int keep_max = min((p.keep + 31) & ~31, p.keep + 8);  // every extra candidate is a 200-byte gather in the re-rank
+      const int pr = mb * 128 + quad * 32 + src;
+      const int ca = half_cnt[pr], cb = half_cnt[TC_M + pr];
+      uint2 *la = p.cand + tt * 2 * TC_CAP, *lb = la + TC_CAP;
+      // every rejected entry has key >= the threshold in force in its half when it was rejected >= that half's
+      // final tau, and every row of a cell the sweep skipped has key >= both
+      float thr = fminf(half_tau[pr], half_tau[TC_M + pr]);
+      // the row's two buffers are contiguous: append the second list right behind the first (the copy may
+      // run into the second buffer's own head, which has been read by then)
+      for (int i0 = 0; i0 < cb; i0 += 32) {
+        uint2 v = make_uint2(0u, 0u);
+        if (i0 + lane < cb) v = lb[i0 + lane];
+        __syncwarp();
+        if (i0 + lane < cb) la[ca + i0 + lane] = v;
+        __syncwarp();
+      }
+      const int c = ca + cb;
+      // keep the m smallest and at most 8 more: the re-rank kernel sorts by the exact distance anyway, so a
+      // cheap threshold selection replaces a sort, and every extra candidate is a 200-byte gather there
+      const int keep_max = min((p.keep + 31) & ~31, p.keep + 8);
       int nc = c;
-      float thr = inf;
-      if (c > keep_max) thr = tc_select_truncate(p.cand + tt * TC_CAP, c, p.keep, keep_max, lane, &nc);
-      // every rejected entry has key >= the threshold in force when it was rejected >= tau_src, and every
-      // row of a cell the sweep skipped has key >= the row's tau at that moment >= tau_src;
-      // with fewer than `keep` entries the sort has no keep-th key and tau_src is the bound
-      thr = fminf(thr, tau_src);
+      if (c > TC_CAP) thr = fminf(thr, tc_select_truncate_wide(la, c, p.keep, keep_max, lane, &nc));
+      else if (c > keep_max) thr = fminf(thr, tc_select_truncate(la, c, p.keep, keep_max, lane, &nc));
       if (lane == 0) {
         p.cand_cnt[tt] = nc;
         p.cand_thr[tt] = thr;
@@ -952,7 +970,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
     float acc = 0.0f;
     if (!WIDE) {
       if (pos < cnt) {
-        j = static_cast<uint32_t>(perm[cand[t * TC_CAP + pos].y]);
+        j = static_cast<uint32_t>(perm[cand[t * 2 * TC_CAP + pos].y]);
         const float *y = x + static_cast<int64_t>(j) * d;
         for (int c = 0; c < d; ++c) {  // the contract's chain: left to right, one rounding per fmaf
           const float df = __fsub_rn(__ldg(xq + c), __ldg(y + c));
@@ -961,7 +979,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
       }
     } else {
       if (e * 32 < cnt) {  // warp-uniform: this group of 32 candidates is not empty
-        if (pos < cnt) j = static_cast<uint32_t>(perm[cand[t * TC_CAP + pos].y]);
+        if (pos < cnt) j = static_cast<uint32_t>(perm[cand[t * 2 * TC_CAP + pos].y]);
         const int in_group = min(32, cnt - e * 32);
         for (int c0 = 0; c0 < d; c0 += 32) {
           const float xv = (c0 + lane < d) ? __ldg(xq + c0 + lane) : 0.0f;
@@ -1127,10 +1145,10 @@ static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
   L.cand_thr = cv.take<float>(static_cast<size_t>(L.chunk_pad));
   L.fb_count = cv.take<int>(1);
   L.fb_rows = cv.take<int64_t>(static_cast<size_t>(L.chunk_pad));
-  L.cand = cv.take<uint2>(static_cast<size_t>(L.chunk_pad) * TC_CAP);
+  L.cand = cv.take<uint2>(static_cast<size_t>(L.chunk_pad) * 2 * TC_CAP);  // two lists per row (one per column half)
   // the fallback's candidate lists reuse the screening lists (dead after the re-rank)
   L.brute_ws = L.cand;
-  L.brute_ws_bytes = static_cast<size_t>(L.chunk_pad) * TC_CAP * 8;
+  L.brute_ws_bytes = static_cast<size_t>(L.chunk_pad) * 2 * TC_CAP * 8;
   size_t need_brute = brute_workspace_bytes(chunk, k);
   if (knn_brute_few_workspace_bytes(k) > need_brute) need_brute = knn_brute_few_workspace_bytes(k);
   if (need_brute > L.brute_ws_bytes) {  // never for the supported k, kept for safety
@@ -1394,7 +1412,7 @@ int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, i
   }
   if (!rc) {
     TcLayout &L = reinterpret_cast<TcSession *>(session)->L;
-    std::vector<uint2> cl(static_cast<size_t>(nq) * TC_CAP);
+    std::vector<uint2> cl(static_cast<size_t>(nq) * 2 * TC_CAP);
     std::vector<float> ct(nq), xn(nq);
     std::vector<int> cc(nq), ql(nq), perm(static_cast<size_t>(L.n_rows_b));
     cudaMemcpy(cl.data(), L.cand, cl.size() * sizeof(uint2), cudaMemcpyDeviceToHost);
@@ -1410,9 +1428,9 @@ int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, i
       xnorm_out[o] = xn[t];
       for (int e = 0; e < TC_CAP; ++e) {
         float key;
-        memcpy(&key, &cl[t * TC_CAP + e].x, sizeof(float));
+        memcpy(&key, &cl[t * 2 * TC_CAP + e].x, sizeof(float));
         cand_key_out[o * TC_CAP + e] = key;
-        cand_idx_out[o * TC_CAP + e] = e < cc[t] ? static_cast<uint32_t>(perm[cl[t * TC_CAP + e].y]) : 0u;
+        cand_idx_out[o * TC_CAP + e] = e < cc[t] ? static_cast<uint32_t>(perm[cl[t * 2 * TC_CAP + e].y]) : 0u;
       }
     }
     cudaMemcpy(scale_ymax_out, L.scalars, 2 * sizeof(float), cudaMemcpyDeviceToHost);
