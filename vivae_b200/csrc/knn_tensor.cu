@@ -13,21 +13,20 @@
 //
 // Kernel shape (one CTA per SM, persistent over the database):
 //   CTA = 256 query rows (two M=128 MMAs share every database tile), database tile N=128,
-//   warp 0 lane 0 : TMA producer  (database tiles through a 4-stage ring)
-//   warp 1 lane 0 : tcgen05.mma issuer.  For d + 3 <= 64 the query operand lives in TENSOR MEMORY
-//                   (128 columns, written once with tcgen05.st) and is the MMA's A operand from there:
-//                   an M=128,N=128,K=16 MMA with both operands in shared memory reads 8 KB per 64
-//                   cycles = the whole 128 B/clk shared-memory bandwidth of the SM (measured: the
-//                   all-shared-memory version ran at 63 % of the tensor rate even with the epilogue
-//                   switched off); with A in TMEM it reads 4 KB.  The remaining 384 columns hold THREE
-//                   accumulator slots used round-robin by the (tile, M block) sequence, which gives each
-//                   epilogue group the same 2 x MMA time to drain a slot as full double buffering.
+//   warp 0 lane 0 : TMA producer  (database tiles through a 4-stage ring, in the CTA's cell order; it ends the
+//                   sweep once the remaining cells are provably too far -- knn_cells.cu)
+//   warp 1, one elected lane : tcgen05.mma issuer.  For d + 3 <= 64 the query operand lives in TENSOR MEMORY
+//                   (128 columns, written once with tcgen05.st) and is the MMA's A operand from there (an
+//                   M=128,N=128,K=16 MMA with both operands in shared memory reads 8 KB per 64 cycles = the
+//                   whole 128 B/clk shared-memory bandwidth of the SM; with A in TMEM it reads 4 KB).  The
+//                   remaining 384 columns hold THREE accumulator slots used round-robin by the (tile, M block)
+//                   sequence.
 //   warp 2        : TMEM allocator
-//   warps 4..11   : epilogue -- tcgen05.ld 32x32b, ONE THREAD OWNS ONE QUERY ROW, so the
-//                   running threshold tau and the candidate count are registers; a 32-column
-//                   chunk is screened with a min-tree + one compare, survivors are appended to
-//                   the row's candidate list (global memory, L2 resident); a nearly full list is
-//                   sorted by the warp in registers and truncated to the best m, tightening tau.
+//   warps 4..19   : epilogue -- tcgen05.ld 32x32b, lane = query row; TWO threads own a row (one per 64-column
+//                   half of a tile), each with its running threshold tau and list length in registers and
+//                   its own candidate list (global memory, L2 resident); a 32-column chunk is screened with a
+//                   min-tree + one compare, survivors are appended with one 8-byte store; a nearly full list is
+//                   compacted by the warp with a bitwise threshold selection, tightening tau.
 // Everything a row ever rejected has key >= its final tau, which is what the certificate uses.
 //
 // Exactness.  The re-rank kernel recomputes the contract's FP32 fmaf-chain distance for the m
