@@ -196,16 +196,17 @@ __global__ void __launch_bounds__(128) cell_assign_kernel(const float *__restric
     }
     __syncthreads();
     for (int pl = 0; pl < np; ++pl) {
-      float dot = 0.0f;
-      const float4 *pv = reinterpret_cast<const float4 *>(piv[pl]);
+      float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;  // four independent chains: the FMA latency, not the
+      const float4 *pv = reinterpret_cast<const float4 *>(piv[pl]);  // issue rate, bounded the single chain
 #pragma unroll
       for (int c4 = 0; c4 < CELL_DIMS / 4; ++c4) {
         const float4 q = pv[c4];
-        dot = fmaf(xr[4 * c4 + 0], q.x, dot);
-        dot = fmaf(xr[4 * c4 + 1], q.y, dot);
-        dot = fmaf(xr[4 * c4 + 2], q.z, dot);
-        dot = fmaf(xr[4 * c4 + 3], q.w, dot);
+        d0 = fmaf(xr[4 * c4 + 0], q.x, d0);
+        d1 = fmaf(xr[4 * c4 + 1], q.y, d1);
+        d2 = fmaf(xr[4 * c4 + 2], q.z, d2);
+        d3 = fmaf(xr[4 * c4 + 3], q.w, d3);
       }
+      const float dot = (d0 + d1) + (d2 + d3);
       const float score = fmaf(-2.0f, dot, pn[pl]);
       if (score < best) {
         best = score;
@@ -408,16 +409,17 @@ __global__ void __launch_bounds__(128) cell_extent_kernel(const float *__restric
     emax[tid] = neg_inf;
     __syncthreads();
     for (int bl = 0; bl < nb; ++bl) {
-      float tb = 0.0f;
+      float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;  // four independent chains (FMA latency)
       const float4 *pv = reinterpret_cast<const float4 *>(cwb[bl]);
 #pragma unroll
       for (int c4 = 0; c4 < CELL_DIMS / 4; ++c4) {
         const float4 q = pv[c4];
-        tb = fmaf(xr[4 * c4 + 0], q.x, tb);
-        tb = fmaf(xr[4 * c4 + 1], q.y, tb);
-        tb = fmaf(xr[4 * c4 + 2], q.z, tb);
-        tb = fmaf(xr[4 * c4 + 3], q.w, tb);
+        t0 = fmaf(xr[4 * c4 + 0], q.x, t0);
+        t1 = fmaf(xr[4 * c4 + 1], q.y, t1);
+        t2 = fmaf(xr[4 * c4 + 2], q.z, t2);
+        t3 = fmaf(xr[4 * c4 + 3], q.w, t3);
       }
+      const float tb = (t0 + t1) + (t2 + t3);
       const float proj = tb * __ldg(inv_norm + static_cast<size_t>(a) * P + b0 + bl);
       const unsigned int o = (r >= 0) ? f2ord(proj) : neg_inf;
       const unsigned int m = __reduce_max_sync(FULL, o);
