@@ -11,6 +11,7 @@ input/output vectors of
   * `vivae.losses.MDSLoss()` + autograd  (/root/reference/src/vivae/losses.py:266-349)
   * `vivae.knn.ensure_valid_knn`         (/root/reference/src/vivae/knn.py:24-63)
   * a short `ViVAE.fit` run              (/root/reference/src/vivae/model.py:188-279)
+  * the diagnostics of a trained model   (/root/reference/src/vivae/geometry.py, diagnostics.py)
 
 The fixtures are committed; the tests (CPU and GPU) only read the .npz files,
 so nothing at test time needs /root/reference.
@@ -203,7 +204,40 @@ def gen_fit_cpu(vv):
     print("fit_cpu_nomds:", buf.getvalue().strip().splitlines()[-1])
 
 
+
+def gen_geometry(vv):
+    """Diagnostics of a small trained reference model (geometry.py / diagnostics.py): embedding, grid pick,
+    indicatrix centres, decoder metric patches.  The encoder polygons themselves (`zp`) depend on the basis the
+    SVD picks for a null space (see vivae_b200/geometry.py) and are not recorded."""
+    import torch
+    from vivae.geometry import EncoderIndicatome, jacobian, metric_tensor
+
+    rng = np.random.default_rng(5)
+    centres = rng.uniform(0.0, 6.0, size=(5, 10))
+    X = (centres[rng.integers(0, 5, 900)] + 0.4 * rng.standard_normal((900, 10))).astype(np.float32)
+    model = vv.ViVAE(input_dim=10, latent_dim=2, random_state=4)
+    model.fit(X, n_epochs=3, batch_size=128, lam_mds=10.0, verbose=False)
+    sd = {k: v.detach().cpu().numpy() for k, v in model.net.state_dict().items()}
+    ei = model.encoder_indicatrices(X, batch_size=200, radius=1e-3, n_steps=7, n_polygon=16)
+    act = ei.act.detach()
+    xs = torch.linspace(act[:, 0].min().item(), act[:, 0].max().item(), steps=7)
+    ny = int(np.ceil((act[:, 1].max().item() - act[:, 1].min().item()) / (act[:, 0].max().item() - act[:, 0].min().item()) * 7))
+    ys = torch.linspace(act[:, 1].min().item(), act[:, 1].max().item(), steps=ny)
+    idcs = EncoderIndicatome.gridpoint_idcs(ref=act, xgrid=xs, ygrid=ys)
+    di = model.decoder_indicatrices(X, batch_size=200, n_steps=7, n_polygon=12)
+    z = act[:50]
+    dets = torch.linalg.det(metric_tensor(jacobian(model.net.decoder, z))).detach()
+    out = {f"sd__{k}": v for k, v in sd.items()}
+    out.update(X=X, act=act.numpy(), idcs=idcs.numpy(), zr=ei.zr.detach().numpy(), stepsize=np.float64(ei.stepsize),
+               n_zp=np.int64(len(ei.zp)), zp_shape=np.array(ei.zp[0].shape), dcoords=di.coords.numpy(),
+               dpatches=di.patches.detach().numpy(), dstepsize=np.float64(di.stepsize), dets50=dets.numpy())
+    np.savez_compressed(os.path.join(GOLD, "geometry_a.npz"), **out)
+    print("geometry_a:", idcs.shape[0], "grid points,", di.coords.shape[0], "decoder grid points")
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "geometry":  # regenerate one fixture only
+        gen_geometry(refshim.load_reference())
+        return
     os.makedirs(GOLD, exist_ok=True)
     orc.build()
     vv = refshim.load_reference()
@@ -212,6 +246,7 @@ def main():
     gen_validators(vv)
     gen_fit(vv)
     gen_fit_cpu(vv)
+    gen_geometry(vv)
 
 
 if __name__ == "__main__":

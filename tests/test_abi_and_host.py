@@ -175,3 +175,80 @@ def test_reference_smoke_test_shape_cpu():
               verbose=False)
     emb = model.transform(x)
     assert emb.shape == (50, 2)
+
+
+# ---------------------------------------------------------------------- diagnostics
+def _geometry_model():
+    g = np.load(os.path.join(GOLDEN, "geometry_a.npz"))
+    m = vv.ViVAE(input_dim=10, latent_dim=2, random_state=4)
+    sd = {k[4:]: torch.tensor(g[k]) for k in g.files if k.startswith("sd__")}
+    m.net.load_state_dict(sd)
+    m.trained = True
+    m.decoder_active = True
+    return g, m
+
+
+def _grid_pick_loops(ref, xgrid, ygrid, padding=0.1):
+    """The reference's nested tile loops (geometry.py:99-151), restated in NumPy for the test."""
+    xstep, ystep = xgrid[1] - xgrid[0], ygrid[1] - ygrid[0]
+    out = []
+    for gx in xgrid:
+        for gy in ygrid:
+            x0, x1 = gx - xstep / 2 * (1 - padding), gx + xstep / 2 * (1 - padding)
+            y0, y1 = gy - ystep / 2 * (1 - padding), gy + ystep / 2 * (1 - padding)
+            pool = np.nonzero((ref[:, 0] > x0) & (ref[:, 0] <= x1) & (ref[:, 1] > y0) & (ref[:, 1] <= y1))[0]
+            if len(pool):
+                c = np.array([(x0 + x1) / 2, (y0 + y1) / 2], dtype=ref.dtype)
+                out.append(pool[np.argmin(((ref[pool] - c) ** 2).sum(1))])
+    return np.array(out, dtype=np.int64)
+
+
+def test_encoder_and_decoder_indicatrices_match_reference_fixture():
+    from vivae_b200.geometry import EncoderIndicatome, jacobian, metric_tensor
+
+    g, m = _geometry_model()
+    tol = dict(rtol=2e-4, atol=2e-5)
+    assert np.allclose(m.transform(g["X"]), g["act"], **tol)
+    ei = m.encoder_indicatrices(g["X"], batch_size=200, radius=1e-3, n_steps=7, n_polygon=16)
+    assert np.allclose(ei.act.detach().cpu().numpy(), g["act"], **tol)
+    assert abs(ei.stepsize - float(g["stepsize"])) < 1e-5
+    assert np.allclose(ei.zr.detach().cpu().numpy(), g["zr"], **tol)
+    assert len(ei.zp) == int(g["n_zp"]) and tuple(ei.zp[0].shape) == tuple(g["zp_shape"])
+    # every polygon is a small closed curve around its centre
+    for c, p in zip(ei.zr.detach().cpu(), ei.zp):
+        assert torch.linalg.norm(p.detach().cpu() - c, dim=1).max() < 1.0
+    # grid pick on the REFERENCE embedding: identical indices
+    act = torch.tensor(g["act"])
+    xs = torch.linspace(act[:, 0].min().item(), act[:, 0].max().item(), steps=7)
+    ny = int(np.ceil((act[:, 1].max().item() - act[:, 1].min().item()) / (act[:, 0].max().item() - act[:, 0].min().item()) * 7))
+    ys = torch.linspace(act[:, 1].min().item(), act[:, 1].max().item(), steps=ny)
+    assert np.array_equal(EncoderIndicatome.gridpoint_idcs(ref=act, xgrid=xs, ygrid=ys).numpy(), g["idcs"])
+    di = m.decoder_indicatrices(g["X"], batch_size=200, n_steps=7, n_polygon=12)
+    assert np.allclose(di.coords.numpy(), g["dcoords"], **tol)
+    assert np.allclose(di.patches.numpy(), g["dpatches"], rtol=1e-3, atol=1e-4)
+    assert abs(di.stepsize - float(g["dstepsize"])) < 1e-5
+    dev = next(m.net.parameters()).device
+    dets = torch.linalg.det(metric_tensor(jacobian(m.net.decoder, act[:50].to(dev)))).cpu().detach().numpy()
+    assert np.allclose(dets, g["dets50"], rtol=1e-3)
+    rel = m.decoder_jacobian_determinants(g["X"][:120], batch_size=50)
+    assert rel.shape == (120,) and np.isfinite(rel).all()
+
+
+@pytest.mark.parametrize("n,steps,seed", [(5000, 30, 0), (300, 12, 1), (40_000, 50, 2)])
+def test_bucketed_grid_pick_equals_the_reference_loops(n, steps, seed):
+    from vivae_b200.geometry import EncoderIndicatome
+
+    rng = np.random.default_rng(seed)
+    ref = (rng.standard_normal((n, 2)) * np.array([3.0, 1.3])).astype(np.float32)
+    ref[: n // 10] = np.round(ref[: n // 10], 1)      # ties inside tiles
+    xs = torch.linspace(float(ref[:, 0].min()), float(ref[:, 0].max()), steps)
+    ys = torch.linspace(float(ref[:, 1].min()), float(ref[:, 1].max()), max(2, steps // 2))
+    got = EncoderIndicatome.gridpoint_idcs(ref=torch.tensor(ref), xgrid=xs, ygrid=ys).numpy()
+    assert np.array_equal(got, _grid_pick_loops(ref, xs.numpy(), ys.numpy()))
+
+
+def test_decoder_indicatrices_need_a_decoder():
+    m = vv.ViVAE(input_dim=4)
+    m.decoder_active = False
+    with pytest.raises(RuntimeError, match="decoder was not active"):
+        m.decoder_indicatrices(np.zeros((8, 4), dtype=np.float32))

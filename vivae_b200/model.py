@@ -283,3 +283,28 @@ class ViVAE:
                  mds_distf_hd=mds_distf_hd, mds_distf_ld=mds_distf_ld, mds_nsamp=mds_nsamp, lam_imit=lam_imit,
                  ref_model=ref_model, verbose=verbose)
         return self.transform(X, batch_size=batch_size)
+
+    # ---- diagnostics (reference: model.py:352-431; implementation in vivae_b200/geometry.py)
+    def decoder_jacobian_determinants(self, X: np.ndarray, batch_size: int = 256) -> np.ndarray:
+        """Scaled Jacobian determinants of the decoder per row of `X` (model.py:352-364)."""
+        from .geometry import decoder_jacobian_determinants
+
+        return decoder_jacobian_determinants(model=self.net, x=np.ascontiguousarray(X, dtype=np.float32),
+                                             batch_size=batch_size)
+
+    def encoder_indicatrices(self, X: np.ndarray, batch_size: int = 256, radius: float = 1e-4, n_steps: int = 50,
+                             all_points: bool = False, n_polygon: int = 100):
+        """Encoder indicatrices on a grid over the embedding (model.py:366-398)."""
+        from .geometry import encoder_indicatrices
+
+        return encoder_indicatrices(model=self.net, x=np.ascontiguousarray(X, dtype=np.float32), batch_size=batch_size,
+                                    radius=radius, n_steps=n_steps, all_points=all_points, n_polygon=n_polygon)
+
+    def decoder_indicatrices(self, X: np.ndarray, batch_size: int = 256, n_steps: int = 50, n_polygon: int = 100):
+        """Decoder indicatrices on a grid inside the embedding's hull (model.py:400-431)."""
+        if not self.decoder_active:
+            raise RuntimeError("Cannot compute decoder indicatrices if decoder was not active in training")
+        from .geometry import decoder_indicatrices
+
+        return decoder_indicatrices(model=self.net, x=np.ascontiguousarray(X, dtype=np.float32), batch_size=batch_size,
+                                    n_steps=n_steps, n_polygon=n_polygon)
