@@ -252,3 +252,50 @@ def test_decoder_indicatrices_need_a_decoder():
     m.decoder_active = False
     with pytest.raises(RuntimeError, match="decoder was not active"):
         m.decoder_indicatrices(np.zeros((8, 4), dtype=np.float32))
+
+
+# ---------------------------------------------------------------------- closed-form Jacobians
+@pytest.mark.parametrize("variational", [True, False])
+@pytest.mark.parametrize("act", [torch.nn.GELU(), torch.nn.Tanh(), torch.nn.SiLU(), torch.nn.ELU()])
+def test_closed_form_jacobians_and_geometric_losses_equal_autodiff(variational, act):
+    from vivae_b200.jacobians import analytic_jacobian, supports_closed_form
+    from vivae_b200.losses import EncoderGeometricLoss, GeometricLoss, _batched_jacobian, _logdet_variance
+
+    torch.manual_seed(3)
+    with torch.device("cpu"):
+        net = vv.Autoencoder(input_dim=13, latent_dim=2, hidden_dims=[16, 24, 8], variational=variational,
+                             activation=act).double()
+    assert supports_closed_form(net)
+    x = torch.randn(37, 13, dtype=torch.float64)
+    z = torch.randn(37, 2, dtype=torch.float64)
+    for f, inp, enc_side, loss in ((net.immersion, z, False, GeometricLoss()), (net.submersion, x, True, EncoderGeometricLoss())):
+        ref_jac = _batched_jacobian(f, inp)
+        assert torch.allclose(analytic_jacobian(f, inp), ref_jac, rtol=1e-12, atol=1e-14)
+        net.zero_grad()
+        a = loss(f, inp)
+        a.backward()
+        ga = [None if p.grad is None else p.grad.clone() for p in net.parameters()]
+        net.zero_grad()
+        b = _logdet_variance(ref_jac, encoder_side=enc_side)
+        b.backward()
+        assert abs(a.item() - b.item()) <= 1e-12 * max(1.0, abs(b.item()))
+        for u, p in zip(ga, net.parameters()):
+            assert (u is None) == (p.grad is None)
+            if u is not None:
+                assert torch.allclose(u, p.grad, rtol=1e-9, atol=1e-12)
+    # a bare decoder module (what the indicatrix code passes) takes the same route
+    assert torch.allclose(analytic_jacobian(net.decoder, z), _batched_jacobian(net.decoder, z), rtol=1e-12, atol=1e-14)
+
+
+def test_unknown_activation_keeps_the_autodiff_route():
+    from vivae_b200.jacobians import analytic_jacobian, supports_closed_form
+
+    class Odd(torch.nn.Module):
+        def forward(self, t):
+            return torch.sin(t)
+
+    with torch.device("cpu"):
+        net = vv.Autoencoder(input_dim=5, latent_dim=2, hidden_dims=[8, 8], variational=True, activation=Odd())
+    assert not supports_closed_form(net)
+    assert analytic_jacobian(net.submersion, torch.randn(4, 5)) is None
+    assert torch.isfinite(vv.losses.EncoderGeometricLoss()(net.submersion, torch.randn(9, 5)))

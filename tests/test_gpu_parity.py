@@ -347,6 +347,36 @@ def test_cuda_graph_step_matches_eager_training():
     assert np.abs(runs[0][1] - runs[1][1]).max() < 2e-3 * np.abs(runs[0][1]).max()
 
 
+def test_geometric_terms_closed_form_on_gpu_and_inside_the_captured_step():
+    """the geometric losses with closed-form Jacobians equal the autodiff route on the
+    device, and a training run with both terms switched on replays as a CUDA graph like the eager loop."""
+    from vivae_b200.losses import EncoderGeometricLoss, GeometricLoss, _batched_jacobian, _logdet_variance
+
+    torch.manual_seed(5)
+    m = vv.ViVAE(input_dim=20, random_state=2)
+    xb = torch.randn(256, 20, device="cuda")
+    zb = torch.randn(256, 2, device="cuda")
+    for f, inp, enc, loss in ((m.net.immersion, zb, False, GeometricLoss()), (m.net.submersion, xb, True, EncoderGeometricLoss())):
+        a = loss(f, inp)
+        b = _logdet_variance(_batched_jacobian(f, inp), encoder_side=enc)
+        assert abs(a.item() - b.item()) <= 2e-4 * max(1.0, abs(b.item()))
+    x = clustered(4_096, 20, 6, seed=17)
+    runs = []
+    for use_graph in (False, True):
+        mm = vv.ViVAE(input_dim=20, random_state=11)
+        mm.use_cuda_graph = use_graph
+        buf = io.StringIO()
+        with redirect_stdout(buf):
+            mm.fit(x, n_epochs=2, batch_size=512, lam_mds=10.0, lam_geom=1.0, lam_egeom=1.0)
+        runs.append((buf.getvalue(), mm.transform(x), mm._graph))
+    assert runs[1][2] is not None and runs[1][2][1] is not None, "graph path not taken with geometric terms"
+    a = [[float(t.split()[1]) for t in ln.split("\t")[1:]] for ln in runs[0][0].strip().splitlines()]
+    b = [[float(t.split()[1]) for t in ln.split("\t")[1:]] for ln in runs[1][0].strip().splitlines()]
+    assert all(v[2] > 0 and v[3] > 0 for v in a), "geometric terms missing from the log"
+    np.testing.assert_allclose(a, b, rtol=2e-3, atol=2e-4)
+    assert np.abs(runs[0][1] - runs[1][1]).max() < 5e-3 * np.abs(runs[0][1]).max()
+
+
 def test_full_pipeline_through_public_api():
     x = clustered(20_000, 38, 12, seed=10)
     knn = vv.make_knn(x, k=50, verbose=False)

@@ -24,9 +24,15 @@ import numpy as np
 import torch
 import torch.func
 
+from .jacobians import analytic_jacobian
+
 
 def jacobian(f: Callable, x: torch.Tensor) -> torch.Tensor:
-    """Per-row Jacobian matrices of `f` at the rows of `x` (geometry.py:43-58)."""
+    """Per-row Jacobian matrices of `f` at the rows of `x` (geometry.py:43-58): closed form for the
+    network's own MLPs (`jacobians.py`), autodiff for anything else."""
+    jac = analytic_jacobian(f, x)
+    if jac is not None:
+        return jac
     try:
         return torch.func.vmap(torch.func.jacfwd(f), in_dims=(0,))(x)
     except NotImplementedError:

@@ -3,7 +3,8 @@
 `MDSLoss` (the stochastic quartet loss, reference: /root/reference/src/vivae/losses.py:134-349)
 is the hot operator: forward and backward run as fused sm_100a kernels
 (`csrc/quartet.cu`) behind a `torch.autograd.Function`.  The remaining terms are
-small and stay ordinary PyTorch, as the reference has them (losses.py:58-131, 352-415).
+small and stay ordinary PyTorch, as the reference has them (losses.py:58-131); the two geometric
+terms (losses.py:352-415) use closed-form Jacobians of the MLPs (`jacobians.py`) instead of `vmap(jacfwd)`.
 """
 
 from __future__ import annotations
@@ -14,6 +15,7 @@ from collections.abc import Callable
 import torch
 
 from . import _lib
+from .jacobians import analytic_jacobian, logdet_gram
 
 __all__ = ["MDSLoss", "KLDivLoss", "ImitationLoss", "FirstNDimsExtractor", "GeometricLoss", "EncoderGeometricLoss",
            "quartet_loss"]
@@ -144,14 +146,23 @@ def _logdet_variance(jac: torch.Tensor, encoder_side: bool) -> torch.Tensor:
 
 
 class GeometricLoss:
-    """Variance of log-det of the decoder pull-back metric (losses.py:352-382)."""
+    """Variance of log-det of the decoder pull-back metric (losses.py:352-382).  For the network's own
+    decoder the Jacobian is propagated in closed form (`jacobians.py`); any other callable goes through
+    autodiff like the reference."""
 
     def __call__(self, immersion: Callable, z: torch.Tensor) -> torch.Tensor:
+        jac = analytic_jacobian(immersion, z) if z.dim() == 2 and z.shape[0] > 1 else None
+        if jac is not None:
+            return torch.var(logdet_gram(jac.transpose(1, 2)))  # J^T J = Gram matrix of the rows of J^T
         return _logdet_variance(_batched_jacobian(immersion, z), encoder_side=False)
 
 
 class EncoderGeometricLoss:
-    """Variance of log-det of J J^T of the encoder (losses.py:385-415)."""
+    """Variance of log-det of J J^T of the encoder (losses.py:385-415); closed-form Jacobian for the
+    network's own encoder."""
 
     def __call__(self, submersion: Callable, x: torch.Tensor) -> torch.Tensor:
+        jac = analytic_jacobian(submersion, x) if x.dim() == 2 and x.shape[0] > 1 else None
+        if jac is not None:
+            return torch.var(logdet_gram(jac))
         return _logdet_variance(_batched_jacobian(submersion, x), encoder_side=True)

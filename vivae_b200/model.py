@@ -30,6 +30,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .jacobians import supports_closed_form
 from .network import Autoencoder
 
 __all__ = ["ViVAE", "DeviceBatchLoader"]
@@ -125,7 +126,9 @@ class ViVAE:
                    mds_distf_hd=mds_distf_hd, mds_distf_ld=mds_distf_ld, mds_nsamp=mds_nsamp, lam_imit=lam_imit,
                    ref_model=ref_model)
         sums = torch.zeros(len(_TERMS), dtype=torch.float32, device=dev)
-        graph_ok = (self.use_cuda_graph and dev.type == "cuda" and lam_geom == 0.0 and lam_egeom == 0.0
+        # the geometric terms are graph-safe only with the closed-form Jacobians (no torch.func, no LU logdet)
+        geom_ok = (lam_geom == 0.0 and lam_egeom == 0.0) or (supports_closed_form(self.net) and self.net.latent_dim <= 2)
+        graph_ok = (self.use_cuda_graph and dev.type == "cuda" and geom_ok
                     and mds_nsamp == 1 and (lam_imit == 0.0 or ref_model is None)
                     and isinstance(self.data_loader, DeviceBatchLoader))
         full = getattr(self.data_loader, "batch_size", None)
