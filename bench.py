@@ -184,7 +184,8 @@ def run_reference(args) -> None:
 
 def workload_config(args, n_gpus: int) -> dict:
     return {"workload": f"synthetic {args.n} cells x {args.d} PCs, exact kNN k={args.k} + smooth(k={args.k}, coef=1, n_iter=1)",
-            "n": args.n, "d": args.d, "k": args.k, "parallelism": f"query-row shards x{n_gpus}, smooth replicated",
+            "n": args.n, "d": args.d, "k": args.k, "parallelism": (f"query-row shards x{n_gpus}, smooth replicated" if getattr(args, "exchange", "replicated") != "ring" else
+                            f"query-row AND database-row shards x{n_gpus} (NCCL ring exchange + running merge), smooth replicated"),
             "l2": f"inputs larger than L2 (matrix {args.n * args.d * 4 / 1e6:.0f} MB, graph "
                   f"{args.n * (args.k + 1) * 12 / 1e6:.0f} MB vs 126 MB L2)"}
 
@@ -197,7 +198,7 @@ def run_ours(args) -> None:
     import vivae_b200 as vv
     from vivae_b200 import _lib
     from vivae_b200.device import knn_device, smooth_device
-    from vivae_b200.sharded import all_gather_rows, shard_bounds
+    from vivae_b200.sharded import all_gather_rows, make_knn_ring, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -218,8 +219,13 @@ def run_ours(args) -> None:
         x_dev = torch.from_numpy(x_host).to(dev)
     q0, nq = shard_bounds(n, world, rank)
 
+    x_local = x_dev[q0:q0 + nq].contiguous() if args.exchange == "ring" else None
+
     def step_device(stats=None):
-        idx, dist_ = knn_device(x_dev, k, q0, nq, algo=args.algo, stats=stats)
+        if args.exchange == "ring":  # database-sharded build: shards travel around the NCCL ring
+            idx, dist_ = make_knn_ring(x_local, n, k, algo=args.algo)
+        else:
+            idx, dist_ = knn_device(x_dev, k, q0, nq, algo=args.algo, stats=stats)
         if world > 1:
             idx = all_gather_rows(idx, n)  # the smoother needs the whole graph (NCCL all-gather)
         out = smooth_device(x_dev, idx, k=k, coef=1.0, n_iter=1)
@@ -448,6 +454,8 @@ def main():
     ap.add_argument("--dims", "--d", dest="d", type=int, default=50)
     ap.add_argument("--neighbours", "--k", dest="k", type=int, default=50)
     ap.add_argument("--algo", default="auto")
+    ap.add_argument("--exchange", default="replicated", choices=["replicated", "ring"],
+                    help="N>1: every rank holds the matrix (default) or only its rows, shards passed around an NCCL ring")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-fit", action="store_true")

@@ -114,6 +114,32 @@ int vvb_knn_screen_debug_host(const float *x_host, int64_t n, int d, int k, int6
                               float *cand_thr_out, float *xnorm_out, float *scale_ymax_out, float *mu_out);
 
 /* ------------------------------------------------------------------------
+ * Database-sharded ("ring") graph build: running top-k merge.
+ *   Same reference call site as make_knn (knn.py:135-141), for a matrix whose rows are spread
+ *   over several GPUs.  A rank keeps, for each of its nq query rows, a running list
+ *   run_idx (nq, k+1) int64 GLOBAL row indices and run_d2 (nq, k+1) float32 SQUARED distances
+ *   (column 0 = the row itself, unfilled entries -1 / +inf).  For every database shard that
+ *   passes by it calls vvb_make_knn_device on the stacked matrix xc = [shard ; own rows]
+ *   (stacked in global row order) and then vvb_knn_merge_device, which
+ *     - keeps the entries of new_idx (nq, kn+1; local row indices into xc, column 0 = self)
+ *       whose index is in [keep_lo, keep_hi) (the shard's rows; the rank's own rows are ranked
+ *       once, in its first step),
+ *     - gives them global indices (local + global_off) and the contract's squared distance
+ *       (recomputed fmaf chain),
+ *     - merges them into the running lists by the key (d2, global index) and keeps the k best.
+ *   vvb_knn_merge_finish_device turns squared distances into distances (correctly rounded sqrt).
+ *   The result is bit-identical to vvb_make_knn_device over the whole matrix.
+ * ------------------------------------------------------------------------ */
+int vvb_knn_merge_init_device(int64_t *run_idx_dev, float *run_d2_dev, int64_t nq, int k, int64_t self0,
+                              void *stream);
+
+int vvb_knn_merge_device(const float *xc_dev, int64_t nc, int d, int64_t q0, int64_t nq,
+                         const int64_t *new_idx_dev, int kn, int64_t keep_lo, int64_t keep_hi,
+                         int64_t global_off, int64_t *run_idx_dev, float *run_d2_dev, int k, void *stream);
+
+int vvb_knn_merge_finish_device(const float *run_d2_dev, int64_t count, float *dist_out_dev, void *stream);
+
+/* ------------------------------------------------------------------------
  * smooth -- replaces the sweep loop of /root/reference/src/vivae/knn.py:173-185
  *   (argument validation and ensure_valid_knn, knn.py:165-171, stay in Python).
  *   Row i moves by `coef` toward the mean of rows idx[i, 0:k]; in

@@ -571,3 +571,31 @@ def test_cell_sweep_skips_far_clusters_and_stays_exact(monkeypatch):
     q0, nq = 77_777, 3_001
     si, sd = _knn_host(x, 50, q0, nq, "tensor", None)
     assert np.array_equal(si, idx[q0:q0 + nq]) and np.array_equal(sd, dist[q0:q0 + nq])
+
+
+# ============================================================================ database-sharded (ring) build
+@pytest.mark.parametrize("kind,n,d,k,world", [("clustered", 30_000, 50, 50, 3), ("ties", 6_000, 6, 20, 4),
+                                               ("clustered", 5_000, 130, 100, 2), ("iid", 700, 20, 300, 3)])
+def test_ring_steps_with_merge_kernel_equal_whole_matrix_build(kind, n, d, k, world):
+    """The ring build's per-step work (builder on [shard ; own rows] + csrc/knn_merge.cu), run here for every
+    'rank' in one process, is bit-identical to one build over the whole matrix -- including tie-breaks across
+    shard borders and k larger than a shard."""
+    from vivae_b200.sharded import _DeviceOps, ring_fold, shard_bounds
+
+    x = {"clustered": lambda: clustered(n, d, 8, seed=21), "ties": lambda: tie_data(n, d, seed=22),
+         "iid": lambda: np.random.default_rng(23).standard_normal((n, d)).astype(np.float32)}[kind]()
+    xd = torch.tensor(x, device="cuda")
+    whole_idx, whole_dist = vv.device.knn_device(xd, k)
+    ops = _DeviceOps()
+    before = vv._lib.launch_count()
+    for rank in range(world):
+        q0, nq = shard_bounds(n, world, rank)
+        own = xd[q0:q0 + nq].contiguous()
+        run_idx, run_d2 = ops.init(nq, k, q0, xd.device)
+        for s in range(world):
+            s0, sn = shard_bounds(n, world, (rank + s) % world)
+            ring_fold(ops, own, q0, xd[s0:s0 + sn].contiguous(), s0, run_idx, run_d2)
+        dist = ops.finish(run_d2)
+        assert torch.equal(run_idx, whole_idx[q0:q0 + nq])
+        assert torch.equal(dist, whole_dist[q0:q0 + nq])
+    assert vv._lib.launch_count() > before

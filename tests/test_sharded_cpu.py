@@ -4,6 +4,7 @@ replicated smoother).  The CUDA kernels are replaced by the CPU oracle through t
 
 import os
 import socket
+from fractions import Fraction
 
 import numpy as np
 import pytest
@@ -12,7 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import oracle as orc
-from vivae_b200.sharded import all_gather_rows, knn_smooth_sharded, make_knn_sharded, shard_bounds
+from vivae_b200.sharded import all_gather_rows, knn_smooth_sharded, make_knn_ring, make_knn_sharded, shard_bounds
 
 
 def _free_port():
@@ -73,3 +74,80 @@ def test_shard_bounds_cover_all_rows():
             for q0, c in spans:
                 assert q0 == min(pos, n) and c >= 0
                 pos += c
+
+
+# ---------------------------------------------------------------------------- database-sharded ring build
+class _CpuRingOps:
+    """CPU restatements of the four device entry points the ring build calls (csrc/knn_merge.cu)."""
+
+    @staticmethod
+    def knn(xc, k, q0, nq, algo):
+        return _oracle_knn(xc, k, q0, nq, algo)
+
+    @staticmethod
+    def init(nq, k, self0, device):
+        run_idx = torch.full((nq, k + 1), -1, dtype=torch.int64)
+        run_d2 = torch.full((nq, k + 1), float("inf"), dtype=torch.float32)
+        run_idx[:, 0] = torch.arange(self0, self0 + nq)
+        run_d2[:, 0] = 0.0
+        return run_idx, run_d2
+
+    @staticmethod
+    def merge(xc, q0, nq, new_idx, keep_lo, keep_hi, global_off, run_idx, run_d2):
+        x = xc.numpy()
+        k = run_idx.shape[1] - 1
+        for t in range(nq):
+            ents = [(float(run_d2[t, c]), int(run_idx[t, c])) for c in range(1, k + 1) if run_idx[t, c] >= 0]
+            for j in new_idx[t, 1:].tolist():
+                if keep_lo <= j < keep_hi:
+                    acc = np.float32(0.0)
+                    for c in range(x.shape[1]):  # the contract's chain with an exactly rounded fmaf (exact rationals)
+                        df = Fraction(float(np.float32(x[q0 + t, c] - x[j, c])))
+                        acc = orc._round_to_f32(df * df + Fraction(float(acc)))
+                    ents.append((float(acc), j + global_off))
+            ents.sort()
+            for c in range(1, k + 1):
+                if c - 1 < len(ents):
+                    run_d2[t, c], run_idx[t, c] = ents[c - 1][0], ents[c - 1][1]
+                else:
+                    run_d2[t, c], run_idx[t, c] = float("inf"), -1
+
+    @staticmethod
+    def finish(run_d2):
+        return torch.from_numpy(np.sqrt(run_d2.numpy()))  # hardware sqrt: correctly rounded
+
+
+def _ring_data(n, kind):
+    rng = np.random.default_rng(7)
+    if kind == "ties":  # integer lattice with duplicate rows: every tie-break rule is exercised across shards
+        x = rng.integers(0, 3, size=(n, 3)).astype(np.float32)
+    else:
+        x = rng.standard_normal((n, 5)).astype(np.float32)
+    return x
+
+
+def _ring_worker(rank, world, port, n, k, kind, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x = torch.from_numpy(_ring_data(n, kind))
+        q0, nq = shard_bounds(n, world, rank)
+        idx, dst = make_knn_ring(x[q0:q0 + nq].clone(), n, k, _ops=_CpuRingOps())
+        np.savez(os.path.join(out_dir, f"ring{rank}.npz"), idx=idx.numpy(), dist=dst.numpy(), q0=q0, nq=nq)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,k,kind", [(2, 150, 7, "normal"), (3, 100, 5, "ties"), (2, 90, 60, "ties"), (3, 7, 4, "normal")])
+def test_ring_build_equals_whole_matrix_build(tmp_path, world, n, k, kind):
+    """Shards passed around the ring + running merge == one build over the whole matrix, byte for byte
+    (k larger than a shard, ragged and short shards, ties and duplicate rows across shard borders)."""
+    port = _free_port()
+    mp.spawn(_ring_worker, args=(world, port, n, k, kind, str(tmp_path)), nprocs=world, join=True)
+    wi, wd = orc.knn(_ring_data(n, kind), k)
+    for r in range(world):
+        g = np.load(tmp_path / f"ring{r}.npz")
+        q0, nq = int(g["q0"]), int(g["nq"])
+        assert np.array_equal(g["idx"], wi[q0:q0 + nq])
+        assert np.array_equal(g["dist"], wd[q0:q0 + nq])

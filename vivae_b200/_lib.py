@@ -56,6 +56,9 @@ SYMBOLS = {
                                    ctypes.POINTER(KnnStats)]),
     "vvb_knn_screen_debug_capacity": (_int, []),
     "vvb_knn_screen_debug_host": (_int, [_vp, _i64, _int, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vvb_knn_merge_init_device": (_int, [_vp, _vp, _i64, _int, _i64, _vp]),
+    "vvb_knn_merge_device": (_int, [_vp, _i64, _int, _i64, _i64, _vp, _int, _i64, _i64, _i64, _vp, _vp, _int, _vp]),
+    "vvb_knn_merge_finish_device": (_int, [_vp, _i64, _vp, _vp]),
     "vvb_smooth_host": (_int, [_vp, _int, _i64, _int, _vp, _i64, _int, _dbl, _int, _int, _vp]),
     "vvb_smooth_workspace_bytes": (_int, [_int, _i64, _int, _int, ctypes.POINTER(_sz)]),
     "vvb_smooth_device": (_int, [_vp, _int, _i64, _int, _vp, _i64, _int, _dbl, _int, _int, _vp, _vp, _sz, _vp]),

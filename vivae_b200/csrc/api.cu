@@ -64,6 +64,11 @@ size_t quartet_workspace_bytes(int64_t B);
 int launch_quartet_fwd(const float *x, const float *z, int64_t B, int D, int L, const int64_t *const *perms,
                        int n_sampling, int mhd, int mld, float *loss_out, float *grad_unit, void *workspace,
                        cudaStream_t st);
+int launch_knn_merge(const float *xc, int64_t nc, int d, int64_t q0, int64_t nq, const int64_t *new_idx, int kn,
+                     int64_t keep_lo, int64_t keep_hi, int64_t global_off, int64_t *run_idx, float *run_d2, int k,
+                     cudaStream_t st);
+int launch_knn_merge_init(int64_t *run_idx, float *run_d2, int64_t nq, int k, int64_t self0, cudaStream_t st);
+int launch_knn_merge_finish(const float *run_d2, int64_t count, float *dist, cudaStream_t st);
 int launch_quartet_bwd(const float *grad_unit, const float *grad_out, int64_t count, float *grad_z,
                        cudaStream_t st);
 
@@ -598,6 +603,25 @@ int vvb_smooth_host(const void *x_host, int elem_size, int64_t n, int d, const i
   VVB_CUDA(cudaStreamSynchronize(st));
   VVB_REQUIRE(bad == 0, "Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed");
   return VVB_OK;
+}
+
+// -------------------------------------------------------------------- ring merge
+int vvb_knn_merge_init_device(int64_t *run_idx_dev, float *run_d2_dev, int64_t nq, int k, int64_t self0, void *stream) {
+  VVB_REQUIRE(run_idx_dev && run_d2_dev, "knn merge init: null pointer argument");
+  return launch_knn_merge_init(run_idx_dev, run_d2_dev, nq, k, self0, static_cast<cudaStream_t>(stream));
+}
+
+int vvb_knn_merge_device(const float *xc_dev, int64_t nc, int d, int64_t q0, int64_t nq, const int64_t *new_idx_dev,
+                         int kn, int64_t keep_lo, int64_t keep_hi, int64_t global_off, int64_t *run_idx_dev,
+                         float *run_d2_dev, int k, void *stream) {
+  VVB_REQUIRE(xc_dev && new_idx_dev && run_idx_dev && run_d2_dev, "knn merge: null pointer argument");
+  return launch_knn_merge(xc_dev, nc, d, q0, nq, new_idx_dev, kn, keep_lo, keep_hi, global_off, run_idx_dev,
+                          run_d2_dev, k, static_cast<cudaStream_t>(stream));
+}
+
+int vvb_knn_merge_finish_device(const float *run_d2_dev, int64_t count, float *dist_out_dev, void *stream) {
+  VVB_REQUIRE(run_d2_dev && dist_out_dev, "knn merge finish: null pointer argument");
+  return launch_knn_merge_finish(run_d2_dev, count, dist_out_dev, static_cast<cudaStream_t>(stream));
 }
 
 // -------------------------------------------------------------------- quartet

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["knn_device", "smooth_device"]
+__all__ = ["knn_device", "smooth_device", "knn_merge_init", "knn_merge", "knn_merge_finish"]
 
 
 def _require_cuda(name: str, t: torch.Tensor, dtype) -> torch.Tensor:
@@ -76,4 +76,50 @@ def smooth_device(x: torch.Tensor, idx: torch.Tensor, k: int = 50, coef: float =
                                          float(coef), int(n_iter), _lib.SMOOTH_MODES[mode], out.data_ptr(),
                                          ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
         ws.record_stream(torch.cuda.current_stream())
+    return out
+
+
+# ------------------------------------------------------------------ running top-k merge (database-sharded build)
+def knn_merge_init(nq: int, k: int, self0: int, device) -> tuple[torch.Tensor, torch.Tensor]:
+    """Empty running lists for query rows [self0, self0+nq): `(run_idx int64, run_d2 float32)`, both (nq, k+1)."""
+    lib = _lib.load()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("knn_merge_init: a CUDA device is required (vivae_b200 has no CPU path)")
+    with torch.cuda.device(device):
+        run_idx = torch.empty((nq, k + 1), dtype=torch.int64, device=device)
+        run_d2 = torch.empty((nq, k + 1), dtype=torch.float32, device=device)
+        _lib.check(lib.vvb_knn_merge_init_device(run_idx.data_ptr(), run_d2.data_ptr(), nq, k, self0,
+                                                 torch.cuda.current_stream().cuda_stream))
+    return run_idx, run_d2
+
+
+def knn_merge(xc: torch.Tensor, q0: int, nq: int, new_idx: torch.Tensor, keep_lo: int, keep_hi: int, global_off: int,
+              run_idx: torch.Tensor, run_d2: torch.Tensor) -> None:
+    """Fold the neighbour lists `new_idx` (nq, kn+1; local rows of the stacked matrix `xc`, whose rows
+    [q0, q0+nq) are the queries) into the running lists, in place (include/vivae_b200.h: vvb_knn_merge_device)."""
+    lib = _lib.load()
+    xc = _require_cuda("xc", xc, torch.float32)
+    new_idx = _require_cuda("new_idx", new_idx, torch.int64)
+    _require_cuda("run_idx", run_idx, torch.int64)
+    _require_cuda("run_d2", run_d2, torch.float32)
+    if not (run_idx.is_contiguous() and run_d2.is_contiguous()):
+        raise ValueError("running lists must be contiguous")
+    if new_idx.shape[0] != nq or run_idx.shape[0] != nq or run_d2.shape != run_idx.shape:
+        raise ValueError("list shapes do not match the number of query rows")
+    with torch.cuda.device(xc.device):
+        _lib.check(lib.vvb_knn_merge_device(xc.data_ptr(), xc.shape[0], xc.shape[1], q0, nq, new_idx.data_ptr(),
+                                            new_idx.shape[1] - 1, keep_lo, keep_hi, global_off, run_idx.data_ptr(),
+                                            run_d2.data_ptr(), run_idx.shape[1] - 1,
+                                            torch.cuda.current_stream().cuda_stream))
+
+
+def knn_merge_finish(run_d2: torch.Tensor) -> torch.Tensor:
+    """Distances (correctly rounded square roots) of the running squared distances."""
+    lib = _lib.load()
+    run_d2 = _require_cuda("run_d2", run_d2, torch.float32)
+    out = torch.empty_like(run_d2)
+    with torch.cuda.device(run_d2.device):
+        _lib.check(lib.vvb_knn_merge_finish_device(run_d2.data_ptr(), run_d2.numel(), out.data_ptr(),
+                                                   torch.cuda.current_stream().cuda_stream))
     return out

@@ -1,5 +1,12 @@
 """Row-sharded kNN graph + smoothing over several GPUs (one process per GPU, torch.distributed).
 
+Two ways to build the graph:
+  * `make_knn_sharded`  -- every rank holds the whole matrix (2 GB at 10M x 50, 16 GB at 2M x 2000: it fits
+    a 180 GB B200 many times over) and computes its query rows; no data-path collective.
+  * `make_knn_ring`     -- every rank holds ONLY its rows; the shards travel around an NCCL ring
+    (send to rank-1 / receive from rank+1 over NVLink, overlapped with the step's kernels) and each rank
+    folds what passes by into running top-k lists.  For matrices beyond one GPU's memory; bit-identical.
+
 The graph builder shards by query rows with no data-path collective: every rank holds the whole
 matrix and computes rows [q0, q0+nq) of the graph; neighbour indices are global.  The only
 exchange is the all-gather of the index shards, needed because the Gauss-Seidel smoother reads
@@ -14,7 +21,7 @@ from typing import Callable, Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "all_gather_rows", "make_knn_sharded", "knn_smooth_sharded"]
+__all__ = ["shard_bounds", "all_gather_rows", "make_knn_sharded", "make_knn_ring", "ring_fold", "knn_smooth_sharded"]
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -56,6 +63,72 @@ def make_knn_sharded(x: torch.Tensor, k: int, group=None, algo: str = "auto", ga
         idx = all_gather_rows(idx, n, group)
         dst = all_gather_rows(dst, n, group)
     return idx, dst
+
+
+class _DeviceOps:
+    """The CUDA entry points the ring build is made of (tests substitute CPU restatements under gloo)."""
+
+    def __init__(self):
+        from . import device
+
+        self.knn, self.init, self.merge, self.finish = (device.knn_device, device.knn_merge_init, device.knn_merge,
+                                                        device.knn_merge_finish)
+
+
+def ring_fold(ops, x_local: torch.Tensor, q0: int, shard: torch.Tensor, s0: int, run_idx: torch.Tensor,
+              run_d2: torch.Tensor, algo: str = "auto") -> None:
+    """One ring step: fold database rows [s0, s0+len(shard)) into the running lists of query rows
+    [q0, q0+len(x_local)).  `s0 == q0` means the shard IS the rank's own rows (step 0)."""
+    nq, sn, k = x_local.shape[0], shard.shape[0], run_idx.shape[1] - 1
+    if nq == 0 or sn == 0:
+        return
+    if s0 == q0:
+        xc, qoff, keep_lo, keep_hi, goff = x_local, 0, 0, nq, q0
+    elif s0 < q0:
+        xc, qoff, keep_lo, keep_hi, goff = torch.cat([shard, x_local]), sn, 0, sn, s0
+    else:
+        xc, qoff, keep_lo, keep_hi, goff = torch.cat([x_local, shard]), 0, nq, nq + sn, s0 - nq
+    kn = min(k, xc.shape[0] - 1)
+    if kn >= 1:
+        new_idx, _ = ops.knn(xc, kn, qoff, nq, algo)
+        ops.merge(xc, qoff, nq, new_idx, keep_lo, keep_hi, goff, run_idx, run_d2)
+
+
+def make_knn_ring(x_local: torch.Tensor, n: int, k: int, group=None, algo: str = "auto", _ops=None):
+    """Exact kNN graph of an (n, d) matrix whose rows are spread over the ranks: `x_local` holds this rank's rows
+    [q0, q0+nq) = `shard_bounds(n, world, rank)`.  Returns `(idx, dist)` of those rows, global indices.
+
+    `world` ring steps.  In step s the rank holds the shard of rank (rank+s) % world; it forwards it to rank-1
+    while the graph builder runs on [shard ; own rows] stacked in global row order (so the builder's tie-break by
+    local index is the contract's tie-break by global index), and the merge kernel folds the shard's rows of the
+    result into the running lists (`csrc/knn_merge.cu` explains why that is exact).  Step 0 ranks the own rows."""
+    ops = _ops or _DeviceOps()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if k < 1 or k > n - 1:
+        raise ValueError("`k` must be between 1 and (n-1)")
+    q0, nq = shard_bounds(n, world, rank)
+    if x_local.shape[0] != nq:
+        raise ValueError(f"rank {rank} must hold rows [{q0}, {q0 + nq}) of the matrix, got {x_local.shape[0]} rows")
+    per = (n + world - 1) // world
+    d = x_local.shape[1]
+    run_idx, run_d2 = ops.init(nq, k, q0, x_local.device)
+    cur = torch.zeros((per, d), dtype=x_local.dtype, device=x_local.device)
+    cur[:nq] = x_local
+    nxt = torch.empty_like(cur)
+    for s in range(world):
+        s0, sn = shard_bounds(n, world, (rank + s) % world)
+        reqs = []
+        if s + 1 < world:  # pass the shard on while this step computes on it
+            to, frm = (rank - 1) % world, (rank + 1) % world
+            if group is not None:
+                to, frm = dist.get_global_rank(group, to), dist.get_global_rank(group, frm)
+            reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, cur, to, group), dist.P2POp(dist.irecv, nxt, frm, group)])
+        ring_fold(ops, x_local, q0, cur[:sn], s0, run_idx, run_d2, algo)
+        for r in reqs:
+            r.wait()
+        cur, nxt = nxt, cur
+    return run_idx, ops.finish(run_d2)
 
 
 def knn_smooth_sharded(x: torch.Tensor, k: int, coef: float = 1.0, n_iter: int = 1, group=None, algo: str = "auto",
