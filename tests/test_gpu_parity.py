@@ -585,8 +585,8 @@ def test_ring_steps_with_merge_kernel_equal_whole_matrix_build(kind, n, d, k, wo
     x = {"clustered": lambda: clustered(n, d, 8, seed=21), "ties": lambda: tie_data(n, d, seed=22),
          "iid": lambda: np.random.default_rng(23).standard_normal((n, d)).astype(np.float32)}[kind]()
     xd = torch.tensor(x, device="cuda")
-    whole_idx, whole_dist = vv.device.knn_device(xd, k)
     ops = _DeviceOps()
+    whole_idx, whole_dist = ops.knn(xd, k)
     before = vv._lib.launch_count()
     for rank in range(world):
         q0, nq = shard_bounds(n, world, rank)
