@@ -194,6 +194,26 @@ def test_smooth_is_identity_for_coef_zero_and_idempotent_on_constant_data():
     assert np.array_equal(vv.smooth(c, [idx, np.zeros((500, 8), np.float32)], k=8, coef=1.0, n_iter=3), c)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode,m", [("gauss_seidel", 0), ("jacobi", 1)])
+def test_smooth_pipelined_host_path_equals_single_launch_and_oracle(monkeypatch, dtype, mode, m):
+    """vvb_smooth_host with one sweep and a large neighbour matrix runs the sweep in row chunks while the
+    neighbour rows of the next chunk upload and finished rows download; same bytes as the single launch."""
+    n, d, k = 160_000, 24, 40  # 160k x 41 int64 = 52 MB: above the pipeline threshold, ragged last chunk
+    x = clustered(n, d, 12, seed=41).astype(dtype)
+    idx, dist = vv.make_knn(x.astype(np.float32), k=k, verbose=False)
+    single = vv.smooth(x, [idx, dist], k=k, coef=0.6, n_iter=1, mode=mode)
+    monkeypatch.setenv("VVB_SMOOTH_PIPELINE", "1")  # opt-in: neutral on the bench host (host-memory bound)
+    piped = vv.smooth(x, [idx, dist], k=k, coef=0.6, n_iter=1, mode=mode)
+    assert piped.dtype == dtype and np.array_equal(piped, single)
+    assert np.array_equal(piped, orc.smooth(x, idx, k, 0.6, 1, mode=m))
+    bad = idx.copy()
+    bad[n - 5, 7] = n + 3  # in the last chunk
+    with pytest.raises(ValueError, match="must include self"):
+        vv.smooth(x, [bad, dist], k=k, coef=0.6)
+    monkeypatch.delenv("VVB_SMOOTH_PIPELINE")
+
+
 # ======================================================================== quartet
 @pytest.mark.parametrize("name", QUARTET)
 def test_quartet_loss_and_grad_vs_reference_golden(name):

@@ -2,6 +2,8 @@
 #include <sys/mman.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -64,6 +66,11 @@ size_t quartet_workspace_bytes(int64_t B);
 int launch_quartet_fwd(const float *x, const float *z, int64_t B, int D, int L, const int64_t *const *perms,
                        int n_sampling, int mhd, int mld, float *loss_out, float *grad_unit, void *workspace,
                        cudaStream_t st);
+int smooth_begin(void *workspace, int elem_size, int64_t n, int d, int n_iter, cudaStream_t st);
+int launch_smooth_rows(const void *x, int elem_size, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
+                       double coef, int mode, void *out, void *workspace, size_t workspace_bytes, int chunk,
+                       int64_t row_lo, int64_t row_hi, cudaStream_t st);
+int smooth_max_chunks();
 int launch_knn_merge(const float *xc, int64_t nc, int d, int64_t q0, int64_t nq, const int64_t *new_idx, int kn,
                      int64_t keep_lo, int64_t keep_hi, int64_t global_off, int64_t *run_idx, float *run_d2, int k,
                      cudaStream_t st);
@@ -250,6 +257,7 @@ struct DeviceCache {
   size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   StagedCopier copier;
+  StagedCopier copier2;  // second set of bounce buffers: uploads and downloads that run at the same time
   int last_rc = VVB_OK;
   static DeviceCache &get() {
     static DeviceCache c;
@@ -265,6 +273,7 @@ struct DeviceCache {
     if (s_copy) cudaStreamDestroy(s_copy);
     s_compute = s_copy = nullptr;
     copier.release();
+    copier2.release();
   }
   void check_device() {
     int dev = 0;
@@ -583,10 +592,78 @@ int vvb_smooth_host(const void *x_host, int elem_size, int64_t n, int d, const i
   if (!x || !out || !idx || !ws) return dc.last_rc;
   cudaStream_t st = dc.compute_stream();
   if (!st) return VVB_ECUDA;
-  // the whole index matrix goes over as ONE contiguous copy (a pitched copy of the first k columns
-  // moves fewer bytes but runs far slower from pageable memory); the kernel strides by ld_idx
+  // the whole index matrix goes over contiguously (a pitched copy of the first k columns moves fewer
+  // bytes but runs far slower from pageable memory); the kernel strides by ld_idx
   rc = dc.copier.copy(x, x_host, xb, cudaMemcpyHostToDevice, nullptr);
-  if (!rc) rc = dc.copier.copy(idx, idx_host, ib, cudaMemcpyHostToDevice, nullptr);
+  if (rc) return rc;
+  // Opt-in (VVB_SMOOTH_PIPELINE=1): measured neutral on the bench host (1M x 50: 42 ms against 40 ms for the
+  // plain sequence) -- the staging memcpys of both directions share the host's memory bandwidth (~20 GB/s
+  // net), PCIe (54 GB/s pinned, each way) is not the limit.  Pays off on hosts with faster memory.
+  const char *pipe_env = getenv("VVB_SMOOTH_PIPELINE");
+  const bool pipeline = n_iter == 1 && ib >= (32u << 20) && pipe_env && atoi(pipe_env) == 1;
+  if (pipeline) {
+    // One sweep: rows are final as soon as they are written and (Gauss-Seidel) only read rows below them, so
+    // the sweep runs chunk by chunk while a helper thread uploads the neighbour rows of the next chunk and
+    // this thread downloads the finished ones -- PCIe carries both directions at once.
+    VVB_REQUIRE(k <= n - 1, "`k` must be between 1 and (n-1)");
+    VVB_REQUIRE(coef >= 0.0 && coef <= 1.0, "`coef` must be more than 0. and at most 1.");
+    int nchunks = static_cast<int>(ib / (48u << 20));
+    if (nchunks > smooth_max_chunks()) nchunks = smooth_max_chunks();
+    if (nchunks < 2) nchunks = 2;
+    const int64_t per = (n + nchunks - 1) / nchunks;
+    int dev = 0;
+    VVB_CUDA(cudaGetDevice(&dev));
+    rc = smooth_begin(ws, elem_size, n, d, 1, st);
+    if (rc) return rc;
+    std::vector<cudaEvent_t> ev(nchunks, nullptr);
+    for (auto &e : ev) VVB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    std::atomic<int> ready{0}, prc{VVB_OK};
+    std::string perr;
+    std::thread producer([&]() {
+      cudaSetDevice(dev);
+      for (int c = 0; c < nchunks; ++c) {
+        const int64_t r0 = std::min<int64_t>(n, per * c), r1 = std::min<int64_t>(n, r0 + per);
+        int r = dc.copier2.copy(static_cast<char *>(idx) + static_cast<size_t>(r0) * ld_idx * sizeof(int64_t),
+                                reinterpret_cast<const char *>(idx_host) + static_cast<size_t>(r0) * ld_idx * sizeof(int64_t),
+                                static_cast<size_t>(r1 - r0) * ld_idx * sizeof(int64_t), cudaMemcpyHostToDevice, nullptr);
+        if (!r)
+          r = launch_smooth_rows(x, elem_size, n, d, static_cast<const int64_t *>(idx), ld_idx, k, coef, mode, out, ws,
+                                 ws_bytes, c, r0, r1, st);
+        if (!r && cudaEventRecord(ev[c], st) != cudaSuccess) r = VVB_ECUDA;
+        if (r) {
+          perr = vvb_last_error();  // the message is per thread: hand it to the caller's
+          prc = r;
+          ready = nchunks;
+          return;
+        }
+        ready = c + 1;
+      }
+    });
+    pf.join();
+    int crc = VVB_OK;
+    for (int c = 0; c < nchunks && !crc; ++c) {
+      while (ready.load() <= c) std::this_thread::yield();
+      if (prc.load()) break;
+      const int64_t r0 = std::min<int64_t>(n, per * c), r1 = std::min<int64_t>(n, r0 + per);
+      crc = dc.copier.copy(static_cast<char *>(out_host) + static_cast<size_t>(r0) * d * elem_size,
+                           static_cast<const char *>(out) + static_cast<size_t>(r0) * d * elem_size,
+                           static_cast<size_t>(r1 - r0) * d * elem_size, cudaMemcpyDeviceToHost, ev[c]);
+    }
+    producer.join();
+    int bad = 0;
+    cudaError_t ce = cudaMemcpyAsync(&bad, ws, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    for (auto &e : ev) cudaEventDestroy(e);
+    if (prc.load()) {
+      set_error("%s", perr.c_str());
+      return prc.load();
+    }
+    if (crc) return crc;
+    VVB_CUDA(ce);
+    VVB_REQUIRE(bad == 0, "Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed");
+    return VVB_OK;
+  }
+  rc = dc.copier.copy(idx, idx_host, ib, cudaMemcpyHostToDevice, nullptr);
   if (rc) return rc;
   rc = vvb_smooth_device(x, elem_size, n, d, static_cast<const int64_t *>(idx), ld_idx, k, coef, n_iter, mode, out, ws,
                          ws_bytes, st);

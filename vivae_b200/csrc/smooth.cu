@@ -42,15 +42,16 @@ template <> struct Arith<double> {
 template <typename T, int DPL, int KPL, bool GS>
 __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
     const T *__restrict__ prev, T *next, const int64_t *__restrict__ idx, int64_t ld_idx, int64_t n,
-    int d, int k, T coef, int *flags, int epoch, unsigned long long *ticket, int *bad_index, int rows_per_ticket) {
+    int d, int k, T coef, int *flags, int epoch, unsigned long long *ticket, int *bad_index, int rows_per_ticket,
+    int64_t row_lo, int64_t row_hi) {
   const int lane = threadIdx.x & 31;
   const T kk = static_cast<T>(k);
   for (;;) {
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(ticket, 1ull) * rows_per_ticket;
+    if (lane == 0) base = static_cast<unsigned long long>(row_lo) + atomicAdd(ticket, 1ull) * rows_per_ticket;
     base = __shfl_sync(FULL, base, 0);
-    if (base >= static_cast<unsigned long long>(n)) break;
-    const int64_t row_end = min(static_cast<int64_t>(base) + rows_per_ticket, n);
+    if (base >= static_cast<unsigned long long>(row_hi)) break;
+    const int64_t row_end = min(static_cast<int64_t>(base) + rows_per_ticket, row_hi);
     for (int64_t i = static_cast<int64_t>(base); i < row_end; ++i) {
       // the row's neighbour list, coalesced, into registers: lane l holds entries l, l+32, ...
       const int64_t *nb = idx + i * ld_idx;
@@ -137,19 +138,40 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
   }
 }
 
-template <typename T, int DPL, int KPL>
-static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
-                         double coef, int n_iter, int mode, T *out, void *workspace, cudaStream_t st) {
-  // workspace: [bad-index flag][scratch (n*d) T][flags n int][tickets n_iter u64]
-  Carver cv(workspace);
-  int *bad = cv.take<int>(1);
-  T *scratch = cv.take<T>(static_cast<size_t>(n) * d);
-  int *flags = cv.take<int>(static_cast<size_t>(n));
-  unsigned long long *tickets = cv.take<unsigned long long>(static_cast<size_t>(n_iter));
-  VVB_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
-  VVB_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(n) * sizeof(int), st));
-  VVB_CUDA(cudaMemsetAsync(tickets, 0, static_cast<size_t>(n_iter) * sizeof(unsigned long long), st));
+constexpr int SM_MAX_CHUNKS = 64;  // row-range launches of one sweep (the pipelined host path), one ticket each
 
+struct SmoothWs {
+  int *bad;
+  void *scratch;
+  int *flags;
+  unsigned long long *tickets;  // n_iter sweep tickets, then SM_MAX_CHUNKS chunk tickets
+};
+
+static SmoothWs carve_smooth_ws(void *workspace, int elem_size, int64_t n, int d, int n_iter) {
+  // workspace: [bad-index flag][scratch (n*d) T][flags n int][tickets n_iter + SM_MAX_CHUNKS u64]
+  Carver cv(workspace);
+  SmoothWs w;
+  w.bad = cv.take<int>(1);
+  w.scratch = cv.take<char>(static_cast<size_t>(n) * d * elem_size);
+  w.flags = cv.take<int>(static_cast<size_t>(n));
+  w.tickets = cv.take<unsigned long long>(static_cast<size_t>(n_iter) + SM_MAX_CHUNKS);
+  return w;
+}
+
+// Zero the bad-index flag, the publish flags and the tickets: once per smooth call, before any sweep.
+int smooth_begin(void *workspace, int elem_size, int64_t n, int d, int n_iter, cudaStream_t st) {
+  SmoothWs w = carve_smooth_ws(workspace, elem_size, n, d, n_iter);
+  VVB_CUDA(cudaMemsetAsync(w.bad, 0, sizeof(int), st));
+  VVB_CUDA(cudaMemsetAsync(w.flags, 0, static_cast<size_t>(n) * sizeof(int), st));
+  VVB_CUDA(cudaMemsetAsync(w.tickets, 0, (static_cast<size_t>(n_iter) + SM_MAX_CHUNKS) * sizeof(unsigned long long), st));
+  return VVB_OK;
+}
+
+// One launch of sweep `epoch` (1-based) over rows [row_lo, row_hi) with its own ticket.
+template <typename T, int DPL, int KPL>
+static int launch_rows(const T *src, T *dst, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k, double coef,
+                       int mode, const SmoothWs &w, int epoch, unsigned long long *ticket, int64_t row_lo,
+                       int64_t row_hi, cudaStream_t st) {
   int blocks_per_sm = 0;
   auto kern_gs = smooth_sweep_kernel<T, DPL, KPL, true>;
   auto kern_ja = smooth_sweep_kernel<T, DPL, KPL, false>;
@@ -158,7 +180,8 @@ static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64
   if (blocks_per_sm < 1) blocks_per_sm = 1;
   int rpt = SM_ROWS_PER_TICKET_DEFAULT;
   if (const char *e = getenv("VVB_SMOOTH_RPT")) rpt = atoi(e) > 0 ? atoi(e) : rpt;
-  const int64_t warps_needed = (n + rpt - 1) / rpt;
+  const int64_t rows = row_hi - row_lo;
+  const int64_t warps_needed = (rows + rpt - 1) / rpt;
   int64_t grid = static_cast<int64_t>(sm_count()) * blocks_per_sm;
   const int64_t max_useful = (warps_needed + SM_THREADS / 32 - 1) / (SM_THREADS / 32);
   if (grid > max_useful) grid = max_useful;
@@ -169,19 +192,33 @@ static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64
     if (grid > cap) grid = cap;
   }
   if (grid < 1) grid = 1;
+  if (mode == VVB_SMOOTH_JACOBI)
+    kern_ja<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k, static_cast<T>(coef),
+                                                               w.flags, epoch, ticket, w.bad, rpt, row_lo, row_hi);
+  else
+    kern_gs<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k, static_cast<T>(coef),
+                                                               w.flags, epoch, ticket, w.bad, rpt, row_lo, row_hi);
+  VVB_CHECK_LAUNCH();
+  return VVB_OK;
+}
 
-  // ping-pong so that the LAST sweep lands in `out`:  sweep s reads a_s, writes b_s
+// chunk < 0: all n_iter sweeps over all rows (ping-pong so that the LAST sweep lands in `out`: sweep s reads
+// a_s, writes b_s).  chunk >= 0: rows [row_lo, row_hi) of a ONE-sweep call, x -> out; the caller issues the
+// chunks in increasing row order on one stream after smooth_begin().
+template <typename T, int DPL, int KPL>
+static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k, double coef,
+                         int n_iter, int mode, T *out, void *workspace, int chunk, int64_t row_lo, int64_t row_hi,
+                         cudaStream_t st) {
+  SmoothWs w = carve_smooth_ws(workspace, sizeof(T), n, d, n_iter);
+  if (chunk >= 0)
+    return launch_rows<T, DPL, KPL>(x, out, n, d, idx, ld_idx, k, coef, mode, w, 1, w.tickets + n_iter + chunk, row_lo,
+                                    row_hi, st);
   const T *src = x;
   for (int it = 0; it < n_iter; ++it) {
     const bool to_out = ((n_iter - 1 - it) % 2) == 0;
-    T *dst = to_out ? out : scratch;
-    if (mode == VVB_SMOOTH_JACOBI)
-      kern_ja<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k,
-                                                                 static_cast<T>(coef), flags, it + 1, tickets + it, bad, rpt);
-    else
-      kern_gs<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k,
-                                                                 static_cast<T>(coef), flags, it + 1, tickets + it, bad, rpt);
-    VVB_CHECK_LAUNCH();
+    T *dst = to_out ? out : static_cast<T *>(w.scratch);
+    int rc = launch_rows<T, DPL, KPL>(src, dst, n, d, idx, ld_idx, k, coef, mode, w, it + 1, w.tickets + it, 0, n, st);
+    if (rc) return rc;
     src = dst;
   }
   return VVB_OK;
@@ -189,23 +226,22 @@ static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64
 
 size_t smooth_workspace_bytes(int elem_size, int64_t n, int d, int n_iter) {
   return 256 + align_up(static_cast<size_t>(n) * d * elem_size, 256) + align_up(static_cast<size_t>(n) * sizeof(int), 256) +
-         align_up(static_cast<size_t>(n_iter) * sizeof(unsigned long long), 256) + 256;
+         align_up((static_cast<size_t>(n_iter) + SM_MAX_CHUNKS) * sizeof(unsigned long long), 256) + 256;
 }
 
-int launch_smooth(const void *x, int elem_size, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
-                  double coef, int n_iter, int mode, void *out, void *workspace, size_t workspace_bytes,
-                  cudaStream_t st) {
-  VVB_REQUIRE(elem_size == 4 || elem_size == 8, "smooth: elem_size must be 4 or 8");
-  VVB_REQUIRE(n >= 1 && d >= 1 && k >= 1 && ld_idx >= k && n_iter >= 1, "smooth: bad shape arguments");
-  VVB_REQUIRE(mode == VVB_SMOOTH_GAUSS_SEIDEL || mode == VVB_SMOOTH_JACOBI, "smooth: unknown mode %d", mode);
-  VVB_REQUIRE(out != x, "smooth: out must not alias x");
-  VVB_REQUIRE(workspace_bytes >= smooth_workspace_bytes(elem_size, n, d, n_iter), "smooth: workspace too small");
-  VVB_REQUIRE(k <= 1024, "smooth: k=%d above the supported maximum of 1024", k);
-#define VVB_SM_K(T, DPL, xp, op)                                                                          \
-  do {                                                                                                    \
-    if (k <= 64) return launch_sweeps<T, DPL, 2>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, st);   \
-    if (k <= 128) return launch_sweeps<T, DPL, 4>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, st);  \
-    return launch_sweeps<T, DPL, 32>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, st);    \
+static int smooth_dispatch(const void *x, int elem_size, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
+                           double coef, int n_iter, int mode, void *out, void *workspace, int chunk, int64_t row_lo,
+                           int64_t row_hi, cudaStream_t st) {
+#define VVB_SM_K(T, DPL, xp, op)                                                                                      \
+  do {                                                                                                                \
+    if (k <= 64)                                                                                                      \
+      return launch_sweeps<T, DPL, 2>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,     \
+                                      row_hi, st);                                                                    \
+    if (k <= 128)                                                                                                     \
+      return launch_sweeps<T, DPL, 4>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,     \
+                                      row_hi, st);                                                                    \
+    return launch_sweeps<T, DPL, 32>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,      \
+                                     row_hi, st);                                                                     \
   } while (0)
   if (elem_size == 4) {
     const float *xf = static_cast<const float *>(x);
@@ -221,5 +257,43 @@ int launch_smooth(const void *x, int elem_size, int64_t n, int d, const int64_t 
   VVB_SM_K(double, 4, xd, od);
 #undef VVB_SM_K
 }
+
+static int smooth_check(const void *x, int elem_size, int64_t n, int d, int64_t ld_idx, int k, int n_iter, int mode,
+                        const void *out, size_t workspace_bytes) {
+  VVB_REQUIRE(elem_size == 4 || elem_size == 8, "smooth: elem_size must be 4 or 8");
+  VVB_REQUIRE(n >= 1 && d >= 1 && k >= 1 && ld_idx >= k && n_iter >= 1, "smooth: bad shape arguments");
+  VVB_REQUIRE(mode == VVB_SMOOTH_GAUSS_SEIDEL || mode == VVB_SMOOTH_JACOBI, "smooth: unknown mode %d", mode);
+  VVB_REQUIRE(out != x, "smooth: out must not alias x");
+  VVB_REQUIRE(workspace_bytes >= smooth_workspace_bytes(elem_size, n, d, n_iter), "smooth: workspace too small");
+  VVB_REQUIRE(k <= 1024, "smooth: k=%d above the supported maximum of 1024", k);
+  return VVB_OK;
+}
+
+int launch_smooth(const void *x, int elem_size, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
+                  double coef, int n_iter, int mode, void *out, void *workspace, size_t workspace_bytes,
+                  cudaStream_t st) {
+  int rc = smooth_check(x, elem_size, n, d, ld_idx, k, n_iter, mode, out, workspace_bytes);
+  if (rc) return rc;
+  rc = smooth_begin(workspace, elem_size, n, d, n_iter, st);
+  if (rc) return rc;
+  return smooth_dispatch(x, elem_size, n, d, idx, ld_idx, k, coef, n_iter, mode, out, workspace, -1, 0, n, st);
+}
+
+// Rows [row_lo, row_hi) of a one-sweep smooth (chunk = 0, 1, ... < smooth_max_chunks(), increasing row ranges,
+// all on one stream, after smooth_begin): lets the host entry point overlap the upload of the neighbour matrix and
+// the download of the result with the sweep itself.  In Gauss-Seidel mode a row only reads rows below it from the
+// output, so a chunk never needs anything a later chunk produces.
+int launch_smooth_rows(const void *x, int elem_size, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
+                       double coef, int mode, void *out, void *workspace, size_t workspace_bytes, int chunk,
+                       int64_t row_lo, int64_t row_hi, cudaStream_t st) {
+  int rc = smooth_check(x, elem_size, n, d, ld_idx, k, 1, mode, out, workspace_bytes);
+  if (rc) return rc;
+  VVB_REQUIRE(chunk >= 0 && chunk < SM_MAX_CHUNKS && row_lo >= 0 && row_lo <= row_hi && row_hi <= n,
+              "smooth: bad row chunk");
+  if (row_lo == row_hi) return VVB_OK;
+  return smooth_dispatch(x, elem_size, n, d, idx, ld_idx, k, coef, 1, mode, out, workspace, chunk, row_lo, row_hi, st);
+}
+
+int smooth_max_chunks() { return SM_MAX_CHUNKS; }
 
 }  // namespace vvb
