@@ -90,7 +90,16 @@ static inline int tc_atoms(int d) { return (d + 3 + 63) / 64; }
 
 static inline int tc_candidates(int k) {
   const int slack = k / 4 > 16 ? k / 4 : 16;
-  return k + 1 + slack;
+  int m = k + 1 + slack;
+  // The re-rank kernel works in groups of 32 candidates (a 200-byte gather, an fmaf chain and a slot of the
+  // bitonic sort each), and the screening kernel hands over between m and min(round_up_32(m), m + 8) of them:
+  // a list that spills a few entries into one more group pays for the whole group.  If m is just above a
+  // group boundary, step 4 below it (k = 50: 67 -> 60, at most 64 candidates: two groups instead of three and
+  // a sort of 64 instead of 128 keys).  Exactness does not depend on m -- a row whose k-th distance is not
+  // below its admission threshold goes to the brute-force fallback whatever m is.
+  const int g = m & ~31;
+  if (m - g <= 4 && g - 4 - (k + 1) >= 8) m = g - 4;
+  return m;
 }
 // List length that triggers a compaction.  Measured on B200 (1M x 50, k=50; screening kernel time):
 // trigger 224 of capacity 256: 380 ms; trigger 96 (fresher thresholds, 3x the compactions): 445 ms;

@@ -43,9 +43,9 @@ def knn_device(x: torch.Tensor, k: int, q0: int = 0, nq: Optional[int] = None, a
     with torch.cuda.device(x.device):
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.vvb_make_knn_workspace_bytes(n, d, k, nq, a, ctypes.byref(nbytes)))
-        ws = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=x.device)
-        idx = torch.empty((nq, k + 1), dtype=torch.int64, device=x.device)
-        dist = torch.empty((nq, k + 1), dtype=torch.float32, device=x.device)
+        ws = _lib.raw_empty(max(int(nbytes.value), 256), torch.uint8, x.device)
+        idx = _lib.raw_empty((nq, k + 1), torch.int64, x.device)
+        dist = _lib.raw_empty((nq, k + 1), torch.float32, x.device)
         st = _lib.KnnStats() if stats is not None else None
         _lib.check(lib.vvb_make_knn_device(x.data_ptr(), n, d, k, q0, nq, a, idx.data_ptr(), dist.data_ptr(),
                                            ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream,
@@ -70,8 +70,8 @@ def smooth_device(x: torch.Tensor, idx: torch.Tensor, k: int = 50, coef: float =
     with torch.cuda.device(x.device):
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.vvb_smooth_workspace_bytes(x.element_size(), n, d, n_iter, ctypes.byref(nbytes)))
-        ws = torch.empty(int(nbytes.value), dtype=torch.uint8, device=x.device)
-        out = torch.empty_like(x)
+        ws = _lib.raw_empty(int(nbytes.value), torch.uint8, x.device)
+        out = _lib.raw_empty(x.shape, x.dtype, x.device)
         _lib.check(lib.vvb_smooth_device(x.data_ptr(), x.element_size(), n, d, idx.data_ptr(), idx.shape[1], int(k),
                                          float(coef), int(n_iter), _lib.SMOOTH_MODES[mode], out.data_ptr(),
                                          ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
@@ -87,8 +87,8 @@ def knn_merge_init(nq: int, k: int, self0: int, device) -> tuple[torch.Tensor, t
     if device.type != "cuda":
         raise RuntimeError("knn_merge_init: a CUDA device is required (vivae_b200 has no CPU path)")
     with torch.cuda.device(device):
-        run_idx = torch.empty((nq, k + 1), dtype=torch.int64, device=device)
-        run_d2 = torch.empty((nq, k + 1), dtype=torch.float32, device=device)
+        run_idx = _lib.raw_empty((nq, k + 1), torch.int64, device)
+        run_d2 = _lib.raw_empty((nq, k + 1), torch.float32, device)
         _lib.check(lib.vvb_knn_merge_init_device(run_idx.data_ptr(), run_d2.data_ptr(), nq, k, self0,
                                                  torch.cuda.current_stream().cuda_stream))
     return run_idx, run_d2
@@ -118,7 +118,7 @@ def knn_merge_finish(run_d2: torch.Tensor) -> torch.Tensor:
     """Distances (correctly rounded square roots) of the running squared distances."""
     lib = _lib.load()
     run_d2 = _require_cuda("run_d2", run_d2, torch.float32)
-    out = torch.empty_like(run_d2)
+    out = _lib.raw_empty(run_d2.shape, run_d2.dtype, run_d2.device)
     with torch.cuda.device(run_d2.device):
         _lib.check(lib.vvb_knn_merge_finish_device(run_d2.data_ptr(), run_d2.numel(), out.data_ptr(),
                                                    torch.cuda.current_stream().cuda_stream))

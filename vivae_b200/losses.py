@@ -42,9 +42,9 @@ class _QuartetLossFn(torch.autograd.Function):
         B, D = x.shape
         L = zc.shape[1]
         need_grad = ctx.needs_input_grad[1]
-        loss = torch.empty((), dtype=torch.float32, device=x.device)
-        grad_unit = torch.empty_like(zc) if need_grad else None
-        ws = torch.empty(int(lib.vvb_quartet_workspace_bytes(B)), dtype=torch.uint8, device=x.device)
+        loss = _lib.raw_empty((), torch.float32, x.device)
+        grad_unit = _lib.raw_empty(zc.shape, zc.dtype, zc.device) if need_grad else None
+        ws = _lib.raw_empty(int(lib.vvb_quartet_workspace_bytes(B)), torch.uint8, x.device)
         n_sampling = len(perms)
         keep = [None if p is None else p.to(device=x.device, dtype=torch.int64).contiguous() for p in perms]
         arr = (ctypes.c_void_p * n_sampling)(*[None if p is None else p.data_ptr() for p in keep])
@@ -63,7 +63,7 @@ class _QuartetLossFn(torch.autograd.Function):
         (grad_unit,) = ctx.saved_tensors
         lib = _lib.load()
         go = grad_out.detach().to(dtype=torch.float32).contiguous()
-        gz = torch.empty_like(grad_unit)
+        gz = _lib.raw_empty(grad_unit.shape, grad_unit.dtype, grad_unit.device)
         with torch.cuda.device(grad_unit.device):
             stream = torch.cuda.current_stream().cuda_stream
             _lib.check(lib.vvb_quartet_loss_bwd_device(grad_unit.data_ptr(), go.data_ptr(), grad_unit.numel(),
