@@ -372,8 +372,9 @@ def run_ours(args) -> None:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        h2d = n * d * 4 + (n * d * 4 + n * (k + 1) * 8 if world == 1 else 0)
-        d2h = nq * (k + 1) * 12 + (n * d * 4 if world == 1 else 0)
+        # bytes that cross PCIe: neighbour indices travel as int32 (widened / narrowed in the staging copy)
+        h2d = n * d * 4 + (n * d * 4 + n * (k + 1) * 4 if world == 1 else 0)
+        d2h = nq * (k + 1) * 8 + (n * d * 4 if world == 1 else 0)
         e2e = {"value": n / dt, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "path": "vv.make_knn + vv.smooth (host NumPy in/out)" if world == 1 else
@@ -456,7 +457,7 @@ def main():
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--exchange", default="replicated", choices=["replicated", "ring"],
                     help="N>1: every rank holds the matrix (default) or only its rows, shards passed around an NCCL ring")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-fit", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

@@ -468,7 +468,7 @@ def test_tensor_path_is_used_and_fallback_is_rare():
     x = clustered(50_000, 50, 30, seed=1)
     st = {}
     idx, dist = vv.make_knn(x, k=50, verbose=False, algo="tensor", stats=st)
-    assert st["algo_used"] == 2 and st["candidates"] == 67
+    assert st["algo_used"] == 2 and st["candidates"] == 60  # tc_candidates(50)
     assert st["rows_fallback"] <= 0.01 * st["rows"], st
     for q0 in (0, 25_000, 49_000):
         wi, wd = orc.knn(x, 50, q0, q0 + 500)

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -160,6 +161,22 @@ struct HostPrefault {
 // (~10 GB/s measured on the bench host).  Here T worker threads each own a slice of the array, two pinned
 // bounce buffers and a stream: memcpy into pinned memory and DMA out of it overlap, and the T memcpys run in
 // parallel.  Blocking: returns when the data has arrived.
+// Neighbour indices cross PCIe as int32 and live as int64 on both sides (the reference's dtype, knn.py:137):
+// the staging memcpy is where they are widened / narrowed, so the conversion costs no extra pass and the
+// copies -- bound by the host's memory bandwidth, not by PCIe -- move a third less.
+enum CopyConv { CONV_NONE = 0, CONV_WIDEN_I32 = 1 /* D2H: device int32 -> host int64 */,
+                CONV_NARROW_I64 = 2 /* H2D: host int64 -> device int32, out-of-range -> -1 */ };
+
+static void widen_i32(int64_t *dst, const int32_t *src, size_t count) {
+  for (size_t i = 0; i < count; ++i) dst[i] = src[i];
+}
+static void narrow_i64(int32_t *dst, const int64_t *src, size_t count) {
+  for (size_t i = 0; i < count; ++i) {
+    const int64_t v = src[i];
+    dst[i] = (v >= 0 && v <= INT32_MAX) ? static_cast<int32_t>(v) : -1;  // -1 is flagged by the kernel
+  }
+}
+
 struct StagedCopier {
   static constexpr int T = 6;
   static constexpr size_t CH = 4u << 20;
@@ -193,7 +210,8 @@ struct StagedCopier {
   }
   // dir = cudaMemcpyHostToDevice: dst device, src host;  cudaMemcpyDeviceToHost: dst host, src device.
   // `after`: event the device side must wait for before it is read (D2H) or overwritten (H2D); may be null.
-  int copy(void *dst, const void *src, size_t bytes, cudaMemcpyKind dir, cudaEvent_t after) {
+  // `bytes` counts the DEVICE side; with a conversion the host side is twice as large.
+  int copy(void *dst, const void *src, size_t bytes, cudaMemcpyKind dir, cudaEvent_t after, int conv = CONV_NONE) {
     if (bytes == 0) return VVB_OK;
     int rc = init();
     if (rc) return rc;
@@ -213,7 +231,10 @@ struct StagedCopier {
           const int b = static_cast<int>((c - c0) & 1);
           const size_t off = c * CH, len = (off + CH <= bytes) ? CH : bytes - off;
           if (c - c0 >= 2 && cudaEventSynchronize(ev[t][b]) != cudaSuccess) failed = 1;  // bounce buffer free again
-          memcpy(pin[t][b], s + off, len);
+          if (conv == CONV_NARROW_I64)
+            narrow_i64(reinterpret_cast<int32_t *>(pin[t][b]), reinterpret_cast<const int64_t *>(s + 2 * off), len / 4);
+          else
+            memcpy(pin[t][b], s + off, len);
           if (cudaMemcpyAsync(d + off, pin[t][b], len, cudaMemcpyHostToDevice, st[t]) != cudaSuccess) failed = 1;
           cudaEventRecord(ev[t][b], st[t]);
         }
@@ -230,7 +251,10 @@ struct StagedCopier {
             const int b = static_cast<int>((c - 1 - c0) & 1);
             const size_t off = (c - 1) * CH, len = (off + CH <= bytes) ? CH : bytes - off;
             if (cudaEventSynchronize(ev[t][b]) != cudaSuccess) failed = 1;
-            memcpy(d + off, pin[t][b], len);
+            if (conv == CONV_WIDEN_I32)
+              widen_i32(reinterpret_cast<int64_t *>(d + 2 * off), reinterpret_cast<const int32_t *>(pin[t][b]), len / 4);
+            else
+              memcpy(d + off, pin[t][b], len);
           }
         }
       }
@@ -327,6 +351,15 @@ struct DeviceCache {
     return s_copy;
   }
 };
+
+__global__ void narrow_idx_kernel(const int64_t *__restrict__ in, int32_t *__restrict__ out, int64_t count) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = static_cast<int32_t>(in[i]);  // row indices (or -1) of a matrix with n <= INT32_MAX rows
+}
+__global__ void widen_idx_kernel(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t count) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = in[i];
+}
 
 static int knn_check_args(const void *x, int64_t n, int d, int k, int64_t q0, int64_t nq, const void *idx,
                           const void *dist) {
@@ -466,7 +499,9 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
   int64_t *idx_dev = static_cast<int64_t *>(dc.slot(1, idx_bytes));
   float *dist_dev = static_cast<float *>(dc.slot(2, dist_bytes));
   void *ws = dc.slot(3, ws_bytes);
-  if (!x_dev || !idx_dev || !dist_dev || !ws) return dc.last_rc;
+  const bool narrow = n <= INT32_MAX;  // indices travel as int32 (see CopyConv)
+  int32_t *idx32_dev = narrow ? static_cast<int32_t *>(dc.slot(5, idx_bytes / 2)) : nullptr;
+  if (!x_dev || !idx_dev || !dist_dev || !ws || (narrow && !idx32_dev)) return dc.last_rc;
   cudaStream_t st = dc.compute_stream();
   if (!st) return VVB_ECUDA;
   const int64_t launches0 = g_launches.load();
@@ -492,10 +527,14 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
       pf.join();
       joined = true;
     }
-    bg = std::thread([&dc, &bg_rc, dev, c0, rows, ev, k, idx_out_host, dist_out_host, idx_dev, dist_dev]() {
+    bg = std::thread([&dc, &bg_rc, dev, c0, rows, ev, k, idx_out_host, dist_out_host, idx_dev, idx32_dev, dist_dev]() {
       cudaSetDevice(dev);
-      int r = dc.copier.copy(idx_out_host + c0 * (k + 1), idx_dev + c0 * (k + 1),
-                             static_cast<size_t>(rows) * (k + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ev);
+      int r = idx32_dev ? dc.copier.copy(idx_out_host + c0 * (k + 1), idx32_dev + c0 * (k + 1),
+                                         static_cast<size_t>(rows) * (k + 1) * sizeof(int32_t),
+                                         cudaMemcpyDeviceToHost, ev, CONV_WIDEN_I32)
+                        : dc.copier.copy(idx_out_host + c0 * (k + 1), idx_dev + c0 * (k + 1),
+                                         static_cast<size_t>(rows) * (k + 1) * sizeof(int64_t),
+                                         cudaMemcpyDeviceToHost, ev);
       if (!r)
         r = dc.copier.copy(dist_out_host + c0 * (k + 1), dist_dev + c0 * (k + 1),
                            static_cast<size_t>(rows) * (k + 1) * sizeof(float), cudaMemcpyDeviceToHost, ev);
@@ -507,6 +546,12 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
   cudaEvent_t pend_ev = nullptr;
   rc = knn_run(x_dev, n, d, k, q0, nq, use, idx_dev, dist_dev, ws, ws_bytes, st, stats, /*host_path=*/true,
                [&](int64_t c0, int64_t rows) -> int {
+                 if (idx32_dev && rows > 0) {  // right behind the chunk's kernels, ahead of the next chunk's
+                   const int64_t cnt = rows * (k + 1);
+                   narrow_idx_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, st>>>(
+                       idx_dev + c0 * (k + 1), idx32_dev + c0 * (k + 1), cnt);
+                   VVB_CHECK_LAUNCH();
+                 }
                  cudaEvent_t e = nullptr;
                  VVB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                  events.push_back(e);
@@ -663,8 +708,19 @@ int vvb_smooth_host(const void *x_host, int elem_size, int64_t n, int d, const i
     VVB_REQUIRE(bad == 0, "Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed");
     return VVB_OK;
   }
-  rc = dc.copier.copy(idx, idx_host, ib, cudaMemcpyHostToDevice, nullptr);
-  if (rc) return rc;
+  if (n <= INT32_MAX) {
+    void *idx32 = dc.slot(5, ib / 2);
+    if (!idx32) return dc.last_rc;
+    rc = dc.copier.copy(idx32, idx_host, ib / 2, cudaMemcpyHostToDevice, nullptr, CONV_NARROW_I64);
+    if (rc) return rc;
+    const int64_t cnt = n * ld_idx;
+    widen_idx_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, st>>>(static_cast<const int32_t *>(idx32),
+                                                                              static_cast<int64_t *>(idx), cnt);
+    VVB_CHECK_LAUNCH();
+  } else {
+    rc = dc.copier.copy(idx, idx_host, ib, cudaMemcpyHostToDevice, nullptr);
+    if (rc) return rc;
+  }
   rc = vvb_smooth_device(x, elem_size, n, d, static_cast<const int64_t *>(idx), ld_idx, k, coef, n_iter, mode, out, ws,
                          ws_bytes, st);
   if (rc) return rc;
