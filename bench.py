@@ -361,7 +361,8 @@ def run_ours(args) -> None:
             idx_h, dist_h = _knn_host(xq, k, q0, nq, args.algo, None)
             return float(dist_h[0, 1]) if nq else 0.0
 
-        step_e2e()  # warm-up
+        for _ in range(3):  # warm-up: device buffers, bounce buffers and the pool of page-locked result blocks
+            step_e2e()
         sync_all()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):

@@ -74,6 +74,13 @@ int64_t vvb_launch_count(void);
  * this frees them */
 int vvb_release_cached_memory(void);
 
+/* Page-locked host memory for result arrays.  The *_host entry points recognise page-locked host
+ * pointers (these, or any cudaHostAlloc / cudaHostRegister memory the caller owns) and DMA to / from
+ * them directly; pageable pointers are staged through bounce buffers.  The Python layer returns its
+ * result arrays (knn.py:137-141, 185) in recycled blocks from here. */
+int vvb_host_alloc(size_t bytes, void **ptr_out);
+int vvb_host_free(void *ptr);
+
 /* ------------------------------------------------------------------------
  * make_knn  -- replaces the cache-miss branch of
  *   /root/reference/src/vivae/knn.py:133-141

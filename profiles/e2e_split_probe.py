@@ -6,7 +6,7 @@ from bench import synth_cells
 import vivae_b200 as vv
 x = synth_cells(1_000_000, 50)
 res = {}
-for rep in range(3):
+for rep in range(6):
     t0 = time.perf_counter(); knn = vv.make_knn(x, k=50, verbose=False); t1 = time.perf_counter()
     out = vv.smooth(x, knn, k=50, coef=1.0, n_iter=1); t2 = time.perf_counter()
     res[f"rep{rep}"] = {"make_knn_ms": 1e3 * (t1 - t0), "smooth_ms": 1e3 * (t2 - t1)}

@@ -214,6 +214,43 @@ def test_smooth_pipelined_host_path_equals_single_launch_and_oracle(monkeypatch,
     monkeypatch.delenv("VVB_SMOOTH_PIPELINE")
 
 
+def test_results_live_in_recycled_page_locked_blocks(monkeypatch):
+    """Large result arrays are NumPy views of page-locked blocks (direct DMA instead of a staged copy); a block
+    returns to the pool when its arrays die and is reused by the next call; VVB_PINNED_RESULTS=0 gives plain
+    arrays with the same contents; pinned arrays are accepted as inputs (smooth reads the graph directly)."""
+    import gc
+
+    x = clustered(60_000, 50, 10, seed=3)
+
+    def owner(a):
+        while isinstance(a, np.ndarray) and a.base is not None:
+            a = a.base
+        return a
+
+    first = vv.make_knn(x, k=50, verbose=False)
+    idx, dist = vv.make_knn(x, k=50, verbose=False)
+    assert type(idx) is np.ndarray and idx.flags.c_contiguous and idx.flags.writeable and idx.dtype == np.int64
+    blk = owner(idx)
+    assert type(blk).__name__ == "_PinnedBlock" and type(owner(dist)).__name__ == "_PinnedBlock"
+    ptr = blk.ptr
+    sm = vv.smooth(x, [idx, dist], k=50, coef=1.0)
+    want_sm = orc.smooth(x, idx, 50, 1.0, 1)
+    assert np.array_equal(sm, want_sm) and np.array_equal(first[0], idx) and np.array_equal(first[1], dist)
+    del first
+    keep_idx, keep_dist = idx.copy(), dist.copy()
+    del idx, dist, blk
+    gc.collect()
+    idx2, dist2 = vv.make_knn(x, k=50, verbose=False)
+    assert owner(idx2).ptr == ptr, "freed block was not recycled"
+    assert np.array_equal(idx2, keep_idx) and np.array_equal(dist2, keep_dist)
+    monkeypatch.setenv("VVB_PINNED_RESULTS", "0")
+    idx3, dist3 = vv.make_knn(x, k=50, verbose=False)
+    assert not isinstance(owner(idx3), type(owner(idx2))) and np.array_equal(idx3, keep_idx) and np.array_equal(dist3, keep_dist)
+    assert np.array_equal(vv.smooth(x, [idx3, dist3], k=50, coef=1.0), want_sm)
+    wi, wd = orc.knn(x, 50, 1000, 1400)
+    assert np.array_equal(keep_idx[1000:1400], wi) and np.array_equal(keep_dist[1000:1400], wd)
+
+
 # ======================================================================== quartet
 @pytest.mark.parametrize("name", QUARTET)
 def test_quartet_loss_and_grad_vs_reference_golden(name):

@@ -50,6 +50,8 @@ SYMBOLS = {
     "vvb_last_error": (ctypes.c_char_p, []),
     "vvb_launch_count": (_i64, []),
     "vvb_release_cached_memory": (_int, []),
+    "vvb_host_alloc": (_int, [_sz, ctypes.POINTER(ctypes.c_void_p)]),
+    "vvb_host_free": (_int, [_vp]),
     "vvb_make_knn_host": (_int, [_vp, _i64, _int, _int, _i64, _i64, _int, _vp, _vp, ctypes.POINTER(KnnStats)]),
     "vvb_make_knn_workspace_bytes": (_int, [_i64, _int, _int, _i64, _int, ctypes.POINTER(_sz)]),
     "vvb_make_knn_device": (_int, [_vp, _i64, _int, _int, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp,
@@ -145,3 +147,96 @@ def raw_empty(shape, dtype, device):
         return torch.empty(shape, dtype=dtype, device=device)
     finally:
         det.fill_uninitialized_memory = True
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Result arrays in page-locked memory.  A D2H copy into a fresh pageable NumPy array is bound by the host
+# (page faults, then a staging memcpy: ~20 GB/s on the bench host); into page-locked memory it is one DMA at
+# PCIe speed (54 GB/s).  Pinning is slow (~0.5 s per GB), so blocks are recycled: when the last array that
+# views a block is garbage-collected the block goes back to the pool, and the next call of the same size reuses
+# it.  The first request of a size gets ordinary memory (a one-off call never pays for pinning); repeated
+# calls of the same shape reach the steady state after two or three calls.  `VVB_PINNED_RESULTS=0` switches this off; `VVB_PINNED_MAX_MB` (default 4096) caps the pool -- beyond it
+# results are ordinary NumPy arrays.
+class _PinnedBlock:
+    """Owner of one page-locked block; NumPy arrays made from it keep it alive through `.base`."""
+
+    def __init__(self, ptr: int, cap: int, nbytes: int):
+        self.ptr, self.cap, self.nbytes = ptr, cap, nbytes
+
+    @property
+    def __array_interface__(self):
+        return {"data": (self.ptr, False), "shape": (self.nbytes,), "typestr": "|u1", "version": 3}
+
+    def __del__(self):
+        try:
+            _pinned_pool.give_back(self.ptr, self.cap)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+class _PinnedPool:
+    def __init__(self):
+        import threading
+
+        self.lock = threading.Lock()
+        self.free = []   # (cap, ptr)
+        self.total = 0   # bytes pinned by this pool (in use + free)
+        self.seen = {}   # size class -> requests that found no free block
+
+    def _limit(self) -> int:
+        return int(os.environ.get("VVB_PINNED_MAX_MB", "4096")) << 20
+
+    def take(self, nbytes: int):
+        """A free block of this size class, or -- from the second request of the class on -- a newly pinned
+        one; None when the caller should use ordinary memory.  The very first request of a size is never
+        pinned: a one-off call would pay the pinning and never get it back."""
+        lib = load()
+        cap = (nbytes + (1 << 21) - 1) >> 21 << 21
+        with self.lock:
+            for c, p in self.free:
+                if c == cap:
+                    self.free.remove((c, p))
+                    return _PinnedBlock(p, cap, nbytes)
+            self.seen[cap] = self.seen.get(cap, 0) + 1
+            if self.seen[cap] < 2:
+                return None
+            while self.total + cap > self._limit() and self.free:  # make room: drop idle blocks, largest first
+                c, p = max(self.free)
+                self.free.remove((c, p))
+                lib.vvb_host_free(p)
+                self.total -= c
+            if self.total + cap > self._limit():
+                return None
+            ptr = ctypes.c_void_p()
+            if lib.vvb_host_alloc(cap, ctypes.byref(ptr)) != OK or not ptr.value:
+                return None
+            self.total += cap
+            return _PinnedBlock(ptr.value, cap, nbytes)
+
+    def give_back(self, ptr: int, cap: int) -> None:
+        with self.lock:
+            self.free.append((cap, ptr))
+
+    def release(self) -> None:
+        lib = load()
+        with self.lock:
+            for c, p in self.free:
+                lib.vvb_host_free(p)
+                self.total -= c
+            self.free = []
+
+
+_pinned_pool = _PinnedPool()
+
+
+def result_empty(shape, dtype):
+    """Uninitialised result array: page-locked (pool above) when large and allowed, else `np.empty`."""
+    import numpy as np
+
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    if nbytes >= (8 << 20) and os.environ.get("VVB_PINNED_RESULTS", "1") != "0":
+        block = _pinned_pool.take(nbytes)
+        if block is not None:
+            return np.asarray(block).view(dtype).reshape(shape)
+    return np.empty(shape, dtype=dtype)

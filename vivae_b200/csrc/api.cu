@@ -119,6 +119,23 @@ struct EventTimer {
   }
 };
 
+// True if [p, p + bytes) is page-locked memory CUDA knows about (cudaHostAlloc / cudaHostRegister): the arrays
+// this package returns come from such a pool (vvb_host_alloc), and callers may pass their own pinned buffers.
+static bool host_range_is_pinned(const void *p, size_t bytes) {
+  if (!p || bytes == 0) return false;
+  cudaPointerAttributes a0, a1;
+  if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || a0.type != cudaMemoryTypeHost) {
+    cudaGetLastError();
+    return false;
+  }
+  if (cudaPointerGetAttributes(&a1, static_cast<const char *>(p) + bytes - 1) != cudaSuccess ||
+      a1.type != cudaMemoryTypeHost) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
 // Touch the pages of freshly allocated host output arrays on helper threads.
 struct HostPrefault {
   struct Range {
@@ -128,7 +145,7 @@ struct HostPrefault {
   std::vector<Range> ranges;
   std::vector<std::thread> threads;
   void add(void *p, size_t bytes) {
-    if (p && bytes >= (8u << 20)) ranges.push_back({static_cast<char *>(p), bytes});
+    if (p && bytes >= (8u << 20) && !host_range_is_pinned(p, bytes)) ranges.push_back({static_cast<char *>(p), bytes});
   }
   void start() {
     const size_t page = static_cast<size_t>(sysconf(_SC_PAGESIZE));
@@ -217,6 +234,14 @@ struct StagedCopier {
     if (rc) return rc;
     int dev = 0;
     VVB_CUDA(cudaGetDevice(&dev));
+    if (conv == CONV_NONE &&
+        host_range_is_pinned(dir == cudaMemcpyHostToDevice ? src : static_cast<const void *>(dst), bytes)) {
+      // page-locked host memory: one DMA at PCIe speed, no bounce buffers, no CPU pass
+      if (after) VVB_CUDA(cudaStreamWaitEvent(st[0], after, 0));
+      VVB_CUDA(cudaMemcpyAsync(dst, src, bytes, dir, st[0]));
+      VVB_CUDA(cudaStreamSynchronize(st[0]));
+      return VVB_OK;
+    }
     const size_t nch = (bytes + CH - 1) / CH;
     const int nt = static_cast<int>(nch < static_cast<size_t>(T) ? nch : T);
     std::atomic<int> failed{0};
@@ -499,7 +524,8 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
   int64_t *idx_dev = static_cast<int64_t *>(dc.slot(1, idx_bytes));
   float *dist_dev = static_cast<float *>(dc.slot(2, dist_bytes));
   void *ws = dc.slot(3, ws_bytes);
-  const bool narrow = n <= INT32_MAX;  // indices travel as int32 (see CopyConv)
+  // indices travel as int32 (see CopyConv) unless the output array is page-locked: then the DMA writes it directly
+  const bool narrow = n <= INT32_MAX && !host_range_is_pinned(idx_out_host, idx_bytes);
   int32_t *idx32_dev = narrow ? static_cast<int32_t *>(dc.slot(5, idx_bytes / 2)) : nullptr;
   if (!x_dev || !idx_dev || !dist_dev || !ws || (narrow && !idx32_dev)) return dc.last_rc;
   cudaStream_t st = dc.compute_stream();
@@ -578,6 +604,25 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
     return VVB_ECUDA;
   }
   if (stats) stats->kernel_launches = g_launches.load() - launches0;
+  return VVB_OK;
+}
+
+int vvb_host_alloc(size_t bytes, void **ptr_out) {
+  VVB_REQUIRE(ptr_out && bytes > 0, "host alloc: bad arguments");
+  *ptr_out = nullptr;
+  cudaError_t e = cudaHostAlloc(ptr_out, bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    *ptr_out = nullptr;
+    set_error("cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? VVB_ENOMEM : VVB_ECUDA;
+  }
+  return VVB_OK;
+}
+
+int vvb_host_free(void *ptr) {
+  if (!ptr) return VVB_OK;
+  VVB_CUDA(cudaFreeHost(ptr));
   return VVB_OK;
 }
 
@@ -708,7 +753,7 @@ int vvb_smooth_host(const void *x_host, int elem_size, int64_t n, int d, const i
     VVB_REQUIRE(bad == 0, "Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed");
     return VVB_OK;
   }
-  if (n <= INT32_MAX) {
+  if (n <= INT32_MAX && !host_range_is_pinned(idx_host, ib)) {
     void *idx32 = dc.slot(5, ib / 2);
     if (!idx32) return dc.last_rc;
     rc = dc.copier.copy(idx32, idx_host, ib / 2, cudaMemcpyHostToDevice, nullptr, CONV_NARROW_I64);

@@ -82,8 +82,8 @@ def _knn_host(x: np.ndarray, k: int, q0: int, nq: int, algo: str, stats: Optiona
     """One call of `vvb_make_knn_host` (HOST buffers in and out)."""
     lib = _lib.load()
     n, d = x.shape
-    idx = np.empty((nq, k + 1), dtype=np.int64)
-    dist = np.empty((nq, k + 1), dtype=np.float32)
+    idx = _lib.result_empty((nq, k + 1), np.int64)  # page-locked when large: the D2H copy is then one DMA
+    dist = _lib.result_empty((nq, k + 1), np.float32)
     st = _lib.KnnStats()
     if algo not in _lib.KNN_ALGOS:
         raise ValueError(f"`algo` must be one of {sorted(_lib.KNN_ALGOS)}")
@@ -178,8 +178,8 @@ def smooth(
     xin = x if x.dtype in (np.float32, np.float64) else x.astype(np.float64)
     xin = np.ascontiguousarray(xin)
     idx = np.ascontiguousarray(knn[0], dtype=np.int64)  # index range is validated on the device
-    out = np.empty_like(xin)
     lib = _lib.load()
+    out = _lib.result_empty(xin.shape, xin.dtype)
     _lib.check(lib.vvb_smooth_host(_ptr(xin), xin.dtype.itemsize, xin.shape[0], xin.shape[1], _ptr(idx),
                                    idx.shape[1], int(k), float(coef), int(n_iter), _lib.SMOOTH_MODES[mode], _ptr(out)))
     return out
