@@ -74,6 +74,12 @@ int64_t vvb_launch_count(void);
  * this frees them */
 int vvb_release_cached_memory(void);
 
+/* The two row scans of ensure_valid_knn (/root/reference/src/vivae/knn.py:58-61): is idx[i, 0] == i for
+ * every row, and is dist[i, 0] == 0 for every row.  Host arrays, row-major with leading dimensions
+ * ld_idx / ld_dist (elements); dist is float32 (dist_elem_size 4) or float64 (8).  No GPU involved. */
+int vvb_knn_validate_host(const int64_t *idx_host, int64_t ld_idx, const void *dist_host, int dist_elem_size,
+                          int64_t ld_dist, int64_t n, int *self_first_out, int *dist0_zero_out);
+
 /* Page-locked host memory for result arrays.  The *_host entry points recognise page-locked host
  * pointers (these, or any cudaHostAlloc / cudaHostRegister memory the caller owns) and DMA to / from
  * them directly; pageable pointers are staged through bounce buffers.  The Python layer returns its

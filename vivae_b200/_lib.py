@@ -50,6 +50,7 @@ SYMBOLS = {
     "vvb_last_error": (ctypes.c_char_p, []),
     "vvb_launch_count": (_i64, []),
     "vvb_release_cached_memory": (_int, []),
+    "vvb_knn_validate_host": (_int, [_vp, _i64, _vp, _int, _i64, _i64, ctypes.POINTER(_int), ctypes.POINTER(_int)]),
     "vvb_host_alloc": (_int, [_sz, ctypes.POINTER(ctypes.c_void_p)]),
     "vvb_host_free": (_int, [_vp]),
     "vvb_make_knn_host": (_int, [_vp, _i64, _int, _int, _i64, _i64, _int, _vp, _vp, ctypes.POINTER(KnnStats)]),

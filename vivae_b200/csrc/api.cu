@@ -607,6 +607,38 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
   return VVB_OK;
 }
 
+// The two O(n) scans of ensure_valid_knn (knn.py:58-61: self in column 0, zero distance to self), strided
+// over a row-major matrix: one cache line per row and array, split over a few threads.
+int vvb_knn_validate_host(const int64_t *idx_host, int64_t ld_idx, const void *dist_host, int dist_elem_size,
+                          int64_t ld_dist, int64_t n, int *self_first_out, int *dist0_zero_out) {
+  VVB_REQUIRE(idx_host && dist_host && self_first_out && dist0_zero_out, "knn validate: null pointer argument");
+  VVB_REQUIRE(n >= 0 && ld_idx >= 1 && ld_dist >= 1 && (dist_elem_size == 4 || dist_elem_size == 8),
+              "knn validate: bad shape arguments");
+  const int nt = n >= (1 << 16) ? 8 : 1;
+  std::atomic<int> self_ok{1}, zero_ok{1};
+  auto work = [&](int t) {
+    const int64_t r0 = n * t / nt, r1 = n * (t + 1) / nt;
+    bool s_ok = true, z_ok = true;
+    for (int64_t i = r0; i < r1; ++i) s_ok &= (idx_host[i * ld_idx] == i);
+    if (dist_elem_size == 4) {
+      const float *dp = static_cast<const float *>(dist_host);
+      for (int64_t i = r0; i < r1; ++i) z_ok &= (dp[i * ld_dist] == 0.0f);
+    } else {
+      const double *dp = static_cast<const double *>(dist_host);
+      for (int64_t i = r0; i < r1; ++i) z_ok &= (dp[i * ld_dist] == 0.0);
+    }
+    if (!s_ok) self_ok = 0;
+    if (!z_ok) zero_ok = 0;
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto &x : th) x.join();
+  *self_first_out = self_ok.load();
+  *dist0_zero_out = zero_ok.load();
+  return VVB_OK;
+}
+
 int vvb_host_alloc(size_t bytes, void **ptr_out) {
   VVB_REQUIRE(ptr_out && bytes > 0, "host alloc: bad arguments");
   *ptr_out = nullptr;
@@ -684,13 +716,33 @@ int vvb_smooth_host(const void *x_host, int elem_size, int64_t n, int d, const i
   if (!st) return VVB_ECUDA;
   // the whole index matrix goes over contiguously (a pitched copy of the first k columns moves fewer
   // bytes but runs far slower from pageable memory); the kernel strides by ld_idx
+  // A page-locked neighbour matrix (one this package returned) goes over as one DMA on the copy stream while
+  // the CPU threads stage the pageable `x`.
+  const bool idx_pinned = host_range_is_pinned(idx_host, ib);
+  cudaEvent_t idx_ev = nullptr;
+  if (idx_pinned) {
+    cudaStream_t cs = dc.copy_stream();
+    if (!cs) return VVB_ECUDA;
+    VVB_CUDA(cudaEventCreateWithFlags(&idx_ev, cudaEventDisableTiming));
+    VVB_CUDA(cudaMemcpyAsync(idx, idx_host, ib, cudaMemcpyHostToDevice, cs));
+    VVB_CUDA(cudaEventRecord(idx_ev, cs));
+  }
+  struct EvGuard {
+    cudaEvent_t &e;
+    ~EvGuard() {
+      if (e) {
+        cudaEventSynchronize(e);  // never leave with the DMA still reading the caller's array
+        cudaEventDestroy(e);
+      }
+    }
+  } idx_ev_guard{idx_ev};
   rc = dc.copier.copy(x, x_host, xb, cudaMemcpyHostToDevice, nullptr);
   if (rc) return rc;
   // Opt-in (VVB_SMOOTH_PIPELINE=1): measured neutral on the bench host (1M x 50: 42 ms against 40 ms for the
   // plain sequence) -- the staging memcpys of both directions share the host's memory bandwidth (~20 GB/s
   // net), PCIe (54 GB/s pinned, each way) is not the limit.  Pays off on hosts with faster memory.
   const char *pipe_env = getenv("VVB_SMOOTH_PIPELINE");
-  const bool pipeline = n_iter == 1 && ib >= (32u << 20) && pipe_env && atoi(pipe_env) == 1;
+  const bool pipeline = n_iter == 1 && ib >= (32u << 20) && pipe_env && atoi(pipe_env) == 1 && !idx_pinned;
   if (pipeline) {
     // One sweep: rows are final as soon as they are written and (Gauss-Seidel) only read rows below them, so
     // the sweep runs chunk by chunk while a helper thread uploads the neighbour rows of the next chunk and
@@ -753,7 +805,9 @@ int vvb_smooth_host(const void *x_host, int elem_size, int64_t n, int d, const i
     VVB_REQUIRE(bad == 0, "Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed");
     return VVB_OK;
   }
-  if (n <= INT32_MAX && !host_range_is_pinned(idx_host, ib)) {
+  if (idx_pinned) {
+    VVB_CUDA(cudaStreamWaitEvent(st, idx_ev, 0));
+  } else if (n <= INT32_MAX) {
     void *idx32 = dc.slot(5, ib / 2);
     if (!idx32) return dc.last_rc;
     rc = dc.copier.copy(idx32, idx_host, ib / 2, cudaMemcpyHostToDevice, nullptr, CONV_NARROW_I64);
