@@ -949,18 +949,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
 
 // ------------------------------------------------------------------ re-rank + certificate
 // One warp per query row.  E = ceil(m / 32).
-// WIDE = false: each lane walks its candidate's row directly (fine for d ~ 50).
-// WIDE = true : for wide rows the 32 candidate rows of a group are staged through shared memory in
-//               32-column chunks (coalesced 128 B loads, conflict-free transposed reads); every lane
-//               still evaluates ITS candidate's chain strictly left to right, so the result is bit-identical.
-template <int E, bool WIDE>
+// MODE 0: each lane walks its candidate's row directly.
+// MODE 1: wide rows -- the 32 candidate rows of a group are staged through shared memory in 32-column
+//         chunks (coalesced 128 B loads, conflict-free transposed reads).
+// MODE 2: d <= 64 -- the 32 candidate rows of a group are staged WHOLE (one or two coalesced loads per
+//         row from a shuffled row pointer) next to the query row; 4 warps per CTA.  The kernel is bound
+//         by instruction issue (ncu: 71 % issue-active, 63 % of the warp instructions in the staging
+//         loop of MODE 1 at d = 50), and this mode stages a candidate in ~7 instructions instead of ~34.
+// In every mode each lane evaluates ITS candidate's chain strictly left to right, so the result is
+// bit-identical.
+constexpr int RR_ROW_LD = 65;  // floats per staged row (odd: lane = candidate reads are conflict-free)
+template <int E, int MODE>
 __global__ void __launch_bounds__(256) knn_rerank_kernel(
     const float *__restrict__ x, int64_t n, int d, int64_t q0, int64_t nq, int k, const int *__restrict__ qlist,
     const int *__restrict__ perm, const uint2 *__restrict__ cand, const int *__restrict__ cand_cnt,
     const float *__restrict__ cand_thr,
     const float *__restrict__ xnorm, const PrepScalars *__restrict__ scalars, int64_t *__restrict__ out_idx,
     float *__restrict__ out_dist, int *__restrict__ fb_count, int64_t *__restrict__ fb_rows) {
+  constexpr bool WIDE = MODE == 1;
+  constexpr bool ROWS = MODE == 2;
   __shared__ float stage[WIDE ? 8 : 1][WIDE ? 32 : 1][WIDE ? 33 : 1];
+  __shared__ float rows_stage[ROWS ? 4 * 33 * RR_ROW_LD : 1];  // [warp][32 candidates + query][RR_ROW_LD]
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int64_t t = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -976,7 +985,42 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
     key[e] = ~0ull;
     uint32_t j = 0;
     float acc = 0.0f;
-    if (!WIDE) {
+    if (ROWS) {
+      if (e * 32 < cnt) {  // warp-uniform: this group of 32 candidates is not empty
+        if (pos < cnt) j = static_cast<uint32_t>(perm[cand[t * 2 * TC_CAP + pos].y]);
+        const int in_group = min(32, cnt - e * 32);
+        float *st = rows_stage + wib * 33 * RR_ROW_LD;
+        if (e == 0) {  // the query row, once
+          st[32 * RR_ROW_LD + lane] = (lane < d) ? __ldg(xq + lane) : 0.0f;
+          st[32 * RR_ROW_LD + 32 + lane] = (32 + lane < d) ? __ldg(xq + 32 + lane) : 0.0f;
+        }
+        const unsigned long long rowp = reinterpret_cast<unsigned long long>(x + static_cast<int64_t>(j) * d);
+        const bool c0_ok = lane < d, c1_ok = 32 + lane < d;
+        for (int cc0 = 0; cc0 < in_group; cc0 += 8) {  // 16 loads in flight, then the stores
+          float v0[8], v1[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float *rp = reinterpret_cast<const float *>(__shfl_sync(FULL, rowp, (cc0 + u) & 31));
+            const bool live = cc0 + u < in_group;
+            v0[u] = (live && c0_ok) ? __ldg(rp + lane) : 0.0f;
+            v1[u] = (live && c1_ok) ? __ldg(rp + 32 + lane) : 0.0f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            st[((cc0 + u) & 31) * RR_ROW_LD + lane] = v0[u];
+            if (d > 32) st[((cc0 + u) & 31) * RR_ROW_LD + 32 + lane] = v1[u];
+          }
+        }
+        __syncwarp();
+        // lanes beyond the group read stale rows and are ignored below
+#pragma unroll 5
+        for (int c = 0; c < d; ++c) {  // the contract's chain: left to right, one rounding per fmaf
+          const float df = __fsub_rn(st[32 * RR_ROW_LD + c], st[lane * RR_ROW_LD + c]);
+          acc = __fmaf_rn(df, df, acc);
+        }
+        __syncwarp();
+      }
+    } else if (!WIDE) {
       if (pos < cnt) {
         j = static_cast<uint32_t>(perm[cand[t * 2 * TC_CAP + pos].y]);
         const float *y = x + static_cast<int64_t>(j) * d;
@@ -1332,25 +1376,28 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   }
   if (screen_only) return VVB_OK;
   mark(1);
-  const unsigned rr_grid = static_cast<unsigned>((nq + 7) / 8);
   const int e_need = (S->keep + 31) / 32;
   const char *rrw = getenv("VVB_RR_WIDE_MIN");
-  const int rr_wide_min = rrw ? atoi(rrw) : 32;  // measured at d = 50: 5.8 ms staged vs 6.3 ms direct per 1M rows
-#define VVB_RR(EE)                                                                                                    \
-  do {                                                                                                                \
-    if (S->d >= rr_wide_min)                                                                                                \
-      knn_rerank_kernel<EE, true><<<rr_grid, 256, 0, st>>>(S->x, S->n, S->d, q0, nq, S->k, L.qlist, L.cells.perm,    \
-                                                           L.cand, L.cand_cnt, L.cand_thr, L.xnorm, L.scalars,   \
-                                                           out_idx, out_dist, L.fb_count, L.fb_rows);               \
-    else                                                                                                              \
-      knn_rerank_kernel<EE, false><<<rr_grid, 256, 0, st>>>(S->x, S->n, S->d, q0, nq, S->k, L.qlist, L.cells.perm,   \
-                                                            L.cand, L.cand_cnt, L.cand_thr, L.xnorm, L.scalars,  \
-                                                            out_idx, out_dist, L.fb_count, L.fb_rows);              \
+  const int rr_wide_min = rrw ? atoi(rrw) : 65;  // d <= 64: whole-row staging (MODE 2); VVB_RR_WIDE_MIN=32 forces MODE 1
+  const char *rrm = getenv("VVB_RR_ROWS");
+  const bool rr_rows = S->d <= 64 && S->d < rr_wide_min && !(rrm && atoi(rrm) == 0);
+  const unsigned rr_grid = static_cast<unsigned>(rr_rows ? (nq + 3) / 4 : (nq + 7) / 8);
+#define VVB_RR_ARGS S->x, S->n, S->d, q0, nq, S->k, L.qlist, L.cells.perm, L.cand, L.cand_cnt, L.cand_thr, L.xnorm, \
+                    L.scalars, out_idx, out_dist, L.fb_count, L.fb_rows
+#define VVB_RR(EE)                                                                            \
+  do {                                                                                        \
+    if (rr_rows)                                                                              \
+      knn_rerank_kernel<EE, 2><<<rr_grid, 128, 0, st>>>(VVB_RR_ARGS);                         \
+    else if (S->d >= 32)                                                                      \
+      knn_rerank_kernel<EE, 1><<<rr_grid, 256, 0, st>>>(VVB_RR_ARGS);                         \
+    else                                                                                      \
+      knn_rerank_kernel<EE, 0><<<rr_grid, 256, 0, st>>>(VVB_RR_ARGS);                         \
   } while (0)
   if (e_need <= 2) VVB_RR(2);
   else if (e_need <= 4) VVB_RR(4);
   else VVB_RR(8);
 #undef VVB_RR
+#undef VVB_RR_ARGS
   VVB_CHECK_LAUNCH();
   mark(2);
   // rows the certificate rejected: exact FP32 brute force.  The count comes back to the host (one
