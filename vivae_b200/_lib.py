@@ -133,6 +133,24 @@ def launch_count() -> int:
     return int(load().vvb_launch_count()) + _graph_replayed
 
 
+class no_uninitialised_fill:
+    """Context: suspend the NaN fill that deterministic mode adds to every `torch.empty` (11-13 extra kernels in
+    each training step, inside autograd's own allocations).  A debugging aid of torch, not part of determinism:
+    results are unchanged."""
+
+    def __enter__(self):
+        import torch
+
+        self.det = torch.utils.deterministic
+        self.prev = self.det.fill_uninitialized_memory
+        self.det.fill_uninitialized_memory = False
+        return self
+
+    def __exit__(self, *exc):
+        self.det.fill_uninitialized_memory = self.prev
+        return False
+
+
 def raw_empty(shape, dtype, device):
     """`torch.empty` without the fill kernel that `torch.use_deterministic_algorithms(True)` (the package
     default, like the reference's) adds to every uninitialised allocation: on a 1.6 GB kNN workspace that fill
@@ -179,7 +197,7 @@ class _PinnedPool:
     def __init__(self):
         import threading
 
-        self.lock = threading.Lock()
+        self.lock = threading.RLock()  # re-entrant: a garbage collection inside take() may run a block's __del__
         self.free = []   # (cap, ptr)
         self.total = 0   # bytes pinned by this pool (in use + free)
         self.seen = {}   # size class -> requests that found no free block

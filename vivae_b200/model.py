@@ -132,19 +132,20 @@ class ViVAE:
                     and mds_nsamp == 1 and (lam_imit == 0.0 or ref_model is None)
                     and isinstance(self.data_loader, DeviceBatchLoader))
         full = getattr(self.data_loader, "batch_size", None)
-        for batch in self.data_loader:
-            x = batch[0]
-            if graph_ok and x.shape[0] == full and full >= 4:
-                g = self._graphed_step(x, cfg)
-                if g is not None:
-                    _, graph, static_x, static_sums, n_kernels = g
-                    static_x.copy_(x)
-                    static_sums.zero_()
-                    graph.replay()
-                    _lib.note_graph_replay(n_kernels)
-                    sums += static_sums
-                    continue
-            self._eager_step(x, cfg, sums)
+        with _lib.no_uninitialised_fill():  # also in force while the step is captured
+            for batch in self.data_loader:
+                x = batch[0]
+                if graph_ok and x.shape[0] == full and full >= 4:
+                    g = self._graphed_step(x, cfg)
+                    if g is not None:
+                        _, graph, static_x, static_sums, n_kernels = g
+                        static_x.copy_(x)
+                        static_sums.zero_()
+                        graph.replay()
+                        _lib.note_graph_replay(n_kernels)
+                        sums += static_sums
+                        continue
+                self._eager_step(x, cfg, sums)
         host = sums.tolist()  # the only host sync of the epoch
         return dict(zip(_TERMS, host))
 
