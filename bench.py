@@ -138,6 +138,7 @@ def cpu_baseline(x: np.ndarray, k: int, knn_queries: int, smooth_rows: int) -> d
     n, d = x.shape
     knn_queries = min(knn_queries, n)
     smooth_rows = min(smooth_rows, n)
+    orc.set_threads(os.cpu_count() or 1)  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     t0 = time.perf_counter()
     orc.knn(x, k, 0, knn_queries)
     t_knn = time.perf_counter() - t0

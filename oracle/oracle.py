@@ -58,6 +58,14 @@ def num_threads() -> int:
     return int(lib().vv_oracle_num_threads())
 
 
+def set_threads(n: int) -> None:
+    """OpenMP threads of the oracle's kNN (torchrun sets OMP_NUM_THREADS=1 in its workers)."""
+    L = lib()
+    L.vv_oracle_set_threads.restype = None
+    L.vv_oracle_set_threads.argtypes = [ctypes.c_int]
+    L.vv_oracle_set_threads(int(n))
+
+
 def _ptr(a: np.ndarray):
     return a.ctypes.data_as(ctypes.c_void_p)
 

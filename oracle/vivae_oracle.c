@@ -45,6 +45,15 @@
 
 int vv_oracle_version(void) { return 1; }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline must still use all host cores */
+void vv_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n >= 1) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int vv_oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
