@@ -131,6 +131,32 @@ def test_knn_medium_scale_properties_and_sampled_oracle():
     print("knn stats:", st)
 
 
+def test_full_size_config_1M_x_50_properties_sampled_oracle_and_smooth():
+    """BASELINE.json configs[1] at full size (1M cells x 50 PCs, k=50, smooth k=50): size-independent properties on
+    every row, bit-exact oracle check of three query slices, the whole smoothed matrix bit-exact against the oracle's
+    sweep, and the device-resident entry point equal to the host one."""
+    from vivae_b200.device import knn_device
+
+    n, d, k = 1_000_000, 50, 50
+    x = clustered(n, d, 30, seed=1)
+    st = {}
+    idx, dist = vv.make_knn(x, k=k, verbose=False, stats=st)
+    assert st["algo_used"] == 2 and st["rows_fallback"] <= 1000 and st["tiles_swept"] < 0.25 * st["tiles_dense"], st
+    assert np.array_equal(idx[:, 0], np.arange(n)) and np.all(dist[:, 0] == 0)
+    assert np.all(np.diff(dist, axis=1) >= 0)
+    assert idx.min() >= 0 and idx.max() < n
+    srt = np.sort(idx[::7], axis=1)
+    assert np.all(srt[:, 1:] != srt[:, :-1])
+    for q0 in (0, 500_123, n - 128):
+        wi, wd = orc.knn(x, k, q0, q0 + 128)
+        assert np.array_equal(idx[q0:q0 + 128], wi) and np.array_equal(dist[q0:q0 + 128], wd)
+    di, dd = knn_device(torch.from_numpy(x).cuda(), k)
+    assert np.array_equal(di.cpu().numpy(), idx) and np.array_equal(dd.cpu().numpy(), dist)
+    del di, dd
+    out = vv.smooth(x, [idx, dist], k=k, coef=1.0, n_iter=1)
+    assert np.array_equal(out, orc.smooth(x, idx, k, 1.0, 1))
+
+
 def test_make_knn_cache_write_then_load(tmp_path):
     x = clustered(500, 8, 3, seed=4)
     f = str(tmp_path / "graph.npy")
