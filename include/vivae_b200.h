@@ -173,6 +173,15 @@ int vvb_smooth_device(const void *x_dev, int elem_size, int64_t n, int d, const 
                       int64_t ld_idx, int k, double coef, int n_iter, int mode, void *out_dev,
                       void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* Rows [row_lo, row_hi) of ONE sweep in VVB_SMOOTH_JACOBI mode (row ranges of a Jacobi sweep are independent:
+ * several GPUs each take a range and exchange the new rows between sweeps).  x (n, d) is the whole matrix;
+ * idx_rows (row_hi-row_lo, ld_idx) and out_rows (row_hi-row_lo, d) hold only the range.  Workspace as
+ * vvb_smooth_workspace_bytes(elem_size, n, d, 1); its first int is set non-zero by an out-of-range index.
+ * VVB_SMOOTH_GAUSS_SEIDEL is refused (VVB_ENOTSUP): a row of the reference's sweep depends on the rows below. */
+int vvb_smooth_rows_device(const void *x_dev, int elem_size, int64_t n, int d, const int64_t *idx_rows_dev,
+                           int64_t ld_idx, int k, double coef, int mode, int64_t row_lo, int64_t row_hi,
+                           void *out_rows_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------
  * quartet ("stochastic MDS") loss -- replaces MDSLoss.__call__,
  *   /root/reference/src/vivae/losses.py:266-349, and its autograd backward.

@@ -277,6 +277,37 @@ def test_results_live_in_recycled_page_locked_blocks(monkeypatch):
     assert np.array_equal(keep_idx[1000:1400], wi) and np.array_equal(keep_dist[1000:1400], wd)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_smooth_rows_entry_point_jacobi_shards_equal_whole_sweep(dtype):
+    """vvb_smooth_rows_device: row ranges of a Jacobi sweep computed separately (what each rank of
+    smooth_jacobi_sharded does) equal the whole-matrix sweep; a Gauss-Seidel range is refused; bad indices raise."""
+    from vivae_b200.device import smooth_rows_device
+    from vivae_b200.sharded import shard_bounds, smooth_jacobi_sharded
+
+    n, d, k = 20_000, 30, 25
+    x = clustered(n, d, 7, seed=9).astype(dtype)
+    idx, dist = vv.make_knn(x.astype(np.float32), k=k, verbose=False)
+    want = orc.smooth(x, idx, k, 0.5, 1, mode=1)
+    xd, idd = torch.tensor(x, device="cuda"), torch.tensor(idx, device="cuda")
+    parts = []
+    for rank in range(3):
+        q0, nq = shard_bounds(n, 3, rank)
+        parts.append(smooth_rows_device(xd, idd[q0:q0 + nq].contiguous(), k, 0.5, q0))
+    assert np.array_equal(torch.cat(parts).cpu().numpy(), want)
+    # single-process call of the sharded driver (world = 1): two sweeps
+    two = smooth_jacobi_sharded(xd, idd, k, coef=0.5, n_iter=2)
+    assert np.array_equal(two.cpu().numpy(), orc.smooth(x, idx, k, 0.5, 2, mode=1))
+    bad = idd[:100].clone()
+    bad[5, 3] = n + 1
+    with pytest.raises(ValueError, match="must include self"):
+        smooth_rows_device(xd, bad, k, 0.5, 0)
+    lib = vv._lib.load()
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    rc = lib.vvb_smooth_rows_device(xd.data_ptr(), xd.element_size(), n, d, idd.data_ptr(), idd.shape[1], k, 0.5, 0, 0, 10,
+                                    ws.data_ptr(), ws.data_ptr(), ws.numel(), None)
+    assert rc == vv._lib.ENOTSUP
+
+
 # ======================================================================== quartet
 @pytest.mark.parametrize("name", QUARTET)
 def test_quartet_loss_and_grad_vs_reference_golden(name):

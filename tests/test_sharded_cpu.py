@@ -13,7 +13,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import oracle as orc
-from vivae_b200.sharded import all_gather_rows, knn_smooth_sharded, make_knn_ring, make_knn_sharded, shard_bounds
+from vivae_b200.sharded import (all_gather_rows, knn_smooth_sharded, make_knn_ring, make_knn_sharded, shard_bounds,
+                                smooth_jacobi_sharded)
 
 
 def _free_port():
@@ -151,3 +152,38 @@ def test_ring_build_equals_whole_matrix_build(tmp_path, world, n, k, kind):
         q0, nq = int(g["q0"]), int(g["nq"])
         assert np.array_equal(g["idx"], wi[q0:q0 + nq])
         assert np.array_equal(g["dist"], wd[q0:q0 + nq])
+
+
+# ---------------------------------------------------------------------------- row-sharded Jacobi smoother
+def _oracle_jacobi_rows(x, idx_rows, k, coef, row_lo):
+    """CPU stand-in for `smooth_rows_device`: one Jacobi sweep, rows [row_lo, row_lo+len(idx_rows))."""
+    n = x.shape[0]
+    full = np.tile(np.arange(n, dtype=np.int64)[:, None], (1, idx_rows.shape[1]))  # other rows: self only (unused)
+    full[row_lo:row_lo + idx_rows.shape[0]] = idx_rows.numpy()
+    out = orc.smooth(x.numpy(), full, k, coef, 1, mode=1)
+    return torch.from_numpy(out[row_lo:row_lo + idx_rows.shape[0]].copy())
+
+
+def _jacobi_worker(rank, world, port, n, k, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x = torch.from_numpy(np.random.default_rng(3).standard_normal((n, 5)).astype(np.float32))
+        idx_local, _ = make_knn_sharded(x, k, gather=False, _knn_fn=_oracle_knn)
+        out = smooth_jacobi_sharded(x, idx_local, k, coef=0.6, n_iter=3, _rows_fn=_oracle_jacobi_rows)
+        np.save(os.path.join(out_dir, f"jac{rank}.npy"), out.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 203), (3, 50)])
+def test_row_sharded_jacobi_smoother_equals_single_process(tmp_path, world, n):
+    k = 6
+    port = _free_port()
+    mp.spawn(_jacobi_worker, args=(world, port, n, k, str(tmp_path)), nprocs=world, join=True)
+    x = np.random.default_rng(3).standard_normal((n, 5)).astype(np.float32)
+    wi, _ = orc.knn(x, k)
+    want = orc.smooth(x, wi, k, 0.6, 3, mode=1)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"jac{r}.npy"), want)

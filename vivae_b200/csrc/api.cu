@@ -195,8 +195,25 @@ static void narrow_i64(int32_t *dst, const int64_t *src, size_t count) {
 }
 
 struct StagedCopier {
-  static constexpr int T = 6;
-  static constexpr size_t CH = 4u << 20;
+  static constexpr int T = 16;  // bounce-buffer sets; threads() of them are used
+  static constexpr size_t CH_MAX = 4u << 20;
+  static size_t chunk() {  // bytes per bounce buffer actually used (VVB_COPY_CHUNK_KB, multiple of 4 KB, <= 4 MB)
+    static size_t c = [] {
+      const char *e = getenv("VVB_COPY_CHUNK_KB");
+      size_t v = (e ? static_cast<size_t>(atoi(e)) : 4096) << 10;
+      v = v / 4096 * 4096;
+      return v < 4096 ? static_cast<size_t>(4096) : (v > CH_MAX ? CH_MAX : v);
+    }();
+    return c;
+  }
+  static int threads() {
+    static int t = [] {
+      const char *e = getenv("VVB_COPY_THREADS");
+      const int v = e ? atoi(e) : 6;  // measured on the bench host: see DESIGN.md section 5
+      return v < 1 ? 1 : (v > T ? T : v);
+    }();
+    return t;
+  }
   char *pin[T][2] = {};
   cudaStream_t st[T] = {};
   cudaEvent_t ev[T][2] = {};
@@ -206,7 +223,7 @@ struct StagedCopier {
     for (int t = 0; t < T; ++t) {
       VVB_CUDA(cudaStreamCreateWithFlags(&st[t], cudaStreamNonBlocking));
       for (int b = 0; b < 2; ++b) {
-        VVB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&pin[t][b]), CH, cudaHostAllocDefault));
+        VVB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&pin[t][b]), CH_MAX, cudaHostAllocDefault));
         VVB_CUDA(cudaEventCreateWithFlags(&ev[t][b], cudaEventDisableTiming));
       }
     }
@@ -242,8 +259,9 @@ struct StagedCopier {
       VVB_CUDA(cudaStreamSynchronize(st[0]));
       return VVB_OK;
     }
+    const size_t CH = chunk();
     const size_t nch = (bytes + CH - 1) / CH;
-    const int nt = static_cast<int>(nch < static_cast<size_t>(T) ? nch : T);
+    const int nt = static_cast<int>(nch < static_cast<size_t>(threads()) ? nch : threads());
     std::atomic<int> failed{0};
     auto work = [&](int t) {
       cudaSetDevice(dev);
@@ -835,6 +853,30 @@ int vvb_smooth_host(const void *x_host, int elem_size, int64_t n, int d, const i
   VVB_CUDA(cudaStreamSynchronize(st));
   VVB_REQUIRE(bad == 0, "Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed");
   return VVB_OK;
+}
+
+// Rows [row_lo, row_hi) of ONE Jacobi sweep: every row reads only `x`, so row ranges are independent and can
+// live on different GPUs.  idx_rows / out_rows hold just those rows.
+int vvb_smooth_rows_device(const void *x_dev, int elem_size, int64_t n, int d, const int64_t *idx_rows_dev,
+                           int64_t ld_idx, int k, double coef, int mode, int64_t row_lo, int64_t row_hi,
+                           void *out_rows_dev, void *workspace_dev, size_t workspace_bytes, void *stream) {
+  VVB_REQUIRE(x_dev && idx_rows_dev && out_rows_dev && workspace_dev, "smooth rows: null pointer argument");
+  VVB_REQUIRE(k >= 1 && k <= n - 1, "`k` must be between 1 and (n-1)");
+  VVB_REQUIRE(coef >= 0.0 && coef <= 1.0, "`coef` must be more than 0. and at most 1.");
+  VVB_REQUIRE(row_lo >= 0 && row_lo <= row_hi && row_hi <= n, "smooth rows: bad row range");
+  VVB_REQUIRE(elem_size == 4 || elem_size == 8, "smooth: elem_size must be 4 or 8");
+  if (mode != VVB_SMOOTH_JACOBI) {
+    set_error("smooth rows: only VVB_SMOOTH_JACOBI sweeps split by rows (a Gauss-Seidel row depends on the rows below it)");
+    return VVB_ENOTSUP;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = smooth_begin(workspace_dev, elem_size, n, d, 1, st);
+  if (rc) return rc;
+  // the kernel addresses rows globally: hand it the bases the full matrices would have
+  const int64_t *idx_base = idx_rows_dev - row_lo * ld_idx;
+  char *out_base = static_cast<char *>(out_rows_dev) - static_cast<size_t>(row_lo) * d * elem_size;
+  return launch_smooth_rows(x_dev, elem_size, n, d, idx_base, ld_idx, k, coef, mode, out_base, workspace_dev,
+                            workspace_bytes, 0, row_lo, row_hi, st);
 }
 
 // -------------------------------------------------------------------- ring merge

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["knn_device", "smooth_device", "knn_merge_init", "knn_merge", "knn_merge_finish"]
+__all__ = ["knn_device", "smooth_device", "smooth_rows_device", "knn_merge_init", "knn_merge", "knn_merge_finish"]
 
 
 def _require_cuda(name: str, t: torch.Tensor, dtype) -> torch.Tensor:
@@ -76,6 +76,31 @@ def smooth_device(x: torch.Tensor, idx: torch.Tensor, k: int = 50, coef: float =
                                          float(coef), int(n_iter), _lib.SMOOTH_MODES[mode], out.data_ptr(),
                                          ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
         ws.record_stream(torch.cuda.current_stream())
+    return out
+
+
+def smooth_rows_device(x: torch.Tensor, idx_rows: torch.Tensor, k: int, coef: float, row_lo: int) -> torch.Tensor:
+    """Rows [row_lo, row_lo + len(idx_rows)) of ONE Jacobi sweep over `x` (n, d): `idx_rows` holds the neighbour
+    lists of just those rows.  Returns the new rows.  (A Gauss-Seidel sweep does not split by rows.)"""
+    lib = _lib.load()
+    if x.dtype not in (torch.float32, torch.float64):
+        raise ValueError("`x` must be float32 or float64")
+    x = _require_cuda("x", x, x.dtype)
+    idx_rows = _require_cuda("idx_rows", idx_rows, torch.int64)
+    n, d = x.shape
+    rows = idx_rows.shape[0]
+    with torch.cuda.device(x.device):
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.vvb_smooth_workspace_bytes(x.element_size(), n, d, 1, ctypes.byref(nbytes)))
+        ws = _lib.raw_empty(int(nbytes.value), torch.uint8, x.device)
+        out = _lib.raw_empty((rows, d), x.dtype, x.device)
+        _lib.check(lib.vvb_smooth_rows_device(x.data_ptr(), x.element_size(), n, d, idx_rows.data_ptr(),
+                                              idx_rows.shape[1], int(k), float(coef), _lib.SMOOTH_MODES["jacobi"],
+                                              int(row_lo), int(row_lo) + rows, out.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), torch.cuda.current_stream().cuda_stream))
+        bad = int(ws[:4].view(torch.int32).item())  # device-side index validation (synchronises)
+    if bad:
+        raise ValueError("Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed")
     return out
 
 

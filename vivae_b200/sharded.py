@@ -21,7 +21,8 @@ from typing import Callable, Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "all_gather_rows", "make_knn_sharded", "make_knn_ring", "ring_fold", "knn_smooth_sharded"]
+__all__ = ["shard_bounds", "all_gather_rows", "make_knn_sharded", "make_knn_ring", "ring_fold", "knn_smooth_sharded",
+           "smooth_jacobi_sharded"]
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -143,3 +144,31 @@ def knn_smooth_sharded(x: torch.Tensor, k: int, coef: float = 1.0, n_iter: int =
     if world > 1:
         idx = all_gather_rows(idx, x.shape[0], group)
     return idx, _smooth_fn(x, idx, k, coef, n_iter)
+
+
+def smooth_jacobi_sharded(x: torch.Tensor, idx_local: torch.Tensor, k: int, coef: float = 0.1, n_iter: int = 1, group=None,
+                          _rows_fn: Optional[Callable] = None) -> torch.Tensor:
+    """`smooth(..., mode='jacobi')` with the rows of every sweep split over the ranks.
+
+    `x` is the whole (n, d) matrix on every rank; `idx_local` holds the neighbour lists of this rank's rows
+    (`shard_bounds`), e.g. straight from `make_knn_sharded(..., gather=False)` -- the graph itself is never
+    gathered.  Each sweep: a rank computes its rows from the current `x`, then the new rows are all-gathered
+    (n*d*4 bytes per sweep, against n*(k+1)*8 for the graph).  This is the order-independent variant, NOT the
+    reference's in-place sweep (that one runs replicated: `knn_smooth_sharded`)."""
+    if _rows_fn is None:
+        from .device import smooth_rows_device
+
+        _rows_fn = smooth_rows_device
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = x.shape[0]
+    q0, nq = shard_bounds(n, world, rank)
+    if idx_local.shape[0] != nq:
+        raise ValueError(f"rank {rank} must hold the neighbour lists of rows [{q0}, {q0 + nq})")
+    if n_iter < 1 or n_iter > 10000:
+        raise ValueError("`n_iter` must be at least 1 and at most 10000")
+    cur = x
+    for _ in range(n_iter):
+        new_rows = _rows_fn(cur, idx_local, k, coef, q0)
+        cur = all_gather_rows(new_rows, n, group) if world > 1 else new_rows
+    return cur
