@@ -295,17 +295,19 @@ def run_ours(args) -> None:
         # three fp16 products of the hi/lo split, K padded to the MMA's k-step (16) or to the 64-column atom
         return 16 * ((dd + 3 + 15) // 16 + 2 * ((dd + 15) // 16)) if dd + 3 <= 64 else 3 * 64 * ((dd + 3 + 63) // 64)
 
-    cap = os.path.join(ROOT, "profiles", "r01_screen_final_raw.csv")
+    cap = os.path.join(ROOT, "profiles", "r01_hot_kernels_s3_raw.csv")
     if st.get("algo_used") == 2 and (n, d, k) == (1_000_000, 50, 50) and os.path.isfile(cap):
         import csv
         with open(cap) as f:
             rows_ = list(csv.reader(f))
         col = {h: i for i, h in enumerate(rows_[0])}
         gb = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-        tr = sum(float(rows_[2][col[m]]) * gb[rows_[1][col[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        roofline["traffic"] = tr
-        roofline["traffic_note"] = ("dram__bytes_read + dram__bytes_write of the launch (1,000,000 query rows) from the committed "
-                                    "ncu --set full capture profiles/r01_screen_final_raw.csv")
+        srow = next((r for r in rows_[2:] if "knn_screen" in r[col["Kernel Name"]]), None)
+        if srow is not None:
+            tr = sum(float(srow[col[m]]) * gb[rows_[1][col[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            roofline["traffic"] = tr
+            roofline["traffic_note"] = ("dram__bytes_read + dram__bytes_write of the launch (1,000,000 query rows) from the "
+                                        "committed ncu --set full capture profiles/r01_hot_kernels_s3_raw.csv")
     dense_roof = None
     if st.get("algo_used") == 2:
         # The sweep is exact but not dense: cells whose distance lower bound exceeds every row's k-th candidate
