@@ -106,9 +106,9 @@ class KLDivLoss:
         key = (mu.device, mu.dtype)
         if key not in self._cache:
             e = torch.tensor([self.eps_sq], dtype=mu.dtype, device=mu.device)
-            self._cache[key] = e
-        eps_sq = self._cache[key]
-        inner = logvar + torch.log(eps_sq) - mu.square() - eps_sq * logvar.exp()
+            self._cache[key] = (e, torch.log(e))  # the logarithm once, not once per batch
+        eps_sq, log_eps_sq = self._cache[key]
+        inner = logvar + log_eps_sq - mu.square() - eps_sq * logvar.exp()
         return -0.5 * inner.mean() / mu.shape[0]
 
 

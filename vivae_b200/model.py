@@ -165,7 +165,9 @@ class ViVAE:
             vals.append(t.detach().reshape(()))
             loss = t if loss is None else loss + t
         with torch.no_grad():  # graph-capture safe: no host-side index tensors
-            zero = torch.zeros((), dtype=torch.float32, device=sums.device)
+            zero = getattr(self, "_zero", None)
+            if zero is None or zero.device != sums.device:
+                zero = self._zero = torch.zeros((), dtype=torch.float32, device=sums.device)  # once, not per step
             sums += torch.stack([zero if v is None else v.to(torch.float32) for v in vals])
         loss.backward()
         self.optimizer.step()

@@ -22,6 +22,12 @@ from .losses import EncoderGeometricLoss, GeometricLoss, ImitationLoss, KLDivLos
 __all__ = ["Autoencoder"]
 
 
+def _weighted(lam: float, term: torch.Tensor) -> torch.Tensor:
+    """lam * term (network.py:262-293); a weight of exactly 1 is the identity bit for bit, so the two kernels
+    (forward and backward multiply) are skipped -- the training step is bound by its kernel count."""
+    return term if lam == 1.0 else lam * term
+
+
 def _mlp(prefix: str, dims: list[int], activation, final_linear_to: Optional[int]) -> nn.Sequential:
     """Linear(+activation) stack named like the reference: '01<prefix>Potential', '01<prefix>Activation', ..."""
     layers = OrderedDict()
@@ -104,20 +110,20 @@ class Autoencoder(nn.Module):
         out = {"recon": None, "kldiv": None, "geom": None, "egeom": None, "mds": None, "imit": None}
         if self.variational:
             mu, logvar, z = self.encode(x)
-            out["kldiv"] = lam_kldiv * self.kldiv_error(mu, logvar)
+            out["kldiv"] = _weighted(lam_kldiv, self.kldiv_error(mu, logvar))
         else:
             z = self.encode(x)
         if lam_recon > 0.0:
-            out["recon"] = lam_recon * self.reconstruction_error(x, self.decode(z))
+            out["recon"] = _weighted(lam_recon, self.reconstruction_error(x, self.decode(z)))
         if lam_geom > 0.0:
-            out["geom"] = lam_geom * self.geometric_error(self.immersion, z)
+            out["geom"] = _weighted(lam_geom, self.geometric_error(self.immersion, z))
         if lam_egeom > 0.0:
-            out["egeom"] = lam_egeom * self.encoder_geometric_error(self.submersion, x)
+            out["egeom"] = _weighted(lam_egeom, self.encoder_geometric_error(self.submersion, x))
         if lam_mds > 0.0:
-            out["mds"] = lam_mds * self.mds_error(x, z, distf_hd=mds_distf_hd, distf_ld=mds_distf_ld,
-                                                  n_sampling=mds_nsamp)
+            out["mds"] = _weighted(lam_mds, self.mds_error(x, z, distf_hd=mds_distf_hd, distf_ld=mds_distf_ld,
+                                                           n_sampling=mds_nsamp))
         if lam_imit > 0.0 and ref_model is not None:
-            out["imit"] = lam_imit * self.imit_error(x, z, ref_model)
+            out["imit"] = _weighted(lam_imit, self.imit_error(x, z, ref_model))
         return out
 
     # ------------------------------------------------------------------- embed
