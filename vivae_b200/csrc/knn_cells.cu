@@ -162,11 +162,23 @@ int cells_select_dims(const float *x, int64_t n, int d, const float *mu, double 
 }
 
 // ------------------------------------------------------------------ partition
+// Pivot p is row floor((p + 0.5) n / P); its first dsub centred coordinates, gathered once (every CTA of the
+// assignment kernel used to redo this gather -- three dependent loads and a double-precision division per
+// element -- for all P pivots: a quarter of that kernel's instructions).
+__global__ void __launch_bounds__(CELL_DIMS) cell_pivots_kernel(const float *__restrict__ x, int64_t n, int d, int dsub,
+                                                               const int *__restrict__ dims,
+                                                               const float *__restrict__ mu, int P,
+                                                               float *__restrict__ piv) {
+  const int p = blockIdx.x, c = threadIdx.x;
+  const int64_t pr = static_cast<int64_t>((static_cast<double>(p) + 0.5) * static_cast<double>(n) / P);
+  piv[p * CELL_DIMS + c] = (c < dsub) ? __ldg(x + pr * d + __ldg(dims + c)) - __ldg(mu + __ldg(dims + c)) : 0.0f;
+}
+
 // Thread per row: nearest pivot in the first dsub centred coordinates (ties -> lowest pivot).
-// Pivot p is row floor((p + 0.5) n / P).
 __global__ void __launch_bounds__(128) cell_assign_kernel(const float *__restrict__ x, int64_t n, int d, int dsub,
                                                          const int *__restrict__ dims,
                                                          const float *__restrict__ mu, int P,
+                                                         const float *__restrict__ pivots,
                                                          int *__restrict__ cell_of, int *__restrict__ cnt) {
   __shared__ __align__(16) float piv[128][CELL_DIMS];
   __shared__ float pn[128];
@@ -183,10 +195,10 @@ __global__ void __launch_bounds__(128) cell_assign_kernel(const float *__restric
   for (int p0 = 0; p0 < P; p0 += 128) {
     __syncthreads();
     const int np = min(128, P - p0);
-    for (int i = tid; i < np * CELL_DIMS; i += 128) {
-      const int pl = i / CELL_DIMS, c = i % CELL_DIMS;
-      const int64_t pr = static_cast<int64_t>((static_cast<double>(p0 + pl) + 0.5) * static_cast<double>(n) / P);
-      piv[pl][c] = (c < dsub) ? __ldg(x + pr * d + __ldg(dims + c)) - __ldg(mu + __ldg(dims + c)) : 0.0f;
+    {
+      const float4 *src = reinterpret_cast<const float4 *>(pivots + static_cast<size_t>(p0) * CELL_DIMS);
+      float4 *dst = reinterpret_cast<float4 *>(&piv[0][0]);
+      for (int i = tid; i < np * (CELL_DIMS / 4); i += 128) dst[i] = __ldg(src + i);
     }
     __syncthreads();
     if (tid < np) {
@@ -468,8 +480,11 @@ int cells_build(const CellPlan &L, const float *x, int d, const float *mu, const
   VVB_CUDA(cudaMemsetAsync(L.perm, 0xFF, sizeof(int) * static_cast<size_t>(L.n_perm_cap), st));
   VVB_CUDA(cudaMemsetAsync(L.sums, 0, sizeof(double) * static_cast<size_t>(P) * CELL_DIMS, st));
   VVB_CUDA(cudaMemsetAsync(L.sqs, 0, sizeof(double) * static_cast<size_t>(P) * CELL_DIMS, st));
-  cell_assign_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(x, n, d, L.dsub, dims, mu, P, L.cell_of,
-                                                                             L.cnt);
+  // the pivot block borrows the centres' buffer (P x CELL_DIMS floats), which is only written further down
+  cell_pivots_kernel<<<P, CELL_DIMS, 0, st>>>(x, n, d, L.dsub, dims, mu, P, L.cen);
+  VVB_CHECK_LAUNCH();
+  cell_assign_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(x, n, d, L.dsub, dims, mu, P, L.cen,
+                                                                             L.cell_of, L.cnt);
   VVB_CHECK_LAUNCH();
   cell_scan_kernel<<<1, 1024, 0, st>>>(L.cnt, P, CELL_GROUP, L.off, L.cursor);
   VVB_CHECK_LAUNCH();
