@@ -299,3 +299,79 @@ def test_unknown_activation_keeps_the_autodiff_route():
     assert not supports_closed_form(net)
     assert analytic_jacobian(net.submersion, torch.randn(4, 5)) is None
     assert torch.isfinite(vv.losses.EncoderGeometricLoss()(net.submersion, torch.randn(9, 5)))
+
+
+# ---------------------------------------------------------------------- page-locked result pool (host logic)
+class _FakeHostAllocLib:
+    """Stands in for vvb_host_alloc / vvb_host_free (libc malloc): the pool's policy is what is under test."""
+
+    def __init__(self):
+        self.libc = ctypes.CDLL(None)
+        self.libc.malloc.restype = ctypes.c_void_p
+        self.libc.malloc.argtypes = [ctypes.c_size_t]
+        self.libc.free.argtypes = [ctypes.c_void_p]
+        self.live = {}
+
+    def vvb_host_alloc(self, nbytes, out):
+        p = self.libc.malloc(nbytes)
+        out._obj.value = p
+        self.live[p] = nbytes
+        return 0
+
+    def vvb_host_free(self, p):
+        p = p if isinstance(p, int) else p.value
+        del self.live[p]
+        self.libc.free(p)
+        return 0
+
+
+def test_pinned_result_pool_policy(monkeypatch):
+    import gc
+
+    fake = _FakeHostAllocLib()
+    monkeypatch.setattr(_lib, "load", lambda: fake)
+    monkeypatch.setattr(_lib, "_pinned_pool", _lib._PinnedPool())
+    monkeypatch.setenv("VVB_PINNED_MAX_MB", "64")
+    shape, big = (1 << 20, 3), 12 << 20  # 12 MiB of float32
+
+    def owner(a):
+        while isinstance(a, np.ndarray) and a.base is not None:
+            a = a.base
+        return a
+
+    a = _lib.result_empty(shape, np.float32)
+    assert not isinstance(owner(a), _lib._PinnedBlock) and not fake.live      # first request of a size: ordinary memory
+    b = _lib.result_empty(shape, np.float32)
+    blk = owner(b)
+    assert isinstance(blk, _lib._PinnedBlock) and blk.cap == big and b.shape == shape and b.dtype == np.float32
+    b[:] = 7.0                                                                 # writable, normal ndarray semantics
+    assert type(b) is np.ndarray and float(b.sum()) == 7.0 * b.size
+    ptr = blk.ptr
+    c = _lib.result_empty(shape, np.float32)                                   # b still alive: a second block
+    assert owner(c).ptr != ptr and len(fake.live) == 2
+    del b, blk
+    gc.collect()
+    d = _lib.result_empty(shape, np.float32)
+    assert owner(d).ptr == ptr and len(fake.live) == 2                         # recycled, nothing new pinned
+    view = d[10:20]                                                            # a view keeps the block alive
+    del d
+    gc.collect()
+    e = _lib.result_empty(shape, np.float32)
+    assert owner(e).ptr != ptr and owner(view).ptr == ptr
+    # cap: 64 MB total; 3 blocks of 12 MB are pinned, a 40 MB class cannot fit while they are all in use ...
+    assert _lib.result_empty((10 << 20,), np.float32).base is None            # 1st request of the class anyway
+    big_arr = _lib.result_empty((10 << 20,), np.float32)
+    assert not isinstance(owner(big_arr), _lib._PinnedBlock)
+    # ... and fits once idle blocks can be dropped to make room
+    del c, e, view
+    gc.collect()
+    big_arr2 = _lib.result_empty((10 << 20,), np.float32)
+    assert isinstance(owner(big_arr2), _lib._PinnedBlock) and sum(fake.live.values()) <= 64 << 20
+    small = _lib.result_empty((1000, 10), np.float32)                          # small results never use the pool
+    assert small.base is None
+    monkeypatch.setenv("VVB_PINNED_RESULTS", "0")
+    assert _lib.result_empty(shape, np.float32).base is None
+    del big_arr2
+    gc.collect()
+    _lib._pinned_pool.release()
+    assert not fake.live
