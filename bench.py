@@ -32,6 +32,7 @@ import subprocess
 import sys
 import threading
 import time
+from typing import Optional
 
 import numpy as np
 
@@ -128,7 +129,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arms
-def cpu_baseline(x: np.ndarray, k: int, knn_queries: int, smooth_rows: int) -> dict:
+def cpu_baseline(x: np.ndarray, k: int, knn_queries: int, smooth_rows: int, keep: Optional[dict] = None) -> dict:
     """The oracle port of the reference path, timed on the host cores on a bounded sample:
     brute-force kNN of `knn_queries` query rows against the FULL matrix (all threads) plus
     the single-threaded smooth sweep over `smooth_rows` rows; per-cell costs are added."""
@@ -140,15 +141,17 @@ def cpu_baseline(x: np.ndarray, k: int, knn_queries: int, smooth_rows: int) -> d
     smooth_rows = min(smooth_rows, n)
     orc.set_threads(os.cpu_count() or 1)  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     t0 = time.perf_counter()
-    orc.knn(x, k, 0, knn_queries)
+    o_idx, o_dist = orc.knn(x, k, 0, knn_queries)
     t_knn = time.perf_counter() - t0
     rng = np.random.default_rng(0)
     idx = rng.integers(0, smooth_rows, size=(smooth_rows, k), dtype=np.int64)
     idx[:, 0] = np.arange(smooth_rows)
     xs = np.ascontiguousarray(x[:smooth_rows])
     t0 = time.perf_counter()
-    orc.smooth(xs, idx, k, 1.0, 1)
+    o_smooth = orc.smooth(xs, idx, k, 1.0, 1)
     t_sm = time.perf_counter() - t0
+    if keep is not None:  # the checker's outputs, for the parity gates printed beside the numbers
+        keep.update(knn_idx=o_idx, knn_dist=o_dist, smooth_x=xs, smooth_idx=idx, smooth_out=o_smooth)
     per_cell = t_knn / knn_queries + t_sm / smooth_rows
     return {"value": 1.0 / per_cell, "unit": "cells/s", "cores": orc.num_threads(), "kind": "port",
             "sample": f"kNN: {knn_queries} query rows vs all {n} rows ({t_knn:.2f} s, OpenMP x{orc.num_threads()}); "
@@ -270,7 +273,7 @@ def run_ours(args) -> None:
     sync_all()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
-    idx_s, _ = knn_device(x_dev, k, q0, nq, algo=args.algo, stats=st)
+    idx_s, dist_s = knn_device(x_dev, k, q0, nq, algo=args.algo, stats=st)
     e1.record()
     idx_full = idx_s if world == 1 else None
     torch.cuda.synchronize()
@@ -428,8 +431,22 @@ def run_ours(args) -> None:
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     base = None
+    gates = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        base = cpu_baseline(x_host, k, args.cpu_knn_queries, args.cpu_smooth_rows)
+        kept = {}
+        base = cpu_baseline(x_host, k, args.cpu_knn_queries, args.cpu_smooth_rows, keep=kept)
+        # parity gates on the sample the CPU arm has just computed: the oracle is the checker here
+        qn = kept["knn_idx"].shape[0]
+        g_idx, g_dist = idx_s[:qn].cpu().numpy(), dist_s[:qn].cpu().numpy()
+        rows_equal = (g_idx == kept["knn_idx"]).all(axis=1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rel = np.abs(g_dist - kept["knn_dist"]) / np.where(kept["knn_dist"] > 0, kept["knn_dist"], 1.0)
+        g_sm = smooth_device(torch.from_numpy(kept["smooth_x"]).to(dev), torch.from_numpy(kept["smooth_idx"]).to(dev), k=k,
+                             coef=1.0, n_iter=1).cpu().numpy()
+        gates = {"knn_rows_checked": int(qn), "knn_rows_exact": float(rows_equal.mean()),
+                 "knn_dist_max_rel_err": float(rel.max()), "knn_rows_fallback": int(st.get("rows_fallback", 0)),
+                 "smooth_rows_checked": int(g_sm.shape[0]),
+                 "smooth_max_abs_err": float(np.abs(g_sm - kept["smooth_out"]).max())}
 
     if rank == 0:
         line = {
@@ -440,6 +457,7 @@ def run_ours(args) -> None:
             "config": workload_config(args, world), "clocks": clocks.summary(),
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_dense": dense_roof, "roofline_smooth": smooth_roof, "quartet": quartet,
             "knn_stats": st, "ms_knn": ms_knn, "ms_smooth": ms_smooth, "cpu_baseline": base, "fit": fit,
+            "parity_gates": gates,
             "parity": {"knn": "bit-exact vs FP32 brute-force oracle (tests/test_gpu_parity.py)",
                        "smooth": "bit-exact vs reference smooth()", "quartet": "1e-4 relative"},
         }
