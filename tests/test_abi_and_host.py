@@ -375,3 +375,24 @@ def test_pinned_result_pool_policy(monkeypatch):
     gc.collect()
     _lib._pinned_pool.release()
     assert not fake.live
+
+
+# ---------------------------------------------------------------------- bench.py contract (CPU arm)
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores, no GPU): one JSON line with the arm's keys."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cells", "20000",
+                          "--cpu-knn-queries", "64", "--cpu-smooth-rows", "2000", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "cells/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["metric"].startswith("cells/sec exact kNN") and d["config"]["workload"].startswith("synthetic 20000 cells")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1
