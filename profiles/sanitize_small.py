@@ -1,4 +1,5 @@
-"""Small invocation of every kernel of libvivae_b200.so, for compute-sanitizer runs:
+"""Small invocation of every kernel of libvivae_b200.so (written for compute-sanitizer, which is closed on this pool;
+still useful as a quick all-kernel self-check):
    compute-sanitizer --tool memcheck  --error-exitcode 9 python profiles/sanitize_small.py
    compute-sanitizer --tool synccheck --error-exitcode 9 python profiles/sanitize_small.py
 Sizes are tiny (the tools slow kernels down 10-100x); results are still checked against each other."""
