@@ -53,3 +53,15 @@ print(json.dumps({"pairs_passing_filter": pair_frac, "own_cluster_share": float(
                   "db_rows_passing_for_over_half_of_the_queries": int((per_db_row > 0.5).sum()),
                   "top_1pct_db_rows_mean_pass_rate": float(per_db_row[hubs].mean()),
                   "their_mean_centred_norm": float(np.sqrt(sq[hubs]).mean()), "all_rows_mean_centred_norm": float(np.sqrt(sq).mean())}, indent=1))
+
+# the same tile test with the database (and the queries) ordered by Voronoi cells of 64 pivot rows in Z-space
+piv = z[rng.choice(n, 64, replace=False)]
+cell = np.argmin(((z[:, None, :] - piv[None, :, :]) ** 2).sum(-1) if n <= 4000 else
+                 (zs[:, None] + (piv * piv).sum(1)[None, :] - 2.0 * (z @ piv.T)), axis=1)
+o2 = np.argsort(cell, kind="stable")
+hit2 = hit[o2][:, o2]
+surv2 = 0
+for a in range(qb):
+    rows = hit2[a * 256:(a + 1) * 256]
+    surv2 += int(np.add.reduceat(rows.any(0), np.arange(0, n, 128)).astype(bool).sum())
+print(json.dumps({"tiles_surviving_with_z_space_cells": surv2, "tiles_total": qb * tb, "fraction": surv2 / (qb * tb)}))
