@@ -1,31 +1,41 @@
 #!/usr/bin/env python
-"""Benchmark of the ViVAE hot path on B200: exact kNN (k=50) + smooth, cells/s.
+"""Benchmark of the ViVAE hot path on B200: exact kNN (k=50) + smooth, cells/s; ViVAE.fit s/epoch.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1]): synthetic 1,000,000 cells x 50 PCs (30-cluster
-mixture with a PCA-like decaying spectrum, seed 1), exact kNN k=50, then smooth(k=50,
-coef=1, n_iter=1).  One "step" = one full pass (graph + smoothing) over all cells.
+Headline workload (BASELINE.json configs[1]): synthetic 1,000,000 cells x 50 PCs (30-cluster mixture with a
+PCA-like decaying spectrum, seed 1), exact kNN k=50, then smooth(k=50, coef=1, n_iter=1).  One "step" = one full pass
+(graph + smoothing) over all cells.
 
 Timed quantities
-  value : cells/s with the matrix already resident in HBM (CUDA events, max over ranks)
-  e2e   : cells/s through the public drop-in API (`vv.make_knn` + `vv.smooth`): HOST NumPy
-          in, HOST NumPy out, H2D/D2H copies inside the timed region (wall clock around
-          calls that synchronise internally)
-N > 1 (launched under torchrun): the query rows are sharded across ranks (strong scaling:
-total work fixed); each rank holds the whole matrix, computes the graph rows of its shard,
-the index shards are all-gathered over NCCL and the Gauss-Seidel smoother -- which does
-not shard by rows -- runs replicated on every rank.
+  value : cells/s with the matrix already resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e   : cells/s with HOST buffers in and out, H2D / D2H copies inside the timed region.  N = 1: the drop-in API
+          (`vv.make_knn` + `vv.smooth`, NumPy in / NumPy out).  N > 1: `vv.sharded.knn_smooth_host_sharded` -- every
+          rank uploads ONLY its rows from page-locked memory, the matrix is assembled by an NCCL all-gather, and the
+          smoother is part of the path; the same function is also timed at N = 1 (`e2e_sharded_api`) so that the
+          per-N numbers of one path can be compared.
+  roofline : dominant kernel (tensor-core screening).  `frac` = EXECUTED MMA flops / measured dense peak (what the
+          tensor pipe really did: tiles swept x 256 x 128 pairs x executed MACs); the ALGORITHMIC rate 2*nq*n*d/t --
+          which exceeds the peak when the exact cell bounds skip most of the cross product -- is under `algorithmic`.
+  config_c3 / config_c5 : the north-star configurations (10M x 50, k=100 at every N; 2M x 2000, k=50 at N >= 4),
+          device-generated data, a few steps each, beside the headline without changing it.
+  fit   : `ViVAE.fit` s/epoch at the headline's 1M rows, with the reference's fit (restated operation for operation
+          in oracle/ref_fit.py) timed on this box's host cores and on this GPU in eager mode beside it.
 
-`--impl reference` times the reference's CPU path for the same metric on the host cores:
-the oracle port (oracle/, C + OpenMP) on a bounded sample -- the reference's own kNN
-(pynndescent) is not installable here and its smoother is the single-threaded Python loop
-the oracle's C function restates.
+N > 1 (launched under torchrun): the query rows are sharded across ranks (strong scaling: total work fixed); each
+rank holds the whole matrix, the preparation of the cell plan is split across the ranks, the index shards are
+all-gathered over NCCL (int32) and the Gauss-Seidel smoother -- which does not shard by rows -- runs
+replicated on every rank.
+
+`--impl reference` times the reference's CPU path for the same metric on the host cores: the oracle port (oracle/,
+C + OpenMP) on a bounded sample -- the reference's own kNN (pynndescent) is not installable here and its smoother is
+the single-threaded Python loop the oracle's C function restates.
 """
 
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -40,8 +50,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+# ----------------------------------------------------------------------------- synthetic inputs
 def synth_cells(n: int, d: int, seed: int = 1, n_clusters: int = 30) -> np.ndarray:
-    """C2-syn of SURVEY.md section 8(d): Gaussian mixture, per-dimension scale 5/sqrt(1+c)."""
+    """C2-syn: Gaussian mixture, per-dimension scale 5/sqrt(1+c)."""
     rng = np.random.default_rng(seed)
     spec = (5.0 / np.sqrt(1.0 + np.arange(d))).astype(np.float32)
     centres = rng.standard_normal((n_clusters, d)).astype(np.float32) * spec
@@ -54,10 +65,27 @@ def synth_cells(n: int, d: int, seed: int = 1, n_clusters: int = 30) -> np.ndarr
     return out
 
 
+def synth_pca_device(n: int, d: int, dev, seed: int = 2, n_clusters: int = 30):
+    """C3-syn: the same mixture as C2-syn, drawn on the device (identical on every rank: same seed)."""
+    import torch
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    spec = 5.0 / torch.sqrt(1.0 + torch.arange(d, device=dev, dtype=torch.float32))
+    centres = torch.randn(n_clusters, d, device=dev, generator=g) * spec
+    out = torch.empty((n, d), dtype=torch.float32, device=dev)
+    chunk = 1 << 20
+    for s0 in range(0, n, chunk):
+        e0 = min(n, s0 + chunk)
+        lab = torch.randint(0, n_clusters, (e0 - s0,), device=dev, generator=g)
+        out[s0:e0] = centres[lab] + 0.3 * spec * torch.randn(e0 - s0, d, device=dev, generator=g)
+    return out
+
+
 def synth_cells_device(n: int, d: int, dev, seed: int = 4, n_clusters: int = 40):
-    """C5-syn of SURVEY.md section 8(d), generated on the device (a 2M x 2000 float32 matrix is 16 GB per rank:
-    too large to draw on the host of every rank): non-negative log1p-transformed counts, ~65 % zeros, 40 clusters
-    with Gamma-distributed expression programmes."""
+    """C5-syn, generated on the device (a 2M x 2000 float32 matrix is 16 GB per rank: too large to draw on the host
+    of every rank): non-negative log1p-transformed counts, ~65 % zeros, 40 clusters with Gamma-distributed
+    expression programmes."""
     import torch
 
     g = torch.Generator(device=dev)
@@ -129,19 +157,26 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arms
-def cpu_baseline(x: np.ndarray, k: int, knn_queries: int, smooth_rows: int, keep: Optional[dict] = None) -> dict:
-    """The oracle port of the reference path, timed on the host cores on a bounded sample:
-    brute-force kNN of `knn_queries` query rows against the FULL matrix (all threads) plus
-    the single-threaded smooth sweep over `smooth_rows` rows; per-cell costs are added."""
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
 
+    return orc
+
+
+def cpu_baseline(x: np.ndarray, k: int, knn_queries: int, smooth_rows: int, keep: Optional[dict] = None,
+                 q_first: int = 0) -> dict:
+    """The oracle port of the reference path, timed on the host cores on a bounded sample: brute-force kNN of
+    `knn_queries` query rows (starting at `q_first`) against the FULL matrix (all threads) plus the single-threaded
+    smooth sweep over `smooth_rows` rows on a RANDOM neighbour graph of those rows (a timing sample: the sweep's cost
+    does not depend on which rows are neighbours); per-cell costs are added."""
+    orc = _oracle()
     n, d = x.shape
-    knn_queries = min(knn_queries, n)
+    knn_queries = min(knn_queries, n - q_first)
     smooth_rows = min(smooth_rows, n)
     orc.set_threads(os.cpu_count() or 1)  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     t0 = time.perf_counter()
-    o_idx, o_dist = orc.knn(x, k, 0, knn_queries)
+    o_idx, o_dist = orc.knn(x, k, q_first, q_first + knn_queries)
     t_knn = time.perf_counter() - t0
     rng = np.random.default_rng(0)
     idx = rng.integers(0, smooth_rows, size=(smooth_rows, k), dtype=np.int64)
@@ -151,12 +186,31 @@ def cpu_baseline(x: np.ndarray, k: int, knn_queries: int, smooth_rows: int, keep
     o_smooth = orc.smooth(xs, idx, k, 1.0, 1)
     t_sm = time.perf_counter() - t0
     if keep is not None:  # the checker's outputs, for the parity gates printed beside the numbers
-        keep.update(knn_idx=o_idx, knn_dist=o_dist, smooth_x=xs, smooth_idx=idx, smooth_out=o_smooth)
+        keep.update(knn_idx=o_idx, knn_dist=o_dist, smooth_x=xs, smooth_idx=idx, smooth_out=o_smooth, q_first=q_first)
     per_cell = t_knn / knn_queries + t_sm / smooth_rows
     return {"value": 1.0 / per_cell, "unit": "cells/s", "cores": orc.num_threads(), "kind": "port",
             "sample": f"kNN: {knn_queries} query rows vs all {n} rows ({t_knn:.2f} s, OpenMP x{orc.num_threads()}); "
-                      f"smooth: {smooth_rows} rows, k={k}, 1 thread ({t_sm:.2f} s); per-cell costs added",
+                      f"smooth: first {smooth_rows} rows on a random neighbour graph, k={k}, 1 thread ({t_sm:.2f} s); "
+                      "per-cell costs added",
             "seconds": t_knn + t_sm}
+
+
+def ref_fit_cpu(x: np.ndarray, rows: int, batch: int) -> dict:
+    """The reference's `fit` (oracle/ref_fit.py: restated operation for operation) on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+
+    import ref_fit
+
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
+    det = torch.are_deterministic_algorithms_enabled()
+    torch.use_deterministic_algorithms(False)
+    try:
+        r = ref_fit.time_ref_fit(np.ascontiguousarray(x[:rows]), batch_size=batch, epochs=1, device="cpu")
+    finally:
+        torch.use_deterministic_algorithms(det)
+    r["kind"] = "port (oracle/ref_fit.py: the reference's fit restated op for op; reference model.py:130-177, losses.py:266-349)"
+    return r
 
 
 def run_reference(args) -> None:
@@ -173,6 +227,7 @@ def run_reference(args) -> None:
             vals.append(base["value"])
     v = float(np.mean(vals))
     base["value"] = v
+    fit = None if args.skip_fit else ref_fit_cpu(x, min(args.n, args.ref_fit_rows), args.fit_batch)
     line = {
         "impl": "reference", "metric": "cells/sec exact kNN(k=50)+smooth", "value": v, "unit": "cells/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.n / v,
@@ -180,18 +235,50 @@ def run_reference(args) -> None:
         "config": workload_config(args, args.gpus),
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "fit": fit,
         "wall_s": time.perf_counter() - t_all0,
-        "note": "ms_per_step is extrapolated to the full workload from the bounded sample (brute force is linear in queries)",
+        "note": "ms_per_step is extrapolated to the full workload from the bounded sample (brute force is linear in "
+                "queries); the smoother leg runs on a random neighbour graph of the first rows (timing only)",
     }
     print(json.dumps(line))
 
 
 def workload_config(args, n_gpus: int) -> dict:
     return {"workload": f"synthetic {args.n} cells x {args.d} PCs, exact kNN k={args.k} + smooth(k={args.k}, coef=1, n_iter=1)",
-            "n": args.n, "d": args.d, "k": args.k, "parallelism": (f"query-row shards x{n_gpus}, smooth replicated" if getattr(args, "exchange", "replicated") != "ring" else
+            "n": args.n, "d": args.d, "k": args.k,
+            "parallelism": (f"query-row shards x{n_gpus} (cell plan prepared in row shards), smooth replicated"
+                            if getattr(args, "exchange", "replicated") != "ring" else
                             f"query-row AND database-row shards x{n_gpus} (NCCL ring exchange + running merge), smooth replicated"),
             "l2": f"inputs larger than L2 (matrix {args.n * args.d * 4 / 1e6:.0f} MB, graph "
                   f"{args.n * (args.k + 1) * 12 / 1e6:.0f} MB vs 126 MB L2)"}
+
+
+def executed_macs_per_pair(dd: int) -> int:
+    """MACs the tensor pipe executes per (query, database row) pair: three fp16 products of the hi/lo split, K padded
+    to the MMA's k-step (16) for d + 3 <= 64, to the 64-column atom otherwise."""
+    return 16 * ((dd + 3 + 15) // 16 + 2 * ((dd + 15) // 16)) if dd + 3 <= 64 else 3 * 64 * ((dd + 3 + 63) // 64)
+
+
+def screen_roofline(st: dict, nq: int, n: int, d: int, peaks: dict, sustained: bool = False) -> dict:
+    """Roofline object of the screening kernel from the stats of one call (see the module docstring)."""
+    ms = st.get("ms_screen") or st.get("ms_fallback")
+    peak = (peaks["tf_sustained"] or peaks["tf"]) if sustained else peaks["tf"]
+    alg = 2.0 * nq * n * d
+    if st.get("algo_used") != 2:
+        ach = alg / (ms / 1e3) / 1e12
+        return {"kernel": "knn_brute_ffma", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peaks["source"], "ms": ms}
+    ex = float(st["tiles_swept"]) * 256 * 128 * executed_macs_per_pair(d) * 2
+    ach = ex / (ms / 1e3) / 1e12
+    return {"kernel": "knn_screen_tcgen05", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + (" (sustained)" if sustained else " (burst)"),
+            "ms": ms, "what": "EXECUTED MMA flops (tiles swept x 256 x 128 pairs x executed MACs x 2) / duration",
+            "executed_macs_per_pair": executed_macs_per_pair(d), "algorithmic_macs_per_pair": d,
+            "tiles_swept": st["tiles_swept"], "tiles_dense": st["tiles_dense"], "cells": st["cells"],
+            "algorithmic": {"flops": alg, "tflops": alg / (ms / 1e3) / 1e12, "x_peak": alg / (ms / 1e3) / 1e12 / peak,
+                            "note": "2*nq*n*d over the duration; NOT a utilisation: the exact cell bounds skipped "
+                                    f"{100.0 * (1.0 - st['tiles_swept'] / max(1, st['tiles_dense'])):.1f} % of the tiles "
+                                    "(tiles_swept includes the threshold pre-pass)"}}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -202,7 +289,7 @@ def run_ours(args) -> None:
     import vivae_b200 as vv
     from vivae_b200 import _lib
     from vivae_b200.device import knn_device, smooth_device
-    from vivae_b200.sharded import all_gather_rows, make_knn_ring, shard_bounds
+    from vivae_b200.sharded import (all_gather_indices, knn_smooth_host_sharded, make_knn_ring, shard_bounds)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -211,6 +298,56 @@ def run_ours(args) -> None:
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    peaks = measured_peaks()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v: int) -> int:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def knn_step(xd, kk, q0_, nq_, stats=None):
+        """Graph rows [q0_, q0_+nq_) of the replicated matrix; at N > 1 the cell plan is prepared in row shards."""
+        return knn_device(xd, kk, q0_, nq_, algo=args.algo, stats=stats, group=(dist.group.WORLD if world > 1 else None))
+
+    def pipeline(xd, kk, q0_, nq_, x_local=None, stats=None):
+        n_ = xd.shape[0]
+        if args.exchange == "ring" and x_local is not None:
+            idx, dist_ = make_knn_ring(x_local, n_, kk, algo=args.algo)
+        else:
+            idx, dist_ = knn_step(xd, kk, q0_, nq_, stats)
+        if world > 1:
+            idx = all_gather_indices(idx, n_)  # the smoother needs the whole graph (NCCL all-gather, int32)
+        out = smooth_device(xd, idx, k=kk, coef=1.0, n_iter=1)
+        return idx, dist_, out
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        sync_all()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, sum_over_ranks(_lib.launch_count() - l0)
 
     n, d, k = args.n, args.d, args.k
     device_data = args.device_data or n * d > 1_000_000_000
@@ -222,50 +359,11 @@ def run_ours(args) -> None:
         x_host = synth_cells(n, d)
         x_dev = torch.from_numpy(x_host).to(dev)
     q0, nq = shard_bounds(n, world, rank)
-
     x_local = x_dev[q0:q0 + nq].contiguous() if args.exchange == "ring" else None
 
-    def step_device(stats=None):
-        if args.exchange == "ring":  # database-sharded build: shards travel around the NCCL ring
-            idx, dist_ = make_knn_ring(x_local, n, k, algo=args.algo)
-        else:
-            idx, dist_ = knn_device(x_dev, k, q0, nq, algo=args.algo, stats=stats)
-        if world > 1:
-            idx = all_gather_rows(idx, n)  # the smoother needs the whole graph (NCCL all-gather)
-        out = smooth_device(x_dev, idx, k=k, coef=1.0, n_iter=1)
-        return idx, dist_, out
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # ---- warm-up
-    for _ in range(args.warmup):
-        step_device()
-    sync_all()
-
-    # ---- timed region: EXACTLY `steps` steps, CUDA events on the launching stream
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = _lib.launch_count()
+    # ---- headline: warm-up, then EXACTLY `steps` steps between CUDA events on the launching stream
     with ClockSampler(local) as clocks:
-        sync_all()
-        ev0.record()
-        for _ in range(args.steps):
-            step_device()
-        ev1.record()
-        sync_all()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = _lib.launch_count() - launches0
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
-    ms_step = ms_total / args.steps
+        ms_step, launches = timed(lambda: pipeline(x_dev, k, q0, nq, x_local), args.steps, args.warmup)
     value = n / (ms_step / 1e3)
 
     # ---- per-kernel split of one more (untimed) step, for the roofline of the dominant kernel
@@ -273,33 +371,20 @@ def run_ours(args) -> None:
     sync_all()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
-    idx_s, dist_s = knn_device(x_dev, k, q0, nq, algo=args.algo, stats=st)
+    idx_s, dist_s = knn_step(x_dev, k, q0, nq, st)
     e1.record()
-    idx_full = idx_s if world == 1 else None
     torch.cuda.synchronize()
     ms_knn = e0.elapsed_time(e1)
-    ms_smooth = None
-    if world == 1:
-        e1.record()
-        smooth_device(x_dev, idx_full, k=k, coef=1.0, n_iter=1)
-        e2.record()
-        torch.cuda.synchronize()
-        ms_smooth = e1.elapsed_time(e2)
-    peaks = measured_peaks()
-    dom_ms = st.get("ms_screen") or st.get("ms_fallback") or ms_knn
-    flops = 2.0 * nq * n * d  # ALGORITHMIC: cross-term only, unpadded d
-    achieved = flops / (dom_ms / 1e3) / 1e12
-    roofline = {"kernel": "knn_screen_tcgen05" if st.get("algo_used") == 2 else "knn_brute_ffma",
-                "bound": "tensor", "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tf"], "traffic": None, "peak_source": peaks["source"],
-                "ms": dom_ms, "algorithmic_flops": flops}
-
-    def executed_macs_per_pair(dd):
-        # three fp16 products of the hi/lo split, K padded to the MMA's k-step (16) or to the 64-column atom
-        return 16 * ((dd + 3 + 15) // 16 + 2 * ((dd + 15) // 16)) if dd + 3 <= 64 else 3 * 64 * ((dd + 3 + 63) // 64)
-
-    cap = os.path.join(ROOT, "profiles", "r01_hot_kernels_s3_raw.csv")
-    if st.get("algo_used") == 2 and (n, d, k) == (1_000_000, 50, 50) and os.path.isfile(cap):
+    idx_full = all_gather_indices(idx_s, n) if world > 1 else idx_s
+    torch.cuda.synchronize()
+    e1.record()
+    smooth_device(x_dev, idx_full, k=k, coef=1.0, n_iter=1)
+    e2.record()
+    torch.cuda.synchronize()
+    ms_smooth = e1.elapsed_time(e2)
+    roofline = screen_roofline(st, nq, n, d, peaks)
+    cap = os.path.join(ROOT, "profiles", "r02_knn_screen_1M_raw.csv")
+    if world == 1 and st.get("algo_used") == 2 and (n, d, k) == (1_000_000, 50, 50) and os.path.isfile(cap):
         import csv
         with open(cap) as f:
             rows_ = list(csv.reader(f))
@@ -307,111 +392,116 @@ def run_ours(args) -> None:
         gb = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         srow = next((r for r in rows_[2:] if "knn_screen" in r[col["Kernel Name"]]), None)
         if srow is not None:
-            tr = sum(float(srow[col[m]]) * gb[rows_[1][col[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-            roofline["traffic"] = tr
-            roofline["traffic_note"] = ("dram__bytes_read + dram__bytes_write of the launch (1,000,000 query rows) from the "
-                                        "committed ncu --set full capture profiles/r01_hot_kernels_s3_raw.csv")
+            roofline["traffic"] = sum(float(srow[col[m]]) * gb[rows_[1][col[m]]]
+                                      for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            roofline["traffic_note"] = ("dram__bytes_read + dram__bytes_write of this launch (1,000,000 query rows, one "
+                                        "GPU) from the committed ncu --set full capture profiles/r02_knn_screen_1M_raw.csv")
     dense_roof = None
-    if st.get("algo_used") == 2:
-        # The sweep is exact but not dense: cells whose distance lower bound exceeds every row's k-th candidate
-        # are skipped, so the ALGORITHMIC rate above can exceed the tensor peak.  What the tensor pipe really
-        # executed: tiles swept x 256 x 128 pairs x the executed MACs per pair.
-        ex_flops = float(st["tiles_swept"]) * 256 * 128 * executed_macs_per_pair(d) * 2
-        roofline.update({
-            "executed_tflops": ex_flops / (dom_ms / 1e3) / 1e12,
-            "executed_frac": ex_flops / (dom_ms / 1e3) / 1e12 / peaks["tf"],
-            "tiles_swept": st["tiles_swept"], "tiles_dense": st["tiles_dense"], "cells": st["cells"],
-            "note": "frac uses ALGORITHMIC flops 2*nq*n*d; the cell bounds skipped "
-                    f"{100.0 * (1.0 - st['tiles_swept'] / max(1, st['tiles_dense'])):.1f} % of the tiles "
-                    "(tiles_swept includes the threshold pre-pass), so it is not a tensor-pipe utilisation: "
-                    "executed_frac and roofline_dense are"})
-        if world == 1 and not args.skip_dense:
-            # the same kernel with the partition switched off (every tile swept): the dense tensor roofline
-            os.environ["VVB_TC_CELLS"] = "1"
-            try:
+    if st.get("algo_used") == 2 and world == 1 and not args.skip_dense:
+        # the same kernel with the partition switched off (every tile swept): the dense tensor roofline
+        os.environ["VVB_TC_CELLS"] = "1"
+        try:
+            for _ in range(2):
                 sd = {}
                 knn_device(x_dev, k, q0, nq, algo=args.algo, stats=sd)
                 torch.cuda.synchronize()
-                sd = {}
-                knn_device(x_dev, k, q0, nq, algo=args.algo, stats=sd)
-                torch.cuda.synchronize()
-            finally:
-                del os.environ["VVB_TC_CELLS"]
-            exd = float(sd["tiles_swept"]) * 256 * 128 * executed_macs_per_pair(d) * 2
-            dense_roof = {"kernel": "knn_screen_tcgen05 (VVB_TC_CELLS=1: no tile skipped)", "bound": "tensor",
-                          "achieved": flops / (sd["ms_screen"] / 1e3) / 1e12, "peak": peaks["tf"], "unit": "TFLOP/s",
-                          "frac": flops / (sd["ms_screen"] / 1e3) / 1e12 / peaks["tf"],
-                          "executed_tflops": exd / (sd["ms_screen"] / 1e3) / 1e12,
-                          "executed_frac": exd / (sd["ms_screen"] / 1e3) / 1e12 / peaks["tf"],
-                          "ms": sd["ms_screen"], "executed_macs_per_pair": executed_macs_per_pair(d),
-                          "algorithmic_macs_per_pair": d}
-    smooth_roof = None
-    if ms_smooth:
-        sbytes = float(n) * (k * d * 4 + k * 4 + d * 4)
-        smooth_roof = {"kernel": "smooth_sweep_gs", "bound": "hbm", "achieved": sbytes / (ms_smooth / 1e3) / 1e9,
-                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": sbytes / (ms_smooth / 1e3) / 1e9 / peaks["hbm_gbs"],
-                       "ms": ms_smooth, "algorithmic_bytes": sbytes}
+        finally:
+            del os.environ["VVB_TC_CELLS"]
+        dense_roof = screen_roofline(sd, nq, n, d, peaks)
+        dense_roof["kernel"] += " (VVB_TC_CELLS=1: no tile skipped)"
+    sbytes = float(n) * (k * d * 4 + k * 4 + d * 4)
+    smooth_roof = {"kernel": "smooth_sweep_gs", "bound": "hbm", "achieved": sbytes / (ms_smooth / 1e3) / 1e9,
+                   "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": sbytes / (ms_smooth / 1e3) / 1e9 / peaks["hbm_gbs"],
+                   "ms": ms_smooth, "algorithmic_bytes": sbytes, "traffic": None}
 
-    # ---- end to end through the public API (host buffers in and out)
-    e2e = None
+    # ---- end to end with host buffers
+    e2e = e2e_sharded = None
     if not args.skip_e2e:
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        xq = x_host if world == 1 else x_host  # every rank owns the host matrix; shards by query rows
-        from vivae_b200.knn import _knn_host
+        # (a) the sharded host API: every rank passes only its rows, page-locked; same function at every N
+        xs_pin = torch.from_numpy(x_host[q0:q0 + nq]).pin_memory()
+        outs = (torch.empty((nq, k + 1), dtype=torch.int64).pin_memory(), torch.empty((nq, k + 1), dtype=torch.float32).pin_memory(),
+                torch.empty((nq, d), dtype=torch.float32).pin_memory())
 
-        def step_e2e():
-            if world == 1:
-                knn = vv.make_knn(xq, k=k, verbose=False, algo=args.algo)
-                out = vv.smooth(xq, knn, k=k, coef=1.0, n_iter=1)
-                return float(out[0, 0])
-            idx_h, dist_h = _knn_host(xq, k, q0, nq, args.algo, None)
-            return float(dist_h[0, 1]) if nq else 0.0
+        def step_sharded():
+            o = knn_smooth_host_sharded(xs_pin, n, k, coef=1.0, n_iter=1, algo=args.algo, out=outs,
+                                        _knn_fn=lambda xx, kk, a, b, alg: knn_step(xx, kk, a, b))
+            return float(o[2][0, 0]) if nq else 0.0
 
-        for _ in range(3):  # warm-up: device buffers, bounce buffers and the pool of page-locked result blocks
-            step_e2e()
+        for _ in range(3):
+            step_sharded()
         sync_all()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            step_e2e()
+            step_sharded()
         torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        # bytes that cross PCIe: neighbour indices travel as int32 (widened / narrowed in the staging copy)
-        h2d = n * d * 4 + (n * d * 4 + n * (k + 1) * 4 if world == 1 else 0)
-        d2h = nq * (k + 1) * 8 + (n * d * 4 if world == 1 else 0)
-        e2e = {"value": n / dt, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "path": "vv.make_knn + vv.smooth (host NumPy in/out)" if world == 1 else
-                       "vvb_make_knn_host per rank on its query shard (host in/out); smooth not included at N>1"}
+        dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        h2d = nq * d * 4
+        d2h = nq * (k + 1) * 12 + nq * d * 4
+        e2e_sharded = {"value": n / dt, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "ms_per_step": dt * 1e3, "steps": e2e_steps, "bytes_are": "per rank",
+                       "path": "vv.sharded.knn_smooth_host_sharded: upload of the rank's rows (page-locked) -> NCCL all-gather "
+                               "of the matrix -> graph -> all-gather of indices -> smooth -> download of the rank's graph "
+                               "rows and smoothed rows"}
+        del xs_pin, outs
+        if world == 1:
+            # (b) the drop-in API (what a user of the reference calls): NumPy in, NumPy out
+            def step_dropin():
+                knn = vv.make_knn(x_host, k=k, verbose=False, algo=args.algo)
+                out = vv.smooth(x_host, knn, k=k, coef=1.0, n_iter=1)
+                return float(out[0, 0])
 
-    # ---- quartet loss at a bandwidth-sized batch (rank 0): achieved GB/s of fwd+bwd
+            for _ in range(3):  # warm-up: device buffers, bounce buffers and the pool of page-locked result blocks
+                step_dropin()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                step_dropin()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / e2e_steps
+            # bytes that cross PCIe: neighbour indices travel as int32 (widened / narrowed in the staging copy)
+            e2e = {"value": n / dt, "unit": "cells/s", "h2d_bytes_per_step": int(2 * n * d * 4 + n * (k + 1) * 4),
+                   "d2h_bytes_per_step": int(n * (k + 1) * 8 + n * d * 4), "ms_per_step": dt * 1e3, "steps": e2e_steps,
+                   "path": "vv.make_knn + vv.smooth (host NumPy in/out; the graph goes down and up again between the calls)"}
+        else:
+            e2e = e2e_sharded
+
+    # ---- quartet loss at a bandwidth-sized batch (rank 0): achieved GB/s of forward + backward, C ABI calls
     quartet = None
     if rank == 0 and not args.skip_fit:
+        lib = _lib.load()
         Bq = min(n, 1 << 20)
         xq_ = x_dev[:Bq].contiguous()
-        zq_ = torch.randn(Bq, 2, device=dev, requires_grad=True)
+        zq_ = torch.randn(Bq, 2, device=dev)
+        gu = torch.empty(Bq, 2, device=dev)
+        gz = torch.empty(Bq, 2, device=dev)
+        loss_ = torch.empty((), device=dev)
+        gout = torch.ones((), device=dev)
+        wsq = torch.empty(int(lib.vvb_quartet_workspace_bytes(Bq)), dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def q_step():
+            _lib.check(lib.vvb_quartet_loss_fwd_device(xq_.data_ptr(), zq_.data_ptr(), Bq, d, 2, None, 1, 0, 0,
+                                                       loss_.data_ptr(), gu.data_ptr(), wsq.data_ptr(), stream))
+            _lib.check(lib.vvb_quartet_loss_bwd_device(gu.data_ptr(), gout.data_ptr(), Bq * 2, gz.data_ptr(), stream))
+
         for _ in range(3):
-            l_ = vv.MDSLoss()(xq_, zq_)
-            l_.backward()
+            q_step()
         torch.cuda.synchronize()
         q0e, q1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         q0e.record()
-        for _ in range(10):
-            zq_.grad = None
-            l_ = vv.MDSLoss()(xq_, zq_)
-            l_.backward()
+        for _ in range(20):
+            q_step()
         q1e.record()
         torch.cuda.synchronize()
-        msq = q0e.elapsed_time(q1e) / 10
+        msq = q0e.elapsed_time(q1e) / 20
         qbytes = float(Bq) * (4 * (d + 2) + 4 * (2 + 2 * 2))  # fwd reads x,z; writes unit grad; bwd reads it, writes dz
         quartet = {"batch": Bq, "ms_fwd_bwd": msq, "achieved_gbs": qbytes / (msq / 1e3) / 1e9,
                    "peak_gbs": peaks["hbm_gbs"], "frac": qbytes / (msq / 1e3) / 1e9 / peaks["hbm_gbs"],
-                   "algorithmic_bytes": qbytes}
+                   "algorithmic_bytes": qbytes, "how": "vvb_quartet_loss_fwd_device + bwd_device, 20 calls between CUDA events"}
+        del xq_, zq_, gu, gz, wsq
 
-    # ---- fit (secondary metric: s/epoch), rank 0 only
+    # ---- fit (the metric's second half: s/epoch), rank 0 only, at the headline's row count
     fit = None
     if rank == 0 and not args.skip_fit:
         rows = min(n, args.fit_rows)
@@ -428,14 +518,33 @@ def run_ours(args) -> None:
         fit = {"rows": rows, "batch_size": args.fit_batch, "s_per_epoch": dt, "cells_per_s": rows / dt,
                "epochs_timed": args.fit_epochs,
                "quartet_kernel_launches_per_epoch": (_lib.launch_count() - l0) / args.fit_epochs}
+        del model
+        if world == 1 and not args.skip_cpu:
+            # the reference's fit beside it, same box: host cores, and this GPU in eager mode (dispatch-bound)
+            rr = min(rows, args.ref_fit_rows)
+            fit["reference_cpu"] = ref_fit_cpu(x_host, rr, args.fit_batch)
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import ref_fit
+            det = torch.are_deterministic_algorithms_enabled()
+            torch.use_deterministic_algorithms(False)
+            try:
+                fit["reference_eager_gpu"] = ref_fit.time_ref_fit(np.ascontiguousarray(x_host[:rr]), batch_size=args.fit_batch,
+                                                                 epochs=1, device=f"cuda:{local}")
+            finally:
+                torch.use_deterministic_algorithms(det)
+            fit["speedup_vs_reference_cpu"] = fit["cells_per_s"] / fit["reference_cpu"]["cells_per_s"]
+            fit["speedup_vs_reference_eager_gpu"] = fit["cells_per_s"] / fit["reference_eager_gpu"]["cells_per_s"]
 
-    # ---- CPU baseline beside it (rank 0, N=1 only)
+    # ---- CPU baseline (N = 1 only) and parity gates (every N: the oracle is the checker, rank 0's own shard)
     base = None
     gates = None
-    if rank == 0 and world == 1 and not args.skip_cpu:
+    if rank == 0 and not args.skip_cpu:
         kept = {}
-        base = cpu_baseline(x_host, k, args.cpu_knn_queries, args.cpu_smooth_rows, keep=kept)
-        # parity gates on the sample the CPU arm has just computed: the oracle is the checker here
+        qn = args.cpu_knn_queries if world == 1 else min(args.cpu_knn_queries, 1024)
+        sr = args.cpu_smooth_rows if world == 1 else min(args.cpu_smooth_rows, 50_000)
+        b = cpu_baseline(x_host, k, min(qn, nq), sr, keep=kept, q_first=q0)
+        if world == 1:
+            base = b
         qn = kept["knn_idx"].shape[0]
         g_idx, g_dist = idx_s[:qn].cpu().numpy(), dist_s[:qn].cpu().numpy()
         rows_equal = (g_idx == kept["knn_idx"]).all(axis=1)
@@ -445,8 +554,46 @@ def run_ours(args) -> None:
                              coef=1.0, n_iter=1).cpu().numpy()
         gates = {"knn_rows_checked": int(qn), "knn_rows_exact": float(rows_equal.mean()),
                  "knn_dist_max_rel_err": float(rel.max()), "knn_rows_fallback": int(st.get("rows_fallback", 0)),
+                 "knn_rows_refined": int(st.get("rows_refined", 0)),
                  "smooth_rows_checked": int(g_sm.shape[0]),
-                 "smooth_max_abs_err": float(np.abs(g_sm - kept["smooth_out"]).max())}
+                 "smooth_max_abs_err": float(np.abs(g_sm - kept["smooth_out"]).max()),
+                 "checked": f"rank 0's first {qn} graph rows of this run and a {g_sm.shape[0]}-row smoother sample vs the CPU oracle"}
+
+    # ---- the north-star configurations beside the headline (device-generated data, a few steps)
+    del idx_s, dist_s, idx_full
+    x_dev = None
+    torch.cuda.empty_cache()
+    sub = {}
+
+    def sub_config(name, xs, kk, steps, with_smooth=True):
+        n_, d_ = xs.shape
+        a0, an = shard_bounds(n_, world, rank)
+        fn = (lambda: pipeline(xs, kk, a0, an)) if with_smooth else (lambda: knn_step(xs, kk, a0, an))
+        ms, _ = timed(fn, steps, 1)
+        s_ = {}
+        knn_step(xs, kk, a0, an, s_)
+        torch.cuda.synchronize()
+        ms_kn = max_over_ranks(s_["ms_prepare"] + s_["ms_screen"] + s_["ms_rerank"] + s_["ms_fallback"])
+        rf = screen_roofline(s_, an, n_, d_, peaks, sustained=True)
+        sub[name] = {"workload": f"synthetic {n_} x {d_}, exact kNN k={kk}" + (f" + smooth(k={kk}, coef=1, n_iter=1)" if with_smooth else " (graph only)"),
+                     "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": ms, "value": n_ / (ms / 1e3), "unit": "cells/s",
+                     "data": "synthetic (generated on the device, identical on every rank)", "ms_knn_rank0": ms_kn,
+                     "knn_stats_rank0": s_, "roofline": rf}
+
+    if not args.skip_c3 and args.c3_rows > 0:
+        xs = synth_pca_device(args.c3_rows, 50, dev)
+        sub_config("config_c3", xs, 100, args.sub_steps)
+        del xs
+        torch.cuda.empty_cache()
+    if not args.skip_c5 and args.c5_rows > 0:
+        if world >= 4:
+            xs = synth_cells_device(args.c5_rows, 2000, dev)
+            sub_config("config_c5", xs, 50, 1, with_smooth=False)
+            del xs
+            torch.cuda.empty_cache()
+        else:
+            sub["config_c5"] = {"skipped": "BASELINE quotes 2M x 2000 at 8 GPUs; measured here at N >= 4 only "
+                                           "(one GPU needs about a minute per step)"}
 
     if rank == 0:
         line = {
@@ -455,10 +602,11 @@ def run_ours(args) -> None:
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 (screening operands f16 hi/lo, f32 accumulate; re-rank f32)",
             "data": "synthetic (generated on the device)" if device_data else "synthetic",
             "config": workload_config(args, world), "clocks": clocks.summary(),
-            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_dense": dense_roof, "roofline_smooth": smooth_roof, "quartet": quartet,
+            "e2e": e2e, "e2e_sharded_api": e2e_sharded, "gpu_launches": launches, "roofline": roofline,
+            "roofline_dense": dense_roof, "roofline_smooth": smooth_roof, "quartet": quartet,
             "knn_stats": st, "ms_knn": ms_knn, "ms_smooth": ms_smooth, "cpu_baseline": base, "fit": fit,
-            "parity_gates": gates,
-            "parity": {"knn": "bit-exact vs FP32 brute-force oracle (tests/test_gpu_parity.py)",
+            "parity_gates": gates, **sub,
+            "parity": {"knn": "bit-exact vs FP32 brute-force oracle (tests/test_gpu_parity.py, tests/test_gpu_configs.py)",
                        "smooth": "bit-exact vs reference smooth()", "quartet": "1e-4 relative"},
         }
         print(json.dumps(line))
@@ -484,10 +632,16 @@ def main():
     ap.add_argument("--skip-fit", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-dense", action="store_true")
+    ap.add_argument("--skip-c3", action="store_true")
+    ap.add_argument("--skip-c5", action="store_true")
+    ap.add_argument("--c3-rows", type=int, default=10_000_000)
+    ap.add_argument("--c5-rows", type=int, default=2_000_000)
+    ap.add_argument("--sub-steps", type=int, default=2)
     ap.add_argument("--device-data", action="store_true")
-    ap.add_argument("--fit-rows", type=int, default=200_000)
+    ap.add_argument("--fit-rows", type=int, default=1_000_000)
+    ap.add_argument("--ref-fit-rows", type=int, default=100_000)
     ap.add_argument("--fit-batch", type=int, default=512)
-    ap.add_argument("--fit-epochs", type=int, default=3)
+    ap.add_argument("--fit-epochs", type=int, default=2)
     ap.add_argument("--cpu-knn-queries", type=int, default=4096)
     ap.add_argument("--cpu-smooth-rows", type=int, default=200_000)
     args = ap.parse_args()

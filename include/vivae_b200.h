@@ -49,21 +49,22 @@ extern "C" {
 /* counters filled by the kNN entry points (all optional: pass NULL) */
 typedef struct vvb_knn_stats {
   int64_t rows;            /* query rows processed                                  */
-  int64_t rows_fallback;   /* rows whose certificate failed and were recomputed by
-                              the FP32 brute-force kernel                           */
+  int64_t rows_fallback;   /* rows recomputed by the FP32 brute-force kernel (their
+                              certificate failed AND their refine list overflowed)  */
   int32_t algo_used;       /* VVB_KNN_BRUTE or VVB_KNN_TENSOR                       */
   int32_t candidates;      /* m: candidates kept per row by the screening kernel    */
   float ms_prepare;        /* device time, operand preparation (centre/scale/split) */
   float ms_screen;         /* device time, tensor-core distance GEMM + select       */
   float ms_rerank;         /* device time, FP32 re-rank + certify                   */
-  float ms_fallback;       /* device time, brute-force fallback                     */
+  float ms_fallback;       /* device time, refine pass + brute-force fallback       */
   int64_t kernel_launches; /* kernels launched by this call                         */
   int64_t tiles_swept;     /* (256 query rows x 128 database rows) tiles the screening
                               kernel actually computed                              */
   int64_t tiles_dense;     /* tiles of the full cross product (what a sweep without
                               the cell bounds would compute)                        */
   int32_t cells;           /* spatial cells of the partition (1 = none)             */
-  int32_t reserved;
+  int32_t rows_refined;    /* rows whose certificate failed and were settled by the
+                              fixed-threshold refine sweep on the tensor cores      */
 } vvb_knn_stats;
 
 int vvb_version(void);
@@ -115,12 +116,48 @@ int vvb_make_knn_device(const float *x_dev, int64_t n, int d, int k, int64_t q0,
                         int algo, int64_t *idx_out_dev, float *dist_out_dev, void *workspace_dev,
                         size_t workspace_bytes, void *stream, vvb_knn_stats *stats);
 
+/* ------------------------------------------------------------------------
+ * Multi-GPU preparation of the tensor path (same reference call site, knn.py:135-141; the reference is
+ * single-device).  With the matrix replicated and the QUERY rows sharded over `parts` GPUs, every GPU would
+ * repeat the whole preparation (pivot assignment and cell extents are O(n P) each); instead part `part` runs
+ * vvb_knn_plan_phase_device for phase = 0, 1, 2, 3 on its own workspace, and after each phase the parts combine
+ * the tables it reports in xch[0 .. *n_xch) -- device pointers INTO the workspace -- with the collective `op`
+ * names (NCCL in vivae_b200.device.knn_device; any all-gather / all-reduce will do):
+ *   VVB_XCH_GATHER_ROWS  element i belongs to the part whose row shard holds row i (shards of ceil(n/parts) rows)
+ *   VVB_XCH_SUM          element-wise sum over the parts
+ *   VVB_XCH_MAX_ORD      element-wise max over the parts of uint32 values compared as UNSIGNED
+ * Then vvb_make_knn_planned_device (arguments of vvb_make_knn_device, same workspace, same n/d/k/nq) builds the
+ * graph rows [q0, q0+nq) without preparing again.  parts = 1 needs no exchange and equals vvb_make_knn_device.
+ * Returns VVB_ENOTSUP when (n, d, k) is outside the tensor path (use vvb_make_knn_device).
+ * ------------------------------------------------------------------------ */
+#define VVB_XCH_I32 0
+#define VVB_XCH_U32 1
+#define VVB_XCH_F64 2
+#define VVB_XCH_GATHER_ROWS 0
+#define VVB_XCH_SUM 1
+#define VVB_XCH_MAX_ORD 2
+typedef struct vvb_exchange {
+  void *ptr;      /* device pointer into the workspace */
+  size_t count;   /* elements */
+  int32_t dtype;  /* VVB_XCH_I32 / U32 / F64 */
+  int32_t op;     /* VVB_XCH_GATHER_ROWS / SUM / MAX_ORD */
+} vvb_exchange;
+
+int vvb_knn_plan_phase_device(const float *x_dev, int64_t n, int d, int k, int64_t nq, void *workspace_dev,
+                              size_t workspace_bytes, int phase, int part, int parts, void *stream,
+                              vvb_exchange *xch /* [2] */, int *n_xch);
+
+int vvb_make_knn_planned_device(const float *x_dev, int64_t n, int d, int k, int64_t q0, int64_t nq,
+                                int64_t *idx_out_dev, float *dist_out_dev, void *workspace_dev,
+                                size_t workspace_bytes, void *stream, vvb_knn_stats *stats);
+
 /* Diagnostics (no reference counterpart): run only the preparation and the tensor-core
  * screening of the VVB_KNN_TENSOR path and return the raw per-row candidate lists:
  * cand_idx/cand_key (nq, C) with C = vvb_knn_screen_debug_capacity(), cand_cnt (nq) valid
  * entries per row (sorted by screening key), cand_thr (nq) the final admission threshold,
- * xnorm (nq) |x^|^2 of the scaled/centred query, scale_ymax[2] = {scale, ymax}, mu[64] the
- * column means.  Tests use it to bound the screening error against FP64. */
+ * xnorm (nq) |x^|^2 of the scaled/centred query, scale_ymax[2] = {scale, ymax}, mu the
+ * column means (64 * ceil((d + 3) / 64) floats, zero beyond d).  Tests use it to bound the
+ * screening error against FP64. */
 int vvb_knn_screen_debug_capacity(void);
 int vvb_knn_screen_debug_host(const float *x_host, int64_t n, int d, int k, int64_t q0, int64_t nq,
                               uint32_t *cand_idx_out, float *cand_key_out, int32_t *cand_cnt_out,

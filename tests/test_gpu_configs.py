@@ -1,0 +1,298 @@
+"""GPU parity tests at the shapes of BASELINE.json's configs (run with `-m gpu` on a B200), through the C ABI.
+
+C1  86,864 x 38, k=50          -- the whole graph against the FULL oracle + smooth
+C3  4.2M x 50, k=100           -- m = 126 candidates, P = 1024 cells: sampled oracle slices, size-independent
+                                  properties on every row, the whole smoothed matrix against the oracle's sweep
+C5  100k x 2000, k=50 (slice)  -- the K-loop kernel at its full width (32 K atoms): sampled oracle slices
+ties 200k x 50 log-counts      -- thousands of identical rows and exactly tied distances: the refine pass must settle
+                                  them on the tensor cores (brute-force fallback < 0.1 % of the rows)
+plus the certificate's margin measured against FP64 at d = 50 / 500 / 2000 and the refine pass on its own.
+
+Bars (BASELINE.json north_star): neighbour indices and distances bit-exact against the FP32 brute-force oracle
+(ties by index); smoothed values bit-exact (bar 1e-5 relative)."""
+
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as orc
+from conftest import GOLDEN
+
+import vivae_b200 as vv
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------ synthetic inputs of SURVEY.md section 8(d)
+def c1_syn(n=86_864, d=38, seed=0):
+    """Cytometry-shaped: 24-component Gaussian mixture, centres ~ U(0, 6)^d, sigma 0.5, clipped at 0."""
+    rng = np.random.default_rng(seed)
+    centres = rng.uniform(0.0, 6.0, size=(24, d))
+    lab = rng.integers(0, 24, size=n)
+    return np.maximum(centres[lab] + 0.5 * rng.standard_normal((n, d)), 0.0).astype(np.float32)
+
+
+def pca_syn(n, d, seed, n_clusters=30):
+    """C2 / C3-syn: Gaussian mixture with per-dimension scale 5 / sqrt(1 + c) (bench.py: synth_cells)."""
+    rng = np.random.default_rng(seed)
+    spec = (5.0 / np.sqrt(1.0 + np.arange(d))).astype(np.float32)
+    centres = rng.standard_normal((n_clusters, d)).astype(np.float32) * spec
+    out = np.empty((n, d), dtype=np.float32)
+    for s in range(0, n, 1 << 18):
+        e = min(n, s + (1 << 18))
+        lab = rng.integers(0, n_clusters, size=e - s)
+        out[s:e] = centres[lab] + 0.3 * spec * rng.standard_normal((e - s, d), dtype=np.float32)
+    return out
+
+
+def c5_syn(n, d=2000, seed=4, n_clusters=40):
+    """Gene-expression-shaped: non-negative log1p counts, ~70 % zeros, 40 clusters of Gamma(2, 1) programmes."""
+    rng = np.random.default_rng(seed)
+    prog = rng.gamma(2.0, 1.0, size=(n_clusters, d)).astype(np.float32) * (rng.random((n_clusters, d)) < 0.3)
+    out = np.empty((n, d), dtype=np.float32)
+    for s in range(0, n, 1 << 14):
+        e = min(n, s + (1 << 14))
+        lab = rng.integers(0, n_clusters, size=e - s)
+        depth = np.exp(0.3 * rng.standard_normal((e - s, 1))).astype(np.float32)
+        out[s:e] = np.log1p(rng.poisson(prog[lab] * depth)).astype(np.float32)
+    return out
+
+
+def logcount_ties(n, d=50, seed=7, n_clusters=20):
+    """Tie-heavy: log1p of small Poisson counts at d = 50 -- a few hundred distinct values per column, thousands of
+    exactly identical rows (the all-zero cell alone appears hundreds of times) and exactly tied distances."""
+    rng = np.random.default_rng(seed)
+    lam = rng.gamma(0.6, 1.0, size=(n_clusters, d)) * (rng.random((n_clusters, d)) < 0.5)
+    lam[0] *= 0.02  # a nearly silent population: almost all of its cells are identical
+    lab = rng.integers(0, n_clusters, size=n)
+    return np.log1p(rng.poisson(lam[lab])).astype(np.float32)
+
+
+def check_properties(idx, dist, n, step=1):
+    """Size-independent properties of a (k+1)-NN graph (every `step`-th row)."""
+    rows = np.arange(0, idx.shape[0], step)
+    assert np.array_equal(idx[rows, 0], rows) and np.all(dist[rows, 0] == 0)
+    assert np.all(np.diff(dist[rows], axis=1) >= 0)  # sortedness
+    assert idx.min() >= 0 and idx.max() < n
+    srt = np.sort(idx[rows], axis=1)
+    assert np.all(srt[:, 1:] != srt[:, :-1])  # no repeated neighbour
+    # ties are ordered by index (the contract's key is (d2, j))
+    tied = dist[rows, 1:-1] == dist[rows, 2:]
+    assert np.all(idx[rows, 1:-1][tied] < idx[rows, 2:][tied])
+
+
+def check_slices(x, idx, dist, k, starts, rows):
+    for q0 in starts:
+        wi, wd = orc.knn(x, k, q0, q0 + rows)
+        bad = np.flatnonzero((idx[q0:q0 + rows] != wi).any(axis=1))
+        assert bad.size == 0, f"slice {q0}: {bad.size} rows differ, first {q0 + bad[0]}"
+        assert np.array_equal(dist[q0:q0 + rows], wd)
+
+
+# ------------------------------------------------------------------ BASELINE configs
+def test_config_c1_cytometry_shape_full_oracle_and_smooth():
+    """BASELINE configs[0] (86,864 x 38, k=50): EVERY row of the graph against the oracle, then smooth."""
+    x = c1_syn()
+    n, k = x.shape[0], 50
+    st = {}
+    idx, dist = vv.make_knn(x, k=k, verbose=False, stats=st)
+    orc.set_threads(os.cpu_count() or 1)
+    wi, wd = orc.knn(x, k)
+    bad = np.flatnonzero((idx != wi).any(axis=1))
+    assert bad.size == 0, f"{bad.size} rows differ, first {bad[:5]}"
+    assert np.array_equal(dist, wd)
+    assert st["algo_used"] == 2 and st["rows_fallback"] <= n // 1000, st
+    out = vv.smooth(x, [idx, dist], k=k, coef=1.0, n_iter=1)
+    assert np.array_equal(out, orc.smooth(x, idx, k, 1.0, 1))
+    print("C1 stats:", st)
+
+
+def test_config_c3_shape_4M_k100_sampled_oracle_properties_and_whole_smooth():
+    """BASELINE configs[2] at 4.2M rows on one GPU (k=100: m = 126 candidates, four re-rank groups; P = 1024 cells):
+    device-resident build, properties on every 5th row, four oracle slices, the whole smoothed matrix bit-exact."""
+    from vivae_b200.device import knn_device, smooth_device
+
+    n, d, k = 4_200_000, 50, 100
+    x = pca_syn(n, d, seed=2)
+    xd = torch.from_numpy(x).cuda()
+    st = {}
+    idx_d, dist_d = knn_device(xd, k, stats=st)
+    assert st["algo_used"] == 2 and st["cells"] == 1024 and st["candidates"] == 126, st
+    assert st["rows_fallback"] <= n // 1000 and st["tiles_swept"] < 0.25 * st["tiles_dense"], st
+    idx, dist = idx_d.cpu().numpy(), dist_d.cpu().numpy()
+    check_properties(idx, dist, n, step=5)
+    orc.set_threads(os.cpu_count() or 1)
+    check_slices(x, idx, dist, k, (0, 1_234_567, 3_000_001, n - 96), 96)
+    out = smooth_device(xd, idx_d, k=k, coef=1.0, n_iter=1).cpu().numpy()
+    del idx_d, dist_d, xd
+    assert np.array_equal(out, orc.smooth(x, idx, k, 1.0, 1))
+    print("C3-shaped stats:", st)
+
+
+def test_config_c5_slice_100k_x_2000_k_loop_kernel_sampled_oracle():
+    """BASELINE configs[4] (2M x 2000) as a 100k-row slice: 32 K atoms per key, no tile can be skipped; three
+    oracle slices + properties.  The margin here is eps_rel(32) = 2^-13.4 plus the chain term 2 * 2003 * 2^-24."""
+    n, d, k = 100_000, 2000, 50
+    x = c5_syn(n, d)
+    st = {}
+    idx, dist = vv.make_knn(x, k=k, verbose=False, algo="tensor", stats=st)
+    assert st["algo_used"] == 2, st
+    check_properties(idx, dist, n, step=3)
+    orc.set_threads(os.cpu_count() or 1)
+    check_slices(x, idx, dist, k, (0, 50_001, n - 64), 64)
+    assert st["rows_fallback"] <= n // 1000, st
+    print("C5-slice stats:", st)
+
+
+def test_tie_heavy_log_counts_are_settled_by_the_refine_pass():
+    """200k log-count cells at d = 50: identical rows far beyond m and exactly tied distances.  The certificate
+    rejects those rows; the fixed-threshold refine sweep must settle them (brute-force fallback < 0.1 %)."""
+    n, d, k = 200_000, 50, 50
+    x = logcount_ties(n, d)
+    uniq = np.unique(x, axis=0).shape[0]
+    assert uniq < 0.9 * n  # the data really is duplicate-heavy
+    st = {}
+    idx, dist = vv.make_knn(x, k=k, verbose=False, algo="tensor", stats=st)
+    check_properties(idx, dist, n, step=2)
+    orc.set_threads(os.cpu_count() or 1)
+    zero_rows = np.flatnonzero((x == 0).all(axis=1))
+    starts = [0, 100_003, n - 128] + ([int(zero_rows[0])] if zero_rows.size and zero_rows[0] < n - 128 else [])
+    check_slices(x, idx, dist, k, starts, 128)
+    print("tie-heavy stats:", st, "distinct rows:", uniq)
+    assert st["rows_refined"] > 0, st
+    assert st["rows_fallback"] < 0.001 * n, st
+
+
+@pytest.mark.parametrize("kind", ["ties", "dups", "grid"])
+def test_refine_pass_equals_brute_force_fallback(monkeypatch, kind):
+    """Rows that fail the certificate: refined on the tensor cores (default) or recomputed by brute force
+    (VVB_TC_REFINE=0) -- both must give the oracle's graph."""
+    rng = np.random.default_rng(3)
+    if kind == "ties":
+        x = rng.integers(0, 4, size=(20_000, 6)).astype(np.float32)
+    elif kind == "dups":
+        x = rng.standard_normal((20_000, 20)).astype(np.float32)
+        x[5_000:5_400] = x[5_000]          # 400 copies of one point (> TC_CAP / 2)
+        x[9_000:9_070] = x[9_000]          # 70 copies (> m = 60, < the refine capacity)
+    else:
+        x = np.concatenate([rng.standard_normal((10_000, 8)).astype(np.float32) * 50.0,
+                            rng.integers(0, 3, size=(10_000, 8)).astype(np.float32) * 1e-3 + 40.0])
+    k = 20
+    want = orc.knn(x, k)
+    st = {}
+    got = vv.make_knn(x, k=k, verbose=False, algo="tensor", stats=st)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert st["rows_refined"] > 0, st
+    monkeypatch.setenv("VVB_TC_REFINE", "0")
+    st0 = {}
+    got0 = vv.make_knn(x, k=k, verbose=False, algo="tensor", stats=st0)
+    assert np.array_equal(got0[0], want[0]) and np.array_equal(got0[1], want[1])
+    assert st0["rows_refined"] == 0 and st0["rows_fallback"] >= st["rows_fallback"], (st, st0)
+    print(kind, "refined", st["rows_refined"], "brute after refine", st["rows_fallback"], "brute without", st0["rows_fallback"])
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_cell_plan_prepared_in_parts_gives_the_same_graph(parts):
+    """Multi-GPU preparation (vvb_knn_plan_phase_device): pivot assignment split by rows, extents by cells, the three
+    exchanges restated with torch ops -- all `parts` ranks played by this process.  The bounds must be valid (graph
+    bit-exact) and as tight as the single-GPU plan's (same number of tiles swept, up to the scatter order)."""
+    from vivae_b200.device import knn_device
+
+    x = pca_syn(150_000, 50, seed=11, n_clusters=15)
+    xd = torch.from_numpy(x).cuda()
+    s1, sp = {}, {}
+    i1, d1 = knn_device(xd, 50, stats=s1)
+    q0, nq = 40_000, 70_001  # a query-row shard, like a rank of a multi-GPU build would ask for
+    ip, dp = knn_device(xd, 50, q0, nq, stats=sp, _emulate_parts=parts)
+    assert sp["prepare_parts"] == parts and sp["cells"] == s1["cells"] and sp["algo_used"] == 2
+    assert torch.equal(ip, i1[q0:q0 + nq]) and torch.equal(dp, d1[q0:q0 + nq])
+    wi, wd = orc.knn(x, 50, q0, q0 + 200)
+    assert np.array_equal(ip[:200].cpu().numpy(), wi) and np.array_equal(dp[:200].cpu().numpy(), wd)
+    sq = {}
+    knn_device(xd, 50, q0, nq, stats=sq)  # the same shard with the single-GPU plan
+    assert abs(sp["tiles_swept"] - sq["tiles_swept"]) <= 0.02 * sq["tiles_swept"], (sp, sq)
+
+
+# ------------------------------------------------------------------ certificate margin, measured
+def _screen_debug(x, k, q0, nq):
+    lib = vv._lib.load()
+    cap = lib.vvb_knn_screen_debug_capacity()
+    n, d = x.shape
+    ci = np.zeros((nq, cap), dtype=np.uint32)
+    ck = np.zeros((nq, cap), dtype=np.float32)
+    cc = np.zeros(nq, dtype=np.int32)
+    ct = np.zeros(nq, dtype=np.float32)
+    xn = np.zeros(nq, dtype=np.float32)
+    sy = np.zeros(2, dtype=np.float32)
+    mu = np.zeros(4096, dtype=np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    vv._lib.check(lib.vvb_knn_screen_debug_host(p(x), n, d, k, q0, nq, p(ci), p(ck), p(cc), p(ct), p(xn), p(sy), p(mu)))
+    return ci, ck, cc, ct, xn, float(sy[0]), float(sy[1]), mu[:d]
+
+
+@pytest.mark.parametrize("d,kind", [(50, "pca"), (500, "pca"), (2000, "pca"), (2000, "counts")])
+def test_screening_error_stays_8x_below_the_margin_at_every_width(d, kind):
+    """eps_rel(ka) = 2^-18 + 3 ka 2^-20 models the tensor cores' FP32 accumulation over 12 ka MMA steps.  The
+    hardware's rounding is undocumented, so the model is pinned by measurement: the error of the screening key
+    against FP64, relative to (|x^| + Ymax)^2, must stay at least 8x below eps_rel at d = 50, 500 and 2000."""
+    n, k, nq = 12_000, 30, 512
+    x = pca_syn(n, d, seed=d, n_clusters=9) if kind == "pca" else c5_syn(n, d, seed=5)
+    ci, ck, cc, ct, xn, s, ymax, mu = _screen_debug(x, k, 300, nq)
+    ka = (d + 3 + 63) // 64
+    eps_rel = 2.0 ** -18 + 3.0 * ka * 2.0 ** -20
+    xc = (x.astype(np.float64) - mu.astype(np.float64)) * s
+    worst = 0.0
+    for t in range(0, nq, 5):
+        g = 300 + t
+        j = ci[t, :cc[t]].astype(np.int64)
+        d2 = ((xc[g][None, :] - xc[j]) ** 2).sum(1)
+        err = np.abs(ck[t, :cc[t]].astype(np.float64) + float(xn[t]) - d2)
+        worst = max(worst, float((err / (np.sqrt(float(xn[t])) + ymax) ** 2).max()))
+    print(f"d={d} ({kind}): screening error 2^{np.log2(max(worst, 1e-30)):.1f}, margin 2^{np.log2(eps_rel):.1f}")
+    assert worst < eps_rel / 8.0
+
+
+# ------------------------------------------------------------------ SURVEY 8(f) row 3 on the GPU
+def test_encoder_indicatrices_match_the_reference_fixture_on_the_gpu():
+    """`encoder_indicatrices` / `decoder_indicatrices` (reference geometry.py:216-287, 363-447) with the model and
+    the data on the GPU, against the fixture recorded from the unmodified reference (tests/golden/geometry_a.npz)."""
+    g = np.load(os.path.join(GOLDEN, "geometry_a.npz"))
+    m = vv.ViVAE(input_dim=10, latent_dim=2, random_state=4)
+    m.net.load_state_dict({k[4:]: torch.tensor(g[k]) for k in g.files if k.startswith("sd__")})
+    m.trained = m.decoder_active = True
+    assert next(m.net.parameters()).is_cuda
+    tol = dict(rtol=2e-4, atol=2e-5)
+    assert np.allclose(m.transform(g["X"]), g["act"], **tol)
+    ei = m.encoder_indicatrices(g["X"], batch_size=200, radius=1e-3, n_steps=7, n_polygon=16)
+    assert np.allclose(ei.act.detach().cpu().numpy(), g["act"], **tol)
+    assert abs(ei.stepsize - float(g["stepsize"])) < 1e-5
+    assert np.allclose(ei.zr.detach().cpu().numpy(), g["zr"], **tol)
+    assert len(ei.zp) == int(g["n_zp"]) and tuple(ei.zp[0].shape) == tuple(g["zp_shape"])
+    for c, p in zip(ei.zr.detach().cpu(), ei.zp):  # every polygon is a small closed curve around its centre
+        assert torch.linalg.norm(p.detach().cpu() - c, dim=1).max() < 1.0
+    di = m.decoder_indicatrices(g["X"], batch_size=200, n_steps=7, n_polygon=12)
+    assert np.allclose(di.coords.numpy(), g["dcoords"], **tol)
+    assert np.allclose(di.patches.numpy(), g["dpatches"], rtol=1e-3, atol=1e-4)
+    assert abs(di.stepsize - float(g["dstepsize"])) < 1e-5
+
+
+def test_compact_cache_sidecar_round_trip(tmp_path):
+    """make_knn(fname=...) writes the reference's float64 (2, n, k+1) file AND the int32/float32 sidecar; a load
+    prefers the sidecar, falls back to the reference file when the sidecar is stale or absent."""
+    x = pca_syn(6_000, 20, seed=3, n_clusters=5)
+    f = str(tmp_path / "knn.npy")
+    a = vv.make_knn(x, fname=f, k=15, verbose=False)
+    ref_fmt = np.load(f, allow_pickle=True)
+    assert ref_fmt.dtype == np.float64 and ref_fmt.shape == (2, 6_000, 16)
+    side = f + ".vvb.npz"
+    assert os.path.isfile(side) and os.path.getsize(side) < 0.6 * os.path.getsize(f)
+    b = vv.make_knn(x, fname=f, k=15, verbose=False)  # from the sidecar
+    assert b[0].dtype == np.int64 and b[1].dtype == np.float32
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    os.remove(side)
+    c = vv.make_knn(x, fname=f, k=15, verbose=False)  # from the reference-format file
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[1].astype(np.float64), c[1])
+    assert np.array_equal(vv.smooth(x, b, k=15, coef=0.5), vv.smooth(x, c, k=15, coef=0.5))

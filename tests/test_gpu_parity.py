@@ -525,8 +525,9 @@ def _screen_debug(x, k, q0, nq):
 
 @pytest.mark.parametrize("kind", ["clustered", "offset"])
 def test_screening_error_is_far_below_the_certificate_margin(kind):
-    """The certificate assumes |key + |x^|^2 - s^2 d2| <= 2^-15 (|x^| + Ymax)^2.  Measure the
-    actual tensor-core error against FP64 on the kept candidates: it must stay 8x below."""
+    """The certificate assumes |key + |x^|^2 - s^2 d2| <= eps_rel(ka) (|x^| + Ymax)^2 with eps_rel(1) = 2^-18 + 3 * 2^-20
+    = 2^-17.2 (knn_tensor.cu: tc_eps_rel).  Measure the actual tensor-core error against FP64 on the kept candidates:
+    it must stay 8x below (tests/test_gpu_configs.py repeats this at d = 500 and 2000)."""
     n, d, k = 20_000, 50, 50
     x = clustered(n, d, 12, seed=21)
     if kind == "offset":
@@ -551,7 +552,7 @@ def test_screening_error_is_far_below_the_certificate_margin(kind):
         bound = (np.sqrt(float(xn[t])) + ymax) ** 2
         worst = max(worst, float((err / bound).max()))
     print(f"screening error / (|x|+Ymax)^2 = 2^{np.log2(max(worst, 1e-30)):.1f}")
-    assert worst < 2.0 ** -18
+    assert worst < (2.0 ** -18 + 3 * 2.0 ** -20) / 8.0
     # every true neighbour is among the candidates, self included
     oi, _ = orc.knn(x, k, 500, 500 + nq)
     for t in range(0, nq, 11):

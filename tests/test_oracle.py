@@ -142,3 +142,48 @@ def test_knn_oracle_argument_errors():
         orc.knn(x, 5)  # k must be <= n-1  (knn.py:119-120)
     with pytest.raises(ValueError):
         orc.knn(x, 0)
+
+
+# ---------------------------------------------------------------------- the `fit` reference arm (oracle/ref_fit.py)
+@pytest.mark.parametrize("name", QUARTET)
+def test_ref_fit_quartet_restatement_matches_reference_golden(name, monkeypatch):
+    """oracle/ref_fit.py restates MDSLoss operation for operation (it is the timed reference arm of `fit` in
+    bench.py): value and autograd gradient against the reference-recorded float32 fixtures, recorded
+    permutations replayed through torch.randperm."""
+    import torch
+
+    import ref_fit
+
+    g = _load(name)
+    ns = int(g["n_sampling"])
+    recorded = [torch.tensor(g["perms"][i]) for i in range(ns - 1)]
+    monkeypatch.setattr(torch, "randperm", lambda n, **kw: recorded.pop(0))
+    x = torch.tensor(g["x"])
+    z = torch.tensor(g["z"], requires_grad=True)
+    loss = ref_fit.ref_mds_loss(x, z, str(g["hd"]), str(g["ld"]), ns)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss_f32"])) <= 2e-6 * abs(float(g["loss_f32"]))
+    np.testing.assert_allclose(z.grad.numpy(), g["grad_f32"], rtol=1e-4, atol=1e-6 * np.abs(g["grad_f32"]).max())
+
+
+def test_ref_fit_autoencoder_terms_equal_the_pinned_network_on_cpu():
+    """RefAutoencoder (reference layer names) loaded with the weights of `vivae_b200.network.Autoencoder` -- which is
+    pinned bit-identically against the reference (fit_cpu_nomds.npz) -- gives the same KL and MSE terms."""
+    import torch
+
+    import ref_fit
+    from vivae_b200.network import Autoencoder
+
+    torch.manual_seed(3)
+    ours = Autoencoder(input_dim=9, latent_dim=2, hidden_dims=[32, 64, 128, 32], variational=True)
+    ref = ref_fit.RefAutoencoder(9)
+    ref.load_state_dict({k: v for k, v in ours.state_dict().items()})
+    x = torch.randn(64, 9)
+    torch.manual_seed(11)
+    a = ours(x, lam_recon=1.0, lam_kldiv=0.5, lam_mds=0.0)
+    torch.manual_seed(11)
+    b = ref(x, lam_recon=1.0, lam_kldiv=0.5, lam_mds=0.0)
+    assert torch.equal(a["kldiv"], b["kldiv"]) and torch.equal(a["recon"], b["recon"])
+    t = ref_fit.time_ref_fit(np.random.default_rng(0).standard_normal((600, 9)).astype(np.float32), batch_size=64,
+                             warm_batches=2, lam_mds=10.0)
+    assert t["s_per_epoch"] > 0 and t["rows"] == 600

@@ -13,8 +13,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import oracle as orc
-from vivae_b200.sharded import (all_gather_rows, knn_smooth_sharded, make_knn_ring, make_knn_sharded, shard_bounds,
-                                smooth_jacobi_sharded)
+from vivae_b200.sharded import (all_gather_rows, knn_smooth_host_sharded, knn_smooth_sharded, make_knn_ring,
+                                make_knn_sharded, shard_bounds, smooth_jacobi_sharded)
 
 
 def _free_port():
@@ -45,8 +45,11 @@ def _worker(rank, world, port, n, k, out_dir):
         q0, nq = shard_bounds(n, world, rank)
         loc = torch.arange(q0, q0 + nq, dtype=torch.int64).reshape(-1, 1)
         rows = all_gather_rows(loc, n)
+        # the host pipeline: every rank passes only its rows, gets its rows of the graph and of the smoothed matrix
+        hi, hd, hs = knn_smooth_host_sharded(x[q0:q0 + nq].numpy().copy(), n, k, coef=1.0, n_iter=2, _knn_fn=_oracle_knn,
+                                             _smooth_fn=_oracle_smooth, device=torch.device("cpu"))
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), idx=idx.numpy(), dist=dst.numpy(), idx2=idx2.numpy(),
-                 xs=xs.numpy(), rows=rows.numpy())
+                 xs=xs.numpy(), rows=rows.numpy(), hi=hi.numpy(), hd=hd.numpy(), hs=hs.numpy(), q0=q0, nq=nq)
     finally:
         dist.destroy_process_group()
 
@@ -64,6 +67,9 @@ def test_sharded_graph_and_smooth_equal_single_process(tmp_path, world, n):
         assert np.array_equal(g["idx"], wi) and np.array_equal(g["dist"], wd)       # identical bytes on every rank
         assert np.array_equal(g["idx2"], wi) and np.array_equal(g["xs"], ws)
         assert np.array_equal(g["rows"].ravel(), np.arange(n))
+        q0, nq = int(g["q0"]), int(g["nq"])
+        assert np.array_equal(g["hi"], wi[q0:q0 + nq]) and np.array_equal(g["hd"], wd[q0:q0 + nq])
+        assert np.array_equal(g["hs"], ws[q0:q0 + nq])
 
 
 def test_shard_bounds_cover_all_rows():

@@ -36,12 +36,21 @@ class KnnStats(ctypes.Structure):
         ("tiles_swept", ctypes.c_int64),
         ("tiles_dense", ctypes.c_int64),
         ("cells", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("rows_refined", ctypes.c_int32),
     ]
 
     def as_dict(self) -> dict:
         return {name: getattr(self, name) for name, _ in self._fields_}
 
+
+class Exchange(ctypes.Structure):
+    """Mirror of `vvb_exchange`."""
+
+    _fields_ = [("ptr", ctypes.c_void_p), ("count", ctypes.c_size_t), ("dtype", ctypes.c_int32), ("op", ctypes.c_int32)]
+
+
+XCH_I32, XCH_U32, XCH_F64 = 0, 1, 2
+XCH_GATHER_ROWS, XCH_SUM, XCH_MAX_ORD = 0, 1, 2
 
 # every symbol include/vivae_b200.h declares: (restype, argtypes)
 _i64, _int, _dbl, _vp, _sz = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t
@@ -57,6 +66,9 @@ SYMBOLS = {
     "vvb_make_knn_workspace_bytes": (_int, [_i64, _int, _int, _i64, _int, ctypes.POINTER(_sz)]),
     "vvb_make_knn_device": (_int, [_vp, _i64, _int, _int, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp,
                                    ctypes.POINTER(KnnStats)]),
+    "vvb_knn_plan_phase_device": (_int, [_vp, _i64, _int, _int, _i64, _vp, _sz, _int, _int, _int, _vp, _vp,
+                                         ctypes.POINTER(_int)]),
+    "vvb_make_knn_planned_device": (_int, [_vp, _i64, _int, _int, _i64, _i64, _vp, _vp, _vp, _sz, _vp, _vp]),
     "vvb_knn_screen_debug_capacity": (_int, []),
     "vvb_knn_screen_debug_host": (_int, [_vp, _i64, _int, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vvb_knn_merge_init_device": (_int, [_vp, _vp, _i64, _int, _i64, _vp]),

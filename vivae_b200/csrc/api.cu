@@ -52,7 +52,10 @@ bool knn_tensor_supported(int64_t n, int d, int k);
 int64_t knn_tensor_chunk_rows(int64_t nq, bool host_path);
 size_t knn_tensor_session_bytes();
 int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, int k, int64_t chunk_rows,
-                     void *workspace, size_t workspace_bytes, cudaStream_t st, vvb_knn_stats *stats);
+                     void *workspace, size_t workspace_bytes, cudaStream_t st, vvb_knn_stats *stats, bool planned);
+int knn_tensor_plan_phase(const float *x_dev, int64_t n, int d, int k, int64_t chunk_rows, void *workspace,
+                          size_t workspace_bytes, int phase, int part, int parts, cudaStream_t st, vvb_exchange *xch,
+                          int *n_xch);
 int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx, float *out_dist, cudaStream_t st,
                      vvb_knn_stats *stats, bool screen_only);
 int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, int64_t nq, uint32_t *cand_idx_out,
@@ -354,9 +357,18 @@ struct DeviceCache {
       device = dev;
     }
   }
+  // Slots handed out since begin_request(): a failed allocation may only evict the OTHER slots -- the caller still
+  // holds raw pointers into these (and may have DMAs in flight on the streams, which are never destroyed here).
+  unsigned in_use = 0;
+  void begin_request() {
+    check_device();
+    in_use = 0;
+    last_rc = VVB_OK;
+  }
   void *slot(int i, size_t bytes) {
     check_device();
     if (bytes == 0) bytes = 256;
+    in_use |= 1u << i;
     if (cap[i] >= bytes) return ptr[i];
     if (ptr[i]) cudaFree(ptr[i]);
     ptr[i] = nullptr;
@@ -364,7 +376,13 @@ struct DeviceCache {
     cudaError_t e = cudaMalloc(&ptr[i], bytes);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      release();  // drop everything cached and retry once
+      // make room: drop the cached buffers this request has not been given, then retry once
+      for (int j = 0; j < 8; ++j) {
+        if ((in_use >> j) & 1u) continue;
+        if (ptr[j]) cudaFree(ptr[j]);
+        ptr[j] = nullptr;
+        cap[j] = 0;
+      }
       e = cudaMalloc(&ptr[i], bytes);
     }
     if (e != cudaSuccess) {
@@ -455,13 +473,13 @@ int vvb_make_knn_workspace_bytes(int64_t n, int d, int k, int64_t nq, int algo, 
 template <typename Hook>
 static int knn_run(const float *x_dev, int64_t n, int d, int k, int64_t q0, int64_t nq, int use, int64_t *idx_dev,
                    float *dist_dev, void *ws, size_t ws_bytes, cudaStream_t st, vvb_knn_stats *stats, bool host_path,
-                   Hook after_chunk) {
+                   Hook after_chunk, bool planned = false) {
   const int64_t chunk = knn_tensor_chunk_rows(nq, host_path);
   std::vector<char> session(knn_tensor_session_bytes() + 64);
   void *sess = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(session.data()) + 63) & ~uintptr_t(63));
   int rc;
   if (use == VVB_KNN_TENSOR) {
-    rc = knn_tensor_begin(sess, x_dev, n, d, k, chunk, ws, ws_bytes, st, stats);
+    rc = knn_tensor_begin(sess, x_dev, n, d, k, chunk, ws, ws_bytes, st, stats, planned);
     if (rc) return rc;
   }
   for (int64_t c0 = 0; c0 < nq; c0 += chunk) {
@@ -520,6 +538,46 @@ int vvb_make_knn_device(const float *x_dev, int64_t n, int d, int k, int64_t q0,
   return VVB_OK;
 }
 
+int vvb_knn_plan_phase_device(const float *x_dev, int64_t n, int d, int k, int64_t nq, void *workspace_dev,
+                              size_t workspace_bytes, int phase, int part, int parts, void *stream, vvb_exchange *xch,
+                              int *n_xch) {
+  VVB_REQUIRE(x_dev && workspace_dev && xch && n_xch, "knn plan: null pointer argument");
+  VVB_REQUIRE(n >= 2 && d >= 1 && k >= 1 && k <= n - 1 && nq >= 0, "knn plan: bad shape arguments");
+  if (!knn_tensor_supported(n, d, k)) {
+    set_error("knn plan: n=%lld d=%d k=%d is outside the tensor-core path", (long long)n, d, k);
+    return VVB_ENOTSUP;
+  }
+  return knn_tensor_plan_phase(x_dev, n, d, k, knn_tensor_chunk_rows(nq, false), workspace_dev, workspace_bytes, phase,
+                               part, parts, static_cast<cudaStream_t>(stream), xch, n_xch);
+}
+
+int vvb_make_knn_planned_device(const float *x_dev, int64_t n, int d, int k, int64_t q0, int64_t nq,
+                                int64_t *idx_out_dev, float *dist_out_dev, void *workspace_dev, size_t workspace_bytes,
+                                void *stream, vvb_knn_stats *stats) {
+  int rc = knn_check_args(x_dev, n, d, k, q0, nq, idx_out_dev, dist_out_dev);
+  if (rc) return rc;
+  if (!knn_tensor_supported(n, d, k)) {
+    set_error("make_knn (planned): n=%lld d=%d k=%d is outside the tensor-core path", (long long)n, d, k);
+    return VVB_ENOTSUP;
+  }
+  VVB_REQUIRE(workspace_bytes >= knn_ws_bytes(VVB_KNN_TENSOR, n, d, k, nq, false), "make_knn: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t launches0 = g_launches.load();
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->rows = nq;
+    stats->algo_used = VVB_KNN_TENSOR;
+  }
+  rc = knn_run(x_dev, n, d, k, q0, nq, VVB_KNN_TENSOR, idx_out_dev, dist_out_dev, workspace_dev, workspace_bytes, st,
+               stats, /*host_path=*/false, [](int64_t, int64_t) { return VVB_OK; }, /*planned=*/true);
+  if (rc) return rc;
+  if (stats) {
+    VVB_CUDA(cudaStreamSynchronize(st));
+    stats->kernel_launches = g_launches.load() - launches0;
+  }
+  return VVB_OK;
+}
+
 int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, int64_t nq, int algo,
                       int64_t *idx_out_host, float *dist_out_host, vvb_knn_stats *stats) {
   int rc = knn_check_args(x_host, n, d, k, q0, nq, idx_out_host, dist_out_host);
@@ -538,6 +596,7 @@ int vvb_make_knn_host(const float *x_host, int64_t n, int d, int k, int64_t q0, 
   pf.start();
   DeviceCache &dc = DeviceCache::get();
   std::lock_guard<std::mutex> lock(dc.mu);
+  dc.begin_request();
   float *x_dev = static_cast<float *>(dc.slot(0, static_cast<size_t>(n) * d * sizeof(float)));
   int64_t *idx_dev = static_cast<int64_t *>(dc.slot(1, idx_bytes));
   float *dist_dev = static_cast<float *>(dc.slot(2, dist_bytes));
@@ -728,6 +787,7 @@ int vvb_smooth_host(const void *x_host, int elem_size, int64_t n, int d, const i
   pf.start();
   DeviceCache &dc = DeviceCache::get();
   std::lock_guard<std::mutex> lock(dc.mu);
+  dc.begin_request();
   void *x = dc.slot(0, xb), *out = dc.slot(4, xb), *idx = dc.slot(1, ib), *ws = dc.slot(3, ws_bytes);
   if (!x || !out || !idx || !ws) return dc.last_rc;
   cudaStream_t st = dc.compute_stream();

@@ -41,6 +41,15 @@ inline void count_launch(int64_t n = 1) { g_launches.fetch_add(n, std::memory_or
     }                                                                                        \
   } while (0)
 
+// a valid request outside the implemented envelope (Python: NotImplementedError, never the reference's ValueError)
+#define VVB_SUPPORTED(cond, ...)                                                             \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      ::vvb::set_error(__VA_ARGS__);                                                         \
+      return VVB_ENOTSUP;                                                                    \
+    }                                                                                        \
+  } while (0)
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // carve sub-buffers out of one workspace allocation (256-byte aligned)
@@ -78,6 +87,15 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ int ld_relaxed(const int *p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ void st_release(int *p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

@@ -150,8 +150,8 @@ static int launch_knn_brute_impl(const float *x_dev, int64_t n, int d, int k, co
                                  const int *count_dev, int64_t q0, int64_t nq, int64_t *out_idx, float *out_dist,
                                  int64_t out_row0, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (nq == 0) return VVB_OK;
-  VVB_REQUIRE(n <= 0xffffffffLL, "brute kNN: n=%lld exceeds the 32-bit candidate index", (long long)n);
-  VVB_REQUIRE(k + BR_TJ + 32 <= 2048, "brute kNN: k=%d above the supported maximum of 1984", k);
+  VVB_SUPPORTED(n <= 0xffffffffLL, "brute kNN: n=%lld exceeds the 32-bit candidate index", (long long)n);
+  VVB_SUPPORTED(k + BR_TJ + 32 <= 2048, "brute kNN: k=%d above the supported maximum of 1984", k);
   VVB_REQUIRE(workspace_bytes >= brute_workspace_bytes(nq, k), "brute kNN: workspace too small");
   const int64_t rows = (nq + BR_THREADS - 1) / BR_THREADS * BR_THREADS;
   int cap = 128;

@@ -175,8 +175,9 @@ __global__ void __launch_bounds__(CELL_DIMS) cell_pivots_kernel(const float *__r
 }
 
 // Thread per row: nearest pivot in the first dsub centred coordinates (ties -> lowest pivot).
-__global__ void __launch_bounds__(128) cell_assign_kernel(const float *__restrict__ x, int64_t n, int d, int dsub,
-                                                         const int *__restrict__ dims,
+// Rows [row0, n) of this launch (n = end of the range: a rank of a multi-GPU build assigns only its row shard).
+__global__ void __launch_bounds__(128) cell_assign_kernel(const float *__restrict__ x, int64_t row0, int64_t n, int d,
+                                                         int dsub, const int *__restrict__ dims,
                                                          const float *__restrict__ mu, int P,
                                                          const float *__restrict__ pivots,
                                                          int *__restrict__ cell_of, int *__restrict__ cnt) {
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(128) cell_assign_kernel(const float *__restric
   __shared__ int hist[CELL_MAX];
   const int tid = threadIdx.x;
   for (int i = tid; i < P; i += 128) hist[i] = 0;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * 128 + tid;
+  const int64_t row = row0 + static_cast<int64_t>(blockIdx.x) * 128 + tid;
   float xr[CELL_DIMS];
 #pragma unroll
   for (int c = 0; c < CELL_DIMS; ++c)
@@ -256,26 +257,30 @@ __global__ void __launch_bounds__(1024) cell_scan_kernel(const int *__restrict__
   if (tid == P - 1) off[P] = sh[tid];
 }
 
+// rows: row0 + i, or row_list[i] when a list of (original) rows is given
 __global__ void __launch_bounds__(256) cell_scatter_kernel(const int *__restrict__ cell_of, int64_t row0, int64_t rows,
+                                                          const int64_t *__restrict__ row_list,
                                                           int *__restrict__ cursor, int *__restrict__ list,
                                                           int64_t list_len) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < rows) {
-    const int pos = atomicAdd(cursor + cell_of[row0 + i], 1);
-    list[pos] = static_cast<int>(row0 + i);
+    const int64_t r = row_list ? row_list[i] : row0 + i;
+    const int pos = atomicAdd(cursor + cell_of[r], 1);
+    list[pos] = static_cast<int>(r);
   } else if (i < list_len) {
     list[i] = -1;  // tail of a query list (database lists are pre-filled with -1 by a memset: list_len = -1)
   }
 }
 
-__global__ void __launch_bounds__(256) cell_hist_kernel(const int *__restrict__ cell_of, int64_t row0, int64_t rows, int P,
+__global__ void __launch_bounds__(256) cell_hist_kernel(const int *__restrict__ cell_of, int64_t row0, int64_t rows,
+                                                       const int64_t *__restrict__ row_list, int P,
                                                        int *__restrict__ cnt) {
   __shared__ int hist[CELL_MAX];
   for (int i = threadIdx.x; i < P; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    atomicAdd(&hist[cell_of[row0 + i]], 1);
+    atomicAdd(&hist[cell_of[row_list ? row_list[i] : row0 + i]], 1);
   __syncthreads();
   for (int i = threadIdx.x; i < P; i += blockDim.x)
     if (hist[i]) atomicAdd(cnt + i, hist[i]);
@@ -288,11 +293,12 @@ __global__ void __launch_bounds__(256) cell_moments_kernel(const float *__restri
                                                           const float *__restrict__ mu, const int *__restrict__ perm,
                                                           const int *__restrict__ off, int P,
                                                           const int *__restrict__ cell_of, double *__restrict__ sums,
-                                                          double *__restrict__ sqs) {
+                                                          double *__restrict__ sqs, int part, int parts) {
   __shared__ double sh_s[4][CELL_DIMS], sh_q[4][CELL_DIMS];
   const int64_t p0 = static_cast<int64_t>(blockIdx.x) * CELL_GROUP;
   if (p0 >= off[P]) return;
   const int a = cell_of[perm[p0]];
+  if (a % parts != part) return;  // another rank owns this cell (multi-GPU build); the sums are all-reduced
   const int c = threadIdx.x & 63, rl = threadIdx.x >> 6;
   double s = 0.0, q = 0.0;
   if (c < dsub) {
@@ -390,13 +396,14 @@ __global__ void __launch_bounds__(128) cell_extent_kernel(const float *__restric
                                                          const float *__restrict__ cw,
                                                          const float *__restrict__ inv_norm,
                                                          unsigned int *__restrict__ ext,
-                                                         unsigned int *__restrict__ rad2) {
+                                                         unsigned int *__restrict__ rad2, int part, int parts) {
   __shared__ __align__(16) float cwb[128][CELL_DIMS];
   __shared__ unsigned int emax[128];
   const int64_t p0 = static_cast<int64_t>(blockIdx.x) * CELL_GROUP;
   if (p0 >= off[P]) return;
   const int tid = threadIdx.x, lane = tid & 31;
   const int a = cell_of[perm[p0]];
+  if (a % parts != part) return;  // another rank owns this cell; extents and radii are max-reduced
   const int r = perm[p0 + tid];
   float xr[CELL_DIMS];
   float r2 = 0.0f;
@@ -472,52 +479,84 @@ __global__ void __launch_bounds__(128) cell_lb_kernel(const int *__restrict__ cn
   }
 }
 
-int cells_build(const CellPlan &L, const float *x, int d, const float *mu, const int *dims, const float *scale_dev,
-                cudaStream_t st) {
+// The plan in four phases.  A single-GPU build runs them back to back (part 0 of 1).  A multi-GPU build splits the two
+// O(n P) kernels -- pivot assignment by ROWS, extents by CELLS (cell a belongs to part a % parts) -- and exchanges three
+// small tables between the phases (knn_tensor.cu: knn_tensor_plan_phase says which):
+//   phase 0: pivots, cell_of for rows [row_lo, row_hi)                       -> all-gather cell_of
+//   phase 1: sizes, offsets, perm (all rows); moments of the owned cells     -> all-reduce SUM sums, sqs
+//   phase 2: centres, pooled variance, directions, extents of owned cells    -> all-reduce MAX ext, rad2
+//   phase 3: lower bounds
+// Every rank ends with bit-identical centres / directions / extents, so the bounds mean the same on all of them.
+int cells_build_phase(const CellPlan &L, const float *x, int d, const float *mu, const int *dims, const float *scale_dev,
+                      int phase, int part, int parts, int64_t row_lo, int64_t row_hi, cudaStream_t st) {
   const int P = L.P;
   const int64_t n = L.n;
-  VVB_CUDA(cudaMemsetAsync(L.cnt, 0, sizeof(int) * P, st));
-  VVB_CUDA(cudaMemsetAsync(L.perm, 0xFF, sizeof(int) * static_cast<size_t>(L.n_perm_cap), st));
-  VVB_CUDA(cudaMemsetAsync(L.sums, 0, sizeof(double) * static_cast<size_t>(P) * CELL_DIMS, st));
-  VVB_CUDA(cudaMemsetAsync(L.sqs, 0, sizeof(double) * static_cast<size_t>(P) * CELL_DIMS, st));
-  // the pivot block borrows the centres' buffer (P x CELL_DIMS floats), which is only written further down
-  cell_pivots_kernel<<<P, CELL_DIMS, 0, st>>>(x, n, d, L.dsub, dims, mu, P, L.cen);
-  VVB_CHECK_LAUNCH();
-  cell_assign_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(x, n, d, L.dsub, dims, mu, P, L.cen,
-                                                                             L.cell_of, L.cnt);
-  VVB_CHECK_LAUNCH();
-  cell_scan_kernel<<<1, 1024, 0, st>>>(L.cnt, P, CELL_GROUP, L.off, L.cursor);
-  VVB_CHECK_LAUNCH();
-  cell_scatter_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(L.cell_of, 0, n, L.cursor, L.perm, -1);
-  VVB_CHECK_LAUNCH();
   const unsigned groups = static_cast<unsigned>(L.n_perm_cap / CELL_GROUP);
-  cell_moments_kernel<<<groups, 256, 0, st>>>(x, d, L.dsub, dims, mu, L.perm, L.off, P, L.cell_of, L.sums, L.sqs);
-  VVB_CHECK_LAUNCH();
-  cell_centres_kernel<<<P, CELL_DIMS, 0, st>>>(L.sums, L.cnt, L.cen);
-  VVB_CHECK_LAUNCH();
-  cell_var_kernel<<<1, CELL_DIMS, 0, st>>>(L.sqs, L.cen, L.cnt, P, L.dsub, n, L.var);
-  VVB_CHECK_LAUNCH();
-  cell_cw_kernel<<<P, CELL_DIMS, 0, st>>>(L.cen, L.var, L.cw);
-  VVB_CHECK_LAUNCH();
-  cell_pairs_kernel<<<P, 128, 0, st>>>(L.cen, L.cw, P, L.inv_norm, L.gap, L.cdist, L.ext, L.rad2);
-  VVB_CHECK_LAUNCH();
-  cell_extent_kernel<<<groups, 128, 0, st>>>(x, d, L.dsub, dims, mu, L.perm, L.off, P, L.cell_of, L.cen, L.cw, L.inv_norm,
-                                             L.ext, L.rad2);
-  VVB_CHECK_LAUNCH();
-  cell_lb_kernel<<<P, 128, 0, st>>>(L.cnt, P, L.gap, L.cdist, L.ext, L.rad2, scale_dev, L.lb);
-  VVB_CHECK_LAUNCH();
+  if (phase == 0) {
+    // the pivot block borrows the centres' buffer (P x CELL_DIMS floats), which is only written in phase 2
+    cell_pivots_kernel<<<P, CELL_DIMS, 0, st>>>(x, n, d, L.dsub, dims, mu, P, L.cen);
+    VVB_CHECK_LAUNCH();
+    VVB_CUDA(cudaMemsetAsync(L.cnt, 0, sizeof(int) * P, st));
+    if (row_hi > row_lo) {
+      cell_assign_kernel<<<static_cast<unsigned>((row_hi - row_lo + 127) / 128), 128, 0, st>>>(
+          x, row_lo, row_hi, d, L.dsub, dims, mu, P, L.cen, L.cell_of, L.cnt);
+      VVB_CHECK_LAUNCH();
+    }
+  } else if (phase == 1) {
+    VVB_CUDA(cudaMemsetAsync(L.cnt, 0, sizeof(int) * P, st));
+    VVB_CUDA(cudaMemsetAsync(L.perm, 0xFF, sizeof(int) * static_cast<size_t>(L.n_perm_cap), st));
+    VVB_CUDA(cudaMemsetAsync(L.sums, 0, sizeof(double) * static_cast<size_t>(P) * CELL_DIMS, st));
+    VVB_CUDA(cudaMemsetAsync(L.sqs, 0, sizeof(double) * static_cast<size_t>(P) * CELL_DIMS, st));
+    cell_hist_kernel<<<static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 1184)), 256, 0, st>>>(L.cell_of, 0, n,
+                                                                                                     nullptr, P, L.cnt);
+    VVB_CHECK_LAUNCH();
+    cell_scan_kernel<<<1, 1024, 0, st>>>(L.cnt, P, CELL_GROUP, L.off, L.cursor);
+    VVB_CHECK_LAUNCH();
+    cell_scatter_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(L.cell_of, 0, n, nullptr, L.cursor,
+                                                                                L.perm, -1);
+    VVB_CHECK_LAUNCH();
+    cell_moments_kernel<<<groups, 256, 0, st>>>(x, d, L.dsub, dims, mu, L.perm, L.off, P, L.cell_of, L.sums, L.sqs, part,
+                                                parts);
+    VVB_CHECK_LAUNCH();
+  } else if (phase == 2) {
+    cell_centres_kernel<<<P, CELL_DIMS, 0, st>>>(L.sums, L.cnt, L.cen);
+    VVB_CHECK_LAUNCH();
+    cell_var_kernel<<<1, CELL_DIMS, 0, st>>>(L.sqs, L.cen, L.cnt, P, L.dsub, n, L.var);
+    VVB_CHECK_LAUNCH();
+    cell_cw_kernel<<<P, CELL_DIMS, 0, st>>>(L.cen, L.var, L.cw);
+    VVB_CHECK_LAUNCH();
+    cell_pairs_kernel<<<P, 128, 0, st>>>(L.cen, L.cw, P, L.inv_norm, L.gap, L.cdist, L.ext, L.rad2);
+    VVB_CHECK_LAUNCH();
+    cell_extent_kernel<<<groups, 128, 0, st>>>(x, d, L.dsub, dims, mu, L.perm, L.off, P, L.cell_of, L.cen, L.cw,
+                                               L.inv_norm, L.ext, L.rad2, part, parts);
+    VVB_CHECK_LAUNCH();
+  } else {
+    cell_lb_kernel<<<P, 128, 0, st>>>(L.cnt, P, L.gap, L.cdist, L.ext, L.rad2, scale_dev, L.lb);
+    VVB_CHECK_LAUNCH();
+  }
   return VVB_OK;
 }
 
-int cells_query_list(const CellPlan &L, int64_t q0, int64_t nq, int64_t nq_pad, int *qlist, cudaStream_t st) {
+int cells_build(const CellPlan &L, const float *x, int d, const float *mu, const int *dims, const float *scale_dev,
+                cudaStream_t st) {
+  for (int phase = 0; phase < 4; ++phase) {
+    const int rc = cells_build_phase(L, x, d, mu, dims, scale_dev, phase, 0, 1, 0, L.n, st);
+    if (rc) return rc;
+  }
+  return VVB_OK;
+}
+
+// Cell-sorted list of the query rows [q0, q0+nq) -- or, with `row_list`, of the nq original rows it names.
+int cells_query_list(const CellPlan &L, int64_t q0, int64_t nq, int64_t nq_pad, int *qlist, const int64_t *row_list,
+                     cudaStream_t st) {
   VVB_CUDA(cudaMemsetAsync(L.qcnt, 0, sizeof(int) * L.P, st));
-  cell_hist_kernel<<<static_cast<unsigned>(std::min<int64_t>((nq + 255) / 256, 1184)), 256, 0, st>>>(L.cell_of, q0, nq,
-                                                                                                      L.P, L.qcnt);
+  cell_hist_kernel<<<static_cast<unsigned>(std::min<int64_t>((nq + 255) / 256, 1184)), 256, 0, st>>>(
+      L.cell_of, q0, nq, row_list, L.P, L.qcnt);
   VVB_CHECK_LAUNCH();
   cell_scan_kernel<<<1, 1024, 0, st>>>(L.qcnt, L.P, 1, L.qoff, L.qcursor);
   VVB_CHECK_LAUNCH();
-  cell_scatter_kernel<<<static_cast<unsigned>((nq_pad + 255) / 256), 256, 0, st>>>(L.cell_of, q0, nq, L.qcursor, qlist,
-                                                                                   nq_pad);
+  cell_scatter_kernel<<<static_cast<unsigned>((nq_pad + 255) / 256), 256, 0, st>>>(L.cell_of, q0, nq, row_list, L.qcursor,
+                                                                                   qlist, nq_pad);
   VVB_CHECK_LAUNCH();
   return VVB_OK;
 }

@@ -45,10 +45,15 @@ size_t cells_carve(CellPlan *plan, void *ws, int64_t n, int d, int P);
 // dims: CELL_DIMS column indices (cells_select_dims)
 int cells_build(const CellPlan &plan, const float *x_dev, int d, const float *mu_dev, const int *dims,
                 const float *scale_dev, cudaStream_t st);
+// one phase (0..3) of the same build for part `part` of `parts` (multi-GPU: see knn_cells.cu)
+int cells_build_phase(const CellPlan &plan, const float *x_dev, int d, const float *mu_dev, const int *dims,
+                      const float *scale_dev, int phase, int part, int parts, int64_t row_lo, int64_t row_hi,
+                      cudaStream_t st);
 // the min(d, 64) columns of largest variance; `partial`: nblocks * ceil(d / 64) * 64 doubles of scratch
 int cells_select_dims(const float *x_dev, int64_t n, int d, const float *mu_dev, double *partial, int nblocks,
                       int *dims, cudaStream_t st);
 // cell-sorted list of the query rows [q0, q0 + nq): qlist[0 .. nq) original row ids, qlist[nq .. nq_pad) = -1
-int cells_query_list(const CellPlan &plan, int64_t q0, int64_t nq, int64_t nq_pad, int *qlist, cudaStream_t st);
+int cells_query_list(const CellPlan &plan, int64_t q0, int64_t nq, int64_t nq_pad, int *qlist, const int64_t *row_list,
+                     cudaStream_t st);
 
 }  // namespace vvb

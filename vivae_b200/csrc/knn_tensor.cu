@@ -31,13 +31,23 @@
 //
 // Exactness.  The re-rank kernel recomputes the contract's FP32 fmaf-chain distance for the m
 // candidates, sorts by (d2, index) and emits the k best.  Row i is certified when
-//     s^2 * D_k(i)  <  tau_i + |x^_i|^2 - eps_i,     eps_i = 2^-15 (|x^_i| + Ymax)^2
-// i.e. even after the worst-case screening error no rejected row can beat the k-th neighbour;
-// otherwise the row is recomputed by the FP32 brute-force kernel.  Results are therefore
-// identical to the brute-force contract whatever the tensor cores round.
+//     s^2 * D_k(i)  <  (tau_i + |x^_i|^2 - eps_i) (1 - gamma_d)
+//     eps_i   = tc_eps_rel(ka) (|x^_i| + Ymax)^2      screening error, grows with the K atoms `ka`
+//     gamma_d = 2 (d + 3) 2^-24                        rounding of a rejected row's fmaf chain
+// (derivation: DESIGN.md section 4, "Certificate"), i.e. even after the worst-case screening error
+// and the worst-case rounding of the contract's own chain no rejected row can beat the k-th
+// neighbour.  A row that fails is REFINED: a second sweep of the same kernel with the row's
+// threshold set to T_i = s^2 D_k(i) (1 + gamma_d) - |x^_i|^2 + eps_i collects every database row
+// whose key is below T_i -- that set provably contains every row tied with or better than the k-th
+// candidate -- and the re-rank kernel orders it by (d2, index).  A refine list that fills up is
+// reduced IN the sweep to its k+1 best entries by the contract's own key (exact fmaf chain, index),
+// which also tightens T_i; with k+1 exact duplicates of the query in hand, later duplicates with a
+// larger index are dropped on sight.  The brute-force kernel remains only as the guard behind it.
+// Results are therefore identical to the brute-force contract whatever the tensor cores round.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -76,7 +86,19 @@ constexpr int TC_PRE_TILES = TC_CAP;     // threshold pre-pass: at most this man
 constexpr int TC_PRE_MAX_KA = 2;         // ... only where the epilogue, not the MMA, bounds the sweep (d + 3 <= 128)
 constexpr int TC_SEQ_END = -1;           // tile_seq markers
 constexpr int TC_SEQ_PRE_END = -2;
-constexpr float TC_EPS = 1.0f / 131072.0f;  // 2^-17: 26x the measured screening error (2^-21.7), ~5x its analytic bound
+// Screening-error margin relative to (|x^| + Ymax)^2.  Model: every K=16 tcgen05.mma step
+// commits at most 2^-22 of the accumulator's magnitude bound (|x^| + Ymax)^2 -- 3 * 4 * ka steps per key -- and the
+// operand representation (centring, hi/lo split, dropped lo.lo term, FP32 norms) at most 2^-18 in total:
+//     eps_rel(ka) = 2^-18 + 3 ka 2^-20         ka = 1: 2^-17.2,   ka = 32 (d = 2000): 2^-13.4
+// Measured (tests/test_gpu_parity.py::test_screening_error_is_far_below_the_certificate_margin, d = 50 / 500 /
+// 2000): at least 8x below at every width.
+__host__ __device__ constexpr float tc_eps_rel(int ka) {
+  return 1.0f / 262144.0f + 3.0f * static_cast<float>(ka) / 1048576.0f;
+}
+// Rounding of the contract's own FP32 chain for a REJECTED row (d subtractions squared + d fmaf roundings, first
+// order (d + 2) 2^-24 of the distance): doubled for the second-order terms.
+static inline float tc_gamma(int d) { return 2.0f * static_cast<float>(d + 3) / 16777216.0f; }
+constexpr int TC_REFINE_CAP = 2 * TC_CAP;  // refine pass: candidates a row may collect below its fixed threshold
 
 constexpr size_t TC_SMEM_B = TC_STAGES * 2 * TC_ATOM_BYTES;           // [stage][atom]
 constexpr size_t TC_SMEM_TAIL = 256 /*barriers*/ + 8 * CELL_MAX /*cell order*/ + 4 * TC_RING + 64 /*tau*/ +
@@ -378,6 +400,67 @@ __device__ __noinline__ float tc_select_truncate(uint2 *list, int cnt, int keep,
   return warp_select_truncate_pairs<TC_CAP_E>(list, cnt, keep, keep_max, lane, new_cnt);
 }
 
+
+// Refine pass: reduce a full list to its `keepn` best entries by the CONTRACT's key (fmaf-chain d2, original index;
+// the query itself first).  Warp-cooperative, warp-uniform arguments.  Entries that were beaten by keepn others on
+// the exact key can never be among the row's k nearest, so dropping them is exact.  The key field of the kept
+// entries is overwritten with their exact d2 (nothing reads screening keys after a refine sweep).
+// Returns the new length; *dstar / *jstar = exact d2 and original index of the worst kept entry.
+__device__ __noinline__ int tc_refine_compact(uint2 *list, int cnt, int keepn, const float *__restrict__ x, int d,
+                                              const int *__restrict__ perm, int64_t g, int lane, float *dstar,
+                                              int *jstar) {
+  const float *xq = x + g * d;
+  __syncwarp();
+  for (int pos = lane; pos < cnt; pos += 32) {  // pass 1: the contract's chain for every entry
+    const int j = perm[list[pos].y];
+    const float *y = x + static_cast<int64_t>(j) * d;
+    float acc = 0.0f;
+    for (int c = 0; c < d; ++c) {
+      const float df = __fsub_rn(__ldg(xq + c), __ldg(y + c));
+      acc = __fmaf_rn(df, df, acc);
+    }
+    list[pos].x = (static_cast<int64_t>(j) == g) ? 0u : __float_as_uint(acc) + 1u;  // d2 >= 0: bits are monotone
+  }
+  __syncwarp();
+  uint64_t key[TC_CAP_E];
+  uint2 ent[TC_CAP_E];
+#pragma unroll
+  for (int e = 0; e < TC_CAP_E; ++e) {
+    const int pos = e * 32 + lane;
+    key[e] = ~0ull;
+    ent[e] = make_uint2(0u, 0u);
+    if (pos < cnt) {
+      ent[e] = list[pos];
+      key[e] = (static_cast<uint64_t>(ent[e].x) << 32) | static_cast<uint32_t>(perm[ent[e].y]);
+    }
+  }
+  // keepn-th smallest key (keys are distinct: distinct original rows), bitwise from the top
+  uint64_t T = 0;  // invariant: count(key < T) < keepn
+  for (int b = 63; b >= 0; --b) {
+    const uint64_t trial = T | (1ull << b);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < TC_CAP_E; ++e) c += (key[e] < trial) ? 1 : 0;
+    c = __reduce_add_sync(FULL, c);
+    if (c < keepn) T = trial;
+  }
+  __syncwarp();
+  int base = 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int e = 0; e < TC_CAP_E; ++e) {
+    const bool keep = key[e] <= T;  // padding keys are ~0 > T (cnt > keepn)
+    const unsigned kb = __ballot_sync(FULL, keep);
+    if (keep) list[base + __popc(kb & lt_mask)] = ent[e];
+    base += __popc(kb);
+  }
+  __syncwarp();
+  const uint32_t hi = static_cast<uint32_t>(T >> 32);
+  *dstar = hi ? __uint_as_float(hi - 1u) : 0.0f;
+  *jstar = static_cast<int>(static_cast<uint32_t>(T));
+  return base;
+}
+
 // ------------------------------------------------------------------ the screening kernel
 struct TcParams {
   int64_t nq;       // query rows of this launch (entries of qlist)
@@ -389,6 +472,15 @@ struct TcParams {
   int debug_mode;   // profiling only (env VVB_TC_DEBUG): 1 = drain TMEM but skip the screening,
                     // 2 = screening minima only, no admissions, 3 = no TMEM drain at all.  Results are garbage.
   int n_cells;      // P
+  float eps_rel;    // tc_eps_rel(ka): screening-error margin relative to (|x^| + Ymax)^2
+  // Refine instantiation only: the threshold of query-list entry t starts at fixed_thr[qlist[t] - fixed_q0]; no
+  // pre-pass; a list that fills up is reduced to its k1 best entries by the exact key (tc_refine_compact).
+  const float *fixed_thr;
+  int64_t fixed_q0;
+  const float *x;    // (n, d) the original rows
+  const int *perm;   // permuted database row -> original row
+  int d, k1;         // k1 = k + 1 (self included)
+  float gamma;       // tc_gamma(d)
   const uint32_t *op_a;  // query operand rows as 32-bit words (64 per row), resident variant only
   const int *qlist;      // (nq_pad) original row of every query-list entry, -1 = padding
   const int *cell_of;    // (n) cell of every original row
@@ -430,7 +522,7 @@ struct TcParams {
 // hold a key at or below it -- and a tight one, because the m nearest rows of a query are spread over
 // almost as many tiles.  The real sweep then starts at that threshold: ~100 insertions per row, rarely a
 // compaction.  Exactness never depends on it (a threshold is only ever an upper bound of the m-th key).
-template <bool KLOOP, bool DBG>
+template <bool KLOOP, bool DBG, bool REFINE>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
                                                                    const TcParams p) {
@@ -523,13 +615,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   stamp(1);
-  const bool pre_pass = dbg_mode == 0 && p.ka <= TC_PRE_MAX_KA;
+  const bool pre_pass = dbg_mode == 0 && p.ka <= TC_PRE_MAX_KA && !REFINE;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       const float ymax2 = 2.0f * p.scalars->ymax;
-      const float eps_max = TC_EPS * ymax2 * ymax2;  // the certificate's margin for the longest query row
+      const float eps_max = p.eps_rel * ymax2 * ymax2;  // the certificate's margin for the longest query row
       int t = 0;    // tile_seq entries issued (tiles and markers)
       int it = 0;   // K-loop variant: stage uses
       int swept = 0;
@@ -755,8 +847,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     float tau = active ? inf : -inf;
     const float xn = active ? p.xnorm[t_row] : 0.0f;
     int cnt = 0;
+    // refine state: once a compaction has found k1 exact duplicates of the query (dstar == 0), a later candidate
+    // can only displace one of them with a smaller original index
+    int dup_jmax = 0x7fffffff;
+    float eps_row = 0.0f, scale2 = 1.0f;
+    if constexpr (REFINE) {
+      if (active) tau = p.fixed_thr[p.qlist[t_row] - p.fixed_q0];
+      const float s = p.scalars->scale, rr = sqrtf(xn) + p.scalars->ymax;
+      scale2 = s * s;
+      eps_row = p.eps_rel * rr * rr * 1.0625f;
+    }
     {  // a warp without query rows must not hold the sweep open
-      const unsigned m0 = __reduce_max_sync(FULL, f2ord(tau));
+      const unsigned m0 = __reduce_max_sync(FULL, f2ord(REFINE ? tau + xn : tau));
       if (lane == 0) tau_pub[ew] = ord2f(m0);
     }
 
@@ -767,7 +869,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         return;
       }
       unsigned need = __ballot_sync(FULL, cnt > p.trigger);
-      if (need) {
+      if (REFINE && need) {
+        // a full refine list keeps its k1 best entries by the exact key; the k1-th of them bounds the row's k-th
+        // distance from above, which tightens the threshold (same formula as the re-rank kernel's fb_thr)
+        while (need) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          const int c = __shfl_sync(FULL, cnt, src);
+          const int64_t tr = __shfl_sync(FULL, t_row, src);
+          float dstar;
+          int jstar;
+          const int nc = tc_refine_compact(warp_lists + src * 2 * TC_CAP, c, p.k1, p.x, p.d, p.perm, p.qlist[tr], lane,
+                                           &dstar, &jstar);
+          if (lane == src) {
+            cnt = nc;
+            float T = fmaf(dstar * scale2, 1.0f + p.gamma, eps_row - xn);
+            T += fabsf(T) * 1e-6f + 1e-30f;
+            tau = fminf(tau, T);
+            dup_jmax = (dstar == 0.0f) ? jstar : 0x7fffffff;
+          }
+        }
+        const unsigned m = __reduce_max_sync(FULL, f2ord(tau + xn));
+        if (lane == 0) tau_pub[ew] = ord2f(m);
+      } else if (need) {
         while (need) {
           const int src = __ffs(need) - 1;
           need &= need - 1;
@@ -796,6 +920,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       if (mn < cut && dbg_mode != 2) {
         auto ins = [&](int c) {
           if (__uint_as_float(r[c]) < cut) {
+            if constexpr (REFINE) {
+              if (dup_jmax != 0x7fffffff && p.perm[j0 + c] > dup_jmax) return;  // a later duplicate: cannot enter
+            }
             cl[cnt] = make_uint2(r[c], static_cast<uint32_t>(j0 + c));  // one 8-byte store
             ++cnt;
           }
@@ -928,7 +1055,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       // cheap threshold selection replaces a sort, and every extra candidate is a 200-byte gather there
       const int keep_max = min((p.keep + 31) & ~31, p.keep + 8);
       int nc = c;
-      if (c > TC_CAP) thr = fminf(thr, tc_select_truncate_wide(la, c, p.keep, keep_max, lane, &nc));
+      if (REFINE) {
+        // everything below the row's threshold is handed over (c <= TC_REFINE_CAP)
+      } else if (c > TC_CAP) thr = fminf(thr, tc_select_truncate_wide(la, c, p.keep, keep_max, lane, &nc));
       else if (c > keep_max) thr = fminf(thr, tc_select_truncate(la, c, p.keep, keep_max, lane, &nc));
       if (lane == 0) {
         p.cand_cnt[tt] = nc;
@@ -965,7 +1094,8 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
     const int *__restrict__ perm, const uint2 *__restrict__ cand, const int *__restrict__ cand_cnt,
     const float *__restrict__ cand_thr,
     const float *__restrict__ xnorm, const PrepScalars *__restrict__ scalars, int64_t *__restrict__ out_idx,
-    float *__restrict__ out_dist, int *__restrict__ fb_count, int64_t *__restrict__ fb_rows) {
+    float *__restrict__ out_dist, int *__restrict__ fb_count, int64_t *__restrict__ fb_rows, float eps_rel,
+    float gamma, float *__restrict__ fb_thr, int refine) {
   constexpr bool WIDE = MODE == 1;
   constexpr bool ROWS = MODE == 2;
   __shared__ float stage[WIDE ? 8 : 1][WIDE ? 32 : 1][WIDE ? 33 : 1];
@@ -1090,17 +1220,33 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
       dk = __uint_as_float(static_cast<uint32_t>(kv >> 32) - 1u);
     }
   }
-  // certificate: no rejected row can beat the k-th neighbour, whatever the screening rounded
+  // certificate: no rejected row can beat the k-th neighbour, whatever the screening and the chain rounded
   const float thr = cand_thr[t];
   const float xn = xnorm[t];
   const float s = scalars->scale, ymax = scalars->ymax;
   const float r = sqrtf(xn) + ymax;
-  const float eps = TC_EPS * r * r;
+  const float eps = eps_rel * r * r;
+  const float inf = __int_as_float(0x7f800000);
   bool ok = cnt > pos_k;
-  if (ok && thr < __int_as_float(0x7f800000)) ok = (dk * s * s) < (thr + xn - eps);
+  if (refine) {
+    // the list holds every row that can be among the k nearest (everything below the row's refine threshold, minus
+    // entries beaten by k+1 others on the exact key): nothing to certify
+  } else {
+    if (ok && thr < inf) ok = (dk * s * s) < (thr + xn - eps) * (1.0f - gamma);
+  }
   if (!ok && lane == 0) {
     const int slot = atomicAdd(fb_count, 1);
     fb_rows[slot] = g;
+    if (!refine) {
+      // refine threshold (key space): every row j whose chain distance is <= D_k has
+      //   key_j <= s^2 D_k / (1 - gamma/2) - |x^|^2 + eps  <  T;   no upper bound on D_k known -> +inf
+      float T = inf;
+      if (cnt > pos_k) {
+        T = fmaf(dk * s * s, 1.0f + gamma, eps * 1.0625f - xn);
+        T += fabsf(T) * 1e-6f + 1e-30f;
+      }
+      fb_thr[g - q0] = T;
+    }
   }
 }
 
@@ -1164,6 +1310,7 @@ struct TcLayout {
   float *cand_thr;
   int *fb_count;
   int64_t *fb_rows;
+  float *fb_thr;    // (chunk) refine threshold of the rows the certificate rejected, indexed by row - q0
   void *brute_ws;
   size_t brute_ws_bytes;
   size_t total;
@@ -1197,6 +1344,7 @@ static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
   L.cand_thr = cv.take<float>(static_cast<size_t>(L.chunk_pad));
   L.fb_count = cv.take<int>(1);
   L.fb_rows = cv.take<int64_t>(static_cast<size_t>(L.chunk_pad));
+  L.fb_thr = cv.take<float>(static_cast<size_t>(L.chunk_pad));
   L.cand = cv.take<uint2>(static_cast<size_t>(L.chunk_pad) * 2 * TC_CAP);  // two lists per row (one per column half)
   // the fallback's candidate lists reuse the screening lists (dead after the re-rank)
   L.brute_ws = L.cand;
@@ -1236,12 +1384,31 @@ struct TcSession {
 
 size_t knn_tensor_session_bytes() { return sizeof(TcSession); }
 
-// Once per call: column means, largest centred norm, the cell partition with its pairwise bounds, and
-// the database operand (FP16 hi/lo split) in cell order.
-int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, int k, int64_t chunk_rows,
-                     void *workspace, size_t workspace_bytes, cudaStream_t st, vvb_knn_stats *stats) {
+namespace {
+struct ChunkEvents {  // released on every return path
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool on = false;
+  int init() {
+    for (auto &e : ev) VVB_CUDA(cudaEventCreate(&e));
+    on = true;
+    return VVB_OK;
+  }
+  ~ChunkEvents() {
+    for (auto &e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+};
+struct DeviceFree {
+  void *p = nullptr;
+  ~DeviceFree() {
+    if (p) cudaFree(p);
+  }
+};
+}  // namespace
+
+static int tc_session_init(TcSession *S, const float *x_dev, int64_t n, int d, int k, int64_t chunk_rows,
+                           void *workspace, size_t workspace_bytes) {
   VVB_REQUIRE(knn_tensor_supported(n, d, k), "tensor kNN: unsupported shape n=%lld d=%d k=%d", (long long)n, d, k);
-  TcSession *S = new (session_mem) TcSession();
   S->x = x_dev;
   S->n = n;
   S->d = d;
@@ -1250,58 +1417,126 @@ int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, in
   S->L = tc_layout(workspace, n, d, k, chunk_rows);
   VVB_REQUIRE(workspace_bytes >= S->L.total, "tensor kNN: workspace too small (%zu < %zu)", workspace_bytes,
               S->L.total);
-  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(TC_SMEM_BYTES)));
-  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(TC_SMEM_BYTES_K)));
-  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(TC_SMEM_BYTES)));
-  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(TC_SMEM_BYTES_K)));
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (stats) {
-    VVB_CUDA(cudaEventCreate(&e0));
-    VVB_CUDA(cudaEventCreate(&e1));
-    cudaEventRecord(e0, st);
-  }
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(TC_SMEM_BYTES)));
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(TC_SMEM_BYTES_K)));
+  int rc = make_operand_map(&S->map_a, S->L.opA, S->L.chunk_pad, S->L.op_cols);
+  if (rc) return rc;
+  return make_operand_map(&S->map_b, S->L.opB, S->L.n_rows_b, S->L.op_cols);
+}
+
+// Preparation, phase by phase (knn_cells.cu: cells_build_phase).  Phase 0 also computes the column means, the
+// largest centred norm and the geometry's coordinates (full passes over x, cheap and deterministic: every rank of a
+// multi-GPU build gets the same values); phase 3 also builds the database operand (FP16 hi/lo split) in cell order.
+static int tc_prepare_phase(TcSession *S, int phase, int part, int parts, cudaStream_t st) {
   TcLayout &L = S->L;
-  colsum_partial_kernel<<<dim3(PREP_BLOCKS, L.ka), 256, 0, st>>>(x_dev, n, d, L.partial);
-  VVB_CHECK_LAUNCH();
-  colsum_final_kernel<<<L.ka, 64, 0, st>>>(L.partial, PREP_BLOCKS, n, d, L.mu, L.maxn2);
-  VVB_CHECK_LAUNCH();
+  const int64_t n = S->n;
+  const int d = S->d;
   const int prep_grid = sm_count() * 8;
-  maxnorm_kernel<<<prep_grid, 256, 0, st>>>(x_dev, n, d, L.mu, L.maxn2);
-  VVB_CHECK_LAUNCH();
-  scalars_kernel<<<1, 1, 0, st>>>(L.maxn2, L.scalars);
-  VVB_CHECK_LAUNCH();
-  int rc = cells_select_dims(x_dev, n, d, L.mu, L.partial, PREP_BLOCKS, L.dims, st);
+  int64_t row_lo = 0, row_hi = n;
+  if (parts > 1) {  // the row shard of `part`: same rule as vivae_b200.sharded.shard_bounds
+    const int64_t per = (n + parts - 1) / parts;
+    row_lo = std::min<int64_t>(static_cast<int64_t>(part) * per, n);
+    row_hi = std::min<int64_t>(row_lo + per, n);
+  }
+  if (phase == 0) {
+    colsum_partial_kernel<<<dim3(PREP_BLOCKS, L.ka), 256, 0, st>>>(S->x, n, d, L.partial);
+    VVB_CHECK_LAUNCH();
+    colsum_final_kernel<<<L.ka, 64, 0, st>>>(L.partial, PREP_BLOCKS, n, d, L.mu, L.maxn2);
+    VVB_CHECK_LAUNCH();
+    maxnorm_kernel<<<prep_grid, 256, 0, st>>>(S->x, n, d, L.mu, L.maxn2);
+    VVB_CHECK_LAUNCH();
+    scalars_kernel<<<1, 1, 0, st>>>(L.maxn2, L.scalars);
+    VVB_CHECK_LAUNCH();
+    int rc = cells_select_dims(S->x, n, d, L.mu, L.partial, PREP_BLOCKS, L.dims, st);
+    if (rc) return rc;
+  }
+  int rc = cells_build_phase(L.cells, S->x, d, L.mu, L.dims, reinterpret_cast<const float *>(L.scalars), phase, part,
+                             parts, row_lo, row_hi, st);
   if (rc) return rc;
-  rc = cells_build(L.cells, x_dev, d, L.mu, L.dims, reinterpret_cast<const float *>(L.scalars), st);
-  if (rc) return rc;
-  build_operands_kernel<false><<<prep_grid, 256, 0, st>>>(x_dev, d, L.ka, L.mu, L.scalars, L.cells.perm, L.n_rows_b,
-                                                          L.opB, nullptr);
-  VVB_CHECK_LAUNCH();
-  VVB_CUDA(cudaMemsetAsync(L.tiles_done, 0, 2 * sizeof(unsigned long long), st));
-  rc = make_operand_map(&S->map_a, L.opA, L.chunk_pad, L.op_cols);
-  if (rc) return rc;
-  rc = make_operand_map(&S->map_b, L.opB, L.n_rows_b, L.op_cols);
-  if (rc) return rc;
-  if (stats) {
-    cudaEventRecord(e1, st);
-    cudaEventSynchronize(e1);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    stats->ms_prepare += ms;
-    stats->candidates = S->keep;
-    stats->cells = L.cells.P;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+  if (phase == 3) {
+    build_operands_kernel<false><<<prep_grid, 256, 0, st>>>(S->x, d, L.ka, L.mu, L.scalars, L.cells.perm, L.n_rows_b,
+                                                            L.opB, nullptr);
+    VVB_CHECK_LAUNCH();
+    VVB_CUDA(cudaMemsetAsync(L.tiles_done, 0, 2 * sizeof(unsigned long long), st));
   }
   return VVB_OK;
 }
 
+// Once per call: column means, largest centred norm, the cell partition with its pairwise bounds, and
+// the database operand (FP16 hi/lo split) in cell order.  `planned`: the workspace already holds all of that
+// (knn_tensor_plan_phase ran phases 0..3 on it, with the ranks' exchanges in between).
+int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, int k, int64_t chunk_rows,
+                     void *workspace, size_t workspace_bytes, cudaStream_t st, vvb_knn_stats *stats, bool planned) {
+  TcSession *S = new (session_mem) TcSession();
+  int rc = tc_session_init(S, x_dev, n, d, k, chunk_rows, workspace, workspace_bytes);
+  if (rc) return rc;
+  ChunkEvents ce;
+  if (stats) {
+    rc = ce.init();
+    if (rc) return rc;
+    cudaEventRecord(ce.ev[0], st);
+  }
+  if (!planned)
+    for (int phase = 0; phase < 4; ++phase) {
+      rc = tc_prepare_phase(S, phase, 0, 1, st);
+      if (rc) return rc;
+    }
+  if (stats) {
+    cudaEventRecord(ce.ev[1], st);
+    cudaEventSynchronize(ce.ev[1]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ce.ev[0], ce.ev[1]);
+    stats->ms_prepare += ms;
+    stats->candidates = S->keep;
+    stats->cells = S->L.cells.P;
+  }
+  return VVB_OK;
+}
+
+// One phase of the preparation for part `part` of `parts` (one part per GPU), and the tables the parts must
+// exchange before the next phase: xch[i] = {device pointer into the workspace, element count, dtype, op}.
+//   after phase 0: cell_of (n int32)           VVB_XCH_GATHER_ROWS  every part wrote the rows of its shard
+//   after phase 1: sums, sqs (P x 64 float64)  VVB_XCH_SUM          every part wrote the cells it owns, zeros elsewhere
+//   after phase 2: ext (P x P), rad2 (P)       VVB_XCH_MAX_ORD      ordered-uint32 images of floats: max as UNSIGNED
+int knn_tensor_plan_phase(const float *x_dev, int64_t n, int d, int k, int64_t chunk_rows, void *workspace,
+                          size_t workspace_bytes, int phase, int part, int parts, cudaStream_t st, vvb_exchange *xch,
+                          int *n_xch) {
+  VVB_REQUIRE(phase >= 0 && phase < 4 && parts >= 1 && part >= 0 && part < parts, "knn plan: bad phase / part");
+  alignas(64) char session[sizeof(TcSession)];
+  TcSession *S = new (session) TcSession();
+  int rc = tc_session_init(S, x_dev, n, d, k, chunk_rows, workspace, workspace_bytes);
+  if (rc) return rc;
+  rc = tc_prepare_phase(S, phase, part, parts, st);
+  if (rc) return rc;
+  const CellPlan &C = S->L.cells;
+  const size_t P = static_cast<size_t>(C.P);
+  int m = 0;
+  if (phase == 0) {
+    xch[m++] = {C.cell_of, static_cast<size_t>(n), VVB_XCH_I32, VVB_XCH_GATHER_ROWS};
+  } else if (phase == 1) {
+    xch[m++] = {C.sums, P * CELL_DIMS, VVB_XCH_F64, VVB_XCH_SUM};
+    xch[m++] = {C.sqs, P * CELL_DIMS, VVB_XCH_F64, VVB_XCH_SUM};
+  } else if (phase == 2) {
+    xch[m++] = {C.ext, P * P, VVB_XCH_U32, VVB_XCH_MAX_ORD};
+    xch[m++] = {C.rad2, P, VVB_XCH_U32, VVB_XCH_MAX_ORD};
+  }
+  *n_xch = m;
+  return VVB_OK;
+}
+
 // Query rows [q0, q0+nq) (nq <= the session's chunk size): cell-sorted query list, operand, screen,
-// re-rank, fallback.  out_idx / out_dist point at the output row of query row q0.
+// re-rank, refine, fallback.  out_idx / out_dist point at the output row of query row q0.
+
 int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx, float *out_dist, cudaStream_t st,
                      vvb_knn_stats *stats, bool screen_only) {
   TcSession *S = static_cast<TcSession *>(session_mem);
@@ -1310,14 +1545,16 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   VVB_REQUIRE(nq <= L.chunk_pad, "tensor kNN: chunk of %lld rows exceeds the session's %lld", (long long)nq,
               (long long)L.chunk_pad);
   const int64_t nq_pad = (nq + TC_M - 1) / TC_M * TC_M;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  if (stats)
-    for (auto &e : ev) VVB_CUDA(cudaEventCreate(&e));
+  ChunkEvents ce;
+  if (stats) {
+    int erc = ce.init();
+    if (erc) return erc;
+  }
   auto mark = [&](int i) {
-    if (stats) cudaEventRecord(ev[i], st);
+    if (stats) cudaEventRecord(ce.ev[i], st);
   };
   mark(0);
-  int rc = cells_query_list(L.cells, q0, nq, nq_pad, L.qlist, st);
+  int rc = cells_query_list(L.cells, q0, nq, nq_pad, L.qlist, nullptr, st);
   if (rc) return rc;
   build_operands_kernel<true><<<sm_count() * 4, 256, 0, st>>>(S->x, S->d, L.ka, L.mu, L.scalars, L.qlist, nq_pad, L.opA,
                                                               L.xnorm);
@@ -1335,6 +1572,14 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     p.debug_mode = dbg ? atoi(dbg) : 0;
   }
   p.n_cells = L.cells.P;
+  p.eps_rel = tc_eps_rel(L.ka);
+  p.fixed_thr = nullptr;
+  p.fixed_q0 = q0;
+  p.x = S->x;
+  p.perm = L.cells.perm;
+  p.d = S->d;
+  p.k1 = S->k + 1;
+  p.gamma = tc_gamma(S->d);
   p.op_a = reinterpret_cast<const uint32_t *>(L.opA);
   p.qlist = L.qlist;
   p.cell_of = L.cells.cell_of;
@@ -1345,26 +1590,38 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   p.tiles_done = L.tiles_done;
   p.times = nullptr;
   const bool want_times = getenv("VVB_TC_TIMES") != nullptr;
+  DeviceFree times_mem;
   if (want_times) {
-    VVB_CUDA(cudaMalloc(&p.times, static_cast<size_t>(nq_pad / TC_M) * 8 * sizeof(long long)));
+    VVB_CUDA(cudaMalloc(&times_mem.p, static_cast<size_t>(nq_pad / TC_M) * 8 * sizeof(long long)));
+    p.times = static_cast<long long *>(times_mem.p);
     VVB_CUDA(cudaMemsetAsync(p.times, 0, static_cast<size_t>(nq_pad / TC_M) * 8 * sizeof(long long), st));
   }
   p.cand = L.cand;
   p.cand_cnt = L.cand_cnt;
   p.cand_thr = L.cand_thr;
   const unsigned sgrid = static_cast<unsigned>(nq_pad / TC_M);
-  const bool dbg = p.debug_mode != 0 || p.times != nullptr;
-  if (L.ka == 1 && !dbg) knn_screen_kernel<false, false><<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, p);
-  else if (L.ka == 1) knn_screen_kernel<false, true><<<sgrid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, p);
-  else if (!dbg) knn_screen_kernel<true, false><<<sgrid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, p);
-  else knn_screen_kernel<true, true><<<sgrid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, p);
+  auto launch_screen = [&](const TcParams &pp, unsigned grid) {
+    const bool dbg = pp.debug_mode != 0 || pp.times != nullptr;
+    if (pp.fixed_thr && L.ka == 1)
+      knn_screen_kernel<false, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, pp);
+    else if (pp.fixed_thr)
+      knn_screen_kernel<true, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, pp);
+    else if (L.ka == 1 && !dbg)
+      knn_screen_kernel<false, false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, pp);
+    else if (L.ka == 1)
+      knn_screen_kernel<false, true, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, pp);
+    else if (!dbg)
+      knn_screen_kernel<true, false, false><<<grid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, pp);
+    else
+      knn_screen_kernel<true, true, false><<<grid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, pp);
+  };
+  launch_screen(p, sgrid);
   VVB_CHECK_LAUNCH();
   if (want_times) {  // profiling only: mean duration of the phases of a CTA, in SM clocks
     const size_t nc = static_cast<size_t>(nq_pad / TC_M);
     std::vector<long long> h(nc * 8);
     VVB_CUDA(cudaStreamSynchronize(st));
     VVB_CUDA(cudaMemcpy(h.data(), p.times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    cudaFree(p.times);
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     for (size_t c = 0; c < nc; ++c)
       for (int i = 0; i < 7; ++i)
@@ -1373,17 +1630,20 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
             "[vvb times] CTAs %zu: prologue %.0f | first accumulator %.0f | pre-pass %.0f | pre select %.0f | main sweep "
             "%.0f | final select %.0f | exit barrier %.0f  (mean SM clocks per CTA)\n",
             nc, acc[0] / nc, acc[1] / nc, acc[2] / nc, acc[3] / nc, acc[4] / nc, acc[5] / nc, acc[6] / nc);
+    p.times = nullptr;
   }
   if (screen_only) return VVB_OK;
   mark(1);
-  const int e_need = (S->keep + 31) / 32;
   const char *rrw = getenv("VVB_RR_WIDE_MIN");
   const int rr_wide_min = rrw ? atoi(rrw) : 65;  // d <= 64: whole-row staging (MODE 2); VVB_RR_WIDE_MIN=32 forces MODE 1
   const char *rrm = getenv("VVB_RR_ROWS");
   const bool rr_rows = S->d <= 64 && S->d < rr_wide_min && !(rrm && atoi(rrm) == 0);
-  const unsigned rr_grid = static_cast<unsigned>(rr_rows ? (nq + 3) / 4 : (nq + 7) / 8);
-#define VVB_RR_ARGS S->x, S->n, S->d, q0, nq, S->k, L.qlist, L.cells.perm, L.cand, L.cand_cnt, L.cand_thr, L.xnorm, \
-                    L.scalars, out_idx, out_dist, L.fb_count, L.fb_rows
+  const float gamma = tc_gamma(S->d);
+  // rows = query-list entries to re-rank; e_need = groups of 32 candidates a row may hold; refine = second pass
+  auto launch_rerank = [&](int64_t rows, int e_need, int refine) {
+    const unsigned rr_grid = static_cast<unsigned>(rr_rows ? (rows + 3) / 4 : (rows + 7) / 8);
+#define VVB_RR_ARGS S->x, S->n, S->d, q0, rows, S->k, L.qlist, L.cells.perm, L.cand, L.cand_cnt, L.cand_thr, L.xnorm, \
+                    L.scalars, out_idx, out_dist, L.fb_count, L.fb_rows, p.eps_rel, gamma, L.fb_thr, refine
 #define VVB_RR(EE)                                                                            \
   do {                                                                                        \
     if (rr_rows)                                                                              \
@@ -1393,19 +1653,49 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     else                                                                                      \
       knn_rerank_kernel<EE, 0><<<rr_grid, 256, 0, st>>>(VVB_RR_ARGS);                         \
   } while (0)
-  if (e_need <= 2) VVB_RR(2);
-  else if (e_need <= 4) VVB_RR(4);
-  else VVB_RR(8);
+    if (e_need <= 2) VVB_RR(2);
+    else if (e_need <= 4) VVB_RR(4);
+    else if (e_need <= 8) VVB_RR(8);
+    else VVB_RR(16);
 #undef VVB_RR
 #undef VVB_RR_ARGS
+  };
+  launch_rerank(nq, (S->keep + 31) / 32, 0);
   VVB_CHECK_LAUNCH();
   mark(2);
-  // rows the certificate rejected: exact FP32 brute force.  The count comes back to the host (one
-  // 4-byte copy + stream sync per chunk) so that a handful of rows can be spread over the whole GPU
-  // (database slices) instead of leaving one CTA to sweep the database alone.
+  // Rows the certificate rejected.  The count comes back to the host (one 4-byte copy + stream sync per chunk): it
+  // sizes the refine launch, and lets a handful of brute-force rows be spread over the whole GPU (database slices)
+  // instead of leaving one CTA to sweep the database alone.
   int fb = 0;
   VVB_CUDA(cudaMemcpyAsync(&fb, L.fb_count, sizeof(int), cudaMemcpyDeviceToHost, st));
   VVB_CUDA(cudaStreamSynchronize(st));
+  int refined = 0;
+  const char *rfe = getenv("VVB_TC_REFINE");
+  if (fb > 0 && !(rfe && atoi(rfe) == 0)) {
+    // Refine pass (tie-aware): the failed rows become a query list of their own, swept by the same kernel with every
+    // row's threshold fixed at the value the re-rank kernel derived from its k-th candidate (fb_thr); the lists,
+    // the query operand and the fallback list are reused (the main pass is complete: same stream).
+    refined = fb;
+    const int64_t nr = fb, nr_pad = (nr + TC_M - 1) / TC_M * TC_M;
+    rc = cells_query_list(L.cells, q0, nr, nr_pad, L.qlist, L.fb_rows, st);
+    if (rc) return rc;
+    build_operands_kernel<true><<<sm_count() * 4, 256, 0, st>>>(S->x, S->d, L.ka, L.mu, L.scalars, L.qlist, nr_pad,
+                                                                L.opA, L.xnorm);
+    VVB_CHECK_LAUNCH();
+    VVB_CUDA(cudaMemsetAsync(L.fb_count, 0, sizeof(int), st));
+    TcParams pr = p;
+    pr.nq = nr;
+    pr.fixed_thr = L.fb_thr;
+    pr.fixed_q0 = q0;
+    pr.debug_mode = 0;
+    pr.times = nullptr;
+    launch_screen(pr, static_cast<unsigned>(nr_pad / TC_M));
+    VVB_CHECK_LAUNCH();
+    launch_rerank(nr, TC_REFINE_CAP / 32, 1);
+    VVB_CHECK_LAUNCH();
+    VVB_CUDA(cudaMemcpyAsync(&fb, L.fb_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VVB_CUDA(cudaStreamSynchronize(st));
+  }
   rc = VVB_OK;
   if (fb > 0 && fb <= knn_brute_few_max_rows())
     rc = launch_knn_brute_few(S->x, S->n, S->d, S->k, L.fb_rows, fb, out_idx, out_dist, q0, L.brute_ws,
@@ -1418,20 +1708,20 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   if (stats) {
     VVB_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ev[0], ev[1]);
+    cudaEventElapsedTime(&ms, ce.ev[0], ce.ev[1]);
     stats->ms_screen += ms;
-    cudaEventElapsedTime(&ms, ev[1], ev[2]);
+    cudaEventElapsedTime(&ms, ce.ev[1], ce.ev[2]);
     stats->ms_rerank += ms;
-    cudaEventElapsedTime(&ms, ev[2], ev[3]);
-    stats->ms_fallback += ms;
+    cudaEventElapsedTime(&ms, ce.ev[2], ce.ev[3]);
+    stats->ms_fallback += ms;  // refine pass + brute force
     stats->rows_fallback += fb;
+    stats->rows_refined += refined;
     unsigned long long done = 0;
     int used = 0;
     VVB_CUDA(cudaMemcpy(&done, L.tiles_done, sizeof(done), cudaMemcpyDeviceToHost));
     VVB_CUDA(cudaMemcpy(&used, L.cells.off + L.cells.P, sizeof(int), cudaMemcpyDeviceToHost));
     stats->tiles_swept = static_cast<int64_t>(done);  // cumulative over the chunks of this call
     stats->tiles_dense += static_cast<int64_t>(sgrid) * (used / TC_N);
-    for (auto &e : ev) cudaEventDestroy(e);
   }
   return VVB_OK;
 }
@@ -1454,7 +1744,7 @@ int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, i
   VVB_CUDA(cudaMemcpy(xd, x_host, static_cast<size_t>(n) * d * sizeof(float), cudaMemcpyHostToDevice));
   alignas(64) char session[sizeof(TcSession)];
   cudaStream_t st = nullptr;
-  int rc = knn_tensor_begin(session, static_cast<const float *>(xd), n, d, k, nq, ws, ws_bytes, st, nullptr);
+  int rc = knn_tensor_begin(session, static_cast<const float *>(xd), n, d, k, nq, ws, ws_bytes, st, nullptr, false);
   if (!rc)
     rc = knn_tensor_chunk(session, q0, nq, static_cast<int64_t *>(oi), static_cast<float *>(od), st, nullptr,
                           /*screen_only=*/true);
@@ -1489,7 +1779,7 @@ int knn_screen_debug(const float *x_host, int64_t n, int d, int k, int64_t q0, i
       }
     }
     cudaMemcpy(scale_ymax_out, L.scalars, 2 * sizeof(float), cudaMemcpyDeviceToHost);
-    cudaMemcpy(mu_out, L.mu, static_cast<size_t>(d < 64 ? d : 64) * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaMemcpy(mu_out, L.mu, static_cast<size_t>(L.ka) * 64 * sizeof(float), cudaMemcpyDeviceToHost);
   }
   cudaFree(ws);
   cudaFree(xd);

@@ -2,24 +2,33 @@
 // Replaces MDSLoss.__call__ (/root/reference/src/vivae/losses.py:266-349), which costs
 // ~1.5k ATen dispatches per batch for forward+backward.
 //
-// One warp per quartet q of a sampling pass: rows perm[a*nq + q], a = 0..3
-// (losses.py:326,332-336).  The six pairs, in the order of losses.py:234,263, are
-// (0,1) (1,2) (2,3) (0,2) (0,3) (1,3).  Lanes stride over the D (and L) coordinates,
-// partial sums are combined with xor-shuffles, then every lane holds the six
-// high-dimensional and six latent distances and evaluates
+// EIGHT lanes per quartet q of a sampling pass (four quartets per warp): rows perm[a*nq + q],
+// a = 0..3 (losses.py:326,332-336).  The six pairs, in the order of losses.py:234,263, are
+// (0,1) (1,2) (2,3) (0,2) (0,3) (1,3).  The lanes of a group stride over the D (and L) coordinates
+// with 8-byte loads (D even), partial sums are combined with three xor-shuffles, then every lane
+// holds the six high-dimensional and six latent distances and evaluates
 //     cost_q = sum_p (dz_p/S - dx_p/X)^2,   X = sum_p dx_p,  S = sum_p dz_p
 // and the closed-form gradient
 //     dC/d(dz_p) = (2/S) (e_p - sum_p' e_p' dz_p'/S),   e_p = dz_p/S - dx_p/X.
 // Each row belongs to exactly one quartet per pass, so gradient rows are written
 // without atomics and the result is run-to-run deterministic (VIVAE_DETERMINISTIC).
-// The scalar loss is reduced in a fixed order by the last CTA to finish.
+// CTAs walk the quartets with a grid stride (a grid of SMs x 8 CTAs, 16 row loads in flight per
+// lane: bandwidth-sized batches stream at HBM speed); the scalar loss is reduced in a fixed order:
+// lane tree -> warp slots -> one partial per CTA -> the last CTA to finish adds the partials.
 #include "common.cuh"
 
 namespace vvb {
 
-constexpr int QT_THREADS = 256;  // 8 quartets per CTA
-constexpr int QT_WARPS = QT_THREADS / 32;
+constexpr int QT_THREADS = 256;  // 32 quartets per CTA and iteration
+constexpr int QT_GROUP = 8;      // lanes per quartet
+constexpr int QT_PER_CTA = QT_THREADS / QT_GROUP;
 
+// sum over the 8 lanes of a quartet's group (xor offsets below 8 never leave the aligned group)
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = QT_GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -35,39 +44,57 @@ struct QuadStats {
 };
 
 template <int METRIC>
-__device__ __forceinline__ void quad_stats(const float *base, const int64_t (&r)[4], int dim, int lane,
+__device__ __forceinline__ void quad_accum(QuadStats &s, float v0, float v1, float v2, float v3) {
+  if (METRIC == VVB_DIST_EUCLIDEAN) {
+    float t;
+    t = v0 - v1; s.sq[0] = fmaf(t, t, s.sq[0]);
+    t = v1 - v2; s.sq[1] = fmaf(t, t, s.sq[1]);
+    t = v2 - v3; s.sq[2] = fmaf(t, t, s.sq[2]);
+    t = v0 - v2; s.sq[3] = fmaf(t, t, s.sq[3]);
+    t = v0 - v3; s.sq[4] = fmaf(t, t, s.sq[4]);
+    t = v1 - v3; s.sq[5] = fmaf(t, t, s.sq[5]);
+  } else {
+    s.nrm[0] = fmaf(v0, v0, s.nrm[0]); s.nrm[1] = fmaf(v1, v1, s.nrm[1]);
+    s.nrm[2] = fmaf(v2, v2, s.nrm[2]); s.nrm[3] = fmaf(v3, v3, s.nrm[3]);
+    s.dot[0] = fmaf(v0, v1, s.dot[0]); s.dot[1] = fmaf(v1, v2, s.dot[1]);
+    s.dot[2] = fmaf(v2, v3, s.dot[2]); s.dot[3] = fmaf(v0, v2, s.dot[3]);
+    s.dot[4] = fmaf(v0, v3, s.dot[4]); s.dot[5] = fmaf(v1, v3, s.dot[5]);
+  }
+}
+
+// `sub` = lane within the quartet's group of 8.  VEC2: rows are 8-byte aligned (dim even): float2 loads.
+template <int METRIC, bool VEC2>
+__device__ __forceinline__ void quad_stats(const float *base, const int64_t (&r)[4], int dim, int sub,
                                            QuadStats &s) {
 #pragma unroll
   for (int p = 0; p < 6; ++p) s.sq[p] = 0.f, s.dot[p] = 0.f;
 #pragma unroll
   for (int a = 0; a < 4; ++a) s.nrm[a] = 0.f;
-  for (int c = lane; c < dim; c += 32) {
-    const float v0 = __ldg(base + r[0] * dim + c), v1 = __ldg(base + r[1] * dim + c);
-    const float v2 = __ldg(base + r[2] * dim + c), v3 = __ldg(base + r[3] * dim + c);
-    if (METRIC == VVB_DIST_EUCLIDEAN) {
-      float t;
-      t = v0 - v1; s.sq[0] = fmaf(t, t, s.sq[0]);
-      t = v1 - v2; s.sq[1] = fmaf(t, t, s.sq[1]);
-      t = v2 - v3; s.sq[2] = fmaf(t, t, s.sq[2]);
-      t = v0 - v2; s.sq[3] = fmaf(t, t, s.sq[3]);
-      t = v0 - v3; s.sq[4] = fmaf(t, t, s.sq[4]);
-      t = v1 - v3; s.sq[5] = fmaf(t, t, s.sq[5]);
-    } else {
-      s.nrm[0] = fmaf(v0, v0, s.nrm[0]); s.nrm[1] = fmaf(v1, v1, s.nrm[1]);
-      s.nrm[2] = fmaf(v2, v2, s.nrm[2]); s.nrm[3] = fmaf(v3, v3, s.nrm[3]);
-      s.dot[0] = fmaf(v0, v1, s.dot[0]); s.dot[1] = fmaf(v1, v2, s.dot[1]);
-      s.dot[2] = fmaf(v2, v3, s.dot[2]); s.dot[3] = fmaf(v0, v2, s.dot[3]);
-      s.dot[4] = fmaf(v0, v3, s.dot[4]); s.dot[5] = fmaf(v1, v3, s.dot[5]);
+  if (VEC2) {
+    const float2 *b0 = reinterpret_cast<const float2 *>(base + r[0] * dim);
+    const float2 *b1 = reinterpret_cast<const float2 *>(base + r[1] * dim);
+    const float2 *b2 = reinterpret_cast<const float2 *>(base + r[2] * dim);
+    const float2 *b3 = reinterpret_cast<const float2 *>(base + r[3] * dim);
+    const int half = dim >> 1;
+#pragma unroll 4
+    for (int c = sub; c < half; c += QT_GROUP) {
+      const float2 v0 = __ldg(b0 + c), v1 = __ldg(b1 + c), v2 = __ldg(b2 + c), v3 = __ldg(b3 + c);
+      quad_accum<METRIC>(s, v0.x, v1.x, v2.x, v3.x);
+      quad_accum<METRIC>(s, v0.y, v1.y, v2.y, v3.y);
     }
+  } else {
+    for (int c = sub; c < dim; c += QT_GROUP)
+      quad_accum<METRIC>(s, __ldg(base + r[0] * dim + c), __ldg(base + r[1] * dim + c), __ldg(base + r[2] * dim + c),
+                         __ldg(base + r[3] * dim + c));
   }
   if (METRIC == VVB_DIST_EUCLIDEAN) {
 #pragma unroll
-    for (int p = 0; p < 6; ++p) s.sq[p] = warp_sum(s.sq[p]);
+    for (int p = 0; p < 6; ++p) s.sq[p] = group_sum(s.sq[p]);
   } else {
 #pragma unroll
-    for (int p = 0; p < 6; ++p) s.dot[p] = warp_sum(s.dot[p]);
+    for (int p = 0; p < 6; ++p) s.dot[p] = group_sum(s.dot[p]);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) s.nrm[a] = warp_sum(s.nrm[a]);
+    for (int a = 0; a < 4; ++a) s.nrm[a] = group_sum(s.nrm[a]);
   }
 }
 
@@ -86,10 +113,10 @@ __device__ __forceinline__ void pair_dists(const QuadStats &s, float (&dist)[6])
   }
 }
 
-template <int MHD, int MLD>
+template <int MHD, int MLD, bool VEC2>
 __global__ void __launch_bounds__(QT_THREADS) quartet_fwd_kernel(
     const float *__restrict__ x, const float *__restrict__ z, int64_t B, int D, int L,
-    const int64_t *__restrict__ perm, float *__restrict__ cost_q, float *__restrict__ grad_unit,
+    const int64_t *__restrict__ perm, float *__restrict__ partials, float *__restrict__ grad_unit,
     int accumulate, float grad_scale, float pass_weight, float *__restrict__ loss_out,
     int accumulate_loss, unsigned int *__restrict__ done_counter) {
   constexpr int pa[6] = {0, 1, 2, 0, 0, 1};
@@ -97,16 +124,28 @@ __global__ void __launch_bounds__(QT_THREADS) quartet_fwd_kernel(
   const int64_t nq = B / 4;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int64_t q = static_cast<int64_t>(blockIdx.x) * QT_WARPS + warp;
+  const int sub = lane & (QT_GROUP - 1);
+  float cost_sum = 0.f;  // this lane's quartets (counted by sub == 0 only)
 
-  if (q < nq) {
+  // rows beyond the last whole quartet take no part: their gradient is zero (first pass only)
+  if (grad_unit != nullptr && !accumulate && blockIdx.x == 0)
+    for (int64_t i = 4 * nq * L + threadIdx.x; i < B * L; i += QT_THREADS) {
+      const int64_t row = i / L;
+      grad_unit[(perm ? perm[row] : row) * L + i % L] = 0.f;
+    }
+
+  // whole warps iterate together (the shuffles need every lane): q0 = first quartet of the warp's four
+  for (int64_t q0 = static_cast<int64_t>(blockIdx.x) * QT_PER_CTA + warp * 4; q0 < nq;
+       q0 += static_cast<int64_t>(gridDim.x) * QT_PER_CTA) {
+    const int64_t q = q0 + (lane >> 3);
+    const bool valid = q < nq;
     int64_t r[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) r[a] = perm ? perm[a * nq + q] : a * nq + q;
+    for (int a = 0; a < 4; ++a) r[a] = valid ? (perm ? perm[a * nq + q] : a * nq + q) : 0;
 
     QuadStats sx, sz;
-    quad_stats<MHD>(x, r, D, lane, sx);
-    quad_stats<MLD>(z, r, L, lane, sz);
+    quad_stats<MHD, VEC2>(x, r, D, sub, sx);
+    quad_stats<MLD, false>(z, r, L, sub, sz);
     float dx[6], dz[6];
     pair_dists<MHD>(sx, dx);
     pair_dists<MLD>(sz, dz);
@@ -120,13 +159,13 @@ __global__ void __launch_bounds__(QT_THREADS) quartet_fwd_kernel(
       cost = fmaf(e[p], e[p], cost);
       er = fmaf(e[p], dz[p] / S, er);
     }
-    if (lane == 0) cost_q[q] = cost;
+    if (valid && sub == 0) cost_sum += cost;
 
-    if (grad_unit != nullptr) {
+    if (grad_unit != nullptr && valid) {
       float w[6];
 #pragma unroll
       for (int p = 0; p < 6; ++p) w[p] = (2.0f / S) * (e[p] - er) * grad_scale;
-      for (int c = lane; c < L; c += 32) {
+      for (int c = sub; c < L; c += QT_GROUP) {
         float zv[4], g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int a = 0; a < 4; ++a) zv[a] = __ldg(z + r[a] * L + c);
@@ -159,12 +198,17 @@ __global__ void __launch_bounds__(QT_THREADS) quartet_fwd_kernel(
     }
   }
 
-  // ---- deterministic loss reduction by the last CTA
+  // ---- deterministic loss reduction: lane tree -> warp slots -> CTA partial -> last CTA adds the partials
   __shared__ bool is_last;
   __shared__ float red[QT_THREADS];
-  __threadfence();
+  cost_sum = warp_sum(cost_sum);
+  if (lane == 0) red[warp] = cost_sum;
   __syncthreads();
   if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < QT_THREADS / 32; ++w) t += red[w];
+    partials[blockIdx.x] = t;
+    __threadfence();
     const unsigned int ticket = atomicAdd(done_counter, 1u);
     is_last = (ticket == gridDim.x - 1);
   }
@@ -172,7 +216,7 @@ __global__ void __launch_bounds__(QT_THREADS) quartet_fwd_kernel(
   if (!is_last) return;
   __threadfence();
   float part = 0.f;
-  for (int64_t i = threadIdx.x; i < nq; i += QT_THREADS) part += __ldcg(cost_q + i);
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += QT_THREADS) part += __ldcg(partials + i);
   red[threadIdx.x] = part;
   __syncthreads();
 #pragma unroll
@@ -210,23 +254,33 @@ int launch_quartet_fwd(const float *x, const float *z, int64_t B, int D, int L, 
   VVB_REQUIRE(B >= 0 && D >= 1 && L >= 1 && n_sampling >= 1, "quartet loss: bad shape arguments");
   VVB_REQUIRE((mhd == 0 || mhd == 1) && (mld == 0 || mld == 1), "Invalid distance function specification for MDS loss");
   const int64_t nq = B / 4;
-  if (grad_unit && B > 0) VVB_CUDA(cudaMemsetAsync(grad_unit, 0, static_cast<size_t>(B) * L * sizeof(float), st));
-  if (nq == 0) {  // mean over zero quartets: NaN, like the reference
+  if (nq == 0) {  // mean over zero quartets: NaN, like the reference; no row gets a gradient
+    if (grad_unit && B > 0) VVB_CUDA(cudaMemsetAsync(grad_unit, 0, static_cast<size_t>(B) * L * sizeof(float), st));
     quartet_nan_kernel<<<1, 1, 0, st>>>(loss_out);
     VVB_CHECK_LAUNCH();
     return VVB_OK;
   }
+  // workspace: [done counter (256 B), zero between launches: the last CTA resets it][one partial per CTA]
   unsigned int *counter = static_cast<unsigned int *>(workspace);
-  float *cost_q = reinterpret_cast<float *>(static_cast<char *>(workspace) + 256);
+  float *partials = reinterpret_cast<float *>(static_cast<char *>(workspace) + 256);
   VVB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
-  const unsigned grid = static_cast<unsigned>((nq + QT_WARPS - 1) / QT_WARPS);
+  int64_t grid = (nq + QT_PER_CTA - 1) / QT_PER_CTA;
+  const int64_t resident = static_cast<int64_t>(sm_count()) * 8;
+  if (grid > resident) grid = resident;
+  const bool vec2 = (D % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 8 == 0);
   const float grad_scale = static_cast<float>(static_cast<double>(B) / (static_cast<double>(nq) * nq) / n_sampling);
   const float pass_weight = 1.0f / static_cast<float>(n_sampling);
   for (int s = 0; s < n_sampling; ++s) {
     const int64_t *perm = perms ? perms[s] : nullptr;
-#define VVB_QT_LAUNCH(A, Bm)                                                                              \
-  quartet_fwd_kernel<A, Bm><<<grid, QT_THREADS, 0, st>>>(x, z, B, D, L, perm, cost_q, grad_unit, s > 0,  \
-                                                         grad_scale, pass_weight, loss_out, s > 0, counter)
+#define VVB_QT_LAUNCH(A, Bm)                                                                                        \
+  do {                                                                                                              \
+    if (vec2)                                                                                                       \
+      quartet_fwd_kernel<A, Bm, true><<<static_cast<unsigned>(grid), QT_THREADS, 0, st>>>(                          \
+          x, z, B, D, L, perm, partials, grad_unit, s > 0, grad_scale, pass_weight, loss_out, s > 0, counter);      \
+    else                                                                                                            \
+      quartet_fwd_kernel<A, Bm, false><<<static_cast<unsigned>(grid), QT_THREADS, 0, st>>>(                         \
+          x, z, B, D, L, perm, partials, grad_unit, s > 0, grad_scale, pass_weight, loss_out, s > 0, counter);      \
+  } while (0)
     if (mhd == 0 && mld == 0) VVB_QT_LAUNCH(0, 0);
     else if (mhd == 0 && mld == 1) VVB_QT_LAUNCH(0, 1);
     else if (mhd == 1 && mld == 0) VVB_QT_LAUNCH(1, 0);

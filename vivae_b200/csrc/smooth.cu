@@ -9,6 +9,14 @@
 //   * one warp per row, rows handed out in increasing order through an atomic ticket,
 //     so a warp only ever waits on rows whose owner is already running: no deadlock,
 //     whatever the grid size or the row order of the data.
+//   * publish / wait protocol (PTX memory model, gpu scope): the owner's 32 lanes store the
+//     row, meet at a warp barrier, and ONE lane publishes with st.release.gpu (release is
+//     cumulative over the barrier); a waiting lane polls with ld.relaxed.gpu -- no L1
+//     invalidation per poll -- and the warp executes ONE fence.acq_rel.gpu once all its
+//     polls have succeeded, then a warp barrier, before any lane reads the published rows
+//     (with ld.global.cg: L2 is the point of coherence).
+//   * every neighbour row is prefetched into L2 BEFORE the polling starts, so the DRAM
+//     latency of the gather overlaps the wait instead of following it.
 // Arithmetic per element matches NumPy's: sequential sum over the k gathered rows in
 // neighbour order (starting from the first row, not from zero), true division by k,
 // then r + (target - r) * coef as three separately rounded operations (no FMA).
@@ -39,7 +47,7 @@ template <> struct Arith<double> {
 
 // DPL = columns per lane held in registers (a warp covers 32*DPL columns per pass)
 // KPL = neighbour indices per lane held in registers (k <= 32*KPL)
-template <typename T, int DPL, int KPL, bool GS>
+template <typename T, int DPL, int KPL, bool GS, bool PREFETCH>
 __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
     const T *__restrict__ prev, T *next, const int64_t *__restrict__ idx, int64_t ld_idx, int64_t n,
     int d, int k, T coef, int *flags, int epoch, unsigned long long *ticket, int *bad_index, int rows_per_ticket,
@@ -66,19 +74,36 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
         }
         mine[q] = j;
       }
+      if (PREFETCH) {
+        // the row's gather, started early: every lane pulls ITS neighbours' rows (prev or next, the array the
+        // gather will read) into L2; a line that is rewritten later is updated in L2, never stale
+        const int row_bytes = d * static_cast<int>(sizeof(T));
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+          if (q * 32 + lane < k) {
+            const char *src = reinterpret_cast<const char *>(((GS && mine[q] < i) ? static_cast<const T *>(next) : prev) +
+                                                             mine[q] * d);
+            for (int off = 0; off < row_bytes; off += 128) prefetch_l2(src + off);
+            prefetch_l2(src + row_bytes - 1);
+          }
+        }
+      }
       if (GS) {
-        // wait until every lower-indexed neighbour has been published in this sweep;
-        // exponential back-off keeps thousands of waiting lanes from flooding L2 with polls
+        // wait until every lower-indexed neighbour has been published in this sweep (relaxed polls,
+        // exponential back-off), then one acquire fence for the whole warp
+        bool polled = false;
 #pragma unroll
         for (int q = 0; q < KPL; ++q) {
           if (mine[q] < i) {
-            unsigned ns = 64;
-            while (ld_acquire(flags + mine[q]) < epoch) {
+            polled = true;
+            unsigned ns = 32;
+            while (ld_relaxed(flags + mine[q]) < epoch) {
               __nanosleep(ns);
-              if (ns < 2048) ns <<= 1;
+              if (ns < 1024) ns <<= 1;
             }
           }
         }
+        if (__any_sync(FULL, polled)) fence_acq_rel();
         __syncwarp();
       }
       for (int c0 = 0; c0 < d; c0 += 32 * DPL) {
@@ -130,9 +155,8 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
         }
       }
       if (GS) {
-        __threadfence();  // every lane: its stores to `next` are visible device-wide ...
-        __syncwarp();
-        if (lane == 0) st_release(flags + i, epoch);  // ... before the row is published
+        __syncwarp();  // all 32 lanes' stores to `next` happen before ...
+        if (lane == 0) st_release(flags + i, epoch);  // ... the (cumulative) release that publishes the row
       }
     }
   }
@@ -173,8 +197,12 @@ static int launch_rows(const T *src, T *dst, int64_t n, int d, const int64_t *id
                        int mode, const SmoothWs &w, int epoch, unsigned long long *ticket, int64_t row_lo,
                        int64_t row_hi, cudaStream_t st) {
   int blocks_per_sm = 0;
-  auto kern_gs = smooth_sweep_kernel<T, DPL, KPL, true>;
-  auto kern_ja = smooth_sweep_kernel<T, DPL, KPL, false>;
+  // L2 prefetch of the neighbour rows: rows of at most 512 bytes (wider rows would flood the prefetch queue);
+  // VVB_SMOOTH_PREFETCH=0 switches it off
+  const char *pfe = getenv("VVB_SMOOTH_PREFETCH");
+  const bool pf = static_cast<size_t>(d) * sizeof(T) <= 512 && !(pfe && atoi(pfe) == 0);
+  auto kern_gs = pf ? smooth_sweep_kernel<T, DPL, KPL, true, true> : smooth_sweep_kernel<T, DPL, KPL, true, false>;
+  auto kern_ja = pf ? smooth_sweep_kernel<T, DPL, KPL, false, true> : smooth_sweep_kernel<T, DPL, KPL, false, false>;
   VVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, mode == VVB_SMOOTH_JACOBI ? kern_ja : kern_gs,
                                                          SM_THREADS, 0));
   if (blocks_per_sm < 1) blocks_per_sm = 1;
@@ -265,7 +293,7 @@ static int smooth_check(const void *x, int elem_size, int64_t n, int d, int64_t 
   VVB_REQUIRE(mode == VVB_SMOOTH_GAUSS_SEIDEL || mode == VVB_SMOOTH_JACOBI, "smooth: unknown mode %d", mode);
   VVB_REQUIRE(out != x, "smooth: out must not alias x");
   VVB_REQUIRE(workspace_bytes >= smooth_workspace_bytes(elem_size, n, d, n_iter), "smooth: workspace too small");
-  VVB_REQUIRE(k <= 1024, "smooth: k=%d above the supported maximum of 1024", k);
+  VVB_SUPPORTED(k <= 1024, "smooth: k=%d above the supported maximum of 1024", k);
   return VVB_OK;
 }
 

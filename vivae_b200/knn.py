@@ -9,8 +9,11 @@ there is no CPU implementation in this package.
 Differences from the reference, all deliberate:
   * `make_knn` is EXACT (the reference's pynndescent graph is approximate and
     seeded); `random_state` is accepted and ignored.
-  * additive keyword-only arguments: `make_knn(..., algo=, stats=)`,
+  * additive keyword-only arguments: `make_knn(..., algo=, stats=, compact_cache=)`,
     `smooth(..., mode=)`.
+  * capacity limits of the CUDA kernels surface as `NotImplementedError` (never as one of
+    the reference's `ValueError`s): `make_knn` k > 1984, `smooth` k > 1024.  The tensor-core
+    path covers k <= 152 and d <= 4093; beyond that `algo='auto'` uses the FP32 brute-force kernel.
 """
 
 from __future__ import annotations
@@ -112,6 +115,36 @@ def _knn_host(x: np.ndarray, k: int, q0: int, nq: int, algo: str, stats: Optiona
     return idx, dist
 
 
+def _sidecar_path(fname: str) -> str:
+    return fname + ".vvb.npz"
+
+
+def _save_compact_sidecar(fname: str, idx: np.ndarray, dist: np.ndarray) -> None:
+    """Compact copy of the cache next to the reference-format file: int32 indices + float32 distances
+    (8 bytes per entry instead of 16; at 10M x 101 that is 8 GB instead of 16 GB)."""
+    if idx.shape[0] > np.iinfo(np.int32).max:
+        return
+    with open(_sidecar_path(fname), "wb") as f:
+        np.savez(f, idx=idx.astype(np.int32), dist=np.asarray(dist, dtype=np.float32),
+                 shape=np.asarray(idx.shape, dtype=np.int64))
+
+
+def _load_compact_sidecar(fname: str):
+    """`[idx int64, dist float32]` from the sidecar, or None when it is missing, older than the reference-format
+    file, or does not describe the same graph (then the caller reads the reference-format file)."""
+    side = _sidecar_path(fname)
+    try:
+        if not os.path.isfile(side) or os.path.getmtime(side) < os.path.getmtime(fname):
+            return None
+        with np.load(side) as z:
+            idx, dist, shape = z["idx"], z["dist"], tuple(int(v) for v in z["shape"])
+        if idx.shape != shape or dist.shape != shape or idx.dtype != np.int32 or dist.dtype != np.float32:
+            return None
+        return [idx.astype(np.int64), dist]
+    except Exception:
+        return None
+
+
 def make_knn(
     x: Optional[np.ndarray] = None,
     fname: Optional[str] = None,
@@ -122,6 +155,7 @@ def make_knn(
     *,
     algo: str = "auto",
     stats: Optional[dict] = None,
+    compact_cache: bool = True,
 ) -> list:
     """Construct or load a k-nearest-neighbour graph (reference: knn.py:87-144).
 
@@ -140,6 +174,12 @@ def make_knn(
         algo: 'auto' (tensor-core screening + FP32 re-rank with certified fallback),
             'brute' (FP32 brute force) or 'tensor'.
         stats: optional dict that receives the `vvb_knn_stats` counters.
+        compact_cache: with `fname`, also keep a compact sidecar `<fname>.vvb.npz` (int32 indices, float32
+            distances: half the bytes of the reference's float64 pair and no float->int pass on load).  The
+            reference-format file is always written and stays the source of truth: the sidecar is used on load
+            only when it is at least as new as `fname` and describes the same (n, k+1) graph.
+
+    Raises `NotImplementedError` for k > 1984 (capacity of the brute-force kernel's candidate lists).
     """
     if k < 1 or k > (x.shape[0] - 1):
         raise ValueError("`k` must be between 1 and (n-1)")
@@ -147,8 +187,10 @@ def make_knn(
     if fname is not None and os.path.isfile(fname):
         if verbose:
             print("Loading k-NNG")
-        res = np.load(fname, allow_pickle=True)
-        knn = [np.array(res[0], dtype=np.int64), np.array(res[1])]
+        knn = _load_compact_sidecar(fname) if compact_cache else None
+        if knn is None:
+            res = np.load(fname, allow_pickle=True)
+            knn = [np.array(res[0], dtype=np.int64), np.array(res[1])]
     else:
         if verbose:
             print("Constructing k-NNG")
@@ -158,7 +200,9 @@ def make_knn(
         idx, dist = _knn_host(xf, int(k), 0, xf.shape[0], algo, stats)
         knn = [idx, dist]  # self is pinned to column 0 on the device: no duplicate fix-up needed
         if fname is not None:
-            np.save(fname, knn)
+            np.save(fname, knn)  # the reference's format (knn.py:142-143): one float64 (2, n, k+1) array
+            if compact_cache:
+                _save_compact_sidecar(fname, idx, dist)
     if as_tuple:
         knn = tuple(knn)
     return knn
@@ -180,6 +224,8 @@ def smooth(
     working array in place, so row i sees rows j < i already updated in the same
     sweep.  `mode='jacobi'` (every row reads the previous sweep) is a faster,
     order-independent variant that does NOT match the reference.
+
+    Raises `NotImplementedError` for k > 1024 (a warp keeps a row's neighbour list in registers).
     """
     if k < 1 or k > (x.shape[0] - 1):
         raise ValueError("`k` must be between 1 and (n-1)")

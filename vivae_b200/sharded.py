@@ -21,8 +21,8 @@ from typing import Callable, Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "all_gather_rows", "make_knn_sharded", "make_knn_ring", "ring_fold", "knn_smooth_sharded",
-           "smooth_jacobi_sharded"]
+__all__ = ["shard_bounds", "all_gather_rows", "all_gather_indices", "make_knn_sharded", "make_knn_ring", "ring_fold",
+           "knn_smooth_sharded", "knn_smooth_host_sharded", "smooth_jacobi_sharded"]
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -45,6 +45,14 @@ def all_gather_rows(local: torch.Tensor, n: int, group=None) -> torch.Tensor:
     return full[:n]
 
 
+def all_gather_indices(idx_local: torch.Tensor, n: int, group=None) -> torch.Tensor:
+    """All-gather of neighbour-index shards: the indices cross NVLink as int32 (n < 2^31: half the bytes of the
+    reference's int64) and are widened back on arrival -- the smoother reads int64 like `knn.py:137` returns."""
+    if n <= 0x7FFFFFFF:
+        return all_gather_rows(idx_local.to(torch.int32), n, group).to(torch.int64)
+    return all_gather_rows(idx_local, n, group)
+
+
 def make_knn_sharded(x: torch.Tensor, k: int, group=None, algo: str = "auto", gather: bool = True,
                      _knn_fn: Optional[Callable] = None):
     """Exact kNN graph with query rows sharded over the ranks of `group`.
@@ -61,7 +69,7 @@ def make_knn_sharded(x: torch.Tensor, k: int, group=None, algo: str = "auto", ga
     q0, nq = shard_bounds(n, world, rank)
     idx, dst = _knn_fn(x, k, q0, nq, algo)
     if gather and world > 1:
-        idx = all_gather_rows(idx, n, group)
+        idx = all_gather_indices(idx, n, group)
         dst = all_gather_rows(dst, n, group)
     return idx, dst
 
@@ -142,8 +150,52 @@ def knn_smooth_sharded(x: torch.Tensor, k: int, coef: float = 1.0, n_iter: int =
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     idx, _ = make_knn_sharded(x, k, group=group, algo=algo, gather=False, _knn_fn=_knn_fn)
     if world > 1:
-        idx = all_gather_rows(idx, x.shape[0], group)
+        idx = all_gather_indices(idx, x.shape[0], group)
     return idx, _smooth_fn(x, idx, k, coef, n_iter)
+
+
+def knn_smooth_host_sharded(x_shard, n: int, k: int, coef: float = 1.0, n_iter: int = 1, group=None, algo: str = "auto",
+                            out=None, _knn_fn: Optional[Callable] = None, _smooth_fn: Optional[Callable] = None,
+                            device=None):
+    """The whole path with HOST buffers, one process per GPU: every rank passes ONLY its rows of the matrix.
+
+    `x_shard`: this rank's rows [q0, q0+nq) = `shard_bounds(n, world, rank)` as a host array (NumPy or CPU
+    tensor, float32; page-locked memory makes the upload one DMA).  Steps: upload of the shard -> NCCL all-gather
+    of the matrix -> graph rows of the shard -> all-gather of the indices (int32 over NVLink) -> Gauss-Seidel
+    smoother (replicated, it does not shard by rows) -> download of the shard's graph rows and smoothed rows.
+    Returns host tensors `(idx int64 (nq, k+1), dist float32 (nq, k+1), smoothed (nq, d))`; with `out=` (a tuple of
+    three page-locked CPU tensors of those shapes) the downloads land there.  world = 1 is the plain pipeline."""
+    if _smooth_fn is None:
+        from .device import smooth_device
+
+        _smooth_fn = smooth_device
+    if _knn_fn is None:
+        from .device import knn_device
+
+        _knn_fn = knn_device
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    q0, nq = shard_bounds(n, world, rank)
+    xs = x_shard if isinstance(x_shard, torch.Tensor) else torch.from_numpy(x_shard)
+    if xs.shape[0] != nq:
+        raise ValueError(f"rank {rank} must pass rows [{q0}, {q0 + nq}) of the matrix, got {xs.shape[0]} rows")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    x_loc = xs.to(device, non_blocking=True)
+    x = all_gather_rows(x_loc, n, group) if world > 1 else x_loc
+    idx_loc, dist_loc = _knn_fn(x, k, q0, nq, algo)
+    idx = all_gather_indices(idx_loc, n, group) if world > 1 else idx_loc
+    sm = _smooth_fn(x, idx, k, coef, n_iter)
+    sm_loc = sm[q0:q0 + nq]
+    if out is None:
+        out = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=(device.type == "cuda"))
+                    for t in (idx_loc, dist_loc, sm_loc))
+    out[0].copy_(idx_loc, non_blocking=True)
+    out[1].copy_(dist_loc, non_blocking=True)
+    out[2].copy_(sm_loc, non_blocking=True)
+    if device.type == "cuda":
+        torch.cuda.current_stream(device).synchronize()
+    return out
 
 
 def smooth_jacobi_sharded(x: torch.Tensor, idx_local: torch.Tensor, k: int, coef: float = 0.1, n_iter: int = 1, group=None,
