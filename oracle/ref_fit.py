@@ -124,26 +124,30 @@ def time_ref_fit(X: np.ndarray, batch_size=512, epochs=1, warm_batches=8, device
     reference's eager GPU path).  One short warm-up (first `warm_batches` batches) is excluded."""
     dev = torch.device(device)
     torch.manual_seed(seed)
-    net = RefAutoencoder(X.shape[1]).to(dev)
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
-    loader = DataLoader(TensorDataset(torch.tensor(X, device=dev)), batch_size=batch_size, shuffle=True, generator=g)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4)
-    net.train()
-    it = iter(loader)
-    for _ in range(warm_batches):
-        (xb,) = next(it)
-        opt.zero_grad()
-        t = net(xb, lam_mds=lam_mds)
-        (t["recon"] + t["kldiv"] + t["mds"]).backward()
-        opt.step()
-    if dev.type == "cuda":
-        torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(epochs):
-        ref_train_epoch(net, loader, opt, lam_mds=lam_mds)
-    if dev.type == "cuda":
-        torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / epochs
+    # the reference makes its device the global default (src/vivae/__init__.py:17-27): the DataLoader's own
+    # bookkeeping tensors (base seed, sampler permutation) then live there too, next to the generator
+    with torch.device(dev):
+        net = RefAutoencoder(X.shape[1]).to(dev)
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        loader = DataLoader(TensorDataset(torch.tensor(X, device=dev)), batch_size=batch_size, shuffle=True, generator=g)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4)
+        net.train()
+        it = iter(loader)
+        for _ in range(warm_batches):
+            (xb,) = next(it)
+            opt.zero_grad()
+            t = net(xb, lam_mds=lam_mds)
+            (t["recon"] + t["kldiv"] + t["mds"]).backward()
+            opt.step()
+        del it
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(epochs):
+            ref_train_epoch(net, loader, opt, lam_mds=lam_mds)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / epochs
     return {"rows": int(X.shape[0]), "batch_size": batch_size, "s_per_epoch": dt, "cells_per_s": X.shape[0] / dt,
             "device": device, "threads": torch.get_num_threads() if dev.type == "cpu" else None, "epochs_timed": epochs}

@@ -561,4 +561,75 @@ int cells_query_list(const CellPlan &L, int64_t q0, int64_t nq, int64_t nq_pad, 
   return VVB_OK;
 }
 
+
+// ------------------------------------------------------------------ longest-first order of the query blocks
+// A query block's sweep is roughly as long as its own neighbourhood: the tiles of the cells its bound cannot
+// separate from it (bound <= 0).  Blocks are launched in decreasing order of that estimate, so the long ones start
+// first and the short ones fill the tail of the launch (a few hundred blocks of uneven length over 148 SMs otherwise
+// end with SMs idling behind the longest block: the multi-GPU shards are that small).
+constexpr int CTA_BUCKETS = 1024;
+
+// one warp per block of `rows_per_block` query-list entries: estimate -> bucket histogram
+__global__ void __launch_bounds__(256) cta_estimate_kernel(const int *__restrict__ qlist, int64_t nq, int rows_per_block,
+                                                          int n_blocks, const int *__restrict__ cell_of,
+                                                          const int *__restrict__ off, const float *__restrict__ lb, int P,
+                                                          int *__restrict__ est, int *__restrict__ hist) {
+  const int lane = threadIdx.x & 31;
+  const int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (blk >= n_blocks) return;
+  const int64_t first = static_cast<int64_t>(blk) * rows_per_block;
+  const int64_t last = min(first + rows_per_block, nq) - 1;
+  const int a0 = cell_of[qlist[first]], a1 = cell_of[qlist[last]];  // the list is sorted by cell
+  int tiles = 0;
+  for (int b = lane; b < P; b += 32) {
+    float v = __int_as_float(0x7f800000);
+    for (int a = a0; a <= a1; ++a) v = fminf(v, __ldg(lb + static_cast<size_t>(a) * P + b));
+    if (v <= 0.0f) tiles += (off[b + 1] - off[b]) / CELL_GROUP;
+  }
+  tiles = __reduce_add_sync(FULL, tiles);
+  if (lane == 0) {
+    const int total = off[P] / CELL_GROUP;
+    const int bucket = min(CTA_BUCKETS - 1, static_cast<int>(static_cast<int64_t>(tiles) * CTA_BUCKETS / max(1, total)));
+    est[blk] = bucket;
+    atomicAdd(hist + bucket, 1);
+  }
+}
+// descending exclusive scan of the bucket histogram (largest estimates first)
+__global__ void __launch_bounds__(CTA_BUCKETS) cta_scan_kernel(const int *__restrict__ hist, int *__restrict__ cursor) {
+  __shared__ int sh[CTA_BUCKETS];
+  const int tid = threadIdx.x;
+  const int mine = hist[CTA_BUCKETS - 1 - tid];
+  sh[tid] = mine;
+  __syncthreads();
+  for (int o = 1; o < CTA_BUCKETS; o <<= 1) {
+    const int v = (tid >= o) ? sh[tid - o] : 0;
+    __syncthreads();
+    sh[tid] += v;
+    __syncthreads();
+  }
+  cursor[CTA_BUCKETS - 1 - tid] = sh[tid] - mine;
+}
+__global__ void __launch_bounds__(256) cta_scatter_kernel(const int *__restrict__ est, int n_blocks, int *__restrict__ cursor,
+                                                         int *__restrict__ order) {
+  const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk < n_blocks) order[atomicAdd(cursor + est[blk], 1)] = blk;
+}
+
+size_t cells_cta_order_scratch_ints(int64_t n_blocks) { return static_cast<size_t>(n_blocks) + 2 * CTA_BUCKETS; }
+
+// order[i] = the query block launched i-th; scratch: cells_cta_order_scratch_ints(n_blocks) ints
+int cells_cta_order(const CellPlan &L, const int *qlist, int64_t nq, int rows_per_block, int n_blocks, int *scratch,
+                    int *order, cudaStream_t st) {
+  int *est = scratch, *hist = scratch + n_blocks, *cursor = hist + CTA_BUCKETS;
+  VVB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * CTA_BUCKETS, st));
+  cta_estimate_kernel<<<(n_blocks + 7) / 8, 256, 0, st>>>(qlist, nq, rows_per_block, n_blocks, L.cell_of, L.off, L.lb, L.P,
+                                                         est, hist);
+  VVB_CHECK_LAUNCH();
+  cta_scan_kernel<<<1, CTA_BUCKETS, 0, st>>>(hist, cursor);
+  VVB_CHECK_LAUNCH();
+  cta_scatter_kernel<<<(n_blocks + 255) / 256, 256, 0, st>>>(est, n_blocks, cursor, order);
+  VVB_CHECK_LAUNCH();
+  return VVB_OK;
+}
+
 }  // namespace vvb

@@ -56,4 +56,9 @@ int cells_select_dims(const float *x_dev, int64_t n, int d, const float *mu_dev,
 int cells_query_list(const CellPlan &plan, int64_t q0, int64_t nq, int64_t nq_pad, int *qlist, const int64_t *row_list,
                      cudaStream_t st);
 
+// launch order of the query blocks, longest estimated sweep first (knn_cells.cu)
+size_t cells_cta_order_scratch_ints(int64_t n_blocks);
+int cells_cta_order(const CellPlan &plan, const int *qlist, int64_t nq, int rows_per_block, int n_blocks, int *scratch,
+                    int *order, cudaStream_t st);
+
 }  // namespace vvb

@@ -87,13 +87,15 @@ constexpr int TC_PRE_MAX_KA = 2;         // ... only where the epilogue, not the
 constexpr int TC_SEQ_END = -1;           // tile_seq markers
 constexpr int TC_SEQ_PRE_END = -2;
 // Screening-error margin relative to (|x^| + Ymax)^2.  Model: every K=16 tcgen05.mma step
-// commits at most 2^-22 of the accumulator's magnitude bound (|x^| + Ymax)^2 -- 3 * 4 * ka steps per key -- and the
+// commits at most 2^-21 of the accumulator's magnitude bound (|x^| + Ymax)^2 -- 3 * 4 * ka steps per key -- and the
 // operand representation (centring, hi/lo split, dropped lo.lo term, FP32 norms) at most 2^-18 in total:
-//     eps_rel(ka) = 2^-18 + 3 ka 2^-20         ka = 1: 2^-17.2,   ka = 32 (d = 2000): 2^-13.4
-// Measured (tests/test_gpu_parity.py::test_screening_error_is_far_below_the_certificate_margin, d = 50 / 500 /
-// 2000): at least 8x below at every width.
+//     eps_rel(ka) = 2^-18 + 6 ka 2^-20         ka = 1: 2^-16.7,   ka = 8: 2^-14.3,   ka = 32 (d = 2000): 2^-12.4
+// The tensor cores' internal rounding is undocumented, so the model is pinned by measurement
+// (tests/test_gpu_configs.py::test_screening_error_stays_8x_below_the_margin_at_every_width): on B200 the error
+// against FP64 is 2^-21.5 at d = 50, 2^-18.2 at d = 500, 2^-16.2 at d = 2000 -- linear in ka (truncation adds up,
+// about 2^-24.8 per step), 14x to 28x below the margin.
 __host__ __device__ constexpr float tc_eps_rel(int ka) {
-  return 1.0f / 262144.0f + 3.0f * static_cast<float>(ka) / 1048576.0f;
+  return 1.0f / 262144.0f + 6.0f * static_cast<float>(ka) / 1048576.0f;
 }
 // Rounding of the contract's own FP32 chain for a REJECTED row (d subtractions squared + d fmaf roundings, first
 // order (d + 2) 2^-24 of the distance): doubled for the second-order terms.
@@ -482,6 +484,7 @@ struct TcParams {
   int d, k1;         // k1 = k + 1 (self included)
   float gamma;       // tc_gamma(d)
   const uint32_t *op_a;  // query operand rows as 32-bit words (64 per row), resident variant only
+  const int *cta_order;  // (gridDim.x) query block served by every CTA, longest estimated sweep first; or nullptr
   const int *qlist;      // (nq_pad) original row of every query-list entry, -1 = padding
   const int *cell_of;    // (n) cell of every original row
   const int *cell_off;   // (P + 1) first permuted database row of every cell (multiples of TC_N)
@@ -551,9 +554,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t q_base = static_cast<int64_t>(blockIdx.x) * TC_M;  // first query-list entry of this CTA
+  const int q_block = p.cta_order ? p.cta_order[blockIdx.x] : static_cast<int>(blockIdx.x);
+  const int64_t q_base = static_cast<int64_t>(q_block) * TC_M;  // first query-list entry of this CTA
   auto stamp = [&](int i) {
-    if (DBG && p.times && warp == 4 && lane == 0) p.times[blockIdx.x * 8 + i] = clock64();
+    if (DBG && p.times && warp == 4 && lane == 0) p.times[q_block * 8 + i] = clock64();
   };
   stamp(0);
 
@@ -1310,6 +1314,8 @@ struct TcLayout {
   float *cand_thr;
   int *fb_count;
   int64_t *fb_rows;
+  int *cta_order;   // (chunk / TC_M) launch order of the query blocks
+  int *cta_scratch;
   float *fb_thr;    // (chunk) refine threshold of the rows the certificate rejected, indexed by row - q0
   void *brute_ws;
   size_t brute_ws_bytes;
@@ -1345,6 +1351,8 @@ static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
   L.fb_count = cv.take<int>(1);
   L.fb_rows = cv.take<int64_t>(static_cast<size_t>(L.chunk_pad));
   L.fb_thr = cv.take<float>(static_cast<size_t>(L.chunk_pad));
+  L.cta_order = cv.take<int>(static_cast<size_t>(L.chunk_pad / TC_M));
+  L.cta_scratch = cv.take<int>(cells_cta_order_scratch_ints(L.chunk_pad / TC_M));
   L.cand = cv.take<uint2>(static_cast<size_t>(L.chunk_pad) * 2 * TC_CAP);  // two lists per row (one per column half)
   // the fallback's candidate lists reuse the screening lists (dead after the re-rank)
   L.brute_ws = L.cand;
@@ -1575,6 +1583,21 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   p.eps_rel = tc_eps_rel(L.ka);
   p.fixed_thr = nullptr;
   p.fixed_q0 = q0;
+  p.cta_order = nullptr;
+  {
+    // longest-first launch order: pays when the launch is only a few waves long (the shards of a multi-GPU build).
+    // In a long launch it costs more than the tail it removes: blocks that are neighbours in the cell order sweep
+    // the same database tiles at the same time, and the reordering takes that L2 locality away (1M rows, one
+    // GPU, 26 waves: 21.8 -> 23.3 ms).  VVB_TC_LPT=0/1 forces it.
+    const char *lpt = getenv("VVB_TC_LPT");
+    const int n_blocks = static_cast<int>(nq_pad / TC_M);
+    const bool want = lpt ? atoi(lpt) != 0 : (L.cells.P > 1 && n_blocks > sm_count() && n_blocks <= 8 * sm_count());
+    if (want) {
+      rc = cells_cta_order(L.cells, L.qlist, nq, TC_M, n_blocks, L.cta_scratch, L.cta_order, st);
+      if (rc) return rc;
+      p.cta_order = L.cta_order;
+    }
+  }
   p.x = S->x;
   p.perm = L.cells.perm;
   p.d = S->d;
@@ -1689,6 +1712,7 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     pr.fixed_q0 = q0;
     pr.debug_mode = 0;
     pr.times = nullptr;
+    pr.cta_order = nullptr;
     launch_screen(pr, static_cast<unsigned>(nr_pad / TC_M));
     VVB_CHECK_LAUNCH();
     launch_rerank(nr, TC_REFINE_CAP / 32, 1);

@@ -15,8 +15,8 @@
 //     invalidation per poll -- and the warp executes ONE fence.acq_rel.gpu once all its
 //     polls have succeeded, then a warp barrier, before any lane reads the published rows
 //     (with ld.global.cg: L2 is the point of coherence).
-//   * every neighbour row is prefetched into L2 BEFORE the polling starts, so the DRAM
-//     latency of the gather overlaps the wait instead of following it.
+//   * optionally (VVB_SMOOTH_PREFETCH=1) every neighbour row is prefetched into L2 before the
+//     polling starts; measured slower on B200 (the sweep is issue-bound), so it is off by default.
 // Arithmetic per element matches NumPy's: sequential sum over the k gathered rows in
 // neighbour order (starting from the first row, not from zero), true division by k,
 // then r + (target - r) * coef as three separately rounded operations (no FMA).
@@ -197,10 +197,11 @@ static int launch_rows(const T *src, T *dst, int64_t n, int d, const int64_t *id
                        int mode, const SmoothWs &w, int epoch, unsigned long long *ticket, int64_t row_lo,
                        int64_t row_hi, cudaStream_t st) {
   int blocks_per_sm = 0;
-  // L2 prefetch of the neighbour rows: rows of at most 512 bytes (wider rows would flood the prefetch queue);
-  // VVB_SMOOTH_PREFETCH=0 switches it off
+  // L2 prefetch of the neighbour rows ahead of the polling (rows of at most 512 bytes): opt-in, VVB_SMOOTH_PREFETCH=1.
+  // Measured on B200, 1M x 50, k=50: 3.3 ms with it, 2.96 ms without -- the sweep is bound by instruction issue
+  // (ncu: 61 % issue-active), and three more instructions per neighbour cost more than the latency they hide.
   const char *pfe = getenv("VVB_SMOOTH_PREFETCH");
-  const bool pf = static_cast<size_t>(d) * sizeof(T) <= 512 && !(pfe && atoi(pfe) == 0);
+  const bool pf = static_cast<size_t>(d) * sizeof(T) <= 512 && pfe && atoi(pfe) == 1;
   auto kern_gs = pf ? smooth_sweep_kernel<T, DPL, KPL, true, true> : smooth_sweep_kernel<T, DPL, KPL, true, false>;
   auto kern_ja = pf ? smooth_sweep_kernel<T, DPL, KPL, false, true> : smooth_sweep_kernel<T, DPL, KPL, false, false>;
   VVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, mode == VVB_SMOOTH_JACOBI ? kern_ja : kern_gs,
