@@ -48,6 +48,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -97,9 +98,13 @@ constexpr int TC_SEQ_PRE_END = -2;
 __host__ __device__ constexpr float tc_eps_rel(int ka) {
   return 1.0f / 262144.0f + 6.0f * static_cast<float>(ka) / 1048576.0f;
 }
+// First tier of the K-loop variant: the key drops 2 (xh.yl + xl.yh + xl.yl); |xl| <= 2^-11 |x^| row-wise, so the
+// dropped terms are at most 2 (2 * 2^-11 + 2^-22) |x^||y^| <= 1.001 * 2^-11 (|x^| + Ymax)^2 (|x||y| <= (|x| + |y|)^2 / 4).
+__host__ __device__ constexpr float tc_eps_single(int ka) { return 1.001f / 2048.0f + tc_eps_rel(ka); }
 // Rounding of the contract's own FP32 chain for a REJECTED row (d subtractions squared + d fmaf roundings, first
 // order (d + 2) 2^-24 of the distance): doubled for the second-order terms.
 static inline float tc_gamma(int d) { return 2.0f * static_cast<float>(d + 3) / 16777216.0f; }
+constexpr int TC_SINGLE_MIN_KA = 4;   // rows of at least 190 columns: the sweep is bound by the MMAs, not by the epilogue
 constexpr int TC_REFINE_CAP = 2 * TC_CAP;  // refine pass: candidates a row may collect below its fixed threshold
 
 constexpr size_t TC_SMEM_B = TC_STAGES * 2 * TC_ATOM_BYTES;           // [stage][atom]
@@ -474,7 +479,10 @@ struct TcParams {
   int debug_mode;   // profiling only (env VVB_TC_DEBUG): 1 = drain TMEM but skip the screening,
                     // 2 = screening minima only, no admissions, 3 = no TMEM drain at all.  Results are garbage.
   int n_cells;      // P
-  float eps_rel;    // tc_eps_rel(ka): screening-error margin relative to (|x^| + Ymax)^2
+  float eps_rel;    // screening-error margin relative to (|x^| + Ymax)^2: tc_eps_rel(ka), or tc_eps_single(ka)
+  int single;       // K-loop variant, first tier: ONE product (xh . yh) instead of three -- a third of the MMAs and half
+                    // the operand traffic for a key that is good to 2^-11 (|x^| + Ymax)^2; rows whose certificate
+                    // fails at that margin are re-swept at full precision by the refine pass
   // Refine instantiation only: the threshold of query-list entry t starts at fixed_thr[qlist[t] - fixed_q0]; no
   // pre-pass; a list that fills up is reduced to its k1 best entries by the exact key (tc_refine_compact).
   const float *fixed_thr;
@@ -632,7 +640,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       // a marker: a stage carrying no data, flagged in the tile sequence
       auto issue_marker = [&](int marker) {
         const int u = KLOOP ? it : t;
-        const int ns = KLOOP ? TC_KSTAGES : TC_STAGES;
+        const int ns = KLOOP ? (p.single ? 2 * TC_KSTAGES : TC_KSTAGES) : TC_STAGES;
         const int s = u % ns;
         const uint32_t ph = (u / ns) & 1;
         mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
@@ -680,21 +688,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
             for (int atom = 0; atom < 2; ++atom)
               tma_load_2d(smem_b + (s * 2 + atom) * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, atom * 64, row_b);
           } else {
+            // first tier (p.single): a stage holds [A.hi mb0][A.hi mb1][B.hi] (48 KB, four stages);
+            // full precision: [A.hi mb0][A.lo mb0][A.hi mb1][A.lo mb1][B.hi][B.lo] (96 KB, two stages)
+            const int kst = p.single ? 2 * TC_KSTAGES : TC_KSTAGES;
+            const int stage_atoms = p.single ? 3 : 6;
             for (int a = 0; a < p.ka; ++a, ++it) {
-              const int s = it % TC_KSTAGES;
-              const uint32_t ph = (it / TC_KSTAGES) & 1;
-              const uint32_t st = smem_k + s * 6 * TC_ATOM_BYTES;
+              const int s = it % kst;
+              const uint32_t ph = (it / kst) & 1;
+              const uint32_t st = smem_k + s * stage_atoms * TC_ATOM_BYTES;
               const int c_hi = a * 64, c_lo = (p.ka + a) * 64;
               mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
               if (a == 0) tile_seq[t % TC_RING] = row_b;
-              mbar_expect_tx(bar_b_full + 8 * s, 6 * TC_ATOM_BYTES);
-              // stage layout: [A.hi mb0][A.lo mb0][A.hi mb1][A.lo mb1][B.hi][B.lo]
-              tma_load_2d(st + 0 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_hi, static_cast<int>(q_base));
-              tma_load_2d(st + 1 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_lo, static_cast<int>(q_base));
-              tma_load_2d(st + 2 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_hi, static_cast<int>(q_base + 128));
-              tma_load_2d(st + 3 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_lo, static_cast<int>(q_base + 128));
-              tma_load_2d(st + 4 * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, c_hi, row_b);
-              tma_load_2d(st + 5 * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, c_lo, row_b);
+              mbar_expect_tx(bar_b_full + 8 * s, stage_atoms * TC_ATOM_BYTES);
+              if (p.single) {
+                tma_load_2d(st + 0 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_hi, static_cast<int>(q_base));
+                tma_load_2d(st + 1 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_hi, static_cast<int>(q_base + 128));
+                tma_load_2d(st + 2 * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, c_hi, row_b);
+              } else {
+                tma_load_2d(st + 0 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_hi, static_cast<int>(q_base));
+                tma_load_2d(st + 1 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_lo, static_cast<int>(q_base));
+                tma_load_2d(st + 2 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_hi, static_cast<int>(q_base + 128));
+                tma_load_2d(st + 3 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, c_lo, static_cast<int>(q_base + 128));
+                tma_load_2d(st + 4 * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, c_hi, row_b);
+                tma_load_2d(st + 5 * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, c_lo, row_b);
+              }
             }
           }
         }
@@ -720,8 +737,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       uint32_t use_par = 0;  // parity of (it / NSLOT)
       int it = 0;            // K-loop variant: stage uses
       for (int t = 0;; ++t) {
-        const int s0 = KLOOP ? it % TC_KSTAGES : t % TC_STAGES;
-        const uint32_t ph0 = KLOOP ? (it / TC_KSTAGES) & 1 : (t / TC_STAGES) & 1;
+        const int kst = p.single ? 2 * TC_KSTAGES : TC_KSTAGES;  // K-loop variant: stages in the ring
+        const int s0 = KLOOP ? it % kst : t % TC_STAGES;
+        const uint32_t ph0 = KLOOP ? (it / kst) & 1 : (t / TC_STAGES) & 1;
         mbar_wait(bar_b_full + 8 * s0, ph0);
         const int marker = tile_seq[t % TC_RING];
         if (marker < 0) {
@@ -770,27 +788,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
           // slots of this tile: slot (mb 0) and slot + 1 (mb 1); NSLOT = 4 keeps the pair aligned
           mbar_wait(bar_acc_empty + 8 * slot, use_par ^ 1);
           mbar_wait(bar_acc_empty + 8 * (slot + 1), use_par ^ 1);
+          const int stage_atoms = p.single ? 3 : 6;
           for (int a = 0; a < p.ka; ++a, ++it) {
-            const int s = it % TC_KSTAGES;
-            const uint32_t ph = (it / TC_KSTAGES) & 1;
+            const int s = it % kst;
+            const uint32_t ph = (it / kst) & 1;
             if (a > 0) mbar_wait(bar_b_full + 8 * s, ph);
             tc_fence_after();
-            const uint64_t st = desc_b0 + static_cast<uint64_t>(s * (6 * TC_ATOM_BYTES >> 4));
-            const uint64_t b_hi = st + 4 * (TC_ATOM_BYTES >> 4);
-            const uint64_t b_lo = st + 5 * (TC_ATOM_BYTES >> 4);
+            const uint64_t st = desc_b0 + static_cast<uint64_t>(s * (stage_atoms * TC_ATOM_BYTES >> 4));
+            if (p.single) {
+              const uint64_t b_hi = st + 2 * (TC_ATOM_BYTES >> 4);
 #pragma unroll
-            for (int mb = 0; mb < 2; ++mb) {
-              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((slot + mb) * TC_N);
-              const uint64_t a_hi = st + (mb * 2 + 0) * (TC_ATOM_BYTES >> 4);
-              const uint64_t a_lo = st + (mb * 2 + 1) * (TC_ATOM_BYTES >> 4);
-              // zero-padded columns contribute exactly 0, so every atom runs its 4 k-steps
+              for (int mb = 0; mb < 2; ++mb) {
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((slot + mb) * TC_N);
+                const uint64_t a_hi = st + mb * (TC_ATOM_BYTES >> 4);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                tc_mma_f16(d_tmem, a_hi + 2 * ks, b_hi + 2 * ks, idesc, (a > 0 || ks > 0) ? 1u : 0u);
+                for (int ks = 0; ks < 4; ++ks)
+                  tc_mma_f16(d_tmem, a_hi + 2 * ks, b_hi + 2 * ks, idesc, (a > 0 || ks > 0) ? 1u : 0u);
+              }
+            } else {
+              const uint64_t b_hi = st + 4 * (TC_ATOM_BYTES >> 4);
+              const uint64_t b_lo = st + 5 * (TC_ATOM_BYTES >> 4);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+              for (int mb = 0; mb < 2; ++mb) {
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((slot + mb) * TC_N);
+                const uint64_t a_hi = st + (mb * 2 + 0) * (TC_ATOM_BYTES >> 4);
+                const uint64_t a_lo = st + (mb * 2 + 1) * (TC_ATOM_BYTES >> 4);
+                // zero-padded columns contribute exactly 0, so every atom runs its 4 k-steps
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+                for (int ks = 0; ks < 4; ++ks)
+                  tc_mma_f16(d_tmem, a_hi + 2 * ks, b_hi + 2 * ks, idesc, (a > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+              }
             }
             tc_commit(bar_b_empty + 8 * s);
           }
@@ -1099,7 +1130,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
     const float *__restrict__ cand_thr,
     const float *__restrict__ xnorm, const PrepScalars *__restrict__ scalars, int64_t *__restrict__ out_idx,
     float *__restrict__ out_dist, int *__restrict__ fb_count, int64_t *__restrict__ fb_rows, float eps_rel,
-    float gamma, float *__restrict__ fb_thr, int refine) {
+    float eps_refine_rel, float gamma, float *__restrict__ fb_thr, int refine) {
   constexpr bool WIDE = MODE == 1;
   constexpr bool ROWS = MODE == 2;
   __shared__ float stage[WIDE ? 8 : 1][WIDE ? 32 : 1][WIDE ? 33 : 1];
@@ -1244,9 +1275,10 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
     if (!refine) {
       // refine threshold (key space): every row j whose chain distance is <= D_k has
       //   key_j <= s^2 D_k / (1 - gamma/2) - |x^|^2 + eps  <  T;   no upper bound on D_k known -> +inf
+      // (eps of the REFINE sweep's keys: full precision, whatever tier rejected the row)
       float T = inf;
       if (cnt > pos_k) {
-        T = fmaf(dk * s * s, 1.0f + gamma, eps * 1.0625f - xn);
+        T = fmaf(dk * s * s, 1.0f + gamma, eps_refine_rel * r * r * 1.0625f - xn);
         T += fabsf(T) * 1e-6f + 1e-30f;
       }
       fb_thr[g - q0] = T;
@@ -1386,6 +1418,9 @@ struct TcSession {
   const float *x;
   int64_t n;
   int d, k, keep;
+  bool single;  // first tier with one product per key (K-loop variant, ka >= TC_SINGLE_MIN_KA)
+  unsigned long long tiles_seen;  // tiles_done when it was last read, and the query blocks launched since:
+  double blocks_since;            // what a block of this data sweeps, for the refine-or-brute-force estimate
   TcLayout L;
   CUtensorMap map_a, map_b;
 };
@@ -1422,7 +1457,24 @@ static int tc_session_init(TcSession *S, const float *x_dev, int64_t n, int d, i
   S->d = d;
   S->k = k;
   S->keep = tc_candidates(k);
+  S->tiles_seen = 0;
+  S->blocks_since = 0;
   S->L = tc_layout(workspace, n, d, k, chunk_rows);
+  {
+    // First tier with a single product: on by default where the MMAs bound the sweep (VVB_TC_SINGLE=0/1 forces).
+    // Its margin is 2^-11 of (|x^| + Ymax)^2, so it keeps more candidates per row: a larger m-th key is what lets
+    // the certificate pass at that margin, and the re-rank of a wide row is cheap next to its sweep.
+    const char *se = getenv("VVB_TC_SINGLE");
+    S->single = S->L.ka > 1 && (se ? atoi(se) != 0 : S->L.ka >= TC_SINGLE_MIN_KA);
+    if (S->single || S->L.ka >= TC_SINGLE_MIN_KA) {
+      // wide rows: the margin grows with the width (and the first tier's is 2^-11), so a row needs a larger gap
+      // between its k-th and m-th candidate to be certified (measured, 2M x 2000, k=50: m = 60 certifies 57 % of the
+      // rows, m = 128 99.9 %)
+      int m = 2 * k + 28;
+      if (m > TC_CAP - 64) m = TC_CAP - 64;
+      if (m > S->keep) S->keep = m;
+    }
+  }
   VVB_REQUIRE(workspace_bytes >= S->L.total, "tensor kNN: workspace too small (%zu < %zu)", workspace_bytes,
               S->L.total);
   VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1580,7 +1632,8 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     p.debug_mode = dbg ? atoi(dbg) : 0;
   }
   p.n_cells = L.cells.P;
-  p.eps_rel = tc_eps_rel(L.ka);
+  p.single = S->single ? 1 : 0;
+  p.eps_rel = S->single ? tc_eps_single(L.ka) : tc_eps_rel(L.ka);
   p.fixed_thr = nullptr;
   p.fixed_q0 = q0;
   p.cta_order = nullptr;
@@ -1640,6 +1693,7 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   };
   launch_screen(p, sgrid);
   VVB_CHECK_LAUNCH();
+  S->blocks_since += sgrid;
   if (want_times) {  // profiling only: mean duration of the phases of a CTA, in SM clocks
     const size_t nc = static_cast<size_t>(nq_pad / TC_M);
     std::vector<long long> h(nc * 8);
@@ -1666,7 +1720,7 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   auto launch_rerank = [&](int64_t rows, int e_need, int refine) {
     const unsigned rr_grid = static_cast<unsigned>(rr_rows ? (rows + 3) / 4 : (rows + 7) / 8);
 #define VVB_RR_ARGS S->x, S->n, S->d, q0, rows, S->k, L.qlist, L.cells.perm, L.cand, L.cand_cnt, L.cand_thr, L.xnorm, \
-                    L.scalars, out_idx, out_dist, L.fb_count, L.fb_rows, p.eps_rel, gamma, L.fb_thr, refine
+                    L.scalars, out_idx, out_dist, L.fb_count, L.fb_rows, p.eps_rel, tc_eps_rel(L.ka), gamma, L.fb_thr, refine
 #define VVB_RR(EE)                                                                            \
   do {                                                                                        \
     if (rr_rows)                                                                              \
@@ -1694,7 +1748,24 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   VVB_CUDA(cudaStreamSynchronize(st));
   int refined = 0;
   const char *rfe = getenv("VVB_TC_REFINE");
-  if (fb > 0 && !(rfe && atoi(rfe) == 0)) {
+  bool do_refine = fb > 0 && !(rfe && atoi(rfe) == 0);
+  if (do_refine && fb <= knn_brute_few_max_rows() && !(rfe && atoi(rfe) == 2)) {
+    // A handful of rows: a refine block is MMA-bound and sweeps its neighbourhood alone on one SM, however few rows it
+    // holds, while the few-row brute-force kernel slices the database over the whole GPU.  Estimate both (the main
+    // sweep just measured how many tiles a block of this data sweeps) and take the cheaper.  VVB_TC_REFINE=2 forces
+    // the refine pass.
+    unsigned long long done = 0;
+    VVB_CUDA(cudaMemcpy(&done, L.tiles_done, sizeof(done), cudaMemcpyDeviceToHost));
+    const double tiles_per_block = static_cast<double>(done - S->tiles_seen) / std::max<double>(1.0, S->blocks_since);
+    S->tiles_seen = done;
+    S->blocks_since = 0;
+    const double clocks_per_tile = L.ka > 1 ? 1600.0 * L.ka : 3000.0;
+    const double waves = std::ceil(std::ceil(fb / static_cast<double>(TC_M)) / sm_count());
+    const double t_refine = waves * tiles_per_block * clocks_per_tile / 1.9e9;
+    const double t_brute = static_cast<double>(fb) * static_cast<double>(S->n) * S->d / 8.0e12;
+    if (t_brute < t_refine) do_refine = false;
+  }
+  if (do_refine) {
     // Refine pass (tie-aware): the failed rows become a query list of their own, swept by the same kernel with every
     // row's threshold fixed at the value the re-rank kernel derived from its k-th candidate (fb_thr); the lists,
     // the query operand and the fallback list are reused (the main pass is complete: same stream).
@@ -1710,6 +1781,10 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     pr.nq = nr;
     pr.fixed_thr = L.fb_thr;
     pr.fixed_q0 = q0;
+    pr.single = 0;  // the refine sweep always runs at full precision
+    pr.eps_rel = tc_eps_rel(L.ka);
+    // a first tier that rejects most rows costs more than it saves: the remaining chunks skip it
+    if (S->single && static_cast<int64_t>(fb) * 2 > nq) S->single = false;
     pr.debug_mode = 0;
     pr.times = nullptr;
     pr.cta_order = nullptr;
