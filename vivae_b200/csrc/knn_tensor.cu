@@ -487,6 +487,12 @@ struct TcParams {
   // pre-pass; a list that fills up is reduced to its k1 best entries by the exact key (tc_refine_compact).
   const float *fixed_thr;
   int64_t fixed_q0;
+  // A refine launch of only a few blocks is spread over the GPU by slicing the DATABASE: gridDim.y = slices, block
+  // (x, y) sweeps every slices-th tile of block x's order; the slices append to the SAME per-row lists through global
+  // counters slice_cnt[2 * t + half] (no compaction: a list that overflows sends its row to the brute-force kernel)
+  // and refine_concat_kernel joins the two halves afterwards.
+  int slices;
+  int *slice_cnt;
   const float *x;    // (n, d) the original rows
   const int *perm;   // permuted database row -> original row
   int d, k1;         // k1 = k + 1 (self included)
@@ -533,7 +539,13 @@ struct TcParams {
 // hold a key at or below it -- and a tight one, because the m nearest rows of a query are spread over
 // almost as many tiles.  The real sweep then starts at that threshold: ~100 insertions per row, rarely a
 // compaction.  Exactness never depends on it (a threshold is only ever an upper bound of the m-th key).
-template <bool KLOOP, bool DBG, bool REFINE>
+// WIDE (K-loop variant, first tier only): database tiles of 256 rows.  The K-loop re-streams the block's whole query
+// operand (d x 256 rows) for every database tile, and at d = 2000 that stream -- not the MMAs -- bounds the sweep
+// (148 blocks x 1 MB exceed L2, so it comes from DRAM); a 256-row tile halves it.  One M=128, N=256 MMA per M block
+// and k-step, accumulators = all 512 TMEM columns (columns [256 mb, 256 mb + 256)), no double buffering: a tile is
+// ka x 1024 MMA clocks, its read-out under 1000.  Stage = [A.hi mb0][A.hi mb1][B.hi rows 0..127][B.hi rows 128..255]
+// (64 KB, three stages).  The last tile of a cell may hold 128 rows only (bit 0 of its tile_seq entry).
+template <bool KLOOP, bool DBG, bool REFINE, bool WIDE = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
                                                                    const TcParams p) {
@@ -603,6 +615,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       float v = __int_as_float(0x7f800000);
       if (b < P)
         for (int a = a0; a <= a1; ++a) v = fminf(v, __ldg(p.cell_lb + static_cast<size_t>(a) * P + b));
+      // WIDE: cells that cannot be skipped anyway (bound <= 0) are swept in cell order by EVERY block, so that the
+      // blocks resident at the same time read the same database tiles and all but the first hit L2
+      if (WIDE && v <= 0.0f) v = 0.0f;
       order[b] = (static_cast<unsigned long long>(f2ord(v)) << 32) | static_cast<unsigned>(b);
     }
   }
@@ -637,10 +652,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       int t = 0;    // tile_seq entries issued (tiles and markers)
       int it = 0;   // K-loop variant: stage uses
       int swept = 0;
+      int tile_no = 0;  // sliced refine launch: position of the tile in the block's order
       // a marker: a stage carrying no data, flagged in the tile sequence
       auto issue_marker = [&](int marker) {
         const int u = KLOOP ? it : t;
-        const int ns = KLOOP ? (p.single ? 2 * TC_KSTAGES : TC_KSTAGES) : TC_STAGES;
+        const int ns = WIDE ? 3 : KLOOP ? (p.single ? 2 * TC_KSTAGES : TC_KSTAGES) : TC_STAGES;
         const int s = u % ns;
         const uint32_t ph = (u / ns) & 1;
         mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
@@ -677,8 +693,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
           if (bound * bound >= tmax + eps_max) break;  // ascending order: every later cell is at least as far
         }
         const int row_end = p.cell_off[b + 1];
+        if constexpr (WIDE) {
+          for (int row_b = p.cell_off[b]; row_b < row_end; row_b += 2 * TC_N, ++t) {
+            const bool half_tile = row_b + TC_N >= row_end;
+            pass_tiles += half_tile ? 1 : 2;
+            for (int a = 0; a < p.ka; ++a, ++it) {
+              const int s = it % 3;
+              const uint32_t ph = (it / 3) & 1;
+              const uint32_t st = smem_k + s * 4 * TC_ATOM_BYTES;
+              mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
+              if (a == 0) tile_seq[t % TC_RING] = row_b | (half_tile ? 1 : 0);
+              mbar_expect_tx(bar_b_full + 8 * s, (half_tile ? 3 : 4) * TC_ATOM_BYTES);
+              tma_load_2d(st + 0 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, a * 64, static_cast<int>(q_base));
+              tma_load_2d(st + 1 * TC_ATOM_BYTES, &map_a, bar_b_full + 8 * s, a * 64, static_cast<int>(q_base + 128));
+              tma_load_2d(st + 2 * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, a * 64, row_b);
+              if (!half_tile) tma_load_2d(st + 3 * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, a * 64, row_b + TC_N);
+            }
+          }
+        }
+        if constexpr (!WIDE)
         for (int row_b = p.cell_off[b]; row_b < row_end; row_b += TC_N, ++t, ++pass_tiles) {
           if (pass == 0 && pass_tiles >= pre_tiles) break;
+          if constexpr (REFINE) {
+            if (p.slices > 1 && (tile_no++ % p.slices) != static_cast<int>(blockIdx.y)) {  // another slice's tile
+              --t;
+              --pass_tiles;
+              continue;
+            }
+          }
           if constexpr (!KLOOP) {
             const int s = t % TC_STAGES;
             const uint32_t ph = (t / TC_STAGES) & 1;
@@ -736,6 +778,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       int slot = 0;
       uint32_t use_par = 0;  // parity of (it / NSLOT)
       int it = 0;            // K-loop variant: stage uses
+      if constexpr (WIDE) {
+        constexpr uint32_t idesc2 = make_idesc(2 * TC_N);
+        for (int t = 0;; ++t) {
+          const uint32_t tpar = static_cast<uint32_t>(t) & 1u;
+          mbar_wait(bar_b_full + 8 * (it % 3), (it / 3) & 1);
+          const int marker = tile_seq[t % TC_RING];
+          mbar_wait(bar_acc_empty + 0, tpar ^ 1);
+          mbar_wait(bar_acc_empty + 8, tpar ^ 1);
+          if (marker < 0) {  // end of the sweep: pass the marker on to both M blocks
+            mbar_arrive(bar_acc_full + 0);
+            mbar_arrive(bar_acc_full + 8);
+            break;
+          }
+          for (int a = 0; a < p.ka; ++a, ++it) {
+            const int s = it % 3;
+            if (a > 0) mbar_wait(bar_b_full + 8 * s, (it / 3) & 1);
+            tc_fence_after();
+            const uint64_t st = desc_b0 + static_cast<uint64_t>(s * (4 * TC_ATOM_BYTES >> 4));
+            const uint64_t b_hi = st + 2 * (TC_ATOM_BYTES >> 4);  // 256 rows: two atoms back to back
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(mb * 2 * TC_N);
+              const uint64_t a_hi = st + mb * (TC_ATOM_BYTES >> 4);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                tc_mma_f16(d_tmem, a_hi + 2 * ks, b_hi + 2 * ks, idesc2, (a > 0 || ks > 0) ? 1u : 0u);
+            }
+            tc_commit(bar_b_empty + 8 * s);
+          }
+          tc_commit(bar_acc_full + 0);
+          tc_commit(bar_acc_full + 8);
+        }
+      } else
       for (int t = 0;; ++t) {
         const int kst = p.single ? 2 * TC_KSTAGES : TC_KSTAGES;  // K-loop variant: stages in the ring
         const int s0 = KLOOP ? it % kst : t % TC_STAGES;
@@ -957,6 +1032,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
           if (__uint_as_float(r[c]) < cut) {
             if constexpr (REFINE) {
               if (dup_jmax != 0x7fffffff && p.perm[j0 + c] > dup_jmax) return;  // a later duplicate: cannot enter
+              if (p.slices > 1) {  // the list is shared with the other slices of this block
+                const int pos = atomicAdd(p.slice_cnt + t_row * 2 + half, 1);
+                if (pos < TC_CAP) cl[pos] = make_uint2(r[c], static_cast<uint32_t>(j0 + c));
+                return;
+              }
             }
             cl[cnt] = make_uint2(r[c], static_cast<uint32_t>(j0 + c));  // one 8-byte store
             ++cnt;
@@ -982,12 +1062,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       }
     };
 
+    if constexpr (WIDE) {
+      // one 256-column accumulator per M block and tile: this thread's 64 columns of each 128-row half in turn
+      for (int t = 0;; ++t) {
+        mbar_wait(bar_acc_full + 8 * mb, static_cast<uint32_t>(t) & 1u);
+        const int e = tile_seq[t % TC_RING];
+        if (e == TC_SEQ_END) break;
+        tc_fence_after();
+        const int jt = e & ~1;
+        const int nsub = (e & 1) ? 1 : 2;
+        uint32_t ra[32];
+        for (int sub = 0; sub < nsub; ++sub) {
+          const uint32_t t_acc = t_lane + static_cast<uint32_t>(mb * 2 * TC_N + sub * TC_N + half * 64);
+          tc_ld32_issue(t_acc, ra);
+          tc_ld32_wait(ra);
+          process(ra, jt + sub * TC_N + half * 64);
+          tc_ld32_issue(t_acc + 32, ra);
+          tc_ld32_wait(ra);
+          if (sub == nsub - 1) {  // accumulator drained: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * mb);
+          }
+          process(ra, jt + sub * TC_N + half * 64 + 32);
+        }
+      }
+    }
     int slot = mb % NSLOT;
     uint32_t use_par = 0;  // parity of (it / NSLOT), it = 2 t + mb
     bool in_pre = pre_pass;
     int n_pre = 0;  // tiles recorded by the pre-pass: half-tile minima at [2 n + half] of the row's first list buffer
     float *pre_buf = reinterpret_cast<float *>(p.cand + t_row * 2 * TC_CAP);
-    for (int t = 0;; ++t) {
+    for (int t = 0; !WIDE; ++t) {
       mbar_wait(bar_acc_full + 8 * slot, use_par);
       const int jt = tile_seq[t % TC_RING];  // first (permuted) database row of the tile, or a marker
       if (jt == TC_SEQ_END) break;
@@ -1063,11 +1169,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       }
     }
     // final: the second half's list is appended to the first, the best m are kept, count and threshold published
+    // (a sliced refine launch leaves that to refine_concat_kernel: the lists are complete only when every slice is)
     stamp(5);
     half_cnt[half * TC_M + prow] = cnt;
     half_tau[half * TC_M + prow] = tau;
     pair_sync();
-    for (int src = half * 16; src < half * 16 + 16; ++src) {
+    const bool sliced = REFINE && p.slices > 1;
+    for (int src = half * 16; src < half * 16 + 16 && !sliced; ++src) {
       const int64_t tt = __shfl_sync(FULL, t_row, src);
       if (tt >= p.nq) continue;  // warp-uniform
       const int pr = mb * 128 + quad * 32 + src;
@@ -1108,6 +1216,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// After a SLICED refine launch: one warp per query-list entry joins the row's two half lists (lengths in
+// slice_cnt) into one and publishes its length; a half that overflowed its TC_CAP entries marks the row (thr = -inf).
+__global__ void __launch_bounds__(256) refine_concat_kernel(uint2 *__restrict__ cand, const int *__restrict__ slice_cnt,
+                                                           int64_t nq, int *__restrict__ cand_cnt,
+                                                           float *__restrict__ cand_thr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (t >= nq) return;
+  const int ca = slice_cnt[2 * t], cb = slice_cnt[2 * t + 1];
+  const bool over = ca > TC_CAP || cb > TC_CAP;
+  uint2 *la = cand + t * 2 * TC_CAP, *lb = la + TC_CAP;
+  if (!over)
+    for (int i0 = 0; i0 < cb; i0 += 32) {  // (same in-place append as the screening kernel's final merge)
+      uint2 v = make_uint2(0u, 0u);
+      if (i0 + lane < cb) v = lb[i0 + lane];
+      __syncwarp();
+      if (i0 + lane < cb) la[ca + i0 + lane] = v;
+      __syncwarp();
+    }
+  if (lane == 0) {
+    cand_cnt[t] = over ? 0 : ca + cb;
+    cand_thr[t] = over ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
   }
 }
 
@@ -1265,7 +1398,8 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
   bool ok = cnt > pos_k;
   if (refine) {
     // the list holds every row that can be among the k nearest (everything below the row's refine threshold, minus
-    // entries beaten by k+1 others on the exact key): nothing to certify
+    // entries beaten by k+1 others on the exact key): nothing to certify -- unless a sliced launch overflowed it
+    ok = ok && thr > -inf;
   } else {
     if (ok && thr < inf) ok = (dk * s * s) < (thr + xn - eps) * (1.0f - gamma);
   }
@@ -1346,6 +1480,7 @@ struct TcLayout {
   float *cand_thr;
   int *fb_count;
   int64_t *fb_rows;
+  int *slice_cnt;   // (2 * chunk) list lengths of a sliced refine launch
   int *cta_order;   // (chunk / TC_M) launch order of the query blocks
   int *cta_scratch;
   float *fb_thr;    // (chunk) refine threshold of the rows the certificate rejected, indexed by row - q0
@@ -1383,6 +1518,7 @@ static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
   L.fb_count = cv.take<int>(1);
   L.fb_rows = cv.take<int64_t>(static_cast<size_t>(L.chunk_pad));
   L.fb_thr = cv.take<float>(static_cast<size_t>(L.chunk_pad));
+  L.slice_cnt = cv.take<int>(2 * static_cast<size_t>(L.chunk_pad));
   L.cta_order = cv.take<int>(static_cast<size_t>(L.chunk_pad / TC_M));
   L.cta_scratch = cv.take<int>(cells_cta_order_scratch_ints(L.chunk_pad / TC_M));
   L.cand = cv.take<uint2>(static_cast<size_t>(L.chunk_pad) * 2 * TC_CAP);  // two lists per row (one per column half)
@@ -1488,6 +1624,8 @@ static int tc_session_init(TcSession *S, const float *x_dev, int64_t n, int d, i
   VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(TC_SMEM_BYTES)));
   VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(TC_SMEM_BYTES_K)));
+  VVB_CUDA(cudaFuncSetAttribute(knn_screen_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(TC_SMEM_BYTES_K)));
   int rc = make_operand_map(&S->map_a, S->L.opA, S->L.chunk_pad, S->L.op_cols);
   if (rc) return rc;
@@ -1636,6 +1774,8 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   p.eps_rel = S->single ? tc_eps_single(L.ka) : tc_eps_rel(L.ka);
   p.fixed_thr = nullptr;
   p.fixed_q0 = q0;
+  p.slices = 1;
+  p.slice_cnt = L.slice_cnt;
   p.cta_order = nullptr;
   {
     // longest-first launch order: pays when the launch is only a few waves long (the shards of a multi-GPU build).
@@ -1676,12 +1816,16 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   p.cand_cnt = L.cand_cnt;
   p.cand_thr = L.cand_thr;
   const unsigned sgrid = static_cast<unsigned>(nq_pad / TC_M);
+  const char *wide_env = getenv("VVB_TC_WIDE");
+  const bool wide_ok = !(wide_env && atoi(wide_env) == 0);  // 256-row database tiles in the first tier (default on)
   auto launch_screen = [&](const TcParams &pp, unsigned grid) {
     const bool dbg = pp.debug_mode != 0 || pp.times != nullptr;
     if (pp.fixed_thr && L.ka == 1)
-      knn_screen_kernel<false, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, pp);
+      knn_screen_kernel<false, false, true><<<dim3(grid, pp.slices), TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, pp);
     else if (pp.fixed_thr)
-      knn_screen_kernel<true, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, pp);
+      knn_screen_kernel<true, false, true><<<dim3(grid, pp.slices), TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, pp);
+    else if (pp.single && !dbg && wide_ok)
+      knn_screen_kernel<true, false, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, pp);
     else if (L.ka == 1 && !dbg)
       knn_screen_kernel<false, false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, pp);
     else if (L.ka == 1)
@@ -1749,20 +1893,26 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   int refined = 0;
   const char *rfe = getenv("VVB_TC_REFINE");
   bool do_refine = fb > 0 && !(rfe && atoi(rfe) == 0);
+  // A refine launch of fewer blocks than SMs slices the database over the idle SMs (TcParams::slices).
+  const int refine_blocks = static_cast<int>((fb + TC_M - 1) / TC_M);
+  int slices = 1;
+  if (fb > 0 && 2 * refine_blocks <= sm_count()) slices = std::min(sm_count() / refine_blocks, 64);
+  if (const char *se = getenv("VVB_TC_REFINE_SLICES")) slices = std::max(1, std::min(atoi(se), 1024));
   if (do_refine && fb <= knn_brute_few_max_rows() && !(rfe && atoi(rfe) == 2)) {
-    // A handful of rows: a refine block is MMA-bound and sweeps its neighbourhood alone on one SM, however few rows it
-    // holds, while the few-row brute-force kernel slices the database over the whole GPU.  Estimate both (the main
-    // sweep just measured how many tiles a block of this data sweeps) and take the cheaper.  VVB_TC_REFINE=2 forces
-    // the refine pass.
+    // A handful of rows: the refine blocks sweep their neighbourhoods on the tensor cores (MMA-bound, however few rows
+    // a block holds), the few-row brute-force kernel streams the database once per row with FP32 FMAs.  Estimate
+    // both (the main sweep just measured how many tiles a block of this data sweeps) and take the cheaper.
+    // VVB_TC_REFINE=2 forces the refine pass.
     unsigned long long done = 0;
     VVB_CUDA(cudaMemcpy(&done, L.tiles_done, sizeof(done), cudaMemcpyDeviceToHost));
     const double tiles_per_block = static_cast<double>(done - S->tiles_seen) / std::max<double>(1.0, S->blocks_since);
     S->tiles_seen = done;
     S->blocks_since = 0;
     const double clocks_per_tile = L.ka > 1 ? 1600.0 * L.ka : 3000.0;
-    const double waves = std::ceil(std::ceil(fb / static_cast<double>(TC_M)) / sm_count());
-    const double t_refine = waves * tiles_per_block * clocks_per_tile / 1.9e9;
-    const double t_brute = static_cast<double>(fb) * static_cast<double>(S->n) * S->d / 8.0e12;
+    const double waves = std::ceil(static_cast<double>(refine_blocks) * slices / sm_count());
+    const double t_refine = waves * (tiles_per_block / slices) * clocks_per_tile / 1.9e9 + 30e-6;
+    const double work = static_cast<double>(fb) * static_cast<double>(S->n) * S->d;
+    const double t_brute = std::max(work / 8.0e12, work * 4.0 / 2.0e12);  // FMA rate; database bytes per row at ~2 TB/s
     if (t_brute < t_refine) do_refine = false;
   }
   if (do_refine) {
@@ -1788,8 +1938,15 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     pr.debug_mode = 0;
     pr.times = nullptr;
     pr.cta_order = nullptr;
+    pr.slices = slices;
+    if (slices > 1) VVB_CUDA(cudaMemsetAsync(L.slice_cnt, 0, 2 * static_cast<size_t>(nr_pad) * sizeof(int), st));
     launch_screen(pr, static_cast<unsigned>(nr_pad / TC_M));
     VVB_CHECK_LAUNCH();
+    if (slices > 1) {
+      refine_concat_kernel<<<static_cast<unsigned>((nr + 7) / 8), 256, 0, st>>>(L.cand, L.slice_cnt, nr, L.cand_cnt,
+                                                                               L.cand_thr);
+      VVB_CHECK_LAUNCH();
+    }
     launch_rerank(nr, TC_REFINE_CAP / 32, 1);
     VVB_CHECK_LAUNCH();
     VVB_CUDA(cudaMemcpyAsync(&fb, L.fb_count, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -98,17 +98,22 @@ __device__ __forceinline__ void quad_stats(const float *base, const int64_t (&r)
   }
 }
 
+// dist[p] and, for euclidean, rdist[p] = 1 / dist[p] (one MUFU.RSQ per pair instead of a square root and,
+// in the gradient, a division: the kernel is bound by instruction issue as much as by bandwidth)
 template <int METRIC>
-__device__ __forceinline__ void pair_dists(const QuadStats &s, float (&dist)[6]) {
+__device__ __forceinline__ void pair_dists(const QuadStats &s, float (&dist)[6], float (&rdist)[6]) {
   constexpr int pa[6] = {0, 1, 2, 0, 0, 1};
   constexpr int pb[6] = {1, 2, 3, 2, 3, 3};
 #pragma unroll
   for (int p = 0; p < 6; ++p) {
     if (METRIC == VVB_DIST_EUCLIDEAN) {
-      dist[p] = sqrtf(fmaxf(s.sq[p], 1e-9f));  // losses.py:154-159
+      const float c = fmaxf(s.sq[p], 1e-9f);  // losses.py:154-159: sqrt(max(sum, 1e-9))
+      rdist[p] = rsqrtf(c);
+      dist[p] = c * rdist[p];
     } else {
       const float ca = fmaxf(sqrtf(s.nrm[pa[p]]), 1e-8f), cb = fmaxf(sqrtf(s.nrm[pb[p]]), 1e-8f);
       dist[p] = 1.0f - s.dot[p] / (ca * cb);  // losses.py:176 (ATen clamps each norm at eps=1e-8)
+      rdist[p] = 0.0f;
     }
   }
 }
@@ -146,25 +151,27 @@ __global__ void __launch_bounds__(QT_THREADS) quartet_fwd_kernel(
     QuadStats sx, sz;
     quad_stats<MHD, VEC2>(x, r, D, sub, sx);
     quad_stats<MLD, false>(z, r, L, sub, sz);
-    float dx[6], dz[6];
-    pair_dists<MHD>(sx, dx);
-    pair_dists<MLD>(sz, dz);
+    float dx[6], dz[6], rdx[6], rdz[6];
+    pair_dists<MHD>(sx, dx, rdx);
+    pair_dists<MLD>(sz, dz, rdz);
     float X = 0.f, S = 0.f;
 #pragma unroll
     for (int p = 0; p < 6; ++p) X += dx[p], S += dz[p];
+    const float invX = 1.0f / X, invS = 1.0f / S;
     float e[6], cost = 0.f, er = 0.f;
 #pragma unroll
     for (int p = 0; p < 6; ++p) {
-      e[p] = dz[p] / S - dx[p] / X;
+      const float nz = dz[p] * invS;
+      e[p] = nz - dx[p] * invX;
       cost = fmaf(e[p], e[p], cost);
-      er = fmaf(e[p], dz[p] / S, er);
+      er = fmaf(e[p], nz, er);
     }
     if (valid && sub == 0) cost_sum += cost;
 
     if (grad_unit != nullptr && valid) {
       float w[6];
 #pragma unroll
-      for (int p = 0; p < 6; ++p) w[p] = (2.0f / S) * (e[p] - er) * grad_scale;
+      for (int p = 0; p < 6; ++p) w[p] = 2.0f * invS * (e[p] - er) * grad_scale;
       for (int c = sub; c < L; c += QT_GROUP) {
         float zv[4], g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(QT_THREADS) quartet_fwd_kernel(
           if (MLD == VVB_DIST_EUCLIDEAN) {
             // d sqrt(max(s,1e-9))/dz_a = (z_a - z_b)/dist when s > 1e-9, else 0
             if (sz.sq[p] > 1e-9f) {
-              const float t = w[p] * (zv[a] - zv[b]) / dz[p];
+              const float t = w[p] * (zv[a] - zv[b]) * rdz[p];
               g[a] += t;
               g[b] -= t;
             }
@@ -264,8 +271,27 @@ int launch_quartet_fwd(const float *x, const float *z, int64_t B, int D, int L, 
   unsigned int *counter = static_cast<unsigned int *>(workspace);
   float *partials = reinterpret_cast<float *>(static_cast<char *>(workspace) + 256);
   VVB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+  // grid = the CTAs that are resident at once (a grid-stride loop does the rest: no partial last wave)
+  static int occ_cache[2][2][2] = {};  // per instantiation; 0 = not asked yet
+  const int vi = ((D % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 8 == 0)) ? 1 : 0;
+  int occ = occ_cache[mhd][mld][vi];
+  if (occ == 0) {
+    cudaError_t oe = cudaSuccess;
+#define VVB_QT_OCC(A, Bm, V) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quartet_fwd_kernel<A, Bm, V>, QT_THREADS, 0)
+    const bool v2 = (D % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 8 == 0);
+    if (mhd == 0 && mld == 0) { if (v2) VVB_QT_OCC(0, 0, true); else VVB_QT_OCC(0, 0, false); }
+    else if (mhd == 0) { if (v2) VVB_QT_OCC(0, 1, true); else VVB_QT_OCC(0, 1, false); }
+    else if (mld == 0) { if (v2) VVB_QT_OCC(1, 0, true); else VVB_QT_OCC(1, 0, false); }
+    else { if (v2) VVB_QT_OCC(1, 1, true); else VVB_QT_OCC(1, 1, false); }
+#undef VVB_QT_OCC
+    if (oe != cudaSuccess || occ < 1) {
+      cudaGetLastError();
+      occ = 2;
+    }
+    occ_cache[mhd][mld][vi] = occ;
+  }
   int64_t grid = (nq + QT_PER_CTA - 1) / QT_PER_CTA;
-  const int64_t resident = static_cast<int64_t>(sm_count()) * 8;
+  const int64_t resident = static_cast<int64_t>(sm_count()) * occ;
   if (grid > resident) grid = resident;
   const bool vec2 = (D % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 8 == 0);
   const float grad_scale = static_cast<float>(static_cast<double>(B) / (static_cast<double>(nq) * nq) / n_sampling);

@@ -45,15 +45,29 @@ template <> struct Arith<double> {
   static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
 };
 
-// DPL = columns per lane held in registers (a warp covers 32*DPL columns per pass)
-// KPL = neighbour indices per lane held in registers (k <= 32*KPL)
-template <typename T, int DPL, int KPL, bool GS, bool PREFETCH>
+template <typename T, int V> struct VecOf;
+template <> struct VecOf<float, 1> { using type = float; };
+template <> struct VecOf<double, 1> { using type = double; };
+template <> struct VecOf<float, 2> { using type = float2; };
+template <> struct VecOf<double, 2> { using type = double2; };
+template <typename T> __device__ __forceinline__ T vget(const T &v, int) { return v; }
+__device__ __forceinline__ float vget(const float2 &v, int e) { return e ? v.y : v.x; }
+__device__ __forceinline__ double vget(const double2 &v, int e) { return e ? v.y : v.x; }
+
+// V   = elements per load (2 when d is even: rows are then 8 / 16-byte aligned and a lane fetches two columns of a
+//       neighbour row with ONE load -- the sweep is bound by instruction issue)
+// DPL = loads per lane and neighbour row held in registers (a warp covers 32 * DPL * V columns per pass)
+// KPL = neighbour indices per lane held in registers (k <= 32 * KPL); indices are narrowed to 32 bits once read
+//       (n <= 2^31 - 1 is checked on the host side of this kernel)
+template <typename T, int V, int DPL, int KPL, bool GS, bool PREFETCH>
 __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
     const T *__restrict__ prev, T *next, const int64_t *__restrict__ idx, int64_t ld_idx, int64_t n,
     int d, int k, T coef, int *flags, int epoch, unsigned long long *ticket, int *bad_index, int rows_per_ticket,
     int64_t row_lo, int64_t row_hi) {
+  using TV = typename VecOf<T, V>::type;
   const int lane = threadIdx.x & 31;
   const T kk = static_cast<T>(k);
+  const int dv = d / V;  // vectors per row (V == 2 only when d is even)
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0) base = static_cast<unsigned long long>(row_lo) + atomicAdd(ticket, 1ull) * rows_per_ticket;
@@ -63,7 +77,8 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
     for (int64_t i = static_cast<int64_t>(base); i < row_end; ++i) {
       // the row's neighbour list, coalesced, into registers: lane l holds entries l, l+32, ...
       const int64_t *nb = idx + i * ld_idx;
-      int64_t mine[KPL];
+      const int i32 = static_cast<int>(i);
+      int mine[KPL];
 #pragma unroll
       for (int q = 0; q < KPL; ++q) {
         const int jj = q * 32 + lane;
@@ -72,7 +87,7 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
           *bad_index = 1;
           j = i;
         }
-        mine[q] = j;
+        mine[q] = static_cast<int>(j);
       }
       if (PREFETCH) {
         // the row's gather, started early: every lane pulls ITS neighbours' rows (prev or next, the array the
@@ -81,8 +96,8 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
 #pragma unroll
         for (int q = 0; q < KPL; ++q) {
           if (q * 32 + lane < k) {
-            const char *src = reinterpret_cast<const char *>(((GS && mine[q] < i) ? static_cast<const T *>(next) : prev) +
-                                                             mine[q] * d);
+            const char *src = reinterpret_cast<const char *>(((GS && mine[q] < i32) ? static_cast<const T *>(next) : prev) +
+                                                             static_cast<int64_t>(mine[q]) * d);
             for (int off = 0; off < row_bytes; off += 128) prefetch_l2(src + off);
             prefetch_l2(src + row_bytes - 1);
           }
@@ -94,7 +109,7 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
         bool polled = false;
 #pragma unroll
         for (int q = 0; q < KPL; ++q) {
-          if (mine[q] < i) {
+          if (mine[q] < i32) {
             polled = true;
             unsigned ns = 32;
             while (ld_relaxed(flags + mine[q]) < epoch) {
@@ -106,27 +121,32 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
         if (__any_sync(FULL, polled)) fence_acq_rel();
         __syncwarp();
       }
-      for (int c0 = 0; c0 < d; c0 += 32 * DPL) {
-        T acc[DPL];
+      const TV *prev_v = reinterpret_cast<const TV *>(prev);
+      const TV *next_v = reinterpret_cast<const TV *>(next);
+      for (int c0 = 0; c0 < dv; c0 += 32 * DPL) {
+        T acc[DPL][V];
 #pragma unroll
-        for (int q = 0; q < DPL; ++q) acc[q] = T(0);
+        for (int q = 0; q < DPL; ++q)
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[q][e] = T(0);
         bool first = true;
 #pragma unroll
         for (int kq = 0; kq < KPL; ++kq) {
           if (kq * 32 < k) {  // warp-uniform
             for (int jb = 0; jb < 32 && kq * 32 + jb < k; jb += SM_UNROLL) {
-              T v[SM_UNROLL][DPL];
+              TV v[SM_UNROLL][DPL];
 #pragma unroll
               for (int u = 0; u < SM_UNROLL; ++u) {
-                const int64_t j = __shfl_sync(FULL, mine[kq], (jb + u) & 31);
+                const int j = __shfl_sync(FULL, mine[kq], (jb + u) & 31);
                 if (kq * 32 + jb + u < k) {
-                  const bool from_next = GS && (j < i);
-                  const T *src = (from_next ? static_cast<const T *>(next) : prev) + j * d;
+                  const bool from_next = GS && (j < i32);
+                  const TV *src = (from_next ? next_v : prev_v) + static_cast<int64_t>(j) * dv;
 #pragma unroll
                   for (int q = 0; q < DPL; ++q) {
                     const int c = c0 + q * 32 + lane;
-                    T val = T(0);
-                    if (c < d) val = from_next ? __ldcg(src + c) : __ldg(src + c);
+                    TV val = TV();
+                    // rows this sweep has rewritten are read from L2 (the point of coherence), never through L1
+                    if (c < dv) val = GS ? __ldcg(src + c) : __ldg(src + c);
                     v[u][q] = val;
                   }
                 }
@@ -135,7 +155,10 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
               for (int u = 0; u < SM_UNROLL; ++u) {
                 if (kq * 32 + jb + u < k) {
 #pragma unroll
-                  for (int q = 0; q < DPL; ++q) acc[q] = first ? v[u][q] : Arith<T>::add(acc[q], v[u][q]);
+                  for (int q = 0; q < DPL; ++q)
+#pragma unroll
+                    for (int e = 0; e < V; ++e)
+                      acc[q][e] = first ? vget(v[u][q], e) : Arith<T>::add(acc[q][e], vget(v[u][q], e));
                   first = false;
                 }
               }
@@ -145,12 +168,15 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
 #pragma unroll
         for (int q = 0; q < DPL; ++q) {
           const int c = c0 + q * 32 + lane;
-          if (c < d) {
-            const T r = __ldg(prev + i * d + c);
-            const T target = Arith<T>::div(acc[q], kk);
-            const T vec = Arith<T>::sub(target, r);
-            const T prod = Arith<T>::mul(vec, coef);
-            next[i * d + c] = Arith<T>::add(r, prod);
+          if (c < dv) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+              const T r = __ldg(prev + i * d + c * V + e);
+              const T target = Arith<T>::div(acc[q][e], kk);
+              const T vec = Arith<T>::sub(target, r);
+              const T prod = Arith<T>::mul(vec, coef);
+              next[i * d + c * V + e] = Arith<T>::add(r, prod);
+            }
           }
         }
       }
@@ -192,7 +218,7 @@ int smooth_begin(void *workspace, int elem_size, int64_t n, int d, int n_iter, c
 }
 
 // One launch of sweep `epoch` (1-based) over rows [row_lo, row_hi) with its own ticket.
-template <typename T, int DPL, int KPL>
+template <typename T, int V, int DPL, int KPL>
 static int launch_rows(const T *src, T *dst, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k, double coef,
                        int mode, const SmoothWs &w, int epoch, unsigned long long *ticket, int64_t row_lo,
                        int64_t row_hi, cudaStream_t st) {
@@ -202,8 +228,8 @@ static int launch_rows(const T *src, T *dst, int64_t n, int d, const int64_t *id
   // (ncu: 61 % issue-active), and three more instructions per neighbour cost more than the latency they hide.
   const char *pfe = getenv("VVB_SMOOTH_PREFETCH");
   const bool pf = static_cast<size_t>(d) * sizeof(T) <= 512 && pfe && atoi(pfe) == 1;
-  auto kern_gs = pf ? smooth_sweep_kernel<T, DPL, KPL, true, true> : smooth_sweep_kernel<T, DPL, KPL, true, false>;
-  auto kern_ja = pf ? smooth_sweep_kernel<T, DPL, KPL, false, true> : smooth_sweep_kernel<T, DPL, KPL, false, false>;
+  auto kern_gs = pf ? smooth_sweep_kernel<T, V, DPL, KPL, true, true> : smooth_sweep_kernel<T, V, DPL, KPL, true, false>;
+  auto kern_ja = pf ? smooth_sweep_kernel<T, V, DPL, KPL, false, true> : smooth_sweep_kernel<T, V, DPL, KPL, false, false>;
   VVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, mode == VVB_SMOOTH_JACOBI ? kern_ja : kern_gs,
                                                          SM_THREADS, 0));
   if (blocks_per_sm < 1) blocks_per_sm = 1;
@@ -234,19 +260,19 @@ static int launch_rows(const T *src, T *dst, int64_t n, int d, const int64_t *id
 // chunk < 0: all n_iter sweeps over all rows (ping-pong so that the LAST sweep lands in `out`: sweep s reads
 // a_s, writes b_s).  chunk >= 0: rows [row_lo, row_hi) of a ONE-sweep call, x -> out; the caller issues the
 // chunks in increasing row order on one stream after smooth_begin().
-template <typename T, int DPL, int KPL>
+template <typename T, int V, int DPL, int KPL>
 static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k, double coef,
                          int n_iter, int mode, T *out, void *workspace, int chunk, int64_t row_lo, int64_t row_hi,
                          cudaStream_t st) {
   SmoothWs w = carve_smooth_ws(workspace, sizeof(T), n, d, n_iter);
   if (chunk >= 0)
-    return launch_rows<T, DPL, KPL>(x, out, n, d, idx, ld_idx, k, coef, mode, w, 1, w.tickets + n_iter + chunk, row_lo,
+    return launch_rows<T, V, DPL, KPL>(x, out, n, d, idx, ld_idx, k, coef, mode, w, 1, w.tickets + n_iter + chunk, row_lo,
                                     row_hi, st);
   const T *src = x;
   for (int it = 0; it < n_iter; ++it) {
     const bool to_out = ((n_iter - 1 - it) % 2) == 0;
     T *dst = to_out ? out : static_cast<T *>(w.scratch);
-    int rc = launch_rows<T, DPL, KPL>(src, dst, n, d, idx, ld_idx, k, coef, mode, w, it + 1, w.tickets + it, 0, n, st);
+    int rc = launch_rows<T, V, DPL, KPL>(src, dst, n, d, idx, ld_idx, k, coef, mode, w, it + 1, w.tickets + it, 0, n, st);
     if (rc) return rc;
     src = dst;
   }
@@ -261,29 +287,44 @@ size_t smooth_workspace_bytes(int elem_size, int64_t n, int d, int n_iter) {
 static int smooth_dispatch(const void *x, int elem_size, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
                            double coef, int n_iter, int mode, void *out, void *workspace, int chunk, int64_t row_lo,
                            int64_t row_hi, cudaStream_t st) {
-#define VVB_SM_K(T, DPL, xp, op)                                                                                      \
+#define VVB_SM_K(T, V, DPL, xp, op)                                                                                   \
   do {                                                                                                                \
     if (k <= 64)                                                                                                      \
-      return launch_sweeps<T, DPL, 2>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,     \
-                                      row_hi, st);                                                                    \
+      return launch_sweeps<T, V, DPL, 2>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,  \
+                                         row_hi, st);                                                                 \
     if (k <= 128)                                                                                                     \
-      return launch_sweeps<T, DPL, 4>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,     \
-                                      row_hi, st);                                                                    \
-    return launch_sweeps<T, DPL, 32>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,      \
-                                     row_hi, st);                                                                     \
+      return launch_sweeps<T, V, DPL, 4>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,  \
+                                         row_hi, st);                                                                 \
+    return launch_sweeps<T, V, DPL, 32>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,   \
+                                        row_hi, st);                                                                  \
   } while (0)
+  // two columns per load when the rows allow it (d even, 8 / 16-byte aligned bases): half the load instructions
+  const bool vec2 = (d % 2 == 0) && reinterpret_cast<uintptr_t>(x) % (2 * elem_size) == 0 &&
+                    reinterpret_cast<uintptr_t>(out) % (2 * elem_size) == 0 &&
+                    reinterpret_cast<uintptr_t>(carve_smooth_ws(workspace, elem_size, n, d, n_iter).scratch) % (2 * elem_size) == 0 &&
+                    !(getenv("VVB_SMOOTH_VEC") && atoi(getenv("VVB_SMOOTH_VEC")) == 0);
   if (elem_size == 4) {
     const float *xf = static_cast<const float *>(x);
     float *of = static_cast<float *>(out);
-    if (d <= 32) VVB_SM_K(float, 1, xf, of);
-    if (d <= 64) VVB_SM_K(float, 2, xf, of);
-    VVB_SM_K(float, 4, xf, of);
+    if (vec2) {
+      if (d <= 64) VVB_SM_K(float, 2, 1, xf, of);
+      if (d <= 128) VVB_SM_K(float, 2, 2, xf, of);
+      VVB_SM_K(float, 2, 4, xf, of);
+    }
+    if (d <= 32) VVB_SM_K(float, 1, 1, xf, of);
+    if (d <= 64) VVB_SM_K(float, 1, 2, xf, of);
+    VVB_SM_K(float, 1, 4, xf, of);
   }
   const double *xd = static_cast<const double *>(x);
   double *od = static_cast<double *>(out);
-  if (d <= 32) VVB_SM_K(double, 1, xd, od);
-  if (d <= 64) VVB_SM_K(double, 2, xd, od);
-  VVB_SM_K(double, 4, xd, od);
+  if (vec2) {
+    if (d <= 64) VVB_SM_K(double, 2, 1, xd, od);
+    if (d <= 128) VVB_SM_K(double, 2, 2, xd, od);
+    VVB_SM_K(double, 2, 4, xd, od);
+  }
+  if (d <= 32) VVB_SM_K(double, 1, 1, xd, od);
+  if (d <= 64) VVB_SM_K(double, 1, 2, xd, od);
+  VVB_SM_K(double, 1, 4, xd, od);
 #undef VVB_SM_K
 }
 
