@@ -15,8 +15,8 @@
 //     invalidation per poll -- and the warp executes ONE fence.acq_rel.gpu once all its
 //     polls have succeeded, then a warp barrier, before any lane reads the published rows
 //     (with ld.global.cg: L2 is the point of coherence).
-//   * optionally (VVB_SMOOTH_PREFETCH=1) every neighbour row is prefetched into L2 before the
-//     polling starts; measured slower on B200 (the sweep is issue-bound), so it is off by default.
+//   * tried and dropped: prefetching every neighbour row into L2 before the polling starts
+//     (3.3 ms against 2.96 ms at 1M x 50, k=50: the sweep is bound by instruction issue).
 // Arithmetic per element matches NumPy's: sequential sum over the k gathered rows in
 // neighbour order (starting from the first row, not from zero), true division by k,
 // then r + (target - r) * coef as three separately rounded operations (no FMA).
@@ -59,7 +59,7 @@ __device__ __forceinline__ double vget(const double2 &v, int e) { return e ? v.y
 // DPL = loads per lane and neighbour row held in registers (a warp covers 32 * DPL * V columns per pass)
 // KPL = neighbour indices per lane held in registers (k <= 32 * KPL); indices are narrowed to 32 bits once read
 //       (n <= 2^31 - 1 is checked on the host side of this kernel)
-template <typename T, int V, int DPL, int KPL, bool GS, bool PREFETCH>
+template <typename T, int V, int DPL, int KPL, bool GS>
 __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
     const T *__restrict__ prev, T *next, const int64_t *__restrict__ idx, int64_t ld_idx, int64_t n,
     int d, int k, T coef, int *flags, int epoch, unsigned long long *ticket, int *bad_index, int rows_per_ticket,
@@ -88,20 +88,6 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
           j = i;
         }
         mine[q] = static_cast<int>(j);
-      }
-      if (PREFETCH) {
-        // the row's gather, started early: every lane pulls ITS neighbours' rows (prev or next, the array the
-        // gather will read) into L2; a line that is rewritten later is updated in L2, never stale
-        const int row_bytes = d * static_cast<int>(sizeof(T));
-#pragma unroll
-        for (int q = 0; q < KPL; ++q) {
-          if (q * 32 + lane < k) {
-            const char *src = reinterpret_cast<const char *>(((GS && mine[q] < i32) ? static_cast<const T *>(next) : prev) +
-                                                             static_cast<int64_t>(mine[q]) * d);
-            for (int off = 0; off < row_bytes; off += 128) prefetch_l2(src + off);
-            prefetch_l2(src + row_bytes - 1);
-          }
-        }
       }
       if (GS) {
         // wait until every lower-indexed neighbour has been published in this sweep (relaxed polls,
@@ -223,13 +209,8 @@ static int launch_rows(const T *src, T *dst, int64_t n, int d, const int64_t *id
                        int mode, const SmoothWs &w, int epoch, unsigned long long *ticket, int64_t row_lo,
                        int64_t row_hi, cudaStream_t st) {
   int blocks_per_sm = 0;
-  // L2 prefetch of the neighbour rows ahead of the polling (rows of at most 512 bytes): opt-in, VVB_SMOOTH_PREFETCH=1.
-  // Measured on B200, 1M x 50, k=50: 3.3 ms with it, 2.96 ms without -- the sweep is bound by instruction issue
-  // (ncu: 61 % issue-active), and three more instructions per neighbour cost more than the latency they hide.
-  const char *pfe = getenv("VVB_SMOOTH_PREFETCH");
-  const bool pf = static_cast<size_t>(d) * sizeof(T) <= 512 && pfe && atoi(pfe) == 1;
-  auto kern_gs = pf ? smooth_sweep_kernel<T, V, DPL, KPL, true, true> : smooth_sweep_kernel<T, V, DPL, KPL, true, false>;
-  auto kern_ja = pf ? smooth_sweep_kernel<T, V, DPL, KPL, false, true> : smooth_sweep_kernel<T, V, DPL, KPL, false, false>;
+  auto kern_gs = smooth_sweep_kernel<T, V, DPL, KPL, true>;
+  auto kern_ja = smooth_sweep_kernel<T, V, DPL, KPL, false>;
   VVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, mode == VVB_SMOOTH_JACOBI ? kern_ja : kern_gs,
                                                          SM_THREADS, 0));
   if (blocks_per_sm < 1) blocks_per_sm = 1;
@@ -298,8 +279,17 @@ static int smooth_dispatch(const void *x, int elem_size, int64_t n, int d, const
     return launch_sweeps<T, V, DPL, 32>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,   \
                                         row_hi, st);                                                                  \
   } while (0)
+  // the two-column variant, instantiated for the common shapes only (every instantiation costs seconds of ptxas)
+#define VVB_SM_K2(T, DPL, xp, op)                                                                                     \
+  do {                                                                                                                \
+    if (k <= 64)                                                                                                      \
+      return launch_sweeps<T, 2, DPL, 2>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,  \
+                                         row_hi, st);                                                                 \
+    return launch_sweeps<T, 2, DPL, 4>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,    \
+                                       row_hi, st);                                                                   \
+  } while (0)
   // two columns per load when the rows allow it (d even, 8 / 16-byte aligned bases): half the load instructions
-  const bool vec2 = (d % 2 == 0) && reinterpret_cast<uintptr_t>(x) % (2 * elem_size) == 0 &&
+  const bool vec2 = (d % 2 == 0) && d <= 128 && k <= 128 && reinterpret_cast<uintptr_t>(x) % (2 * elem_size) == 0 &&
                     reinterpret_cast<uintptr_t>(out) % (2 * elem_size) == 0 &&
                     reinterpret_cast<uintptr_t>(carve_smooth_ws(workspace, elem_size, n, d, n_iter).scratch) % (2 * elem_size) == 0 &&
                     !(getenv("VVB_SMOOTH_VEC") && atoi(getenv("VVB_SMOOTH_VEC")) == 0);
@@ -307,9 +297,8 @@ static int smooth_dispatch(const void *x, int elem_size, int64_t n, int d, const
     const float *xf = static_cast<const float *>(x);
     float *of = static_cast<float *>(out);
     if (vec2) {
-      if (d <= 64) VVB_SM_K(float, 2, 1, xf, of);
-      if (d <= 128) VVB_SM_K(float, 2, 2, xf, of);
-      VVB_SM_K(float, 2, 4, xf, of);
+      if (d <= 64) VVB_SM_K2(float, 1, xf, of);
+      VVB_SM_K2(float, 2, xf, of);
     }
     if (d <= 32) VVB_SM_K(float, 1, 1, xf, of);
     if (d <= 64) VVB_SM_K(float, 1, 2, xf, of);
@@ -318,14 +307,14 @@ static int smooth_dispatch(const void *x, int elem_size, int64_t n, int d, const
   const double *xd = static_cast<const double *>(x);
   double *od = static_cast<double *>(out);
   if (vec2) {
-    if (d <= 64) VVB_SM_K(double, 2, 1, xd, od);
-    if (d <= 128) VVB_SM_K(double, 2, 2, xd, od);
-    VVB_SM_K(double, 2, 4, xd, od);
+    if (d <= 64) VVB_SM_K2(double, 1, xd, od);
+    VVB_SM_K2(double, 2, xd, od);
   }
   if (d <= 32) VVB_SM_K(double, 1, 1, xd, od);
   if (d <= 64) VVB_SM_K(double, 1, 2, xd, od);
   VVB_SM_K(double, 1, 4, xd, od);
 #undef VVB_SM_K
+#undef VVB_SM_K2
 }
 
 static int smooth_check(const void *x, int elem_size, int64_t n, int d, int64_t ld_idx, int k, int n_iter, int mode,
