@@ -322,3 +322,35 @@ def test_compact_cache_sidecar_round_trip(tmp_path):
     c = vv.make_knn(x, fname=f, k=15, verbose=False)  # from the reference-format file
     assert np.array_equal(a[0], c[0]) and np.array_equal(a[1].astype(np.float64), c[1])
     assert np.array_equal(vv.smooth(x, b, k=15, coef=0.5), vv.smooth(x, c, k=15, coef=0.5))
+
+
+# ------------------------------------------------------------------ the two lock-free protocols under stress
+@pytest.mark.parametrize("order", ["random", "sorted"])
+def test_smoother_publish_wait_protocol_survives_injected_delays(monkeypatch, order):
+    """compute-sanitizer's racecheck is closed on this pool, so the Gauss-Seidel publish / wait protocol
+    (st.release by one lane after a warp barrier; relaxed polls + one acquire fence) is shaken instead:
+    VVB_SMOOTH_JITTER=1 delays every row by a pseudo-random 0-16 us before it polls and before it publishes, which
+    permutes the order in which rows finish.  The sweep must stay bit-identical to the sequential oracle, also on
+    coordinate-sorted rows (every neighbour just below the row: the longest dependency chains)."""
+    monkeypatch.setenv("VVB_SMOOTH_JITTER", "1")
+    n, d, k = 60_000, 50, 50
+    x = pca_syn(n, d, seed=5, n_clusters=8)
+    if order == "sorted":
+        x = x[np.argsort(x[:, 0])].copy()
+    idx, dist = vv.make_knn(x, k=k, verbose=False)
+    for n_iter in (1, 2):
+        out = vv.smooth(x, [idx, dist], k=k, coef=0.7, n_iter=n_iter)
+        assert np.array_equal(out, orc.smooth(x, idx, k, 0.7, n_iter)), (order, n_iter)
+
+
+@pytest.mark.parametrize("n,d,k", [(40_000, 50, 50), (12_000, 100, 30)])
+def test_screening_pipeline_survives_injected_delays(monkeypatch, n, d, k):
+    """The screening kernel's mbarrier pipeline (TMA producer -> MMA issuer -> 16 epilogue warps, accumulator slots
+    handed back by warp pairs) with pseudo-random delays in the producer and before every hand-over
+    (VVB_TC_DEBUG=4): the graph must not change."""
+    x = pca_syn(n, d, seed=9, n_clusters=10)
+    want = orc.knn(x, k)
+    monkeypatch.setenv("VVB_TC_DEBUG", "4")
+    for _ in range(2):
+        got = vv.make_knn(x, k=k, verbose=False, algo="tensor")
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])

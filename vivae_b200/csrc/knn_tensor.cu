@@ -478,6 +478,8 @@ struct TcParams {
   int ka;           // K atoms per operand half (1: query operand resident; >1: K-loop variant)
   int debug_mode;   // profiling only (env VVB_TC_DEBUG): 1 = drain TMEM but skip the screening,
                     // 2 = screening minima only, no admissions, 3 = no TMEM drain at all.  Results are garbage.
+                    // 4 = stress test: pseudo-random delays in the producer and before every accumulator hand-over
+                    //     (results must stay exact: tests/test_gpu_configs.py)
   int n_cells;      // P
   float eps_rel;    // screening-error margin relative to (|x^| + Ymax)^2: tc_eps_rel(ka), or tc_eps_single(ka)
   int single;       // K-loop variant, first tier: ONE product (xh . yh) instead of three -- a third of the MMAs and half
@@ -642,7 +644,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   stamp(1);
-  const bool pre_pass = dbg_mode == 0 && p.ka <= TC_PRE_MAX_KA && !REFINE;
+  const bool pre_pass = (dbg_mode == 0 || dbg_mode == 4) && p.ka <= TC_PRE_MAX_KA && !REFINE;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -721,6 +723,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
               continue;
             }
           }
+          if (DBG && dbg_mode == 4) __nanosleep((static_cast<unsigned>(t) * 2246822519u >> 21) & 0x7ffu);
           if constexpr (!KLOOP) {
             const int s = t % TC_STAGES;
             const uint32_t ph = (t / TC_STAGES) & 1;
@@ -1155,6 +1158,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         process(ra, jt + half * 64);
         tc_ld32_issue(t_acc + 32, ra);
         tc_ld32_wait(ra);
+        if (DBG && dbg_mode == 4)  // stress mode (VVB_TC_DEBUG=4, tests only): shake the accumulator hand-over
+          __nanosleep(((static_cast<unsigned>(t) * 2654435761u + static_cast<unsigned>(ew) * 40503u) >> 20) & 0xfffu);
         // accumulator half fully drained into registers: hand it back to the MMA issuer
         tc_fence_before();
         __syncwarp();

@@ -63,7 +63,7 @@ template <typename T, int V, int DPL, int KPL, bool GS>
 __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
     const T *__restrict__ prev, T *next, const int64_t *__restrict__ idx, int64_t ld_idx, int64_t n,
     int d, int k, T coef, int *flags, int epoch, unsigned long long *ticket, int *bad_index, int rows_per_ticket,
-    int64_t row_lo, int64_t row_hi) {
+    int64_t row_lo, int64_t row_hi, int jitter) {
   using TV = typename VecOf<T, V>::type;
   const int lane = threadIdx.x & 31;
   const T kk = static_cast<T>(k);
@@ -88,6 +88,11 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
           j = i;
         }
         mine[q] = static_cast<int>(j);
+      }
+      if (GS && jitter) {
+        // stress mode (VVB_SMOOTH_JITTER=1, tests only): pseudo-random delays of up to ~16 us between claiming a row,
+        // polling and publishing shake the order in which rows finish -- the result must not move by a bit
+        __nanosleep((static_cast<unsigned>(i) * 2654435761u >> 18) & 0x3fffu);
       }
       if (GS) {
         // wait until every lower-indexed neighbour has been published in this sweep (relaxed polls,
@@ -166,6 +171,7 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
           }
         }
       }
+      if (GS && jitter) __nanosleep((static_cast<unsigned>(i) * 40503u >> 3) & 0x1fffu);
       if (GS) {
         __syncwarp();  // all 32 lanes' stores to `next` happen before ...
         if (lane == 0) st_release(flags + i, epoch);  // ... the (cumulative) release that publishes the row
@@ -228,12 +234,14 @@ static int launch_rows(const T *src, T *dst, int64_t n, int d, const int64_t *id
     if (grid > cap) grid = cap;
   }
   if (grid < 1) grid = 1;
+  const char *je = getenv("VVB_SMOOTH_JITTER");
+  const int jitter = je ? atoi(je) : 0;
   if (mode == VVB_SMOOTH_JACOBI)
     kern_ja<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k, static_cast<T>(coef),
-                                                               w.flags, epoch, ticket, w.bad, rpt, row_lo, row_hi);
+                                                               w.flags, epoch, ticket, w.bad, rpt, row_lo, row_hi, 0);
   else
     kern_gs<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k, static_cast<T>(coef),
-                                                               w.flags, epoch, ticket, w.bad, rpt, row_lo, row_hi);
+                                                               w.flags, epoch, ticket, w.bad, rpt, row_lo, row_hi, jitter);
   VVB_CHECK_LAUNCH();
   return VVB_OK;
 }
