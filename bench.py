@@ -24,8 +24,9 @@ Timed quantities
 
 N > 1 (launched under torchrun): the query rows are sharded across ranks (strong scaling: total work fixed); each
 rank holds the whole matrix, the preparation of the cell plan is split across the ranks, the index shards are
-all-gathered over NCCL (int32) and the Gauss-Seidel smoother -- which does not shard by rows -- runs
-replicated on every rank.
+all-gathered over NCCL (int32) and the Gauss-Seidel smoother -- which does not shard by rows but never mixes columns
+ -- is sharded by COLUMNS: every rank runs the whole sweep on its slice of the columns and the
+slices are all-gathered; bit-identical to the single-GPU sweep.
 
 `--impl reference` times the reference's CPU path for the same metric on the host cores: the oracle port (oracle/,
 C + OpenMP) on a bounded sample -- the reference's own kNN (pynndescent) is not installable here and its smoother is
@@ -246,17 +247,22 @@ def run_reference(args) -> None:
 def workload_config(args, n_gpus: int) -> dict:
     return {"workload": f"synthetic {args.n} cells x {args.d} PCs, exact kNN k={args.k} + smooth(k={args.k}, coef=1, n_iter=1)",
             "n": args.n, "d": args.d, "k": args.k,
-            "parallelism": (f"query-row shards x{n_gpus} (cell plan prepared in row shards), smooth replicated"
+            "parallelism": (f"graph: query-row shards x{n_gpus} (cell plan prepared in row / cell shards); smoother: column "
+                            f"shards x{n_gpus}; NCCL all-gathers of indices and smoothed columns"
                             if getattr(args, "exchange", "replicated") != "ring" else
-                            f"query-row AND database-row shards x{n_gpus} (NCCL ring exchange + running merge), smooth replicated"),
+                            f"query-row AND database-row shards x{n_gpus} (NCCL ring exchange + running merge), smoother "
+                            f"in column shards"),
             "l2": f"inputs larger than L2 (matrix {args.n * args.d * 4 / 1e6:.0f} MB, graph "
                   f"{args.n * (args.k + 1) * 12 / 1e6:.0f} MB vs 126 MB L2)"}
 
 
-def executed_macs_per_pair(dd: int) -> int:
-    """MACs the tensor pipe executes per (query, database row) pair: three fp16 products of the hi/lo split, K padded
-    to the MMA's k-step (16) for d + 3 <= 64, to the 64-column atom otherwise."""
-    return 16 * ((dd + 3 + 15) // 16 + 2 * ((dd + 15) // 16)) if dd + 3 <= 64 else 3 * 64 * ((dd + 3 + 63) // 64)
+def executed_macs_per_pair(dd: int, products: int = 3) -> int:
+    """MACs the tensor pipe executes per (query, database row) pair: `products` fp16 products (three for the hi/lo
+    split, one in the single-product first tier of wide rows), K padded to the MMA's k-step (16) for d + 3 <= 64, to
+    the 64-column atom otherwise."""
+    if dd + 3 <= 64:
+        return 16 * ((dd + 3 + 15) // 16 + 2 * ((dd + 15) // 16))
+    return products * 64 * ((dd + 3 + 63) // 64)
 
 
 def screen_roofline(st: dict, nq: int, n: int, d: int, peaks: dict, sustained: bool = False) -> dict:
@@ -268,12 +274,13 @@ def screen_roofline(st: dict, nq: int, n: int, d: int, peaks: dict, sustained: b
         ach = alg / (ms / 1e3) / 1e12
         return {"kernel": "knn_brute_ffma", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "peak_source": peaks["source"], "ms": ms}
-    ex = float(st["tiles_swept"]) * 256 * 128 * executed_macs_per_pair(d) * 2
+    macs = executed_macs_per_pair(d, st.get("products") or 3)
+    ex = float(st["tiles_swept"]) * 256 * 128 * macs * 2  # (the few refine sweeps run three products: counted as one)
     ach = ex / (ms / 1e3) / 1e12
     return {"kernel": "knn_screen_tcgen05", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
             "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + (" (sustained)" if sustained else " (burst)"),
             "ms": ms, "what": "EXECUTED MMA flops (tiles swept x 256 x 128 pairs x executed MACs x 2) / duration",
-            "executed_macs_per_pair": executed_macs_per_pair(d), "algorithmic_macs_per_pair": d,
+            "executed_macs_per_pair": macs, "algorithmic_macs_per_pair": d,
             "tiles_swept": st["tiles_swept"], "tiles_dense": st["tiles_dense"], "cells": st["cells"],
             "algorithmic": {"flops": alg, "tflops": alg / (ms / 1e3) / 1e12, "x_peak": alg / (ms / 1e3) / 1e12 / peak,
                             "note": "2*nq*n*d over the duration; NOT a utilisation: the exact cell bounds skipped "
@@ -289,7 +296,8 @@ def run_ours(args) -> None:
     import vivae_b200 as vv
     from vivae_b200 import _lib
     from vivae_b200.device import knn_device, smooth_device
-    from vivae_b200.sharded import (all_gather_indices, knn_smooth_host_sharded, make_knn_ring, shard_bounds)
+    from vivae_b200.sharded import (all_gather_indices, knn_smooth_host_sharded, make_knn_ring, shard_bounds,
+                                    smooth_cols_sharded)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -332,7 +340,9 @@ def run_ours(args) -> None:
             idx, dist_ = knn_step(xd, kk, q0_, nq_, stats)
         if world > 1:
             idx = all_gather_indices(idx, n_)  # the smoother needs the whole graph (NCCL all-gather, int32)
-        out = smooth_device(xd, idx, k=kk, coef=1.0, n_iter=1)
+            out = smooth_cols_sharded(xd, idx, k=kk, coef=1.0, n_iter=1)  # column slices, all-gathered
+        else:
+            out = smooth_device(xd, idx, k=kk, coef=1.0, n_iter=1)
         return idx, dist_, out
 
     def timed(fn, steps, warmup):
@@ -378,10 +388,13 @@ def run_ours(args) -> None:
     idx_full = all_gather_indices(idx_s, n) if world > 1 else idx_s
     torch.cuda.synchronize()
     e1.record()
-    smooth_device(x_dev, idx_full, k=k, coef=1.0, n_iter=1)
+    if world > 1:
+        smooth_cols_sharded(x_dev, idx_full, k=k, coef=1.0, n_iter=1)
+    else:
+        smooth_device(x_dev, idx_full, k=k, coef=1.0, n_iter=1)
     e2.record()
     torch.cuda.synchronize()
-    ms_smooth = e1.elapsed_time(e2)
+    ms_smooth = max_over_ranks(e1.elapsed_time(e2))
     roofline = screen_roofline(st, nq, n, d, peaks)
     cap = os.path.join(ROOT, "profiles", "r02_knn_screen_1M_raw.csv")
     if world == 1 and st.get("algo_used") == 2 and (n, d, k) == (1_000_000, 50, 50) and os.path.isfile(cap):
@@ -410,7 +423,7 @@ def run_ours(args) -> None:
         dense_roof = screen_roofline(sd, nq, n, d, peaks)
         dense_roof["kernel"] += " (VVB_TC_CELLS=1: no tile skipped)"
     sbytes = float(n) * (k * d * 4 + k * 4 + d * 4)
-    smooth_roof = {"kernel": "smooth_sweep_gs", "bound": "hbm", "achieved": sbytes / (ms_smooth / 1e3) / 1e9,
+    smooth_roof = {"kernel": "smooth_sweep_gs" + (f" (column shards x{world} + all-gather)" if world > 1 else ""), "bound": "hbm", "achieved": sbytes / (ms_smooth / 1e3) / 1e9,
                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": sbytes / (ms_smooth / 1e3) / 1e9 / peaks["hbm_gbs"],
                    "ms": ms_smooth, "algorithmic_bytes": sbytes, "traffic": None}
 

@@ -65,6 +65,9 @@ typedef struct vvb_knn_stats {
   int32_t cells;           /* spatial cells of the partition (1 = none)             */
   int32_t rows_refined;    /* rows whose certificate failed and were settled by the
                               fixed-threshold refine sweep on the tensor cores      */
+  int32_t products;        /* fp16 products the main sweep executed per key: 3 (hi/lo split)
+                              or 1 (single-product first tier of wide rows)         */
+  int32_t reserved;
 } vvb_knn_stats;
 
 int vvb_version(void);
@@ -209,6 +212,16 @@ int vvb_smooth_workspace_bytes(int elem_size, int64_t n, int d, int n_iter, size
 int vvb_smooth_device(const void *x_dev, int elem_size, int64_t n, int d, const int64_t *idx_dev,
                       int64_t ld_idx, int k, double coef, int n_iter, int mode, void *out_dev,
                       void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Columns [col0, col0+dcols) of the same computation (all n_iter sweeps, either mode).  The smoother never mixes
+ * columns -- element (i, c) of a sweep depends on column c of row i's neighbours only (knn.py:176-183 is a row-wise
+ * mean) -- so a column slice is bit-identical to the same columns of the full call, Gauss-Seidel order included.
+ * This is how several GPUs share the reference's sweep, which does NOT split by rows: every GPU takes a slice and
+ * the slices are all-gathered (vivae_b200.sharded.smooth_cols_sharded).  x_dev and out_dev are the FULL (n, d)
+ * matrices; only the slice of out_dev is written.  Workspace as vvb_smooth_workspace_bytes(elem_size, n, d, n_iter). */
+int vvb_smooth_cols_device(const void *x_dev, int elem_size, int64_t n, int d, int col0, int dcols,
+                           const int64_t *idx_dev, int64_t ld_idx, int k, double coef, int n_iter, int mode,
+                           void *out_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 
 /* Rows [row_lo, row_hi) of ONE sweep in VVB_SMOOTH_JACOBI mode (row ranges of a Jacobi sweep are independent:
  * several GPUs each take a range and exchange the new rows between sweeps).  x (n, d) is the whole matrix;

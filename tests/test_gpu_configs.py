@@ -354,3 +354,24 @@ def test_screening_pipeline_survives_injected_delays(monkeypatch, n, d, k):
     for _ in range(2):
         got = vv.make_knn(x, k=k, verbose=False, algo="tensor")
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("dtype,d,parts", [(np.float32, 50, 8), (np.float32, 50, 3), (np.float64, 38, 4), (np.float32, 7, 2),
+                                           (np.float32, 300, 5)])
+def test_smoother_column_slices_equal_the_whole_sweep(dtype, d, parts):
+    """vvb_smooth_cols_device: the sweep never mixes columns, so the column slices the ranks of a multi-GPU run compute
+    (here all by this process) are bit-identical to the same columns of the single call -- Gauss-Seidel, two sweeps."""
+    from vivae_b200.device import smooth_cols_device, smooth_device
+    from vivae_b200.sharded import col_bounds
+
+    n, k = 30_000, 20
+    x = pca_syn(n, d, seed=d, n_clusters=6).astype(dtype)
+    idx, _ = vv.make_knn(x.astype(np.float32), k=k, verbose=False)
+    xd, idd = torch.from_numpy(x).cuda(), torch.from_numpy(idx).cuda()
+    whole = smooth_device(xd, idd, k=k, coef=0.8, n_iter=2)
+    assert np.array_equal(whole.cpu().numpy(), orc.smooth(x, idx, k, 0.8, 2))
+    out = torch.full_like(xd, float("nan"))
+    for r in range(parts):
+        c0, w = col_bounds(d, parts, r)
+        smooth_cols_device(xd, idd, c0, w, k=k, coef=0.8, n_iter=2, out=out)
+    assert torch.equal(out, whole)

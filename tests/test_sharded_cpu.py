@@ -13,8 +13,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import oracle as orc
-from vivae_b200.sharded import (all_gather_rows, knn_smooth_host_sharded, knn_smooth_sharded, make_knn_ring,
-                                make_knn_sharded, shard_bounds, smooth_jacobi_sharded)
+from vivae_b200.sharded import (all_gather_rows, col_bounds, knn_smooth_host_sharded, knn_smooth_sharded, make_knn_ring,
+                                make_knn_sharded, shard_bounds, smooth_cols_sharded, smooth_jacobi_sharded)
 
 
 def _free_port():
@@ -34,6 +34,16 @@ def _oracle_smooth(x, idx, k, coef, n_iter):
     return torch.from_numpy(orc.smooth(x.numpy(), idx.numpy(), k, coef, n_iter))
 
 
+def _oracle_smooth_cols(x, idx, c0, w, k, coef, n_iter, mode):
+    """The oracle's sweep on a column slice (what vvb_smooth_cols_device computes): full-width result tensor with
+    only the slice filled."""
+    out = torch.full_like(x, float("nan"))
+    if w:
+        xs = np.ascontiguousarray(x.numpy()[:, c0:c0 + w])
+        out[:, c0:c0 + w] = torch.from_numpy(orc.smooth(xs, idx.numpy(), k, coef, n_iter))
+    return out
+
+
 def _worker(rank, world, port, n, k, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -45,11 +55,13 @@ def _worker(rank, world, port, n, k, out_dir):
         q0, nq = shard_bounds(n, world, rank)
         loc = torch.arange(q0, q0 + nq, dtype=torch.int64).reshape(-1, 1)
         rows = all_gather_rows(loc, n)
+        # the smoother sharded by COLUMNS (the reference's sweep does not split by rows, but never mixes columns)
+        cs = smooth_cols_sharded(x, idx, k, coef=0.6, n_iter=2, _cols_fn=_oracle_smooth_cols)
         # the host pipeline: every rank passes only its rows, gets its rows of the graph and of the smoothed matrix
         hi, hd, hs = knn_smooth_host_sharded(x[q0:q0 + nq].numpy().copy(), n, k, coef=1.0, n_iter=2, _knn_fn=_oracle_knn,
                                              _smooth_fn=_oracle_smooth, device=torch.device("cpu"))
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), idx=idx.numpy(), dist=dst.numpy(), idx2=idx2.numpy(),
-                 xs=xs.numpy(), rows=rows.numpy(), hi=hi.numpy(), hd=hd.numpy(), hs=hs.numpy(), q0=q0, nq=nq)
+                 xs=xs.numpy(), cs=cs.numpy(), rows=rows.numpy(), hi=hi.numpy(), hd=hd.numpy(), hs=hs.numpy(), q0=q0, nq=nq)
     finally:
         dist.destroy_process_group()
 
@@ -67,9 +79,21 @@ def test_sharded_graph_and_smooth_equal_single_process(tmp_path, world, n):
         assert np.array_equal(g["idx"], wi) and np.array_equal(g["dist"], wd)       # identical bytes on every rank
         assert np.array_equal(g["idx2"], wi) and np.array_equal(g["xs"], ws)
         assert np.array_equal(g["rows"].ravel(), np.arange(n))
+        assert np.array_equal(g["cs"], orc.smooth(x, wi, k, 0.6, 2))  # column slices, gathered == the whole sweep
         q0, nq = int(g["q0"]), int(g["nq"])
         assert np.array_equal(g["hi"], wi[q0:q0 + nq]) and np.array_equal(g["hd"], wd[q0:q0 + nq])
         assert np.array_equal(g["hs"], ws[q0:q0 + nq])
+
+
+def test_col_bounds_cover_all_columns_in_whole_pairs():
+    for d in (1, 2, 7, 38, 50, 51, 2000):
+        for world in (1, 2, 3, 8, 64):
+            spans = [col_bounds(d, world, r) for r in range(world)]
+            assert sum(w for _, w in spans) == d
+            pos = 0
+            for c0, w in spans:
+                assert c0 == min(pos, d) and w >= 0 and (d % 2 or (c0 % 2 == 0 and w % 2 == 0))
+                pos += w
 
 
 def test_shard_bounds_cover_all_rows():

@@ -37,6 +37,8 @@ class KnnStats(ctypes.Structure):
         ("tiles_dense", ctypes.c_int64),
         ("cells", ctypes.c_int32),
         ("rows_refined", ctypes.c_int32),
+        ("products", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
     def as_dict(self) -> dict:
@@ -77,6 +79,7 @@ SYMBOLS = {
     "vvb_smooth_host": (_int, [_vp, _int, _i64, _int, _vp, _i64, _int, _dbl, _int, _int, _vp]),
     "vvb_smooth_workspace_bytes": (_int, [_int, _i64, _int, _int, ctypes.POINTER(_sz)]),
     "vvb_smooth_device": (_int, [_vp, _int, _i64, _int, _vp, _i64, _int, _dbl, _int, _int, _vp, _vp, _sz, _vp]),
+    "vvb_smooth_cols_device": (_int, [_vp, _int, _i64, _int, _int, _int, _vp, _i64, _int, _dbl, _int, _int, _vp, _vp, _sz, _vp]),
     "vvb_smooth_rows_device": (_int, [_vp, _int, _i64, _int, _vp, _i64, _int, _dbl, _int, _i64, _i64, _vp, _vp, _sz, _vp]),
     "vvb_quartet_workspace_bytes": (_sz, [_i64]),
     "vvb_quartet_loss_fwd_device": (_int, [_vp, _vp, _i64, _int, _int, _vp, _int, _int, _int, _vp, _vp, _vp, _vp]),

@@ -75,6 +75,9 @@ int launch_smooth_rows(const void *x, int elem_size, int64_t n, int d, const int
                        double coef, int mode, void *out, void *workspace, size_t workspace_bytes, int chunk,
                        int64_t row_lo, int64_t row_hi, cudaStream_t st);
 int smooth_max_chunks();
+int launch_smooth_cols(const void *x, int elem_size, int64_t n, int d, int col0, int dcols, const int64_t *idx,
+                       int64_t ld_idx, int k, double coef, int n_iter, int mode, void *out, void *workspace,
+                       size_t workspace_bytes, cudaStream_t st);
 int launch_knn_merge(const float *xc, int64_t nc, int d, int64_t q0, int64_t nq, const int64_t *new_idx, int kn,
                      int64_t keep_lo, int64_t keep_hi, int64_t global_off, int64_t *run_idx, float *run_d2, int k,
                      cudaStream_t st);
@@ -913,6 +916,17 @@ int vvb_smooth_host(const void *x_host, int elem_size, int64_t n, int d, const i
   VVB_CUDA(cudaStreamSynchronize(st));
   VVB_REQUIRE(bad == 0, "Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed");
   return VVB_OK;
+}
+
+int vvb_smooth_cols_device(const void *x_dev, int elem_size, int64_t n, int d, int col0, int dcols,
+                           const int64_t *idx_dev, int64_t ld_idx, int k, double coef, int n_iter, int mode,
+                           void *out_dev, void *workspace_dev, size_t workspace_bytes, void *stream) {
+  VVB_REQUIRE(x_dev && idx_dev && out_dev && workspace_dev, "smooth: null pointer argument");
+  VVB_REQUIRE(k >= 1 && k <= n - 1, "`k` must be between 1 and (n-1)");
+  VVB_REQUIRE(coef >= 0.0 && coef <= 1.0, "`coef` must be more than 0. and at most 1.");
+  VVB_REQUIRE(n_iter >= 1 && n_iter <= 10000, "`n_iter` must be at least 1 and at most 10000");
+  return launch_smooth_cols(x_dev, elem_size, n, d, col0, dcols, idx_dev, ld_idx, k, coef, n_iter, mode, out_dev,
+                            workspace_dev, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 // Rows [row_lo, row_hi) of ONE Jacobi sweep: every row reads only `x`, so row ranges are independent and can

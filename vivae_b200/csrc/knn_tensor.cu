@@ -1702,6 +1702,7 @@ int knn_tensor_begin(void *session_mem, const float *x_dev, int64_t n, int d, in
     stats->ms_prepare += ms;
     stats->candidates = S->keep;
     stats->cells = S->L.cells.P;
+    stats->products = S->single ? 1 : 3;
   }
   return VVB_OK;
 }

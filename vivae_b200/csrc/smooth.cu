@@ -62,8 +62,10 @@ __device__ __forceinline__ double vget(const double2 &v, int e) { return e ? v.y
 template <typename T, int V, int DPL, int KPL, bool GS>
 __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
     const T *__restrict__ prev, T *next, const int64_t *__restrict__ idx, int64_t ld_idx, int64_t n,
-    int d, int k, T coef, int *flags, int epoch, unsigned long long *ticket, int *bad_index, int rows_per_ticket,
-    int64_t row_lo, int64_t row_hi, int jitter) {
+    int d, int64_t ld, int k, T coef, int *flags, int epoch, unsigned long long *ticket, int *bad_index,
+    int rows_per_ticket, int64_t row_lo, int64_t row_hi, int jitter) {
+  // d columns are processed; rows are `ld` elements apart (ld > d: a column slice of a wider matrix -- the columns of
+  // a sweep are independent of each other, which is how several GPUs share one sweep: vvb_smooth_cols_device)
   using TV = typename VecOf<T, V>::type;
   const int lane = threadIdx.x & 31;
   const T kk = static_cast<T>(k);
@@ -112,8 +114,7 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
         if (__any_sync(FULL, polled)) fence_acq_rel();
         __syncwarp();
       }
-      const TV *prev_v = reinterpret_cast<const TV *>(prev);
-      const TV *next_v = reinterpret_cast<const TV *>(next);
+
       for (int c0 = 0; c0 < dv; c0 += 32 * DPL) {
         T acc[DPL][V];
 #pragma unroll
@@ -131,7 +132,8 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
                 const int j = __shfl_sync(FULL, mine[kq], (jb + u) & 31);
                 if (kq * 32 + jb + u < k) {
                   const bool from_next = GS && (j < i32);
-                  const TV *src = (from_next ? next_v : prev_v) + static_cast<int64_t>(j) * dv;
+                  const TV *src = reinterpret_cast<const TV *>((from_next ? static_cast<const T *>(next) : prev) +
+                                                               static_cast<int64_t>(j) * ld);
 #pragma unroll
                   for (int q = 0; q < DPL; ++q) {
                     const int c = c0 + q * 32 + lane;
@@ -162,11 +164,11 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
           if (c < dv) {
 #pragma unroll
             for (int e = 0; e < V; ++e) {
-              const T r = __ldg(prev + i * d + c * V + e);
+              const T r = __ldg(prev + i * ld + c * V + e);
               const T target = Arith<T>::div(acc[q][e], kk);
               const T vec = Arith<T>::sub(target, r);
               const T prod = Arith<T>::mul(vec, coef);
-              next[i * d + c * V + e] = Arith<T>::add(r, prod);
+              next[i * ld + c * V + e] = Arith<T>::add(r, prod);
             }
           }
         }
@@ -211,7 +213,7 @@ int smooth_begin(void *workspace, int elem_size, int64_t n, int d, int n_iter, c
 
 // One launch of sweep `epoch` (1-based) over rows [row_lo, row_hi) with its own ticket.
 template <typename T, int V, int DPL, int KPL>
-static int launch_rows(const T *src, T *dst, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k, double coef,
+static int launch_rows(const T *src, T *dst, int64_t n, int d, int64_t ld, const int64_t *idx, int64_t ld_idx, int k, double coef,
                        int mode, const SmoothWs &w, int epoch, unsigned long long *ticket, int64_t row_lo,
                        int64_t row_hi, cudaStream_t st) {
   int blocks_per_sm = 0;
@@ -237,10 +239,10 @@ static int launch_rows(const T *src, T *dst, int64_t n, int d, const int64_t *id
   const char *je = getenv("VVB_SMOOTH_JITTER");
   const int jitter = je ? atoi(je) : 0;
   if (mode == VVB_SMOOTH_JACOBI)
-    kern_ja<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k, static_cast<T>(coef),
+    kern_ja<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, ld, k, static_cast<T>(coef),
                                                                w.flags, epoch, ticket, w.bad, rpt, row_lo, row_hi, 0);
   else
-    kern_gs<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, k, static_cast<T>(coef),
+    kern_gs<<<static_cast<unsigned>(grid), SM_THREADS, 0, st>>>(src, dst, idx, ld_idx, n, d, ld, k, static_cast<T>(coef),
                                                                w.flags, epoch, ticket, w.bad, rpt, row_lo, row_hi, jitter);
   VVB_CHECK_LAUNCH();
   return VVB_OK;
@@ -250,18 +252,18 @@ static int launch_rows(const T *src, T *dst, int64_t n, int d, const int64_t *id
 // a_s, writes b_s).  chunk >= 0: rows [row_lo, row_hi) of a ONE-sweep call, x -> out; the caller issues the
 // chunks in increasing row order on one stream after smooth_begin().
 template <typename T, int V, int DPL, int KPL>
-static int launch_sweeps(const T *x, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k, double coef,
+static int launch_sweeps(const T *x, int64_t n, int d, int64_t ld, int col0, const int64_t *idx, int64_t ld_idx, int k, double coef,
                          int n_iter, int mode, T *out, void *workspace, int chunk, int64_t row_lo, int64_t row_hi,
                          cudaStream_t st) {
-  SmoothWs w = carve_smooth_ws(workspace, sizeof(T), n, d, n_iter);
+  SmoothWs w = carve_smooth_ws(workspace, sizeof(T), n, static_cast<int>(ld), n_iter);
   if (chunk >= 0)
-    return launch_rows<T, V, DPL, KPL>(x, out, n, d, idx, ld_idx, k, coef, mode, w, 1, w.tickets + n_iter + chunk, row_lo,
+    return launch_rows<T, V, DPL, KPL>(x, out, n, d, ld, idx, ld_idx, k, coef, mode, w, 1, w.tickets + n_iter + chunk, row_lo,
                                     row_hi, st);
   const T *src = x;
   for (int it = 0; it < n_iter; ++it) {
     const bool to_out = ((n_iter - 1 - it) % 2) == 0;
-    T *dst = to_out ? out : static_cast<T *>(w.scratch);
-    int rc = launch_rows<T, V, DPL, KPL>(src, dst, n, d, idx, ld_idx, k, coef, mode, w, it + 1, w.tickets + it, 0, n, st);
+    T *dst = to_out ? out : static_cast<T *>(w.scratch) + col0;  // (the scratch matrix has the full row width)
+    int rc = launch_rows<T, V, DPL, KPL>(src, dst, n, d, ld, idx, ld_idx, k, coef, mode, w, it + 1, w.tickets + it, 0, n, st);
     if (rc) return rc;
     src = dst;
   }
@@ -273,33 +275,33 @@ size_t smooth_workspace_bytes(int elem_size, int64_t n, int d, int n_iter) {
          align_up((static_cast<size_t>(n_iter) + SM_MAX_CHUNKS) * sizeof(unsigned long long), 256) + 256;
 }
 
-static int smooth_dispatch(const void *x, int elem_size, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
+static int smooth_dispatch(const void *x, int elem_size, int64_t n, int d, int64_t ld, int col0, const int64_t *idx, int64_t ld_idx, int k,
                            double coef, int n_iter, int mode, void *out, void *workspace, int chunk, int64_t row_lo,
                            int64_t row_hi, cudaStream_t st) {
 #define VVB_SM_K(T, V, DPL, xp, op)                                                                                   \
   do {                                                                                                                \
     if (k <= 64)                                                                                                      \
-      return launch_sweeps<T, V, DPL, 2>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,  \
+      return launch_sweeps<T, V, DPL, 2>(xp, n, d, ld, col0, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,  \
                                          row_hi, st);                                                                 \
     if (k <= 128)                                                                                                     \
-      return launch_sweeps<T, V, DPL, 4>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,  \
+      return launch_sweeps<T, V, DPL, 4>(xp, n, d, ld, col0, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,  \
                                          row_hi, st);                                                                 \
-    return launch_sweeps<T, V, DPL, 32>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,   \
+    return launch_sweeps<T, V, DPL, 32>(xp, n, d, ld, col0, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,   \
                                         row_hi, st);                                                                  \
   } while (0)
   // the two-column variant, instantiated for the common shapes only (every instantiation costs seconds of ptxas)
 #define VVB_SM_K2(T, DPL, xp, op)                                                                                     \
   do {                                                                                                                \
     if (k <= 64)                                                                                                      \
-      return launch_sweeps<T, 2, DPL, 2>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,  \
+      return launch_sweeps<T, 2, DPL, 2>(xp, n, d, ld, col0, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,  \
                                          row_hi, st);                                                                 \
-    return launch_sweeps<T, 2, DPL, 4>(xp, n, d, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,    \
+    return launch_sweeps<T, 2, DPL, 4>(xp, n, d, ld, col0, idx, ld_idx, k, coef, n_iter, mode, op, workspace, chunk, row_lo,    \
                                        row_hi, st);                                                                   \
   } while (0)
   // two columns per load when the rows allow it (d even, 8 / 16-byte aligned bases): half the load instructions
-  const bool vec2 = (d % 2 == 0) && d <= 128 && k <= 128 && reinterpret_cast<uintptr_t>(x) % (2 * elem_size) == 0 &&
+  const bool vec2 = (d % 2 == 0) && (ld % 2 == 0) && (col0 % 2 == 0) && d <= 128 && k <= 128 && reinterpret_cast<uintptr_t>(x) % (2 * elem_size) == 0 &&
                     reinterpret_cast<uintptr_t>(out) % (2 * elem_size) == 0 &&
-                    reinterpret_cast<uintptr_t>(carve_smooth_ws(workspace, elem_size, n, d, n_iter).scratch) % (2 * elem_size) == 0 &&
+                    reinterpret_cast<uintptr_t>(carve_smooth_ws(workspace, elem_size, n, static_cast<int>(ld), n_iter).scratch) % (2 * elem_size) == 0 &&
                     !(getenv("VVB_SMOOTH_VEC") && atoi(getenv("VVB_SMOOTH_VEC")) == 0);
   if (elem_size == 4) {
     const float *xf = static_cast<const float *>(x);
@@ -343,7 +345,7 @@ int launch_smooth(const void *x, int elem_size, int64_t n, int d, const int64_t 
   if (rc) return rc;
   rc = smooth_begin(workspace, elem_size, n, d, n_iter, st);
   if (rc) return rc;
-  return smooth_dispatch(x, elem_size, n, d, idx, ld_idx, k, coef, n_iter, mode, out, workspace, -1, 0, n, st);
+  return smooth_dispatch(x, elem_size, n, d, d, 0, idx, ld_idx, k, coef, n_iter, mode, out, workspace, -1, 0, n, st);
 }
 
 // Rows [row_lo, row_hi) of a one-sweep smooth (chunk = 0, 1, ... < smooth_max_chunks(), increasing row ranges,
@@ -358,7 +360,24 @@ int launch_smooth_rows(const void *x, int elem_size, int64_t n, int d, const int
   VVB_REQUIRE(chunk >= 0 && chunk < SM_MAX_CHUNKS && row_lo >= 0 && row_lo <= row_hi && row_hi <= n,
               "smooth: bad row chunk");
   if (row_lo == row_hi) return VVB_OK;
-  return smooth_dispatch(x, elem_size, n, d, idx, ld_idx, k, coef, 1, mode, out, workspace, chunk, row_lo, row_hi, st);
+  return smooth_dispatch(x, elem_size, n, d, d, 0, idx, ld_idx, k, coef, 1, mode, out, workspace, chunk, row_lo, row_hi, st);
+}
+
+// Columns [col0, col0 + dcols) of all n_iter sweeps over an (n, d) matrix: the sweep treats every column on its own
+// (row i's new value in column c depends on column c of its neighbours only), so column slices are independent --
+// whole sweeps, Gauss-Seidel order included, and each slice is bit-identical to the same columns of the full call.
+// `x` and `out` are the FULL matrices; only the slice of `out` is written.
+int launch_smooth_cols(const void *x, int elem_size, int64_t n, int d, int col0, int dcols, const int64_t *idx,
+                       int64_t ld_idx, int k, double coef, int n_iter, int mode, void *out, void *workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
+  int rc = smooth_check(x, elem_size, n, d, ld_idx, k, n_iter, mode, out, workspace_bytes);
+  if (rc) return rc;
+  VVB_REQUIRE(col0 >= 0 && dcols >= 0 && col0 + dcols <= d, "smooth: bad column slice [%d, %d) of %d", col0, col0 + dcols, d);
+  rc = smooth_begin(workspace, elem_size, n, d, n_iter, st);
+  if (rc || dcols == 0) return rc;
+  const char *xs = static_cast<const char *>(x) + static_cast<size_t>(col0) * elem_size;
+  char *os = static_cast<char *>(out) + static_cast<size_t>(col0) * elem_size;
+  return smooth_dispatch(xs, elem_size, n, dcols, d, col0, idx, ld_idx, k, coef, n_iter, mode, os, workspace, -1, 0, n, st);
 }
 
 int smooth_max_chunks() { return SM_MAX_CHUNKS; }

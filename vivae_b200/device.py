@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["knn_device", "smooth_device", "smooth_rows_device", "knn_merge_init", "knn_merge", "knn_merge_finish"]
+__all__ = ["knn_device", "smooth_device", "smooth_cols_device", "smooth_rows_device", "knn_merge_init", "knn_merge", "knn_merge_finish"]
 
 
 def _require_cuda(name: str, t: torch.Tensor, dtype) -> torch.Tensor:
@@ -197,6 +197,40 @@ def smooth_device(x: torch.Tensor, idx: torch.Tensor, k: int = 50, coef: float =
         if not validate:
             return out, flag.clone()
         if int(flag.item()):
+            raise ValueError("Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed")
+    return out
+
+
+def smooth_cols_device(x: torch.Tensor, idx: torch.Tensor, col0: int, dcols: int, k: int = 50, coef: float = 0.1,
+                       n_iter: int = 1, mode: str = "gauss_seidel", out: Optional[torch.Tensor] = None,
+                       validate: bool = True) -> torch.Tensor:
+    """Columns [col0, col0+dcols) of `smooth_device(x, idx, ...)`, written into the same columns of `out` (a full
+    (n, d) tensor, allocated when None; the other columns are left alone).  The smoother never mixes columns, so the
+    slice is bit-identical to the full call's -- this is how several GPUs share one Gauss-Seidel sweep."""
+    lib = _lib.load()
+    if x.dtype not in (torch.float32, torch.float64):
+        raise ValueError("`x` must be float32 or float64")
+    x = _require_cuda("x", x, x.dtype)
+    idx = _require_cuda("idx", idx, torch.int64)
+    n, d = x.shape
+    if mode not in _lib.SMOOTH_MODES:
+        raise ValueError(f"`mode` must be one of {sorted(_lib.SMOOTH_MODES)}")
+    if col0 < 0 or dcols < 0 or col0 + dcols > d:
+        raise ValueError("column slice outside the matrix")
+    with torch.cuda.device(x.device):
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.vvb_smooth_workspace_bytes(x.element_size(), n, d, n_iter, ctypes.byref(nbytes)))
+        ws = _lib.raw_empty(int(nbytes.value), torch.uint8, x.device)
+        if out is None:
+            out = _lib.raw_empty(x.shape, x.dtype, x.device)
+        if out.shape != x.shape or out.dtype != x.dtype or not out.is_contiguous() or out.data_ptr() == x.data_ptr():
+            raise ValueError("`out` must be a contiguous tensor of x's shape and dtype, distinct from x")
+        _lib.check(lib.vvb_smooth_cols_device(x.data_ptr(), x.element_size(), n, d, int(col0), int(dcols), idx.data_ptr(),
+                                              idx.shape[1], int(k), float(coef), int(n_iter), _lib.SMOOTH_MODES[mode],
+                                              out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              torch.cuda.current_stream().cuda_stream))
+        ws.record_stream(torch.cuda.current_stream())
+        if validate and int(ws[:4].view(torch.int32).item()):
             raise ValueError("Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed")
     return out
 

@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_bounds", "all_gather_rows", "all_gather_indices", "make_knn_sharded", "make_knn_ring", "ring_fold",
-           "knn_smooth_sharded", "knn_smooth_host_sharded", "smooth_jacobi_sharded"]
+           "knn_smooth_sharded", "knn_smooth_host_sharded", "smooth_jacobi_sharded", "smooth_cols_sharded", "col_bounds"]
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -30,6 +30,49 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     per = (n + world - 1) // world
     q0 = min(rank * per, n)
     return q0, min(per, n - q0)
+
+
+def col_bounds(d: int, world: int, rank: int) -> Tuple[int, int]:
+    """Column slice of `rank` for the column-sharded smoother: (first column, column count).  Slices are made of whole
+    column PAIRS when d is even (the kernel then fetches two columns per load); trailing slices may be empty."""
+    unit = 2 if d % 2 == 0 else 1
+    units = d // unit
+    per = (units + world - 1) // world
+    c0 = min(rank * per, units)
+    return c0 * unit, min(per, units - c0) * unit
+
+
+def smooth_cols_sharded(x: torch.Tensor, idx: torch.Tensor, k: int = 50, coef: float = 0.1, n_iter: int = 1, group=None,
+                        mode: str = "gauss_seidel", _cols_fn: Optional[Callable] = None) -> torch.Tensor:
+    """`smooth` of the whole matrix with the COLUMNS split over the ranks of `group`.
+
+    The reference's sweep (knn.py:173-185) is sequential in the rows (row i reads rows j < i already updated), so it
+    does not split by rows -- but it never mixes columns: element (i, c) depends on column c of row i's neighbours
+    only.  Every rank therefore runs the complete sweep (all n_iter passes, same row order, same arithmetic) on its
+    slice of the columns, and the slices are all-gathered once at the end.  Bit-identical to the single-GPU call.
+    `x` (n, d) and `idx` (n, >= k) are the whole matrix and the whole graph on every rank."""
+    if _cols_fn is None:
+        from .device import smooth_cols_device
+
+        _cols_fn = smooth_cols_device
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n, d = x.shape
+    c0, w = col_bounds(d, world, rank)
+    out = _cols_fn(x, idx, c0, w, k, coef, n_iter, mode)
+    if world == 1:
+        return out
+    wmax = col_bounds(d, world, 0)[1]
+    mine = torch.zeros((n, wmax), dtype=x.dtype, device=x.device)
+    mine[:, :w] = out[:, c0:c0 + w]
+    flat = torch.empty((world * n, wmax), dtype=x.dtype, device=x.device)  # rank-major concatenation
+    dist.all_gather_into_tensor(flat, mine, group=group)
+    allc = flat.view(world, n, wmax)
+    for r in range(world):
+        r0, rw = col_bounds(d, world, r)
+        if rw and r != rank:
+            out[:, r0:r0 + rw] = allc[r, :, :rw]
+    return out
 
 
 def all_gather_rows(local: torch.Tensor, n: int, group=None) -> torch.Tensor:
@@ -72,6 +115,9 @@ def make_knn_sharded(x: torch.Tensor, k: int, group=None, algo: str = "auto", ga
         idx = all_gather_indices(idx, n, group)
         dst = all_gather_rows(dst, n, group)
     return idx, dst
+
+
+_COLS = object()  # marker: the default smoother of the multi-GPU pipelines (column-sharded, CUDA)
 
 
 class _DeviceOps:
@@ -142,15 +188,16 @@ def make_knn_ring(x_local: torch.Tensor, n: int, k: int, group=None, algo: str =
 
 def knn_smooth_sharded(x: torch.Tensor, k: int, coef: float = 1.0, n_iter: int = 1, group=None, algo: str = "auto",
                        _knn_fn: Optional[Callable] = None, _smooth_fn: Optional[Callable] = None):
-    """make_knn (sharded) -> all-gather of the indices -> smooth (replicated).  Returns (idx, smoothed x)."""
+    """make_knn (sharded by query rows) -> all-gather of the indices -> smooth (sharded by COLUMNS, see
+    `smooth_cols_sharded`; tests pass `_smooth_fn` to run it replicated on the CPU).  Returns (idx, smoothed x)."""
     if _smooth_fn is None:
-        from .device import smooth_device
-
-        _smooth_fn = smooth_device
+        _smooth_fn = _COLS
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     idx, _ = make_knn_sharded(x, k, group=group, algo=algo, gather=False, _knn_fn=_knn_fn)
     if world > 1:
         idx = all_gather_indices(idx, x.shape[0], group)
+    if world > 1 and _smooth_fn is _COLS:
+        return idx, smooth_cols_sharded(x, idx, k, coef, n_iter, group)
     return idx, _smooth_fn(x, idx, k, coef, n_iter)
 
 
@@ -162,13 +209,9 @@ def knn_smooth_host_sharded(x_shard, n: int, k: int, coef: float = 1.0, n_iter: 
     `x_shard`: this rank's rows [q0, q0+nq) = `shard_bounds(n, world, rank)` as a host array (NumPy or CPU
     tensor, float32; page-locked memory makes the upload one DMA).  Steps: upload of the shard -> NCCL all-gather
     of the matrix -> graph rows of the shard -> all-gather of the indices (int32 over NVLink) -> Gauss-Seidel
-    smoother (replicated, it does not shard by rows) -> download of the shard's graph rows and smoothed rows.
+    smoother (sharded by COLUMNS: `smooth_cols_sharded`) -> download of the shard's graph rows and smoothed rows.
     Returns host tensors `(idx int64 (nq, k+1), dist float32 (nq, k+1), smoothed (nq, d))`; with `out=` (a tuple of
     three page-locked CPU tensors of those shapes) the downloads land there.  world = 1 is the plain pipeline."""
-    if _smooth_fn is None:
-        from .device import smooth_device
-
-        _smooth_fn = smooth_device
     if _knn_fn is None:
         from .device import knn_device
 
@@ -185,7 +228,10 @@ def knn_smooth_host_sharded(x_shard, n: int, k: int, coef: float = 1.0, n_iter: 
     x = all_gather_rows(x_loc, n, group) if world > 1 else x_loc
     idx_loc, dist_loc = _knn_fn(x, k, q0, nq, algo)
     idx = all_gather_indices(idx_loc, n, group) if world > 1 else idx_loc
-    sm = _smooth_fn(x, idx, k, coef, n_iter)
+    if _smooth_fn is None:
+        sm = smooth_cols_sharded(x, idx, k, coef, n_iter, group)  # world = 1: the whole sweep on this GPU
+    else:
+        sm = _smooth_fn(x, idx, k, coef, n_iter)
     sm_loc = sm[q0:q0 + nq]
     if out is None:
         out = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=(device.type == "cuda"))
