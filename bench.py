@@ -25,8 +25,8 @@ Timed quantities
 N > 1 (launched under torchrun): the query rows are sharded across ranks (strong scaling: total work fixed); each
 rank holds the whole matrix, the preparation of the cell plan is split across the ranks, the index shards are
 all-gathered over NCCL (int32) and the Gauss-Seidel smoother -- which does not shard by rows but never mixes columns
- -- is sharded by COLUMNS: every rank runs the whole sweep on its slice of the columns and the
-slices are all-gathered; bit-identical to the single-GPU sweep.
+ -- runs in COLUMN shards when the rows are wide (>= 64 columns per rank) and replicated on every
+rank otherwise (at 50 columns a slice costs as many load instructions as the whole row); bit-identical either way.
 
 `--impl reference` times the reference's CPU path for the same metric on the host cores: the oracle port (oracle/,
 C + OpenMP) on a bounded sample -- the reference's own kNN (pynndescent) is not installable here and its smoother is
@@ -247,11 +247,10 @@ def run_reference(args) -> None:
 def workload_config(args, n_gpus: int) -> dict:
     return {"workload": f"synthetic {args.n} cells x {args.d} PCs, exact kNN k={args.k} + smooth(k={args.k}, coef=1, n_iter=1)",
             "n": args.n, "d": args.d, "k": args.k,
-            "parallelism": (f"graph: query-row shards x{n_gpus} (cell plan prepared in row / cell shards); smoother: column "
-                            f"shards x{n_gpus}; NCCL all-gathers of indices and smoothed columns"
+            "parallelism": (f"graph: query-row shards x{n_gpus} (cell plan prepared in row / cell shards), indices all-gathered "
+                            f"over NCCL; smoother: " + (f"column shards x{n_gpus}" if args.d >= 64 * n_gpus else "replicated")
                             if getattr(args, "exchange", "replicated") != "ring" else
-                            f"query-row AND database-row shards x{n_gpus} (NCCL ring exchange + running merge), smoother "
-                            f"in column shards"),
+                            f"query-row AND database-row shards x{n_gpus} (NCCL ring exchange + running merge), smoother replicated"),
             "l2": f"inputs larger than L2 (matrix {args.n * args.d * 4 / 1e6:.0f} MB, graph "
                   f"{args.n * (args.k + 1) * 12 / 1e6:.0f} MB vs 126 MB L2)"}
 
@@ -297,7 +296,7 @@ def run_ours(args) -> None:
     from vivae_b200 import _lib
     from vivae_b200.device import knn_device, smooth_device
     from vivae_b200.sharded import (all_gather_indices, knn_smooth_host_sharded, make_knn_ring, shard_bounds,
-                                    smooth_cols_sharded)
+                                    smooth_auto_sharded)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -340,7 +339,7 @@ def run_ours(args) -> None:
             idx, dist_ = knn_step(xd, kk, q0_, nq_, stats)
         if world > 1:
             idx = all_gather_indices(idx, n_)  # the smoother needs the whole graph (NCCL all-gather, int32)
-            out = smooth_cols_sharded(xd, idx, k=kk, coef=1.0, n_iter=1)  # column slices, all-gathered
+            out = smooth_auto_sharded(xd, idx, k=kk, coef=1.0, n_iter=1)  # column shards only for wide rows
         else:
             out = smooth_device(xd, idx, k=kk, coef=1.0, n_iter=1)
         return idx, dist_, out
@@ -388,10 +387,7 @@ def run_ours(args) -> None:
     idx_full = all_gather_indices(idx_s, n) if world > 1 else idx_s
     torch.cuda.synchronize()
     e1.record()
-    if world > 1:
-        smooth_cols_sharded(x_dev, idx_full, k=k, coef=1.0, n_iter=1)
-    else:
-        smooth_device(x_dev, idx_full, k=k, coef=1.0, n_iter=1)
+    smooth_auto_sharded(x_dev, idx_full, k=k, coef=1.0, n_iter=1)
     e2.record()
     torch.cuda.synchronize()
     ms_smooth = max_over_ranks(e1.elapsed_time(e2))
@@ -423,7 +419,8 @@ def run_ours(args) -> None:
         dense_roof = screen_roofline(sd, nq, n, d, peaks)
         dense_roof["kernel"] += " (VVB_TC_CELLS=1: no tile skipped)"
     sbytes = float(n) * (k * d * 4 + k * 4 + d * 4)
-    smooth_roof = {"kernel": "smooth_sweep_gs" + (f" (column shards x{world} + all-gather)" if world > 1 else ""), "bound": "hbm", "achieved": sbytes / (ms_smooth / 1e3) / 1e9,
+    smooth_roof = {"kernel": "smooth_sweep_gs" + (f" (column shards x{world} + all-gather)" if world > 1 and d >= 64 * world else
+                                                  " (replicated on every rank)" if world > 1 else ""), "bound": "hbm", "achieved": sbytes / (ms_smooth / 1e3) / 1e9,
                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": sbytes / (ms_smooth / 1e3) / 1e9 / peaks["hbm_gbs"],
                    "ms": ms_smooth, "algorithmic_bytes": sbytes, "traffic": None}
 

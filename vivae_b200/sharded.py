@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_bounds", "all_gather_rows", "all_gather_indices", "make_knn_sharded", "make_knn_ring", "ring_fold",
-           "knn_smooth_sharded", "knn_smooth_host_sharded", "smooth_jacobi_sharded", "smooth_cols_sharded", "col_bounds"]
+           "knn_smooth_sharded", "knn_smooth_host_sharded", "smooth_jacobi_sharded", "smooth_cols_sharded", "smooth_auto_sharded", "col_bounds"]
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -73,6 +73,20 @@ def smooth_cols_sharded(x: torch.Tensor, idx: torch.Tensor, k: int = 50, coef: f
         if rw and r != rank:
             out[:, r0:r0 + rw] = allc[r, :, :rw]
     return out
+
+
+def smooth_auto_sharded(x: torch.Tensor, idx: torch.Tensor, k: int = 50, coef: float = 0.1, n_iter: int = 1, group=None,
+                        mode: str = "gauss_seidel") -> torch.Tensor:
+    """The smoother of the multi-GPU pipelines: column shards when a slice still keeps a warp busy (at least 64
+    columns per rank), otherwise the whole sweep on every rank.  Measured on 2 B200 at 1M x 50, k=50: 3.06 ms in
+    two column shards against 2.59 ms replicated -- at that width the sweep costs one load instruction per neighbour
+    whether the row has 50 columns or 26, and it is bound by those instructions and their latency, not by bytes."""
+    from .device import smooth_device
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1 and x.shape[1] >= 64 * world:
+        return smooth_cols_sharded(x, idx, k, coef, n_iter, group, mode)
+    return smooth_device(x, idx, k, coef, n_iter, mode)
 
 
 def all_gather_rows(local: torch.Tensor, n: int, group=None) -> torch.Tensor:
@@ -188,16 +202,16 @@ def make_knn_ring(x_local: torch.Tensor, n: int, k: int, group=None, algo: str =
 
 def knn_smooth_sharded(x: torch.Tensor, k: int, coef: float = 1.0, n_iter: int = 1, group=None, algo: str = "auto",
                        _knn_fn: Optional[Callable] = None, _smooth_fn: Optional[Callable] = None):
-    """make_knn (sharded by query rows) -> all-gather of the indices -> smooth (sharded by COLUMNS, see
-    `smooth_cols_sharded`; tests pass `_smooth_fn` to run it replicated on the CPU).  Returns (idx, smoothed x)."""
+    """make_knn (sharded by query rows) -> all-gather of the indices -> smooth (`smooth_auto_sharded`: column shards
+    for wide rows, replicated otherwise; tests pass `_smooth_fn` to run it on the CPU).  Returns (idx, smoothed x)."""
     if _smooth_fn is None:
         _smooth_fn = _COLS
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     idx, _ = make_knn_sharded(x, k, group=group, algo=algo, gather=False, _knn_fn=_knn_fn)
     if world > 1:
         idx = all_gather_indices(idx, x.shape[0], group)
-    if world > 1 and _smooth_fn is _COLS:
-        return idx, smooth_cols_sharded(x, idx, k, coef, n_iter, group)
+    if _smooth_fn is _COLS:
+        return idx, smooth_auto_sharded(x, idx, k, coef, n_iter, group)
     return idx, _smooth_fn(x, idx, k, coef, n_iter)
 
 
@@ -209,7 +223,7 @@ def knn_smooth_host_sharded(x_shard, n: int, k: int, coef: float = 1.0, n_iter: 
     `x_shard`: this rank's rows [q0, q0+nq) = `shard_bounds(n, world, rank)` as a host array (NumPy or CPU
     tensor, float32; page-locked memory makes the upload one DMA).  Steps: upload of the shard -> NCCL all-gather
     of the matrix -> graph rows of the shard -> all-gather of the indices (int32 over NVLink) -> Gauss-Seidel
-    smoother (sharded by COLUMNS: `smooth_cols_sharded`) -> download of the shard's graph rows and smoothed rows.
+    smoother (`smooth_auto_sharded`: column shards for wide rows, replicated otherwise) -> download of the shard's graph rows and smoothed rows.
     Returns host tensors `(idx int64 (nq, k+1), dist float32 (nq, k+1), smoothed (nq, d))`; with `out=` (a tuple of
     three page-locked CPU tensors of those shapes) the downloads land there.  world = 1 is the plain pipeline."""
     if _knn_fn is None:
@@ -229,7 +243,7 @@ def knn_smooth_host_sharded(x_shard, n: int, k: int, coef: float = 1.0, n_iter: 
     idx_loc, dist_loc = _knn_fn(x, k, q0, nq, algo)
     idx = all_gather_indices(idx_loc, n, group) if world > 1 else idx_loc
     if _smooth_fn is None:
-        sm = smooth_cols_sharded(x, idx, k, coef, n_iter, group)  # world = 1: the whole sweep on this GPU
+        sm = smooth_auto_sharded(x, idx, k, coef, n_iter, group)
     else:
         sm = _smooth_fn(x, idx, k, coef, n_iter)
     sm_loc = sm[q0:q0 + nq]
