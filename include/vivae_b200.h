@@ -256,6 +256,32 @@ int vvb_quartet_loss_fwd_device(const float *x_dev, const float *z_dev, int64_t 
 int vvb_quartet_loss_bwd_device(const float *grad_unit_dev, const float *grad_out_dev, int64_t count,
                                 float *grad_z_dev, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Fused training step -- replaces, for the default configuration, what one batch of
+ *   /root/reference/src/vivae/model.py:130-177 (`train_epoch`) executes between `optimizer.zero_grad()` and
+ *   `optimizer.step()`: `Autoencoder.forward` (network.py:219-296: encode, reparameterise 113-130, KLDivLoss
+ *   losses.py:105-131, decode, nn.MSELoss, MDSLoss losses.py:266-349 with euclidean distances and n_sampling = 1) and
+ *   the autograd backward of `recon + kldiv + mds`.  ONE kernel (+ one deterministic reduction) instead of ~140.
+ *
+ *   Layers, in this order: n_enc encoder Linear layers (GELU, exact erf, after each), the mu head, the logvar head,
+ *   n_dec decoder Linear layers (GELU after all but the last).  w_ptrs / b_ptrs: HOST arrays of n_enc + 2 + n_dec
+ *   DEVICE pointers to the layers' weight (out, in) row-major and bias (out) tensors -- the network's own parameter
+ *   tensors, read in place; in_dims / out_dims: HOST arrays of the layers' shapes.
+ *   x (B, D) the batch, eps (B, L) the reparameterisation noise (drawn by the caller: torch.randn_like, so the RNG
+ *   stream is the reference's); B a multiple of 4.
+ *   Outputs: grad_flat (n_params): d(loss)/d(parameters), layer by layer, weight then bias;
+ *            loss_out[3] = {lam_recon * MSE, lam_kldiv * KL, lam_mds * MDS}; term_sums (6 floats, may be NULL): the
+ *            same three values ADDED to slots 0, 1, 4 (the epoch's running sums, model.py:138-143).
+ *   Scratch: grad_partials (n_cta * n_params floats), loss_partials (4 * n_cta floats).
+ *   Size query: call with grad_partials_dev == NULL; *smem_bytes, *n_params, *n_cta are filled either way.
+ *   VVB_ENOTSUP when the activations of 32 rows do not fit shared memory or the layer count exceeds 16.
+ * ------------------------------------------------------------------------ */
+int vvb_vae_step_device(const float *const *w_ptrs, const float *const *b_ptrs, const int *in_dims, const int *out_dims,
+                        int n_enc, int n_dec, const float *x_dev, const float *eps_dev, int B, int D, int L,
+                        float lam_recon, float lam_kldiv, float lam_mds, float *grad_partials_dev,
+                        float *loss_partials_dev, float *grad_flat_dev, float *term_sums_dev, float *loss_out_dev,
+                        size_t *smem_bytes, int *n_params, int *n_cta, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,9 @@ SYMBOLS = {
     "vvb_smooth_device": (_int, [_vp, _int, _i64, _int, _vp, _i64, _int, _dbl, _int, _int, _vp, _vp, _sz, _vp]),
     "vvb_smooth_cols_device": (_int, [_vp, _int, _i64, _int, _int, _int, _vp, _i64, _int, _dbl, _int, _int, _vp, _vp, _sz, _vp]),
     "vvb_smooth_rows_device": (_int, [_vp, _int, _i64, _int, _vp, _i64, _int, _dbl, _int, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "vvb_vae_step_device": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _int, _int, _int, ctypes.c_float,
+                                   ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_sz),
+                                   ctypes.POINTER(_int), ctypes.POINTER(_int), _vp]),
     "vvb_quartet_workspace_bytes": (_sz, [_i64]),
     "vvb_quartet_loss_fwd_device": (_int, [_vp, _vp, _i64, _int, _int, _vp, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "vvb_quartet_loss_bwd_device": (_int, [_vp, _vp, _i64, _vp, _vp]),

@@ -86,6 +86,11 @@ int launch_knn_merge_finish(const float *run_d2, int64_t count, float *dist, cud
 int launch_quartet_bwd(const float *grad_unit, const float *grad_out, int64_t count, float *grad_z,
                        cudaStream_t st);
 
+int launch_vae_step(const float *const *w_ptrs, const float *const *b_ptrs, const int *in_dims, const int *out_dims,
+                    int n_enc, int n_dec, const float *x, const float *eps, int B, int D, int L, float lam_recon,
+                    float lam_kldiv, float lam_mds, float *gpart, float *lpart, float *gflat, float *sums,
+                    float *loss_out, size_t *smem_bytes, int *n_params, int *n_cta, cudaStream_t st);
+
 struct DevBuf {  // RAII device allocation for the *_host entry points
   void *p = nullptr;
   ~DevBuf() {
@@ -970,6 +975,21 @@ int vvb_knn_merge_device(const float *xc_dev, int64_t nc, int d, int64_t q0, int
 int vvb_knn_merge_finish_device(const float *run_d2_dev, int64_t count, float *dist_out_dev, void *stream) {
   VVB_REQUIRE(run_d2_dev && dist_out_dev, "knn merge finish: null pointer argument");
   return launch_knn_merge_finish(run_d2_dev, count, dist_out_dev, static_cast<cudaStream_t>(stream));
+}
+
+// -------------------------------------------------------------------- fused training step
+int vvb_vae_step_device(const float *const *w_ptrs, const float *const *b_ptrs, const int *in_dims, const int *out_dims,
+                        int n_enc, int n_dec, const float *x_dev, const float *eps_dev, int B, int D, int L,
+                        float lam_recon, float lam_kldiv, float lam_mds, float *grad_partials_dev,
+                        float *loss_partials_dev, float *grad_flat_dev, float *term_sums_dev, float *loss_out_dev,
+                        size_t *smem_bytes, int *n_params, int *n_cta, void *stream) {
+  VVB_REQUIRE(in_dims && out_dims, "fused step: null dimension arrays");
+  if (grad_partials_dev)
+    VVB_REQUIRE(w_ptrs && b_ptrs && x_dev && eps_dev && loss_partials_dev && grad_flat_dev && loss_out_dev,
+                "fused step: null pointer argument");
+  return launch_vae_step(w_ptrs, b_ptrs, in_dims, out_dims, n_enc, n_dec, x_dev, eps_dev, B, D, L, lam_recon, lam_kldiv,
+                         lam_mds, grad_partials_dev, loss_partials_dev, grad_flat_dev, term_sums_dev, loss_out_dev,
+                         smem_bytes, n_params, n_cta, static_cast<cudaStream_t>(stream));
 }
 
 // -------------------------------------------------------------------- quartet

@@ -10,9 +10,10 @@ What is re-plumbed for the GPU:
   * per-term loss sums are accumulated on the device and read back once per epoch,
     instead of three `.item()` host syncs per batch (model.py:151,157,169);
   * the quartet term runs as one fused kernel (see `losses.MDSLoss`);
+  * in the default configuration the forward pass, the three loss terms and the backward pass of a batch are ONE
+    kernel (`fused_step.FusedStep`, csrc/vae_step.cu) instead of ~140; `VIVAE_FUSED_STEP=0` keeps the PyTorch path;
   * full-size batches replay ONE captured CUDA graph of the whole step (forward, backward, Adam,
-    loss bookkeeping): the step is ~100 tiny kernels and was launch-bound.  Disable with
-    `VIVAE_CUDA_GRAPH=0` or `model.use_cuda_graph = False`.
+    loss bookkeeping).  Disable with `VIVAE_CUDA_GRAPH=0` or `model.use_cuda_graph = False`.
 RNG call order is the reference's: the loader permutation comes from a dedicated
 generator seeded with `random_state` (model.py:246-248), `randn_like` and the quartet
 re-sampling permutations from the global generator.
@@ -60,6 +61,13 @@ class DeviceBatchLoader:
         return (self.data.shape[0] + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
+        for idx in self.index_batches():
+            yield (self.data.index_select(0, idx),)
+
+    def index_batches(self):
+        """The row indices of every batch of one epoch (1-D int64 device tensors), drawing from the generator exactly
+        what `__iter__` always drew.  `train_epoch` gathers full-size batches straight into the captured step's input
+        buffer with these (one kernel instead of index_select + copy)."""
         n = self.data.shape[0]
         dev = self.data.device
         if self._perm_override is not None:
@@ -74,7 +82,7 @@ class DeviceBatchLoader:
         else:
             perm = torch.arange(n, device=dev)
         for s in range(0, n, self.batch_size):
-            yield (self.data.index_select(0, perm[s:s + self.batch_size]),)
+            yield perm[s:s + self.batch_size]
         if self._perm_override is None and self.shuffle:
             torch.randperm(n, generator=self.generator, device=dev)
 
@@ -133,24 +141,40 @@ class ViVAE:
                     and isinstance(self.data_loader, DeviceBatchLoader))
         full = getattr(self.data_loader, "batch_size", None)
         with _lib.no_uninitialised_fill():  # also in force while the step is captured
-            for batch in self.data_loader:
-                x = batch[0]
-                if graph_ok and x.shape[0] == full and full >= 4:
-                    g = self._graphed_step(x, cfg)
-                    if g is not None:
-                        _, graph, static_x, static_sums, n_kernels = g
-                        static_x.copy_(x)
-                        static_sums.zero_()
-                        graph.replay()
-                        _lib.note_graph_replay(n_kernels)
-                        sums += static_sums
-                        continue
-                self._eager_step(x, cfg, sums)
+            if graph_ok:
+                data = self.data_loader.data
+                for idx in self.data_loader.index_batches():
+                    if idx.shape[0] == full and full >= 4:
+                        g = self._graph if self._graph is not None and self._graph[1] is not None else None
+                        if g is None or g[2].shape[0] != full:
+                            g = self._graphed_step(data.index_select(0, idx), cfg)
+                        else:
+                            g = self._graphed_step(g[2], cfg)  # same key: returns the captured graph (or re-captures)
+                        if g is not None:
+                            _, graph, static_x, static_sums, n_kernels = g
+                            torch.index_select(data, 0, idx, out=static_x)  # the batch, straight into the graph's input
+                            graph.replay()  # adds the batch's terms into static_sums
+                            _lib.note_graph_replay(n_kernels)
+                            continue
+                    self._eager_step(data.index_select(0, idx), cfg, sums)
+                if self._graph is not None and self._graph[1] is not None:
+                    sums += self._graph[3]  # the captured steps' running sums: read once per epoch
+                    self._graph[3].zero_()
+            else:
+                for batch in self.data_loader:
+                    self._eager_step(batch[0], cfg, sums)
         host = sums.tolist()  # the only host sync of the epoch
         return dict(zip(_TERMS, host))
 
     # one optimisation step on batch x; adds the batch's loss terms into `sums` (device tensor)
     def _eager_step(self, x: torch.Tensor, cfg: dict, sums: torch.Tensor) -> None:
+        fused = self._fused_for(x, cfg)
+        if fused is not None:
+            # forward, the three loss terms and backward as ONE kernel (csrc/vae_step.cu); the gradients land in the
+            # parameters' .grad (views of one flat buffer), the weighted terms in `sums`
+            fused.step(x, sums, cfg["lam_recon"], cfg["lam_kldiv"], cfg["lam_mds"])
+            self.optimizer.step()
+            return
         self.optimizer.zero_grad()
         terms = self.net(x, **cfg)
         loss = None
@@ -171,6 +195,28 @@ class ViVAE:
             sums += torch.stack([zero if v is None else v.to(torch.float32) for v in vals])
         loss.backward()
         self.optimizer.step()
+
+    def _fused_for(self, x: torch.Tensor, cfg: dict):
+        """The fused-step object for this batch, or None when the configuration needs the PyTorch path
+        (`fused_step.fused_step_supported`); built once per (batch size, optimiser)."""
+        from .fused_step import FusedStep, fused_step_supported
+
+        if not fused_step_supported(self.net, cfg, x):
+            return None
+        key = (x.shape[0], id(self.optimizer))
+        cache = getattr(self, "_fused", None)
+        if cache is None:
+            cache = self._fused = {}
+        fs = cache.get(key)
+        if fs is None or not fs.pointers_current():
+            try:
+                fs = FusedStep(self.net, x.shape[0])
+            except NotImplementedError:  # shapes outside the kernel's envelope: PyTorch path
+                fs = False
+            if len(cache) > 8:
+                cache.clear()
+            cache[key] = fs
+        return fs or None
 
     def _graphed_step(self, x: torch.Tensor, cfg: dict):
         """Capture (once per configuration) the whole step as a CUDA graph.  Warm-up steps run on a
