@@ -223,6 +223,33 @@ int vvb_smooth_cols_device(const void *x_dev, int elem_size, int64_t n, int d, i
                            const int64_t *idx_dev, int64_t ld_idx, int k, double coef, int n_iter, int mode,
                            void *out_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------
+ * The reference's (Gauss-Seidel) sweep over SEVERAL GPUs in one pass -- same call site, knn.py:173-185.
+ *   Rows are interleaved over `world` GPUs (row i belongs to rank i mod world); every rank keeps a complete copy of
+ *   the sweep's output in memory its peers can write (vvb_peer_alloc / vvb_peer_open: CUDA IPC over NVLink), as one
+ *   64-bit word {value bits, sweep epoch} per float32 element (two per float64 element).  vvb_smooth_peer_device runs
+ *   ONE sweep on rank `rank`: it computes the rank's rows from its local copies and stores each finished element, value
+ *   and epoch in one 8-byte store, into every rank's copy; a row that needs a neighbour still in flight re-reads the
+ *   word until the epoch matches.  No flags, no fences.  ll_ptrs: HOST array of `world` device pointers -- every rank's
+ *   copy (n * d * 8 bytes for float32, 16 for float64) as mapped into this process; entry [rank] is the local one.
+ *   Contract: the buffers are zero after vvb_peer_alloc; `epoch` >= 1 grows by one per sweep; all ranks call it for
+ *   the same sweep, with a barrier over the ranks before (nobody still reads the previous sweep) and after (all pushes
+ *   landed); then vvb_smooth_peer_unpack_device turns the local copy into plain values.
+ *   x_dev is this rank's copy of the sweep's input.  Bit-identical to vvb_smooth_device on one GPU.
+ *   k <= 128, d <= 128 (VVB_ENOTSUP otherwise).  workspace: vvb_smooth_peer_workspace_bytes(); its first int is set
+ *   non-zero by an out-of-range neighbour index (1) or a word that never arrived (2).
+ * ------------------------------------------------------------------------ */
+int vvb_peer_alloc(size_t bytes, void **ptr_out, unsigned char *handle_out /* 64 bytes */);
+int vvb_peer_open(const unsigned char *handle /* 64 bytes, from another process */, void **ptr_out);
+int vvb_peer_close(void *ptr);
+int vvb_peer_free(void *ptr);
+size_t vvb_smooth_peer_workspace_bytes(void);
+int vvb_smooth_peer_device(const void *x_dev, int elem_size, int64_t n, int d, const int64_t *idx_dev,
+                           int64_t ld_idx, int k, double coef, int epoch, int rank, int world,
+                           void *const *ll_ptrs, void *workspace_dev, void *stream);
+int vvb_smooth_peer_unpack_device(const void *ll_local_dev, int elem_size, int64_t count, int epoch, void *out_dev,
+                                  void *workspace_dev, void *stream);
+
 /* Rows [row_lo, row_hi) of ONE sweep in VVB_SMOOTH_JACOBI mode (row ranges of a Jacobi sweep are independent:
  * several GPUs each take a range and exchange the new rows between sweeps).  x (n, d) is the whole matrix;
  * idx_rows (row_hi-row_lo, ld_idx) and out_rows (row_hi-row_lo, d) hold only the range.  Workspace as

@@ -42,7 +42,44 @@ for n, d, k in ((1_000_000, 50, 50), (200_000, 300, 30)):
                        "prepare_ms_sharded": s_group["ms_prepare"], "screen_ms": s_group["ms_screen"],
                        "tiles_swept_whole_plan": s_plain["tiles_swept"], "tiles_swept_sharded_plan": s_group["tiles_swept"],
                        "parts": s_group["prepare_parts"]}
+# ---- the Gauss-Seidel sweep over all GPUs at once (interleaved rows, pushes over NVLink peer memory)
+from vivae_b200.sharded import release_peer_smoothers, smooth_peer_sharded  # noqa: E402
+
+peer = {}
+for n, d, k, dtype, order in ((1_000_000, 50, 50, torch.float32, "random"), (200_000, 38, 100, torch.float64, "sorted"),
+                              (50_000, 7, 10, torch.float32, "random")):
+    x = synth_cells(n, d, seed=5)
+    if order == "sorted":
+        x = x[np.argsort(x[:, 0])].copy()
+    xd32 = torch.from_numpy(x).to(dev)
+    idx, _ = knn_device(xd32, k)
+    xd = xd32.to(dtype)
+    res = {}
+    for n_iter in (1, 2):
+        want = smooth_device(xd, idx, k=k, coef=0.7, n_iter=n_iter)
+        got = smooth_peer_sharded(xd, idx, k=k, coef=0.7, n_iter=n_iter)
+        res[f"identical_n_iter{n_iter}"] = bool(torch.equal(want, got))
+    for name, fn in (("replicated", lambda: smooth_device(xd, idx, k=k, coef=1.0, n_iter=1)),
+                     ("peer", lambda: smooth_peer_sharded(xd, idx, k=k, coef=1.0, n_iter=1))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[f"ms_{name}"] = float(t.item())
+    flag = torch.tensor([int(all(v for kk, v in res.items() if kk.startswith("identical")))], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["identical_on_all_ranks"] = bool(flag.item())
+    peer[f"{n}x{d}_k{k}_{str(dtype).split('.')[-1]}_{order}"] = res
+release_peer_smoothers()
 if rank == 0:
-    print(json.dumps({"world": world, "checks": out}))
+    print(json.dumps({"world": world, "checks": out, "peer_smoother": peer}))
 dist.barrier()
 dist.destroy_process_group()

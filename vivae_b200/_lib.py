@@ -80,6 +80,13 @@ SYMBOLS = {
     "vvb_smooth_workspace_bytes": (_int, [_int, _i64, _int, _int, ctypes.POINTER(_sz)]),
     "vvb_smooth_device": (_int, [_vp, _int, _i64, _int, _vp, _i64, _int, _dbl, _int, _int, _vp, _vp, _sz, _vp]),
     "vvb_smooth_cols_device": (_int, [_vp, _int, _i64, _int, _int, _int, _vp, _i64, _int, _dbl, _int, _int, _vp, _vp, _sz, _vp]),
+    "vvb_peer_alloc": (_int, [_sz, ctypes.POINTER(ctypes.c_void_p), _vp]),
+    "vvb_peer_open": (_int, [_vp, ctypes.POINTER(ctypes.c_void_p)]),
+    "vvb_peer_close": (_int, [_vp]),
+    "vvb_peer_free": (_int, [_vp]),
+    "vvb_smooth_peer_workspace_bytes": (_sz, []),
+    "vvb_smooth_peer_device": (_int, [_vp, _int, _i64, _int, _vp, _i64, _int, _dbl, _int, _int, _int, _vp, _vp, _vp]),
+    "vvb_smooth_peer_unpack_device": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp]),
     "vvb_smooth_rows_device": (_int, [_vp, _int, _i64, _int, _vp, _i64, _int, _dbl, _int, _i64, _i64, _vp, _vp, _sz, _vp]),
     "vvb_vae_step_device": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _int, _int, _int, ctypes.c_float,
                                    ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_sz),

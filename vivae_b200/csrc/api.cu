@@ -91,6 +91,13 @@ int launch_vae_step(const float *const *w_ptrs, const float *const *b_ptrs, cons
                     float lam_kldiv, float lam_mds, float *gpart, float *lpart, float *gflat, float *sums,
                     float *loss_out, size_t *smem_bytes, int *n_params, int *n_cta, cudaStream_t st);
 
+size_t smooth_peer_workspace_bytes();
+int launch_smooth_peer(const void *x, int elem_size, int64_t n, int d, const int64_t *idx, int64_t ld_idx, int k,
+                       double coef, int epoch, int rank, int world, void *const *ll_ptrs, void *workspace,
+                       cudaStream_t st);
+int launch_smooth_peer_unpack(const void *ll_local, int elem_size, int64_t count, int epoch, void *out, void *workspace,
+                              cudaStream_t st);
+
 struct DevBuf {  // RAII device allocation for the *_host entry points
   void *p = nullptr;
   ~DevBuf() {
@@ -956,6 +963,69 @@ int vvb_smooth_rows_device(const void *x_dev, int elem_size, int64_t n, int d, c
   char *out_base = static_cast<char *>(out_rows_dev) - static_cast<size_t>(row_lo) * d * elem_size;
   return launch_smooth_rows(x_dev, elem_size, n, d, idx_base, ld_idx, k, coef, mode, out_base, workspace_dev,
                             workspace_bytes, 0, row_lo, row_hi, st);
+}
+
+// -------------------------------------------------------------------- smoother over peer memory (several GPUs)
+int vvb_peer_alloc(size_t bytes, void **ptr_out, unsigned char *handle_out) {
+  VVB_REQUIRE(ptr_out && handle_out && bytes > 0, "peer alloc: bad arguments");
+  *ptr_out = nullptr;
+  cudaError_t e = cudaMalloc(ptr_out, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? VVB_ENOMEM : VVB_ECUDA;
+  }
+  VVB_CUDA(cudaMemset(*ptr_out, 0, bytes));
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, *ptr_out);
+  if (e != cudaSuccess) {
+    cudaFree(*ptr_out);
+    *ptr_out = nullptr;
+    set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return VVB_ECUDA;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle_out, &h, 64);
+  return VVB_OK;
+}
+
+int vvb_peer_open(const unsigned char *handle, void **ptr_out) {
+  VVB_REQUIRE(handle && ptr_out, "peer open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  *ptr_out = nullptr;
+  VVB_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return VVB_OK;
+}
+
+int vvb_peer_close(void *ptr) {
+  if (ptr) VVB_CUDA(cudaIpcCloseMemHandle(ptr));
+  return VVB_OK;
+}
+
+int vvb_peer_free(void *ptr) {
+  if (ptr) VVB_CUDA(cudaFree(ptr));
+  return VVB_OK;
+}
+
+size_t vvb_smooth_peer_workspace_bytes(void) { return smooth_peer_workspace_bytes(); }
+
+int vvb_smooth_peer_device(const void *x_dev, int elem_size, int64_t n, int d, const int64_t *idx_dev, int64_t ld_idx,
+                           int k, double coef, int epoch, int rank, int world, void *const *ll_ptrs,
+                           void *workspace_dev, void *stream) {
+  VVB_REQUIRE(x_dev && idx_dev && ll_ptrs && workspace_dev, "smooth (peer): null pointer argument");
+  VVB_REQUIRE(k >= 1 && k <= n - 1, "`k` must be between 1 and (n-1)");
+  VVB_REQUIRE(coef >= 0.0 && coef <= 1.0, "`coef` must be more than 0. and at most 1.");
+  return launch_smooth_peer(x_dev, elem_size, n, d, idx_dev, ld_idx, k, coef, epoch, rank, world, ll_ptrs, workspace_dev,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int vvb_smooth_peer_unpack_device(const void *ll_local_dev, int elem_size, int64_t count, int epoch, void *out_dev,
+                                  void *workspace_dev, void *stream) {
+  VVB_REQUIRE(ll_local_dev && out_dev && workspace_dev && count >= 0, "smooth (peer) unpack: bad arguments");
+  return launch_smooth_peer_unpack(ll_local_dev, elem_size, count, epoch, out_dev, workspace_dev,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 // -------------------------------------------------------------------- ring merge

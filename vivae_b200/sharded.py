@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_bounds", "all_gather_rows", "all_gather_indices", "make_knn_sharded", "make_knn_ring", "ring_fold",
-           "knn_smooth_sharded", "knn_smooth_host_sharded", "smooth_jacobi_sharded", "smooth_cols_sharded", "smooth_auto_sharded", "col_bounds"]
+           "knn_smooth_sharded", "knn_smooth_host_sharded", "smooth_jacobi_sharded", "smooth_cols_sharded", "smooth_auto_sharded", "smooth_peer_sharded", "PeerSmoother", "col_bounds"]
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -75,16 +75,159 @@ def smooth_cols_sharded(x: torch.Tensor, idx: torch.Tensor, k: int = 50, coef: f
     return out
 
 
+class PeerSmoother:
+    """The reference's Gauss-Seidel sweep split over the GPUs of `group` by INTERLEAVED rows, the exchange fused into
+    the kernel (`csrc/smooth_peer.cu`): every rank keeps a complete copy of the sweep's output in memory its peers
+    write over NVLink (CUDA IPC) -- one 64-bit word {value, sweep epoch} per element, so a value and its "published"
+    mark arrive in one store and nothing needs a fence; the owner of a row pushes it into all copies, rows that need a
+    neighbour still in flight re-read its words.  This object owns the buffers of one (n, d, dtype) and the mappings
+    of the peers' buffers.  Bit-identical to `smooth_device`."""
+
+    def __init__(self, n: int, d: int, dtype: torch.dtype, device: torch.device, group=None):
+        import ctypes
+
+        from . import _lib
+
+        self.lib = _lib.load()
+        self._check = _lib.check
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n, self.d, self.dtype, self.device = int(n), int(d), dtype, device
+        self.itemsize = torch.empty((), dtype=dtype).element_size()
+        nbytes = self.n * self.d * 8 * (self.itemsize // 4)  # one word per float32, two per float64
+        self.local, self.opened = [], []
+        with torch.cuda.device(device):
+            ptr, h = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+            self._check(self.lib.vvb_peer_alloc(nbytes, ctypes.byref(ptr), h))
+            self.local.append(ptr.value)
+            mine = torch.frombuffer(bytearray(h), dtype=torch.uint8).to(device)
+            allh = torch.empty((self.world, 64), dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            allh = allh.cpu()
+            self.ptrs = [0] * self.world  # every rank's buffer as mapped into this process
+            err = None
+            for r in range(self.world):
+                if r == self.rank:
+                    self.ptrs[r] = self.local[0]
+                    continue
+                p_ = ctypes.c_void_p()
+                raw = (ctypes.c_ubyte * 64)(*allh[r].tolist())
+                if err is None and self.lib.vvb_peer_open(raw, ctypes.byref(p_)) != 0:
+                    err = _lib.last_error()
+                self.ptrs[r] = p_.value or 0
+                if p_.value:
+                    self.opened.append(p_.value)
+            # every rank must agree on whether the mapping worked (a rank that gave up would leave the others waiting)
+            ok = torch.tensor([0.0 if err else 1.0], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if float(ok.item()) < 1.0:
+                for q_ in self.opened:
+                    self.lib.vvb_peer_close(q_)
+                dist.barrier(group=group)
+                for q_ in self.local:
+                    self.lib.vvb_peer_free(q_)
+                self.local, self.opened = [], []
+                raise RuntimeError(f"peer mapping of the smoother's buffers failed on some rank ({err or 'another rank'})")
+            self.table = (ctypes.c_void_p * self.world)(*self.ptrs)
+            self.ws = torch.zeros(int(self.lib.vvb_smooth_peer_workspace_bytes()), dtype=torch.uint8, device=device)
+            self.token = torch.zeros(1, dtype=torch.float32, device=device)
+        self.epoch = 0
+
+    def _barrier(self):
+        dist.all_reduce(self.token, group=self.group)  # stream-ordered: no rank passes it before every rank's stream got here
+
+    def sweep(self, x: torch.Tensor, idx: torch.Tensor, k: int, coef: float, n_iter: int = 1) -> torch.Tensor:
+        if x.shape != (self.n, self.d) or x.dtype != self.dtype or not x.is_contiguous() or not idx.is_contiguous():
+            raise ValueError("PeerSmoother: x / idx do not match the buffers")
+        if n_iter < 1 or n_iter > 10000:
+            raise ValueError("`n_iter` must be at least 1 and at most 10000")
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            cur = x
+            for _ in range(n_iter):
+                self.epoch += 1
+                self._barrier()  # every rank has unpacked the previous sweep: the copies may be overwritten
+                self._check(self.lib.vvb_smooth_peer_device(cur.data_ptr(), self.itemsize, self.n, self.d, idx.data_ptr(),
+                                                            idx.shape[1], int(k), float(coef), self.epoch, self.rank,
+                                                            self.world, self.table, self.ws.data_ptr(), stream))
+                self._barrier()  # every rank's pushes have landed in this rank's copy
+                out = torch.empty_like(x)
+                self._check(self.lib.vvb_smooth_peer_unpack_device(self.local[0], self.itemsize, self.n * self.d, self.epoch,
+                                                                   out.data_ptr(), self.ws.data_ptr(), stream))
+                cur = out
+            bad = int(self.ws[:4].view(torch.int32).item())
+        if bad == 1:
+            raise ValueError("Neighbourhoods in `knn` must include self and neighbour indices must be 0-indexed")
+        if bad:
+            raise RuntimeError("peer smoother: a row never arrived in this rank's copy")
+        return cur
+
+    def close(self):
+        """Unmap the peers' buffers and free the local one (all ranks, after a barrier: nobody may still push)."""
+        if not self.local:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for p_ in self.opened:
+                self.lib.vvb_peer_close(p_)
+            dist.barrier(group=self.group)
+            for p_ in self.local:
+                self.lib.vvb_peer_free(p_)
+        self.local, self.opened = [], []
+
+
+_PEER_SMOOTHERS: dict = {}
+_PEER_BROKEN = False
+
+
+def smooth_peer_sharded(x: torch.Tensor, idx: torch.Tensor, k: int = 50, coef: float = 0.1, n_iter: int = 1,
+                        group=None) -> torch.Tensor:
+    """`smooth` (the reference's in-place sweep) of the whole matrix on all GPUs of `group` at once -- see
+    `PeerSmoother`.  `x` (n, d) and `idx` (n, >= k) are the whole matrix and graph on every rank; every rank gets the
+    whole smoothed matrix.  The buffers are kept per (n, d, dtype, group) until `release_peer_smoothers()`."""
+    key = (x.shape[0], x.shape[1], x.dtype, x.device.index, id(group))
+    ps = _PEER_SMOOTHERS.get(key)
+    if ps is None:
+        for old in list(_PEER_SMOOTHERS.values()):  # one set of buffers at a time: they are as large as the matrix
+            old.close()
+        _PEER_SMOOTHERS.clear()
+        ps = _PEER_SMOOTHERS[key] = PeerSmoother(x.shape[0], x.shape[1], x.dtype, x.device, group)
+    return ps.sweep(x.contiguous(), idx.contiguous(), k, coef, n_iter)
+
+
+def release_peer_smoothers() -> None:
+    for ps in list(_PEER_SMOOTHERS.values()):
+        ps.close()
+    _PEER_SMOOTHERS.clear()
+
+
 def smooth_auto_sharded(x: torch.Tensor, idx: torch.Tensor, k: int = 50, coef: float = 0.1, n_iter: int = 1, group=None,
                         mode: str = "gauss_seidel") -> torch.Tensor:
-    """The smoother of the multi-GPU pipelines: column shards when a slice still keeps a warp busy (at least 64
-    columns per rank), otherwise the whole sweep on every rank.  Measured on 2 B200 at 1M x 50, k=50: 3.06 ms in
+    """The smoother of the multi-GPU pipelines: column shards when a slice still keeps a warp busy (at least 64 columns
+    per rank), else the whole sweep on every rank.  The interleaved-row sweep over NVLink peer memory (`PeerSmoother`;
+    k <= 128, d <= 128, up to 8 ranks) is bit-identical but measured SLOWER than the replicated sweep on 2 B200 (8.5 ms
+    against 2.6 ms at 1M x 50, `profiles/r02_peer_smoother_2gpu.json`): a row waiting on a row still in flight on the
+    other GPU waits an NVLink round trip, and every gather reads 8-byte {value, epoch} words.  It is therefore opt-in
+    (`VVB_SMOOTH_PEER=1`).  Measured on 2 B200 at 1M x 50, k=50: 3.06 ms in
     two column shards against 2.59 ms replicated -- at that width the sweep costs one load instruction per neighbour
     whether the row has 50 columns or 26, and it is bound by those instructions and their latency, not by bytes."""
+    import os
+    import warnings
+
     from .device import smooth_device
 
+    global _PEER_BROKEN
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    if world > 1 and x.shape[1] >= 64 * world:
+    n, d = x.shape
+    if (world > 1 and world <= 8 and mode == "gauss_seidel" and k <= 128 and d <= 128 and n >= 4096 and x.is_cuda
+            and not _PEER_BROKEN and os.environ.get("VVB_SMOOTH_PEER", "0") == "1"):
+        try:
+            return smooth_peer_sharded(x, idx, k, coef, n_iter, group)
+        except (RuntimeError, NotImplementedError) as exc:  # e.g. no peer access between the GPUs: stay replicated
+            _PEER_BROKEN = True
+            warnings.warn(f"vivae_b200: peer-memory smoother unavailable ({exc}); running the sweep on every rank")
+    if world > 1 and d >= 64 * world:
         return smooth_cols_sharded(x, idx, k, coef, n_iter, group, mode)
     return smooth_device(x, idx, k, coef, n_iter, mode)
 
