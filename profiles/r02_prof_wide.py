@@ -14,5 +14,5 @@ dev = torch.device("cuda", 0)
 x = synth_cells_device(500_000, 2000, dev)
 for _ in range(int(os.environ.get("REPS", "2"))):
     st = {}
-    knn_device(x, 50, 0, 148 * 256, stats=st)
+    knn_device(x, 50, 0, int(os.environ.get("NQ_BLOCKS", "148")) * 256, stats=st)
     print(json.dumps(st))

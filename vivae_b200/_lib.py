@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvivae_b200.so")
+# VVB_LIB_PATH: a differently configured build of the same library (kernel experiments: profiles/)
+LIB_PATH = os.environ.get("VVB_LIB_PATH") or os.path.join(_HERE, "libvivae_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, EINVAL, ECUDA, ENOMEM, ENOTSUP = 0, -1, -2, -3, -4

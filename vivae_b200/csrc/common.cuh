@@ -431,6 +431,7 @@ __device__ __forceinline__ void warp_select_threshold_rows(const float *base, si
   }
   __syncwarp();
 }
+
 #endif  // __CUDACC__
 
 }  // namespace vvb

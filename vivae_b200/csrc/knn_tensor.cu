@@ -70,9 +70,12 @@ int launch_knn_brute_few(const float *x_dev, int64_t n, int d, int k, const int6
                          cudaStream_t stream);
 
 // ------------------------------------------------------------------ compile-time shape
+#ifndef VVB_TC_STAGES
+#define VVB_TC_STAGES 4
+#endif
 constexpr int TC_M = 256;            // query rows per CTA
 constexpr int TC_N = 128;            // database rows per tile
-constexpr int TC_STAGES = 4;         // database-tile ring
+constexpr int TC_STAGES = VVB_TC_STAGES;  // database-tile ring (32 KB per stage)
 constexpr int TC_THREADS = 640;      // 4 control warps + 16 epilogue warps
 constexpr int TC_ATOM_BYTES = 128 * 128;  // 128 rows x 64 fp16 (one 128B-swizzle K atom)
 constexpr int TC_CAP_E = 8;          // candidate list capacity = 32 * 8 = 256
@@ -495,6 +498,18 @@ struct TcParams {
   // and refine_concat_kernel joins the two halves afterwards.
   int slices;
   int *slice_cnt;
+  // WIDE instantiation only: every query block is swept by `wslices` CTAs, CTA (block, w) taking every wslices-th tile
+  // of the order (blockIdx.x = block * wslices + w, so that the CTAs resident at the same time share query operands:
+  // 148 blocks x 1 MB of query operand at d = 2000 do not fit L2 and every tile re-read came from DRAM; 37 blocks x 4
+  // slices do).  Each CTA keeps lists of its own -- list row (block * wslices + w) * TC_M + row, i.e. cand / cand_cnt /
+  // cand_thr are (nq_pad * wslices) long -- and wide_merge_kernel joins them afterwards.
+  int wslices;
+  // Resident variant: the threshold pre-pass evaluates ONE product (xh . yh, the norm riding along) instead of three
+  // and loads only the hi atom of every tile -- a third of the MMAs for a key good to tc_eps_single(1) of
+  // (|x^| + Ymax)^2; the starting threshold it yields is raised by that much (plus the full key's own margin), so it
+  // still bounds the m-th full-precision key from above.  Exactness never depends on the starting threshold.
+  int pre_hi;
+  float pre_slack;   // what the one-product threshold is raised by, relative to (|x^| + Ymax)^2
   const float *x;    // (n, d) the original rows
   const int *perm;   // permuted database row -> original row
   int d, k1;         // k1 = k + 1 (self included)
@@ -576,8 +591,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_block = p.cta_order ? p.cta_order[blockIdx.x] : static_cast<int>(blockIdx.x);
+  const int wsl = WIDE ? p.wslices : 1;                      // CTAs per query block (database slices)
+  const int w_slice = static_cast<int>(blockIdx.x) % wsl;   // this CTA's slice
+  const int q_block = p.cta_order ? p.cta_order[blockIdx.x / wsl] : static_cast<int>(blockIdx.x) / wsl;
   const int64_t q_base = static_cast<int64_t>(q_block) * TC_M;  // first query-list entry of this CTA
+  // list row of query-list entry t: t + l_off (one set of lists per slice)
+  const int64_t l_off = (static_cast<int64_t>(q_block) * (wsl - 1) + w_slice) * TC_M;
   auto stamp = [&](int i) {
     if (DBG && p.times && warp == 4 && lane == 0) p.times[q_block * 8 + i] = clock64();
   };
@@ -697,6 +716,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         const int row_end = p.cell_off[b + 1];
         if constexpr (WIDE) {
           for (int row_b = p.cell_off[b]; row_b < row_end; row_b += 2 * TC_N, ++t) {
+            if (wsl > 1 && (tile_no++ % wsl) != w_slice) {  // another slice's tile
+              --t;
+              continue;
+            }
             const bool half_tile = row_b + TC_N >= row_end;
             pass_tiles += half_tile ? 1 : 2;
             for (int a = 0; a < p.ka; ++a, ++it) {
@@ -729,8 +752,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
             const uint32_t ph = (t / TC_STAGES) & 1;
             mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
             tile_seq[t % TC_RING] = row_b;
-            mbar_expect_tx(bar_b_full + 8 * s, 2 * TC_ATOM_BYTES);
-            for (int atom = 0; atom < 2; ++atom)
+            const int natoms = (pass == 0 && p.pre_hi) ? 1 : 2;  // pre-pass with one product: the hi atom only
+            mbar_expect_tx(bar_b_full + 8 * s, natoms * TC_ATOM_BYTES);
+            for (int atom = 0; atom < natoms; ++atom)
               tma_load_2d(smem_b + (s * 2 + atom) * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, atom * 64, row_b);
           } else {
             // first tier (p.single): a stage holds [A.hi mb0][A.hi mb1][B.hi] (48 KB, four stages);
@@ -781,6 +805,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       int slot = 0;
       uint32_t use_par = 0;  // parity of (it / NSLOT)
       int it = 0;            // K-loop variant: stage uses
+      bool hi_only = !KLOOP && pre_pass && p.pre_hi;  // tiles before the TC_SEQ_PRE_END marker: one product
       if constexpr (WIDE) {
         constexpr uint32_t idesc2 = make_idesc(2 * TC_N);
         for (int t = 0;; ++t) {
@@ -831,6 +856,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
             }
           }
           if (marker == TC_SEQ_END) break;
+          hi_only = false;
           mbar_arrive(bar_b_empty + 8 * s0);
           ++it;
           continue;
@@ -849,12 +875,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               if (ks < p.ks_hi) tc_mma_f16_ts(d_tmem, a_hi + 8 * ks, b_hi + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+            if (!hi_only) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              if (ks < p.ks_lo) tc_mma_f16_ts(d_tmem, a_hi + 8 * ks, b_lo + 2 * ks, idesc, 1u);
+              for (int ks = 0; ks < 4; ++ks)
+                if (ks < p.ks_lo) tc_mma_f16_ts(d_tmem, a_hi + 8 * ks, b_lo + 2 * ks, idesc, 1u);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              if (ks < p.ks_lo) tc_mma_f16_ts(d_tmem, a_lo + 8 * ks, b_hi + 2 * ks, idesc, 1u);
+              for (int ks = 0; ks < 4; ++ks)
+                if (ks < p.ks_lo) tc_mma_f16_ts(d_tmem, a_lo + 8 * ks, b_hi + 2 * ks, idesc, 1u);
+            }
             tc_commit(bar_acc_full + 8 * slot);  // accumulator ready for the epilogue
             if (++slot == NSLOT) {
               slot = 0;
@@ -954,8 +982,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         if (lane == 0) mbar_arrive(bar_a_full);
       }
     }
-    uint2 *cl = p.cand + (t_row * 2 + half) * TC_CAP;  // this thread's candidate list
-    uint2 *warp_lists = p.cand + ((q_base + mb * 128 + quad * 32) * 2 + half) * TC_CAP;  // + 2 * TC_CAP per lane
+    uint2 *cl = p.cand + ((t_row + l_off) * 2 + half) * TC_CAP;  // this thread's candidate list
+    // opaque to the optimiser: kept in a register pair, so that an admission is IMAD.WIDE + STG + count (the compiler
+    // otherwise rebuilds the address from p.cand and the row index with four 64-bit steps per admission)
+    asm volatile("" : "+l"(cl));
+    uint2 *warp_lists = p.cand + ((q_base + l_off + mb * 128 + quad * 32) * 2 + half) * TC_CAP;  // + 2 * TC_CAP per lane
     const float inf = __int_as_float(0x7f800000);
     float tau = active ? inf : -inf;
     const float xn = active ? p.xnorm[t_row] : 0.0f;
@@ -1041,7 +1072,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
                 return;
               }
             }
-            cl[cnt] = make_uint2(r[c], static_cast<uint32_t>(j0 + c));  // one 8-byte store
+            asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(cl + cnt), "r"(r[c]), "r"(static_cast<uint32_t>(j0 + c))
+                         : "memory");  // one 8-byte store
             ++cnt;
           }
         };
@@ -1121,6 +1153,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         }
         pair_sync();
         tau = row_tau[prow];
+        if (!KLOOP && p.pre_hi && active && tau < inf) {
+          // the recorded minima are one-product keys: m tiles hold a one-product key below tau, hence a full key below
+          // tau + (eps_single + eps_rel) (|x^| + Ymax)^2 in the worst case.  That worst case (2^-11: every dropped
+          // product of every column aligned) would loosen the threshold by several key units and cost the main sweep
+          // more insertions than the pre-pass saves (measured: +20 % sweep time); the dropped terms are sums of d
+          // products of random sign, 2^-15 (|x^| + Ymax)^2 at one sigma, so p.pre_slack = 2^-13 is used.  A row whose
+          // threshold turns out too tight ends with a short list, fails the certificate and is settled by the refine
+          // pass: the starting threshold is a matter of speed, never of exactness.
+          const float rr = sqrtf(xn) + p.scalars->ymax;
+          tau += p.pre_slack * rr * rr;
+        }
         {
           const unsigned m = __reduce_max_sync(FULL, f2ord(tau + xn));
           if (lane == 0) tau_pub[ew] = ord2f(m);
@@ -1132,10 +1175,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       } else if (in_pre) {
         // pre-pass tile: minimum key of this thread's 64 columns, nothing else
         float tmin = inf;
-        auto fold = [&](const uint32_t(&r)[32]) {
+        auto fold = [&](const uint32_t(&r)[32]) {  // four independent chains: the dependent-issue latency is what counts
+          float m4[4] = {tmin, inf, inf, inf};
 #pragma unroll
           for (int q = 0; q < 32; q += 2)
-            tmin = fminf(fminf(__uint_as_float(r[q]), __uint_as_float(r[q + 1])), tmin);
+            m4[(q >> 1) & 3] = fminf(fminf(__uint_as_float(r[q]), __uint_as_float(r[q + 1])), m4[(q >> 1) & 3]);
+          tmin = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
         };
         tc_ld32_issue(t_acc, ra);
         tc_ld32_wait(ra);
@@ -1185,7 +1230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       if (tt >= p.nq) continue;  // warp-uniform
       const int pr = mb * 128 + quad * 32 + src;
       const int ca = half_cnt[pr], cb = half_cnt[TC_M + pr];
-      uint2 *la = p.cand + tt * 2 * TC_CAP, *lb = la + TC_CAP;
+      uint2 *la = p.cand + (tt + l_off) * 2 * TC_CAP, *lb = la + TC_CAP;
       // every rejected entry has key >= the threshold in force in its half when it was rejected >= that half's
       // final tau, and every row of a cell the sweep skipped has key >= both
       float thr = fminf(half_tau[pr], half_tau[TC_M + pr]);
@@ -1208,8 +1253,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       } else if (c > TC_CAP) thr = fminf(thr, tc_select_truncate_wide(la, c, p.keep, keep_max, lane, &nc));
       else if (c > keep_max) thr = fminf(thr, tc_select_truncate(la, c, p.keep, keep_max, lane, &nc));
       if (lane == 0) {
-        p.cand_cnt[tt] = nc;
-        p.cand_thr[tt] = thr;
+        p.cand_cnt[tt + l_off] = nc;
+        p.cand_thr[tt + l_off] = thr;
       }
     }
   }
@@ -1246,6 +1291,42 @@ __global__ void __launch_bounds__(256) refine_concat_kernel(uint2 *__restrict__ 
   if (lane == 0) {
     cand_cnt[t] = over ? 0 : ca + cb;
     cand_thr[t] = over ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
+  }
+}
+
+// After a WIDE launch with database slices: one warp per query-list entry joins the row's `wslices` lists (each at most
+// keep_max long, each with its own threshold) into the row's regular list.  The m smallest keys of the union are the m
+// smallest keys of the whole sweep (every slice kept its own m smallest), and every row of the database outside the
+// union was rejected by some slice at a key >= that slice's threshold, so min(thresholds, truncation cuts) is the
+// row's threshold.
+__global__ void __launch_bounds__(256) wide_merge_kernel(const uint2 *__restrict__ cand_v, const int *__restrict__ cnt_v,
+                                                        const float *__restrict__ thr_v, int wslices, int64_t nq, int keep,
+                                                        int keep_max, uint2 *__restrict__ cand, int *__restrict__ cand_cnt,
+                                                        float *__restrict__ cand_thr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (t >= nq) return;
+  const int64_t qb = t / TC_M, pr = t % TC_M;
+  uint2 *la = cand + t * 2 * TC_CAP;
+  int c = 0;
+  float thr = __int_as_float(0x7f800000);
+  for (int w = 0; w < wslices; ++w) {
+    const int64_t vr = (qb * wslices + w) * TC_M + pr;
+    const int cs = min(cnt_v[vr], TC_CAP);
+    thr = fminf(thr, thr_v[vr]);
+    const uint2 *src = cand_v + vr * 2 * TC_CAP;
+    for (int i = lane; i < cs; i += 32) la[c + i] = src[i];
+    c += cs;
+    __syncwarp();
+    if (c > keep_max) {  // c <= keep_max + TC_CAP <= 2 * TC_CAP here
+      int nc;
+      thr = fminf(thr, tc_select_truncate_wide(la, c, keep, keep_max, lane, &nc));
+      c = nc;
+    }
+  }
+  if (lane == 0) {
+    cand_cnt[t] = c;
+    cand_thr[t] = thr;
   }
 }
 
@@ -1486,6 +1567,10 @@ struct TcLayout {
   int *fb_count;
   int64_t *fb_rows;
   int *slice_cnt;   // (2 * chunk) list lengths of a sliced refine launch
+  int wslices;      // database slices of the wide-row first tier (tc_wide_slices); > 1: the three arrays below exist
+  uint2 *cand_v;    // (chunk * wslices, 2 * TC_CAP) per-slice lists
+  int *cand_cnt_v;  // (chunk * wslices)
+  float *cand_thr_v;
   int *cta_order;   // (chunk / TC_M) launch order of the query blocks
   int *cta_scratch;
   float *fb_thr;    // (chunk) refine threshold of the rows the certificate rejected, indexed by row - q0
@@ -1493,6 +1578,21 @@ struct TcLayout {
   size_t brute_ws_bytes;
   size_t total;
 };
+
+// Database slices of the wide-row first tier (TcParams::wslices): the query operands of the CTAs resident at the same
+// time -- sm_count / slices blocks x 256 rows x ka x 128 bytes (hi part) -- should fill no more than about a third of
+// L2, so that they AND the database tiles streaming past stay there.  VVB_TC_WSLICES forces a count (1 = off).
+static int tc_wide_slices(int ka) {
+  if (ka < TC_SINGLE_MIN_KA) return 1;
+  int s = 1;
+  if (const char *e = getenv("VVB_TC_WSLICES")) {
+    s = atoi(e);
+  } else {
+    const double per_block = 256.0 * ka * 128.0;
+    while (s < 8 && sm_count() / s * per_block > 40e6) s *= 2;
+  }
+  return std::max(1, std::min(s, 16));
+}
 
 static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
   TcLayout L;
@@ -1527,6 +1627,15 @@ static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
   L.cta_order = cv.take<int>(static_cast<size_t>(L.chunk_pad / TC_M));
   L.cta_scratch = cv.take<int>(cells_cta_order_scratch_ints(L.chunk_pad / TC_M));
   L.cand = cv.take<uint2>(static_cast<size_t>(L.chunk_pad) * 2 * TC_CAP);  // two lists per row (one per column half)
+  L.wslices = tc_wide_slices(L.ka);
+  L.cand_v = nullptr;
+  L.cand_cnt_v = nullptr;
+  L.cand_thr_v = nullptr;
+  if (L.wslices > 1) {
+    L.cand_cnt_v = cv.take<int>(static_cast<size_t>(L.chunk_pad) * L.wslices);
+    L.cand_thr_v = cv.take<float>(static_cast<size_t>(L.chunk_pad) * L.wslices);
+    L.cand_v = cv.take<uint2>(static_cast<size_t>(L.chunk_pad) * L.wslices * 2 * TC_CAP);
+  }
   // the fallback's candidate lists reuse the screening lists (dead after the re-rank)
   L.brute_ws = L.cand;
   L.brute_ws_bytes = static_cast<size_t>(L.chunk_pad) * 2 * TC_CAP * 8;
@@ -1781,6 +1890,13 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   p.fixed_thr = nullptr;
   p.fixed_q0 = q0;
   p.slices = 1;
+  p.wslices = 1;
+  {
+    const char *ph = getenv("VVB_TC_PRE_HI");
+    p.pre_hi = (ph ? atoi(ph) != 0 : 1) ? 1 : 0;
+    const char *ps = getenv("VVB_TC_PRE_SLACK_LOG2");  // e.g. 11 = the worst-case bound
+    p.pre_slack = ldexpf(1.0f, -(ps ? atoi(ps) : 13));
+  }
   p.slice_cnt = L.slice_cnt;
   p.cta_order = nullptr;
   {
@@ -1830,8 +1946,22 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
       knn_screen_kernel<false, false, true><<<dim3(grid, pp.slices), TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, pp);
     else if (pp.fixed_thr)
       knn_screen_kernel<true, false, true><<<dim3(grid, pp.slices), TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, pp);
-    else if (pp.single && !dbg && wide_ok)
-      knn_screen_kernel<true, false, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, pp);
+    else if (pp.single && !dbg && wide_ok) {
+      TcParams pw = pp;
+      pw.wslices = L.wslices;
+      if (L.wslices > 1) {
+        pw.cand = L.cand_v;
+        pw.cand_cnt = L.cand_cnt_v;
+        pw.cand_thr = L.cand_thr_v;
+      }
+      knn_screen_kernel<true, false, false, true><<<grid * L.wslices, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, pw);
+      if (L.wslices > 1) {
+        const int keep_max = std::min((pp.keep + 31) & ~31, pp.keep + 8);
+        wide_merge_kernel<<<static_cast<unsigned>((pp.nq + 7) / 8), 256, 0, st>>>(L.cand_v, L.cand_cnt_v, L.cand_thr_v, L.wslices,
+                                                                                 pp.nq, pp.keep, keep_max, L.cand, L.cand_cnt,
+                                                                                 L.cand_thr);
+      }
+    }
     else if (L.ka == 1 && !dbg)
       knn_screen_kernel<false, false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, pp);
     else if (L.ka == 1)
