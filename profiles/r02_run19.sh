@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call 19: list appends through a register-resident list pointer (3 instructions less per admission)
+# round 2, GPU call 19+: list appends through a register-resident list pointer; q15 threshold selection
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 timeout -s KILL 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/r19_tests.log 2>&1

@@ -432,6 +432,87 @@ __device__ __forceinline__ void warp_select_threshold_rows(const float *base, si
   __syncwarp();
 }
 
+// ---- the same on 15-bit keys, two per register -------------------------------------------------------------------
+// The search above costs one compare + two dependent integer steps per key and bit (that is how `c += (u < trial)`
+// compiles) over up to 32 bits, and with four warps per scheduler the screening kernel's threshold selection was bound
+// by exactly that instruction count.  A STARTING threshold only has to bound the m-th smallest key from above, so the
+// keys of a row are quantised linearly to 15 bits over [min, max] of the row (q = floor((v - lo) * 32766 / range),
+// monotone), packed two per register with a guard bit each, and one subtraction of the packed trial value compares
+// both: the guard bit of a half survives iff q >= trial.  The guard bits of the row's E / 2 registers are gathered
+// into one word (shift + mask-or per register) and counted with a single POPC: 1.5 instructions per key and bit, at
+// most 15 bits.  The result is rounded UP to the next quantum (range / 32766: a fraction of a key unit).
+// keys of row r: base + r * stride (floats), `cnt` of them (cnt >= m, cnt <= 32 * E); out[r] = a value with at least m
+// of the row's keys strictly below it.  Keys >= ignore_above (the minima of all-padding half tiles, which would stretch
+// the range and coarsen the quantum) are left out; should fewer than m keys remain, the result is just above the
+// largest of them -- too tight to be a bound, which costs such a row the refine pass, never exactness.
+template <int E>
+__device__ __forceinline__ void warp_select_threshold_rows_q15(const float *base, size_t stride, int r0, int r1, int cnt,
+                                                               int m, int slack, float ignore_above, int lane,
+                                                               float *out) {
+  static_assert(E % 2 == 0 && E <= 16, "two keys per register, eight guard-bit pairs per word");
+  if (r0 >= r1) return;
+  const float inf = __int_as_float(0x7f800000);
+  float v[E], vn[E];
+  auto fetch = [&](int r, float(&dst)[E]) {
+    const float *keys = base + static_cast<size_t>(r) * stride;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int p = e * 32 + lane;
+      dst[e] = (p < cnt) ? keys[p] : inf;
+    }
+  };
+  fetch(r0, vn);
+  for (int r = r0; r < r1; ++r) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = vn[e];
+    if (r + 1 < r1) fetch(r + 1, vn);
+    float lo = inf, hi = -inf;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      lo = fminf(lo, v[e]);
+      hi = (v[e] < ignore_above) ? fmaxf(hi, v[e]) : hi;  // (absent keys are +inf)
+    }
+    lo = ord2f(__reduce_min_sync(FULL, f2ord(lo)));
+    hi = ord2f(__reduce_max_sync(FULL, f2ord(hi)));
+    const float range = hi - lo;
+    if (!(range > 0.0f) || !(range < inf)) {  // all keys equal (or not finite): anything above the largest will do
+      if (lane == 0) out[r] = (hi < inf && hi > -inf) ? hi + fabsf(hi) * 2.4e-7f + 1e-30f : inf;
+      continue;
+    }
+    const float scale = 32766.0f / range;
+    uint32_t x[E / 2];
+#pragma unroll
+    for (int e = 0; e < E; e += 2) {
+      const int q0 = (v[e] < ignore_above) ? min(static_cast<int>((v[e] - lo) * scale), 32766) : 32767;
+      const int q1 = (v[e + 1] < ignore_above) ? min(static_cast<int>((v[e + 1] - lo) * scale), 32766) : 32767;
+      x[e / 2] = (static_cast<uint32_t>(q1 | 0x8000) << 16) | static_cast<uint32_t>(q0 | 0x8000);
+    }
+    uint32_t T = 0u, res = 0u;  // invariant: count(q < T) < m
+    bool found = false;
+    for (int b = 14; b >= 0; --b) {
+      const uint32_t trial = T | (1u << b);
+      const uint32_t tt = trial * 0x00010001u;
+      uint32_t bits = 0u;
+#pragma unroll
+      for (int j = 0; j < E / 2; ++j) bits = (bits >> 1) | ((x[j] - tt) & 0x80008000u);  // guard bit kept: q >= trial
+      const int c = __reduce_add_sync(FULL, E - __popc(bits));
+      if (c < m) {
+        T = trial;
+      } else if (c <= m + slack) {
+        res = trial;
+        found = true;
+        break;
+      }
+    }
+    if (!found) res = T + 1u;  // count(q < T + 1) = count(q <= T) >= m
+    // q < res  =>  (v - lo) * scale < res (up to the rounding of that product, < 0.01 quantum)  =>  v < lo + res / scale
+    if (lane == 0) {
+      const float t = lo + (static_cast<float>(res) + 0.02f) * (range * (1.0f / 32766.0f));
+      out[r] = t + fabsf(t) * 2.4e-7f;
+    }
+  }
+  __syncwarp();
+}
 #endif  // __CUDACC__
 
 }  // namespace vvb

@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(256) build_operands_kernel(const float *__rest
 // row at the end of the sweep.
 __device__ __noinline__ void tc_select_threshold_rows(const float *base, int r0, int r1, int cnt, int m, int lane,
                                                       float *out) {
-  warp_select_threshold_rows<2 * TC_CAP_E>(base, 2 * TC_CAP * 2, r0, r1, cnt, m, 3, lane, out);
+  warp_select_threshold_rows_q15<2 * TC_CAP_E>(base, 2 * TC_CAP * 2, r0, r1, cnt, m, 3, TC_PAD_CUT, lane, out);
 }
 __device__ __noinline__ float tc_select_truncate_wide(uint2 *list, int cnt, int keep, int keep_max, int lane,
                                                       int *new_cnt) {  // up to 2 * TC_CAP entries
