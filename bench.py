@@ -274,12 +274,17 @@ def screen_roofline(st: dict, nq: int, n: int, d: int, peaks: dict, sustained: b
         return {"kernel": "knn_brute_ffma", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "peak_source": peaks["source"], "ms": ms}
     macs = executed_macs_per_pair(d, st.get("products") or 3)
-    ex = float(st["tiles_swept"]) * 256 * 128 * macs * 2  # (the few refine sweeps run three products: counted as one)
+    # tiles of the threshold pre-pass run ONE product (d + 3 columns padded to the k-step of 16) since round 2
+    tiles_pre = int(st.get("tiles_pre") or 0)
+    macs_pre = 16 * ((d + 3 + 15) // 16)
+    # (the few refine sweeps run three products: counted as one)
+    ex = (float(st["tiles_swept"] - tiles_pre) * macs + float(tiles_pre) * macs_pre) * 256 * 128 * 2
     ach = ex / (ms / 1e3) / 1e12
     return {"kernel": "knn_screen_tcgen05", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
             "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + (" (sustained)" if sustained else " (burst)"),
             "ms": ms, "what": "EXECUTED MMA flops (tiles swept x 256 x 128 pairs x executed MACs x 2) / duration",
             "executed_macs_per_pair": macs, "algorithmic_macs_per_pair": d,
+            "tiles_pre_pass_one_product": tiles_pre, "executed_macs_per_pair_pre_pass": macs_pre,
             "tiles_swept": st["tiles_swept"], "tiles_dense": st["tiles_dense"], "cells": st["cells"],
             "algorithmic": {"flops": alg, "tflops": alg / (ms / 1e3) / 1e12, "x_peak": alg / (ms / 1e3) / 1e12 / peak,
                             "note": "2*nq*n*d over the duration; NOT a utilisation: the exact cell bounds skipped "
@@ -392,7 +397,7 @@ def run_ours(args) -> None:
     torch.cuda.synchronize()
     ms_smooth = max_over_ranks(e1.elapsed_time(e2))
     roofline = screen_roofline(st, nq, n, d, peaks)
-    cap = os.path.join(ROOT, "profiles", "r02_knn_screen_1M_raw.csv")
+    cap = os.path.join(ROOT, "profiles", "r02b_c2_raw.csv")
     if world == 1 and st.get("algo_used") == 2 and (n, d, k) == (1_000_000, 50, 50) and os.path.isfile(cap):
         import csv
         with open(cap) as f:
@@ -404,7 +409,7 @@ def run_ours(args) -> None:
             roofline["traffic"] = sum(float(srow[col[m]]) * gb[rows_[1][col[m]]]
                                       for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
             roofline["traffic_note"] = ("dram__bytes_read + dram__bytes_write of this launch (1,000,000 query rows, one "
-                                        "GPU) from the committed ncu --set full capture profiles/r02_knn_screen_1M_raw.csv")
+                                        "GPU) from the committed ncu --set full capture profiles/r02b_c2_raw.csv")
     dense_roof = None
     if st.get("algo_used") == 2 and world == 1 and not args.skip_dense:
         # the same kernel with the partition switched off (every tile swept): the dense tensor roofline

@@ -67,7 +67,8 @@ typedef struct vvb_knn_stats {
                               fixed-threshold refine sweep on the tensor cores      */
   int32_t products;        /* fp16 products the main sweep executed per key: 3 (hi/lo split)
                               or 1 (single-product first tier of wide rows)         */
-  int32_t reserved;
+  int32_t tiles_pre;       /* of tiles_swept: tiles of the threshold pre-pass that executed ONE product
+                              per key (resident variant; saturates at INT32_MAX)       */
 } vvb_knn_stats;
 
 int vvb_version(void);

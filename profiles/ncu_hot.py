@@ -3,6 +3,10 @@ address ranges so that loops show up as regions.  usage: python profiles/ncu_hot
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+# a dump may hold several kernels ("Kernel Name" line + header + instructions each): take the first one
+ends = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+if len(ends) > 1:
+    rows = rows[:ends[1]]
 hdr = rows[1]
 ci = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]

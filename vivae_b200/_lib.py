@@ -39,7 +39,7 @@ class KnnStats(ctypes.Structure):
         ("cells", ctypes.c_int32),
         ("rows_refined", ctypes.c_int32),
         ("products", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("tiles_pre", ctypes.c_int32),
     ]
 
     def as_dict(self) -> dict:

@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       const float eps_max = p.eps_rel * ymax2 * ymax2;  // the certificate's margin for the longest query row
       int t = 0;    // tile_seq entries issued (tiles and markers)
       int it = 0;   // K-loop variant: stage uses
-      int swept = 0;
+      int swept = 0, pre_swept = 0;
       int tile_no = 0;  // sliced refine launch: position of the tile in the block's order
       // a marker: a stage carrying no data, flagged in the tile sequence
       auto issue_marker = [&](int marker) {
@@ -786,9 +786,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
         }
       }
       swept += pass_tiles;
+      if (pass == 0 && !KLOOP && p.pre_hi) pre_swept = pass_tiles;
       issue_marker(pass == 0 ? TC_SEQ_PRE_END : TC_SEQ_END);
       }
       atomicAdd(p.tiles_done, static_cast<unsigned long long>(swept));
+      if (pre_swept) atomicAdd(p.tiles_done + 1, static_cast<unsigned long long>(pre_swept));  // one-product tiles
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
@@ -1341,7 +1343,8 @@ __global__ void __launch_bounds__(256) wide_merge_kernel(const uint2 *__restrict
 //         loop of MODE 1 at d = 50), and this mode stages a candidate in ~7 instructions instead of ~34.
 // In every mode each lane evaluates ITS candidate's chain strictly left to right, so the result is
 // bit-identical.
-constexpr int RR_ROW_LD = 65;  // floats per staged row (odd: lane = candidate reads are conflict-free)
+constexpr int RR_ROW_LD = 68;  // floats per staged row: 16-byte aligned rows, and 68 = 4 (mod 32) makes the 16-byte
+                               // reads of eight consecutive lanes (lane = candidate) hit all 32 banks once
 template <int E, int MODE>
 __global__ void __launch_bounds__(256) knn_rerank_kernel(
     const float *__restrict__ x, int64_t n, int d, int64_t q0, int64_t nq, int k, const int *__restrict__ qlist,
@@ -1353,7 +1356,10 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
   constexpr bool WIDE = MODE == 1;
   constexpr bool ROWS = MODE == 2;
   __shared__ float stage[WIDE ? 8 : 1][WIDE ? 32 : 1][WIDE ? 33 : 1];
-  __shared__ float rows_stage[ROWS ? 4 * 33 * RR_ROW_LD : 1];  // [warp][32 candidates + query][RR_ROW_LD]
+  __shared__ __align__(16) float rows_stage[ROWS ? 4 * 33 * RR_ROW_LD : 1];  // [warp][32 candidates + query][RR_ROW_LD]
+  // d even and x 8-byte aligned: a row is fetched with ONE 8-byte load per lane (the kernel is bound by its shared-
+  // memory and load instructions: ncu l1tex 71 %)
+  const bool vec2 = ROWS && (d & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int64_t t = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -1374,33 +1380,68 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(
         if (pos < cnt) j = static_cast<uint32_t>(perm[cand[t * 2 * TC_CAP + pos].y]);
         const int in_group = min(32, cnt - e * 32);
         float *st = rows_stage + wib * 33 * RR_ROW_LD;
-        if (e == 0) {  // the query row, once
-          st[32 * RR_ROW_LD + lane] = (lane < d) ? __ldg(xq + lane) : 0.0f;
-          st[32 * RR_ROW_LD + 32 + lane] = (32 + lane < d) ? __ldg(xq + 32 + lane) : 0.0f;
-        }
         const unsigned long long rowp = reinterpret_cast<unsigned long long>(x + static_cast<int64_t>(j) * d);
-        const bool c0_ok = lane < d, c1_ok = 32 + lane < d;
-        for (int cc0 = 0; cc0 < in_group; cc0 += 8) {  // 16 loads in flight, then the stores
-          float v0[8], v1[8];
+        if (vec2) {
+          const bool c_ok = 2 * lane < d;
+          if (e == 0)  // the query row, once
+            *reinterpret_cast<float2 *>(st + 32 * RR_ROW_LD + 2 * lane) =
+                c_ok ? __ldg(reinterpret_cast<const float2 *>(xq) + lane) : make_float2(0.0f, 0.0f);
+          for (int cc0 = 0; cc0 < in_group; cc0 += 8) {  // 8 loads in flight, then the stores
+            float2 v[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float *rp = reinterpret_cast<const float *>(__shfl_sync(FULL, rowp, (cc0 + u) & 31));
-            const bool live = cc0 + u < in_group;
-            v0[u] = (live && c0_ok) ? __ldg(rp + lane) : 0.0f;
-            v1[u] = (live && c1_ok) ? __ldg(rp + 32 + lane) : 0.0f;
+            for (int u = 0; u < 8; ++u) {
+              const float2 *rp = reinterpret_cast<const float2 *>(__shfl_sync(FULL, rowp, (cc0 + u) & 31));
+              v[u] = (cc0 + u < in_group && c_ok) ? __ldg(rp + lane) : make_float2(0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              *reinterpret_cast<float2 *>(st + ((cc0 + u) & 31) * RR_ROW_LD + 2 * lane) = v[u];
           }
+        } else {
+          if (e == 0) {  // the query row, once
+            st[32 * RR_ROW_LD + lane] = (lane < d) ? __ldg(xq + lane) : 0.0f;
+            st[32 * RR_ROW_LD + 32 + lane] = (32 + lane < d) ? __ldg(xq + 32 + lane) : 0.0f;
+          }
+          const bool c0_ok = lane < d, c1_ok = 32 + lane < d;
+          for (int cc0 = 0; cc0 < in_group; cc0 += 8) {  // 16 loads in flight, then the stores
+            float v0[8], v1[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            st[((cc0 + u) & 31) * RR_ROW_LD + lane] = v0[u];
-            if (d > 32) st[((cc0 + u) & 31) * RR_ROW_LD + 32 + lane] = v1[u];
+            for (int u = 0; u < 8; ++u) {
+              const float *rp = reinterpret_cast<const float *>(__shfl_sync(FULL, rowp, (cc0 + u) & 31));
+              const bool live = cc0 + u < in_group;
+              v0[u] = (live && c0_ok) ? __ldg(rp + lane) : 0.0f;
+              v1[u] = (live && c1_ok) ? __ldg(rp + 32 + lane) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              st[((cc0 + u) & 31) * RR_ROW_LD + lane] = v0[u];
+              if (d > 32) st[((cc0 + u) & 31) * RR_ROW_LD + 32 + lane] = v1[u];
+            }
           }
         }
         __syncwarp();
-        // lanes beyond the group read stale rows and are ignored below
-#pragma unroll 5
-        for (int c = 0; c < d; ++c) {  // the contract's chain: left to right, one rounding per fmaf
-          const float df = __fsub_rn(st[32 * RR_ROW_LD + c], st[lane * RR_ROW_LD + c]);
-          acc = __fmaf_rn(df, df, acc);
+        // lanes beyond the group read stale rows and are ignored below.  The contract's chain: left to right, one
+        // rounding per fmaf; four columns per 16-byte shared-memory read (the query's is a broadcast).
+        {
+          const float4 *q4 = reinterpret_cast<const float4 *>(st + 32 * RR_ROW_LD);
+          const float4 *y4 = reinterpret_cast<const float4 *>(st + lane * RR_ROW_LD);
+          int c = 0;
+#pragma unroll 4
+          for (; c + 4 <= d; c += 4) {
+            const float4 a = q4[c >> 2], b = y4[c >> 2];
+            float df = __fsub_rn(a.x, b.x);
+            acc = __fmaf_rn(df, df, acc);
+            df = __fsub_rn(a.y, b.y);
+            acc = __fmaf_rn(df, df, acc);
+            df = __fsub_rn(a.z, b.z);
+            acc = __fmaf_rn(df, df, acc);
+            df = __fsub_rn(a.w, b.w);
+            acc = __fmaf_rn(df, df, acc);
+          }
+          for (; c < d; ++c) {
+            const float df = __fsub_rn(st[32 * RR_ROW_LD + c], st[lane * RR_ROW_LD + c]);
+            acc = __fmaf_rn(df, df, acc);
+          }
         }
         __syncwarp();
       }
@@ -2113,6 +2154,9 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     VVB_CUDA(cudaMemcpy(&done, L.tiles_done, sizeof(done), cudaMemcpyDeviceToHost));
     VVB_CUDA(cudaMemcpy(&used, L.cells.off + L.cells.P, sizeof(int), cudaMemcpyDeviceToHost));
     stats->tiles_swept = static_cast<int64_t>(done);  // cumulative over the chunks of this call
+    unsigned long long pre = 0;
+    VVB_CUDA(cudaMemcpy(&pre, L.tiles_done + 1, sizeof(pre), cudaMemcpyDeviceToHost));
+    stats->tiles_pre = static_cast<int32_t>(std::min<unsigned long long>(pre, 0x7fffffffull));
     stats->tiles_dense += static_cast<int64_t>(sgrid) * (used / TC_N);
   }
   return VVB_OK;
