@@ -29,6 +29,23 @@
 
 namespace vvb {
 
+// Packed FP32 pairs (sm_100: FFMA2 executes two IEEE fused multiply-adds per instruction).  The two row x P x 64
+// kernels of the preparation (pivot assignment, cell extents) are bound by their FMA issue slots; every lane of a
+// packed FMA rounds exactly like a scalar fmaf, so the four accumulation chains below are bit-identical to the
+// scalar code they replace.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void fma_f32x2(unsigned long long &acc, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
+
 int cells_choose_count(int64_t n) {
   if (const char *e = getenv("VVB_TC_CELLS")) {
     const int v = atoi(e);
@@ -174,8 +191,13 @@ __global__ void __launch_bounds__(CELL_DIMS) cell_pivots_kernel(const float *__r
   piv[p * CELL_DIMS + c] = (c < dsub) ? __ldg(x + pr * d + __ldg(dims + c)) - __ldg(mu + __ldg(dims + c)) : 0.0f;
 }
 
-// Thread per row: nearest pivot in the first dsub centred coordinates (ties -> lowest pivot).
+// Two rows per thread: nearest pivot in the first dsub centred coordinates (ties -> lowest pivot).
 // Rows [row0, n) of this launch (n = end of the range: a rank of a multi-GPU build assigns only its row shard).
+// The pivot block is read from shared memory as 16-byte broadcasts; a warp-wide 16-byte read occupies the shared-
+// memory pipe for four cycles whether or not the lanes share an address, and with ONE row per thread that pipe (one
+// per SM, against four FMA pipes) bounded the kernel at a third of the FP32 rate -- so every value read feeds two
+// rows, and the multiply-adds are issued in packed pairs.  Each row's four accumulation chains are unchanged.
+constexpr int ASSIGN_ROWS = 256;  // rows per CTA of 128 threads
 __global__ void __launch_bounds__(128) cell_assign_kernel(const float *__restrict__ x, int64_t row0, int64_t n, int d,
                                                          int dsub, const int *__restrict__ dims,
                                                          const float *__restrict__ mu, int P,
@@ -186,13 +208,24 @@ __global__ void __launch_bounds__(128) cell_assign_kernel(const float *__restric
   __shared__ int hist[CELL_MAX];
   const int tid = threadIdx.x;
   for (int i = tid; i < P; i += 128) hist[i] = 0;
-  const int64_t row = row0 + static_cast<int64_t>(blockIdx.x) * 128 + tid;
-  float xr[CELL_DIMS];
+  const int64_t row_a = row0 + static_cast<int64_t>(blockIdx.x) * ASSIGN_ROWS + tid, row_b = row_a + 128;
+  unsigned long long xa[CELL_DIMS / 2], xb[CELL_DIMS / 2];
 #pragma unroll
-  for (int c = 0; c < CELL_DIMS; ++c)
-    xr[c] = (row < n && c < dsub) ? __ldg(x + row * d + __ldg(dims + c)) - __ldg(mu + __ldg(dims + c)) : 0.0f;
-  float best = __int_as_float(0x7f800000);
-  int best_p = 0;
+  for (int c = 0; c < CELL_DIMS; c += 2) {
+    float va[2], vb[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const bool on = c + e < dsub;
+      const int col = on ? __ldg(dims + c + e) : 0;
+      const float m = on ? __ldg(mu + col) : 0.0f;
+      va[e] = (on && row_a < n) ? __ldg(x + row_a * d + col) - m : 0.0f;
+      vb[e] = (on && row_b < n) ? __ldg(x + row_b * d + col) - m : 0.0f;
+    }
+    xa[c / 2] = pack_f32x2(va[0], va[1]);
+    xb[c / 2] = pack_f32x2(vb[0], vb[1]);
+  }
+  float best_a = __int_as_float(0x7f800000), best_b = best_a;
+  int best_pa = 0, best_pb = 0;
   for (int p0 = 0; p0 < P; p0 += 128) {
     __syncthreads();
     const int np = min(128, P - p0);
@@ -209,27 +242,41 @@ __global__ void __launch_bounds__(128) cell_assign_kernel(const float *__restric
     }
     __syncthreads();
     for (int pl = 0; pl < np; ++pl) {
-      float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;  // four independent chains: the FMA latency, not the
-      const float4 *pv = reinterpret_cast<const float4 *>(piv[pl]);  // issue rate, bounded the single chain
+      // per row four independent chains (columns 0, 1, 2, 3 mod 4), two per packed accumulator
+      unsigned long long a01 = 0ull, a23 = 0ull, b01 = 0ull, b23 = 0ull;
+      const ulonglong2 *pv = reinterpret_cast<const ulonglong2 *>(piv[pl]);
 #pragma unroll
       for (int c4 = 0; c4 < CELL_DIMS / 4; ++c4) {
-        const float4 q = pv[c4];
-        d0 = fmaf(xr[4 * c4 + 0], q.x, d0);
-        d1 = fmaf(xr[4 * c4 + 1], q.y, d1);
-        d2 = fmaf(xr[4 * c4 + 2], q.z, d2);
-        d3 = fmaf(xr[4 * c4 + 3], q.w, d3);
+        const ulonglong2 q = pv[c4];
+        fma_f32x2(a01, xa[2 * c4 + 0], q.x);
+        fma_f32x2(a23, xa[2 * c4 + 1], q.y);
+        fma_f32x2(b01, xb[2 * c4 + 0], q.x);
+        fma_f32x2(b23, xb[2 * c4 + 1], q.y);
       }
-      const float dot = (d0 + d1) + (d2 + d3);
-      const float score = fmaf(-2.0f, dot, pn[pl]);
-      if (score < best) {
-        best = score;
-        best_p = p0 + pl;
+      float d0, d1, d2, d3;
+      unpack_f32x2(a01, d0, d1);
+      unpack_f32x2(a23, d2, d3);
+      const float score_a = fmaf(-2.0f, (d0 + d1) + (d2 + d3), pn[pl]);
+      unpack_f32x2(b01, d0, d1);
+      unpack_f32x2(b23, d2, d3);
+      const float score_b = fmaf(-2.0f, (d0 + d1) + (d2 + d3), pn[pl]);
+      if (score_a < best_a) {
+        best_a = score_a;
+        best_pa = p0 + pl;
+      }
+      if (score_b < best_b) {
+        best_b = score_b;
+        best_pb = p0 + pl;
       }
     }
   }
-  if (row < n) {
-    cell_of[row] = best_p;
-    atomicAdd(&hist[best_p], 1);
+  if (row_a < n) {
+    cell_of[row_a] = best_pa;
+    atomicAdd(&hist[best_pa], 1);
+  }
+  if (row_b < n) {
+    cell_of[row_b] = best_pb;
+    atomicAdd(&hist[best_pb], 1);
   }
   __syncthreads();
   for (int i = tid; i < P; i += 128)
@@ -386,17 +433,18 @@ __global__ void __launch_bounds__(128) cell_pairs_kernel(const float *__restrict
   }
 }
 
-// one CTA per group of 128 permuted rows of cell a (thread per row): for every other cell b the largest
-// projection of (x - c_a) on the direction a -> b, and the largest squared distance to the centre
-__global__ void __launch_bounds__(128) cell_extent_kernel(const float *__restrict__ x, int d, int dsub,
-                                                         const int *__restrict__ dims,
-                                                         const float *__restrict__ mu, const int *__restrict__ perm,
-                                                         const int *__restrict__ off, int P,
-                                                         const int *__restrict__ cell_of, const float *__restrict__ cen,
-                                                         const float *__restrict__ cw,
-                                                         const float *__restrict__ inv_norm,
-                                                         unsigned int *__restrict__ ext,
-                                                         unsigned int *__restrict__ rad2, int part, int parts) {
+// one CTA (64 threads) per group of 128 permuted rows of cell a, two rows per thread (for the reason given at
+// cell_assign_kernel): for every other cell b the largest projection of (x - c_a) on the direction a -> b, and the
+// largest squared distance to the centre
+__global__ void __launch_bounds__(64) cell_extent_kernel(const float *__restrict__ x, int d, int dsub,
+                                                        const int *__restrict__ dims,
+                                                        const float *__restrict__ mu, const int *__restrict__ perm,
+                                                        const int *__restrict__ off, int P,
+                                                        const int *__restrict__ cell_of, const float *__restrict__ cen,
+                                                        const float *__restrict__ cw,
+                                                        const float *__restrict__ inv_norm,
+                                                        unsigned int *__restrict__ ext,
+                                                        unsigned int *__restrict__ rad2, int part, int parts) {
   __shared__ __align__(16) float cwb[128][CELL_DIMS];
   __shared__ unsigned int emax[128];
   const int64_t p0 = static_cast<int64_t>(blockIdx.x) * CELL_GROUP;
@@ -404,48 +452,64 @@ __global__ void __launch_bounds__(128) cell_extent_kernel(const float *__restric
   const int tid = threadIdx.x, lane = tid & 31;
   const int a = cell_of[perm[p0]];
   if (a % parts != part) return;  // another rank owns this cell; extents and radii are max-reduced
-  const int r = perm[p0 + tid];
-  float xr[CELL_DIMS];
-  float r2 = 0.0f;
+  const int ra = perm[p0 + tid], rb = perm[p0 + 64 + tid];
+  unsigned long long xa[CELL_DIMS / 2], xb[CELL_DIMS / 2];
+  float r2a = 0.0f, r2b = 0.0f;
 #pragma unroll
-  for (int c = 0; c < CELL_DIMS; ++c) {
-    xr[c] = (r >= 0 && c < dsub)
-                ? (__ldg(x + static_cast<int64_t>(r) * d + __ldg(dims + c)) - __ldg(mu + __ldg(dims + c))) -
-                      __ldg(cen + a * CELL_DIMS + c)
-                : 0.0f;
-    r2 = fmaf(xr[c], xr[c], r2);
+  for (int c = 0; c < CELL_DIMS; c += 2) {
+    float va[2], vb[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const bool on = c + e < dsub;
+      const int col = on ? __ldg(dims + c + e) : 0;
+      const float m = on ? __ldg(mu + col) : 0.0f, ce = __ldg(cen + a * CELL_DIMS + c + e);
+      va[e] = (on && ra >= 0) ? (__ldg(x + static_cast<int64_t>(ra) * d + col) - m) - ce : 0.0f;
+      vb[e] = (on && rb >= 0) ? (__ldg(x + static_cast<int64_t>(rb) * d + col) - m) - ce : 0.0f;
+      r2a = fmaf(va[e], va[e], r2a);
+      r2b = fmaf(vb[e], vb[e], r2b);
+    }
+    xa[c / 2] = pack_f32x2(va[0], va[1]);
+    xb[c / 2] = pack_f32x2(vb[0], vb[1]);
   }
   {
-    unsigned int m = __reduce_max_sync(FULL, f2ord(r2));
+    unsigned int m = __reduce_max_sync(FULL, f2ord(fmaxf(r2a, r2b)));
     if (lane == 0) atomicMax(rad2 + a, m);
   }
   const unsigned int neg_inf = f2ord(-__int_as_float(0x7f800000));
   for (int b0 = 0; b0 < P; b0 += 128) {
     __syncthreads();
     const int nb = min(128, P - b0);
-    for (int i = tid; i < nb * CELL_DIMS; i += 128)
+    for (int i = tid; i < nb * CELL_DIMS; i += 64)
       cwb[i / CELL_DIMS][i % CELL_DIMS] = cw[b0 * CELL_DIMS + i] - __ldg(cw + a * CELL_DIMS + i % CELL_DIMS);  // w_ab
     emax[tid] = neg_inf;
+    emax[64 + tid] = neg_inf;
     __syncthreads();
     for (int bl = 0; bl < nb; ++bl) {
-      float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;  // four independent chains (FMA latency)
-      const float4 *pv = reinterpret_cast<const float4 *>(cwb[bl]);
+      unsigned long long a01 = 0ull, a23 = 0ull, b01 = 0ull, b23 = 0ull;  // four chains per row, two per accumulator
+      const ulonglong2 *pv = reinterpret_cast<const ulonglong2 *>(cwb[bl]);
 #pragma unroll
       for (int c4 = 0; c4 < CELL_DIMS / 4; ++c4) {
-        const float4 q = pv[c4];
-        t0 = fmaf(xr[4 * c4 + 0], q.x, t0);
-        t1 = fmaf(xr[4 * c4 + 1], q.y, t1);
-        t2 = fmaf(xr[4 * c4 + 2], q.z, t2);
-        t3 = fmaf(xr[4 * c4 + 3], q.w, t3);
+        const ulonglong2 q = pv[c4];
+        fma_f32x2(a01, xa[2 * c4 + 0], q.x);
+        fma_f32x2(a23, xa[2 * c4 + 1], q.y);
+        fma_f32x2(b01, xb[2 * c4 + 0], q.x);
+        fma_f32x2(b23, xb[2 * c4 + 1], q.y);
       }
-      const float tb = (t0 + t1) + (t2 + t3);
-      const float proj = tb * __ldg(inv_norm + static_cast<size_t>(a) * P + b0 + bl);
-      const unsigned int o = (r >= 0) ? f2ord(proj) : neg_inf;
-      const unsigned int m = __reduce_max_sync(FULL, o);
+      const float inr = __ldg(inv_norm + static_cast<size_t>(a) * P + b0 + bl);
+      float t0, t1, t2, t3;
+      unpack_f32x2(a01, t0, t1);
+      unpack_f32x2(a23, t2, t3);
+      const float proj_a = ((t0 + t1) + (t2 + t3)) * inr;
+      unpack_f32x2(b01, t0, t1);
+      unpack_f32x2(b23, t2, t3);
+      const float proj_b = ((t0 + t1) + (t2 + t3)) * inr;
+      const unsigned int oa = (ra >= 0) ? f2ord(proj_a) : neg_inf, ob = (rb >= 0) ? f2ord(proj_b) : neg_inf;
+      const unsigned int m = __reduce_max_sync(FULL, max(oa, ob));
       if (lane == 0) atomicMax(&emax[bl], m);
     }
     __syncthreads();
-    if (tid < nb && emax[tid] != neg_inf) atomicMax(ext + static_cast<size_t>(a) * P + b0 + tid, emax[tid]);
+    for (int t = tid; t < nb; t += 64)
+      if (emax[t] != neg_inf) atomicMax(ext + static_cast<size_t>(a) * P + b0 + t, emax[t]);
   }
 }
 
@@ -498,7 +562,7 @@ int cells_build_phase(const CellPlan &L, const float *x, int d, const float *mu,
     VVB_CHECK_LAUNCH();
     VVB_CUDA(cudaMemsetAsync(L.cnt, 0, sizeof(int) * P, st));
     if (row_hi > row_lo) {
-      cell_assign_kernel<<<static_cast<unsigned>((row_hi - row_lo + 127) / 128), 128, 0, st>>>(
+      cell_assign_kernel<<<static_cast<unsigned>((row_hi - row_lo + ASSIGN_ROWS - 1) / ASSIGN_ROWS), 128, 0, st>>>(
           x, row_lo, row_hi, d, L.dsub, dims, mu, P, L.cen, L.cell_of, L.cnt);
       VVB_CHECK_LAUNCH();
     }
@@ -527,7 +591,7 @@ int cells_build_phase(const CellPlan &L, const float *x, int d, const float *mu,
     VVB_CHECK_LAUNCH();
     cell_pairs_kernel<<<P, 128, 0, st>>>(L.cen, L.cw, P, L.inv_norm, L.gap, L.cdist, L.ext, L.rad2);
     VVB_CHECK_LAUNCH();
-    cell_extent_kernel<<<groups, 128, 0, st>>>(x, d, L.dsub, dims, mu, L.perm, L.off, P, L.cell_of, L.cen, L.cw,
+    cell_extent_kernel<<<groups, 64, 0, st>>>(x, d, L.dsub, dims, mu, L.perm, L.off, P, L.cell_of, L.cen, L.cw,
                                                L.inv_norm, L.ext, L.rad2, part, parts);
     VVB_CHECK_LAUNCH();
   } else {

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
         }
         mine[q] = static_cast<int>(j);
       }
-      if (GS && jitter) {
+      if (GS && jitter == 1) {
         // stress mode (VVB_SMOOTH_JITTER=1, tests only): pseudo-random delays of up to ~16 us between claiming a row,
         // polling and publishing shake the order in which rows finish -- the result must not move by a bit
         __nanosleep((static_cast<unsigned>(i) * 2654435761u >> 18) & 0x3fffu);
@@ -102,16 +102,16 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
         bool polled = false;
 #pragma unroll
         for (int q = 0; q < KPL; ++q) {
-          if (mine[q] < i32) {
+          if (mine[q] < i32 && jitter != 2) {  // (VVB_SMOOTH_JITTER=2/3: timing probes, results are garbage)
             polled = true;
             unsigned ns = 32;
-            while (ld_relaxed(flags + mine[q]) < epoch) {
+            while (ld_relaxed(flags + mine[q]) < epoch && jitter != 3) {
               __nanosleep(ns);
               if (ns < 1024) ns <<= 1;
             }
           }
         }
-        if (__any_sync(FULL, polled)) fence_acq_rel();
+        if (__any_sync(FULL, polled) && jitter != 4) fence_acq_rel();
         __syncwarp();
       }
 
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
           }
         }
       }
-      if (GS && jitter) __nanosleep((static_cast<unsigned>(i) * 40503u >> 3) & 0x1fffu);
+      if (GS && jitter == 1) __nanosleep((static_cast<unsigned>(i) * 40503u >> 3) & 0x1fffu);
       if (GS) {
         __syncwarp();  // all 32 lanes' stores to `next` happen before ...
         if (lane == 0) st_release(flags + i, epoch);  // ... the (cumulative) release that publishes the row
