@@ -375,3 +375,50 @@ def test_smoother_column_slices_equal_the_whole_sweep(dtype, d, parts):
         c0, w = col_bounds(d, parts, r)
         smooth_cols_device(xd, idd, c0, w, k=k, coef=0.8, n_iter=2, out=out)
     assert torch.equal(out, whole)
+
+
+# ------------------------------------------------------------------ round 2b: the new paths of the screening kernel
+@pytest.mark.parametrize("slices", [1, 2, 3, 5, 8])
+def test_wide_first_tier_database_slices_give_the_same_graph(monkeypatch, slices):
+    """Wide rows (ka >= 4: single-product first tier, 256-row tiles): every query block swept by `slices` CTAs with
+    lists of their own, joined by `wide_merge_kernel`.  Any slice count must give the oracle's graph, bit for bit, and
+    sweep the same tiles."""
+    n, d, k = 24_000, 300, 30
+    x = pca_syn(n, d, seed=21)
+    monkeypatch.setenv("VVB_TC_WSLICES", str(slices))
+    st = {}
+    idx, dist = vv.make_knn(x, k=k, verbose=False, algo="tensor", stats=st)
+    assert st["algo_used"] == 2 and st["products"] == 1, st
+    check_properties(idx, dist, n)
+    orc.set_threads(os.cpu_count() or 1)
+    check_slices(x, idx, dist, k, (0, 11_111, n - 200), 200)
+    if slices == 1:
+        test_wide_first_tier_database_slices_give_the_same_graph.ref = (idx.copy(), dist.copy(), st["tiles_swept"])
+    ref = getattr(test_wide_first_tier_database_slices_give_the_same_graph, "ref", None)
+    if ref is not None:
+        assert np.array_equal(idx, ref[0]) and np.array_equal(dist, ref[1])
+
+
+@pytest.mark.parametrize("env", [{"VVB_TC_PRE_HI": "0"}, {"VVB_TC_PRE_SLACK_LOG2": "11"},
+                                 {"VVB_TC_PRE_SLACK_LOG2": "24"}, {}])
+def test_one_product_pre_pass_never_changes_the_graph(monkeypatch, env):
+    """The threshold pre-pass of the resident variant (one product per key, threshold raised by 2^-13 R^2): whatever
+    the starting threshold -- three products, the worst-case slack, or NO slack at all (thresholds that are too tight
+    for many rows, which then fail the certificate and are settled by the refine pass) -- the graph is the oracle's."""
+    n, d, k = 150_000, 50, 50
+    x = pca_syn(n, d, seed=22)
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    st = {}
+    idx, dist = vv.make_knn(x, k=k, verbose=False, algo="tensor", stats=st)
+    assert st["algo_used"] == 2, st
+    check_properties(idx, dist, n)
+    orc.set_threads(os.cpu_count() or 1)
+    check_slices(x, idx, dist, k, (0, 77_777, n - 256), 256)
+    if env.get("VVB_TC_PRE_HI") == "0":
+        assert st["tiles_pre"] == 0, st
+    else:
+        assert 0 < st["tiles_pre"] < st["tiles_swept"], st
+    if not env:
+        assert st["rows_refined"] <= n // 10_000, st  # the default slack leaves (next to) nothing to the refine pass
+    print("pre-pass", env, {key: st[key] for key in ("tiles_swept", "tiles_pre", "rows_refined", "rows_fallback")})

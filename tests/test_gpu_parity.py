@@ -253,6 +253,14 @@ def test_results_live_in_recycled_page_locked_blocks(monkeypatch):
             a = a.base
         return a
 
+    # idle blocks left by earlier tests of the same size class would be handed out first: start from an empty pool
+    import gc as _gc
+
+    _gc.collect()
+    from vivae_b200 import _lib as _vl
+
+    _vl._pinned_pool.release()
+    _vl._pinned_pool.seen.clear()  # (and the very first request of a size class is never pinned)
     first = vv.make_knn(x, k=50, verbose=False)
     idx, dist = vv.make_knn(x, k=50, verbose=False)
     assert type(idx) is np.ndarray and idx.flags.c_contiguous and idx.flags.writeable and idx.dtype == np.int64

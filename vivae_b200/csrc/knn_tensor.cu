@@ -409,6 +409,10 @@ __device__ __noinline__ float tc_select_truncate_wide(uint2 *list, int cnt, int 
 __device__ __noinline__ float tc_select_truncate(uint2 *list, int cnt, int keep, int keep_max, int lane, int *new_cnt) {
   return warp_select_truncate_pairs<TC_CAP_E>(list, cnt, keep, keep_max, lane, new_cnt);
 }
+__device__ __noinline__ float tc_select_truncate_short(uint2 *list, int cnt, int keep, int keep_max, int lane,
+                                                       int *new_cnt) {  // up to 128 entries: half the compares per bit
+  return warp_select_truncate_pairs<TC_CAP_E / 2>(list, cnt, keep, keep_max, lane, new_cnt);
+}
 
 
 // Refine pass: reduce a full list to its `keepn` best entries by the CONTRACT's key (fmaf-chain d2, original index;
@@ -1253,7 +1257,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       if (REFINE) {
         // everything below the row's threshold is handed over (c <= TC_REFINE_CAP)
       } else if (c > TC_CAP) thr = fminf(thr, tc_select_truncate_wide(la, c, p.keep, keep_max, lane, &nc));
-      else if (c > keep_max) thr = fminf(thr, tc_select_truncate(la, c, p.keep, keep_max, lane, &nc));
+      else if (c > 16 * TC_CAP_E) thr = fminf(thr, tc_select_truncate(la, c, p.keep, keep_max, lane, &nc));
+      else if (c > keep_max) thr = fminf(thr, tc_select_truncate_short(la, c, p.keep, keep_max, lane, &nc));
       if (lane == 0) {
         p.cand_cnt[tt + l_off] = nc;
         p.cand_thr[tt + l_off] = thr;
