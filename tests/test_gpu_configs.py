@@ -422,3 +422,31 @@ def test_one_product_pre_pass_never_changes_the_graph(monkeypatch, env):
     if not env:
         assert st["rows_refined"] <= n // 10_000, st  # the default slack leaves (next to) nothing to the refine pass
     print("pre-pass", env, {key: st[key] for key in ("tiles_swept", "tiles_pre", "rows_refined", "rows_fallback")})
+
+
+@pytest.mark.parametrize("dtype,d,k,order", [(np.float32, 8, 50, "random"), (np.float32, 6, 50, "sorted"),
+                                             (np.float32, 14, 100, "sorted"), (np.float64, 10, 30, "sorted"),
+                                             (np.float32, 26, 50, "sorted"), (np.float64, 32, 20, "random"),
+                                             (np.float32, 2, 5, "sorted")])
+@pytest.mark.parametrize("jitter", ["0", "1"])
+def test_narrow_rows_equal_the_sequential_sweep(monkeypatch, dtype, d, k, order, jitter):
+    """Narrow rows (the width of a rank's column slice of a 50-column matrix on 2 / 4 / 8 GPUs, and narrower), two
+    columns per load.  Coordinate-sorted rows put nearly every neighbour just below the row (the longest dependency
+    chains); the jitter mode delays the warps pseudo-randomly.  Bit-identical to the oracle's sequential sweep, one and
+    two sweeps, Gauss-Seidel and Jacobi."""
+    from vivae_b200.device import smooth_device
+
+    monkeypatch.setenv("VVB_SMOOTH_JITTER", jitter)
+    n = 50_000
+    x = pca_syn(n, max(d, 4), seed=100 + d, n_clusters=5)[:, :d].astype(np.float32).copy()
+    if order == "sorted":
+        x = x[np.argsort(x[:, 0])].copy()
+    idx, _ = vv.make_knn(x, k=k, verbose=False)
+    x = x.astype(dtype)
+    xd, idd = torch.from_numpy(x).cuda(), torch.from_numpy(idx).cuda()
+    for n_iter in (1, 2):
+        want = orc.smooth(x, idx, k, 0.6, n_iter)
+        got = smooth_device(xd, idd, k=k, coef=0.6, n_iter=n_iter)
+        assert np.array_equal(got.cpu().numpy(), want), (d, k, order, n_iter)
+    assert torch.equal(smooth_device(xd, idd, k=k, coef=0.6, n_iter=2, mode="jacobi"),
+                       torch.from_numpy(orc.smooth(x, idx, k, 0.6, 2, mode=1)).cuda())
