@@ -262,9 +262,12 @@ __device__ __forceinline__ float warp_select_truncate(float *keys, uint32_t *idx
 
 // ---- the same selection on a list of interleaved (key bits, index) pairs -----------------
 // (the tensor-core screening kernel appends candidates with ONE 8-byte store)
-template <int E>
-__device__ __forceinline__ float warp_select_truncate_pairs(uint2 *list, int cnt, int m, int keep_max, int lane,
-                                                            int *new_cnt) {
+// `load(p)` fetches entry p of the input (p < cnt); the kept entries are written to list[0 .. *new_cnt).  The input
+// may be `list` itself or span two buffers (the two half lists of a row): every entry is in a register before the
+// first one is written.
+template <int E, typename Load>
+__device__ __forceinline__ float warp_select_truncate_core(Load load, uint2 *list, int cnt, int m, int keep_max, int lane,
+                                                           int *new_cnt) {
   uint32_t u[E], id[E];
   __syncwarp();
 #pragma unroll
@@ -273,7 +276,7 @@ __device__ __forceinline__ float warp_select_truncate_pairs(uint2 *list, int cnt
     u[e] = 0xffffffffu;
     id[e] = 0;
     if (p < cnt) {
-      const uint2 v = list[p];
+      const uint2 v = load(p);
       u[e] = f2ord(__uint_as_float(v.x));
       id[e] = v.y;
     }
@@ -340,6 +343,18 @@ __device__ __forceinline__ float warp_select_truncate_pairs(uint2 *list, int cnt
   __syncwarp();
   *new_cnt = base;
   return ord2f(cut);
+}
+template <int E>
+__device__ __forceinline__ float warp_select_truncate_pairs(uint2 *list, int cnt, int m, int keep_max, int lane,
+                                                            int *new_cnt) {
+  return warp_select_truncate_core<E>([&](int p) { return list[p]; }, list, cnt, m, keep_max, lane, new_cnt);
+}
+// the input is the concatenation of list[0 .. cnt_a) and list_b[0 .. cnt_b); the result goes to `list`
+template <int E>
+__device__ __forceinline__ float warp_select_truncate_pairs_2(uint2 *list, int cnt_a, const uint2 *list_b, int cnt_b, int m,
+                                                              int keep_max, int lane, int *new_cnt) {
+  return warp_select_truncate_core<E>([&](int p) { return p < cnt_a ? list[p] : list_b[p - cnt_a]; }, list, cnt_a + cnt_b,
+                                      m, keep_max, lane, new_cnt);
 }
 
 // ---- m-th smallest of a list of floats: threshold only ------------------------------------

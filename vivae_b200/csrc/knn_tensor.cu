@@ -409,9 +409,15 @@ __device__ __noinline__ float tc_select_truncate_wide(uint2 *list, int cnt, int 
 __device__ __noinline__ float tc_select_truncate(uint2 *list, int cnt, int keep, int keep_max, int lane, int *new_cnt) {
   return warp_select_truncate_pairs<TC_CAP_E>(list, cnt, keep, keep_max, lane, new_cnt);
 }
-__device__ __noinline__ float tc_select_truncate_short(uint2 *list, int cnt, int keep, int keep_max, int lane,
-                                                       int *new_cnt) {  // up to 128 entries: half the compares per bit
-  return warp_select_truncate_pairs<TC_CAP_E / 2>(list, cnt, keep, keep_max, lane, new_cnt);
+// end of the sweep: the row's two half lists (la: ca entries, lb: cb entries) are truncated straight from where they
+// are -- no append pass, which was two dependent global round trips per row -- and the result lands in la
+__device__ __noinline__ float tc_select_truncate_halves_short(uint2 *la, int ca, const uint2 *lb, int cb, int keep,
+                                                              int keep_max, int lane, int *new_cnt) {  // <= 128 entries
+  return warp_select_truncate_pairs_2<TC_CAP_E / 2>(la, ca, lb, cb, keep, keep_max, lane, new_cnt);
+}
+__device__ __noinline__ float tc_select_truncate_halves(uint2 *la, int ca, const uint2 *lb, int cb, int keep, int keep_max,
+                                                        int lane, int *new_cnt) {  // <= 256 entries
+  return warp_select_truncate_pairs_2<TC_CAP_E>(la, ca, lb, cb, keep, keep_max, lane, new_cnt);
 }
 
 
@@ -1240,25 +1246,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
       // every rejected entry has key >= the threshold in force in its half when it was rejected >= that half's
       // final tau, and every row of a cell the sweep skipped has key >= both
       float thr = fminf(half_tau[pr], half_tau[TC_M + pr]);
-      // the row's two buffers are contiguous: append the second list right behind the first (the copy may
-      // run into the second buffer's own head, which has been read by then)
-      for (int i0 = 0; i0 < cb; i0 += 32) {
-        uint2 v = make_uint2(0u, 0u);
-        if (i0 + lane < cb) v = lb[i0 + lane];
-        __syncwarp();
-        if (i0 + lane < cb) la[ca + i0 + lane] = v;
-        __syncwarp();
-      }
       const int c = ca + cb;
       // keep the m smallest and at most 8 more: the re-rank kernel sorts by the exact distance anyway, so a
       // cheap threshold selection replaces a sort, and every extra candidate is a 200-byte gather there
       const int keep_max = min((p.keep + 31) & ~31, p.keep + 8);
       int nc = c;
-      if (REFINE) {
-        // everything below the row's threshold is handed over (c <= TC_REFINE_CAP)
-      } else if (c > TC_CAP) thr = fminf(thr, tc_select_truncate_wide(la, c, p.keep, keep_max, lane, &nc));
-      else if (c > 16 * TC_CAP_E) thr = fminf(thr, tc_select_truncate(la, c, p.keep, keep_max, lane, &nc));
-      else if (c > keep_max) thr = fminf(thr, tc_select_truncate_short(la, c, p.keep, keep_max, lane, &nc));
+      if (!REFINE && c > keep_max && c <= TC_CAP) {  // the common case: truncate straight from the two half lists
+        if (c > 16 * TC_CAP_E) thr = fminf(thr, tc_select_truncate_halves(la, ca, lb, cb, p.keep, keep_max, lane, &nc));
+        else thr = fminf(thr, tc_select_truncate_halves_short(la, ca, lb, cb, p.keep, keep_max, lane, &nc));
+      } else {
+        // the row's two buffers are contiguous: append the second list right behind the first (the copy may
+        // run into the second buffer's own head, which has been read by then)
+        for (int i0 = 0; i0 < cb; i0 += 32) {
+          uint2 v = make_uint2(0u, 0u);
+          if (i0 + lane < cb) v = lb[i0 + lane];
+          __syncwarp();
+          if (i0 + lane < cb) la[ca + i0 + lane] = v;
+          __syncwarp();
+        }
+        // REFINE: everything below the row's threshold is handed over (c <= TC_REFINE_CAP)
+        if (!REFINE && c > TC_CAP) thr = fminf(thr, tc_select_truncate_wide(la, c, p.keep, keep_max, lane, &nc));
+      }
       if (lane == 0) {
         p.cand_cnt[tt + l_off] = nc;
         p.cand_thr[tt + l_off] = thr;
