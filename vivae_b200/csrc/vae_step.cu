@@ -26,7 +26,10 @@ namespace vvb {
 
 constexpr int VS_R = 32;          // rows per CTA
 constexpr int VS_RS = 36;         // row stride of the transposed activation buffers (16-byte aligned, conflict-free)
-constexpr int VS_THREADS = 512;   // 16 warps: the layers are chains of dependent FMAs behind shared-memory reads
+#ifndef VVB_VS_THREADS
+#define VVB_VS_THREADS 512
+#endif
+constexpr int VS_THREADS = VVB_VS_THREADS;  // 16 warps: the layers are chains of dependent FMAs behind shared-memory reads
 constexpr int VS_WARPS = VS_THREADS / 32;
 constexpr int VS_MAX_LAYERS = 16;
 
