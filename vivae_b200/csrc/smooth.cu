@@ -54,6 +54,15 @@ template <typename T> __device__ __forceinline__ T vget(const T &v, int) { retur
 __device__ __forceinline__ float vget(const float2 &v, int e) { return e ? v.y : v.x; }
 __device__ __forceinline__ double vget(const double2 &v, int e) { return e ? v.y : v.x; }
 
+// base + j * ld_bytes as ONE instruction (IMAD.WIDE: 32 x 32 -> 64-bit product plus a 64-bit addend); written as
+// (int64) j * stride the compiler hoists the sign-extended stride and emits a four-instruction 64-bit multiply.
+template <typename P>
+__device__ __forceinline__ const P *row_ptr(const P *base, int j, int ld_bytes) {
+  unsigned long long r;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(j), "r"(ld_bytes), "l"(reinterpret_cast<unsigned long long>(base)));
+  return reinterpret_cast<const P *>(r);
+}
+
 // V   = elements per load (2 when d is even: rows are then 8 / 16-byte aligned and a lane fetches two columns of a
 //       neighbour row with ONE load -- the sweep is bound by instruction issue)
 // DPL = loads per lane and neighbour row held in registers (a warp covers 32 * DPL * V columns per pass)
@@ -122,8 +131,72 @@ __global__ void __launch_bounds__(SM_THREADS) smooth_sweep_kernel(
 #pragma unroll
           for (int e = 0; e < V; ++e) acc[q][e] = T(0);
         bool first = true;
+        if constexpr (KPL <= 4) {
+          // The hot form (k <= 128).  The sweep is bound by its instruction count (ncu: 1,500 warp instructions per row
+          // of 50 neighbours, i.e. ~27 per neighbour: a 64-bit multiply, pointer re-loads, two guards with their
+          // branches).  Here a neighbour is shuffle + compare + two selects + IMAD.WIDE + load: the lane's column
+          // pointers into both arrays are formed once per row (lanes beyond the row are clamped to its last column
+          // and drop what they load), the row stride is a 32-bit multiplier, full batches carry no per-neighbour guard
+          // and the "first addend" is resolved at compile time.
+          const TV *pl[DPL], *nl[DPL];
 #pragma unroll
-        for (int kq = 0; kq < KPL; ++kq) {
+          for (int q = 0; q < DPL; ++q) {
+            const int cc = min(c0 + q * 32 + lane, dv - 1);
+            pl[q] = reinterpret_cast<const TV *>(prev) + cc;
+            nl[q] = reinterpret_cast<const TV *>(static_cast<const T *>(next)) + cc;
+          }
+          const int ld_bytes = static_cast<int>(ld * static_cast<int64_t>(sizeof(T)));  // (checked on the host side)
+#pragma unroll
+          for (int jj0 = 0; jj0 < 32 * KPL; jj0 += SM_UNROLL) {
+            if (jj0 < k) {  // warp-uniform
+              TV v[SM_UNROLL][DPL];
+              if (jj0 + SM_UNROLL <= k) {
+#pragma unroll
+                for (int u = 0; u < SM_UNROLL; ++u) {
+                  const int j = __shfl_sync(FULL, mine[(jj0 + u) / 32], (jj0 + u) & 31);
+                  const bool from_next = GS && (j < i32);
+#pragma unroll
+                  for (int q = 0; q < DPL; ++q) {
+                    const TV *src = row_ptr((from_next ? nl[q] : pl[q]), j, ld_bytes);
+                    v[u][q] = GS ? __ldcg(src) : __ldg(src);
+                  }
+                }
+#pragma unroll
+                for (int u = 0; u < SM_UNROLL; ++u)
+#pragma unroll
+                  for (int q = 0; q < DPL; ++q)
+#pragma unroll
+                    for (int e = 0; e < V; ++e)
+                      acc[q][e] = (jj0 == 0 && u == 0) ? vget(v[u][q], e) : Arith<T>::add(acc[q][e], vget(v[u][q], e));
+              } else {
+#pragma unroll
+                for (int u = 0; u < SM_UNROLL; ++u) {
+                  const int j = __shfl_sync(FULL, mine[(jj0 + u) / 32], (jj0 + u) & 31);
+                  const bool from_next = GS && (j < i32);
+#pragma unroll
+                  for (int q = 0; q < DPL; ++q) {
+                    const TV *src = row_ptr((from_next ? nl[q] : pl[q]), j, ld_bytes);
+                    v[u][q] = TV();
+                    if (jj0 + u < k) v[u][q] = GS ? __ldcg(src) : __ldg(src);
+                  }
+                }
+#pragma unroll
+                for (int u = 0; u < SM_UNROLL; ++u) {
+                  if (jj0 + u < k) {
+#pragma unroll
+                    for (int q = 0; q < DPL; ++q)
+#pragma unroll
+                      for (int e = 0; e < V; ++e)
+                        acc[q][e] = (jj0 == 0 && u == 0) ? vget(v[u][q], e) : Arith<T>::add(acc[q][e], vget(v[u][q], e));
+                  }
+                }
+              }
+            }
+          }
+          first = false;
+        }
+#pragma unroll
+        for (int kq = 0; kq < (KPL <= 4 ? 0 : KPL); ++kq) {
           if (kq * 32 < k) {  // warp-uniform
             for (int jb = 0; jb < 32 && kq * 32 + jb < k; jb += SM_UNROLL) {
               TV v[SM_UNROLL][DPL];
@@ -333,6 +406,7 @@ static int smooth_check(const void *x, int elem_size, int64_t n, int d, int64_t 
   VVB_REQUIRE(n >= 1 && d >= 1 && k >= 1 && ld_idx >= k && n_iter >= 1, "smooth: bad shape arguments");
   VVB_REQUIRE(mode == VVB_SMOOTH_GAUSS_SEIDEL || mode == VVB_SMOOTH_JACOBI, "smooth: unknown mode %d", mode);
   VVB_REQUIRE(out != x, "smooth: out must not alias x");
+  VVB_REQUIRE(static_cast<int64_t>(d) * elem_size <= 0x7fffffffLL, "smooth: rows of more than 2 GB are not supported");
   VVB_REQUIRE(workspace_bytes >= smooth_workspace_bytes(elem_size, n, d, n_iter), "smooth: workspace too small");
   VVB_SUPPORTED(k <= 1024, "smooth: k=%d above the supported maximum of 1024", k);
   return VVB_OK;
