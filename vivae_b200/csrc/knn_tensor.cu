@@ -1102,8 +1102,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
               ins(8 * q + 4);
               ins(8 * q + 5);
             }
-            ins(8 * q + 6);
-            ins(8 * q + 7);
+            if (fminf(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])) < cut) {
+              ins(8 * q + 6);
+              ins(8 * q + 7);
+            }
           }
         }
       }
