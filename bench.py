@@ -574,6 +574,23 @@ def run_ours(args) -> None:
                  "smooth_max_abs_err": float(np.abs(g_sm - kept["smooth_out"]).max()),
                  "checked": f"rank 0's first {qn} graph rows of this run and a {g_sm.shape[0]}-row smoother sample vs the CPU oracle"}
 
+    # ---- the same graph with the DATABASE sharded too: every rank holds only its rows, shards travel around an NCCL
+    # ring (north star; `make_knn_ring`).  Measured beside the replicated layout at every N > 1 and compared bit for bit.
+    ring = None
+    if world > 1 and not args.skip_ring and args.exchange != "ring":
+        xl = x_dev[q0:q0 + nq].contiguous()
+        ms_ring, _ = timed(lambda: make_knn_ring(xl, n, k, algo=args.algo), 2, 1)
+        r_idx, r_dist = make_knn_ring(xl, n, k, algo=args.algo)
+        same = torch.tensor([int(torch.equal(r_idx, idx_s) and torch.equal(r_dist, dist_s))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        ring = {"what": "make_knn_ring: each rank holds n/N rows, N ring steps (isend/irecv of the shard overlapped with the "
+                        "step's sweep), running top-k merge; graph only, no smoother",
+                "ms_knn": ms_ring, "ms_knn_replicated_layout": max_over_ranks(ms_knn), "steps": 2, "warmup": 1,
+                "identical_to_replicated_layout": bool(same.item()),
+                "note": "each step sweeps own x [shard ; own]: about twice the pairs of the replicated layout (DESIGN.md "
+                        "section 8 item 3 says what a bipartite, seeded sweep would need)"}
+        del xl, r_idx, r_dist
+
     # ---- the north-star configurations beside the headline (device-generated data, a few steps)
     del idx_s, dist_s, idx_full
     x_dev = None
@@ -620,7 +637,7 @@ def run_ours(args) -> None:
             "e2e": e2e, "e2e_sharded_api": e2e_sharded, "gpu_launches": launches, "roofline": roofline,
             "roofline_dense": dense_roof, "roofline_smooth": smooth_roof, "quartet": quartet,
             "knn_stats": st, "ms_knn": ms_knn, "ms_smooth": ms_smooth, "cpu_baseline": base, "fit": fit,
-            "parity_gates": gates, **sub,
+            "parity_gates": gates, "ring": ring, **sub,
             "parity": {"knn": "bit-exact vs FP32 brute-force oracle (tests/test_gpu_parity.py, tests/test_gpu_configs.py)",
                        "smooth": "bit-exact vs reference smooth()", "quartet": "1e-4 relative"},
         }
@@ -649,6 +666,7 @@ def main():
     ap.add_argument("--skip-dense", action="store_true")
     ap.add_argument("--skip-c3", action="store_true")
     ap.add_argument("--skip-c5", action="store_true")
+    ap.add_argument("--skip-ring", action="store_true")
     ap.add_argument("--c3-rows", type=int, default=10_000_000)
     ap.add_argument("--c5-rows", type=int, default=2_000_000)
     ap.add_argument("--sub-steps", type=int, default=2)
