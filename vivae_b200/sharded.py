@@ -288,22 +288,25 @@ class _DeviceOps:
 
 
 def ring_fold(ops, x_local: torch.Tensor, q0: int, shard: torch.Tensor, s0: int, run_idx: torch.Tensor,
-              run_d2: torch.Tensor, algo: str = "auto") -> None:
+              run_d2: torch.Tensor, algo: str = "auto", with_own: bool = False) -> None:
     """One ring step: fold database rows [s0, s0+len(shard)) into the running lists of query rows
-    [q0, q0+len(x_local)).  `s0 == q0` means the shard IS the rank's own rows (step 0)."""
+    [q0, q0+len(x_local)).  `s0 == q0` means the shard IS the rank's own rows.  `with_own`: the rank's own rows are
+    folded in by the same call (the builder sweeps [shard ; own] anyway, so the first step with a foreign shard also
+    settles own x own and no separate step is spent on it)."""
     nq, sn, k = x_local.shape[0], shard.shape[0], run_idx.shape[1] - 1
-    if nq == 0 or sn == 0:
+    if nq == 0 or (sn == 0 and not with_own):
         return
-    if s0 == q0:
-        xc, qoff, keep_lo, keep_hi, goff = x_local, 0, 0, nq, q0
+    if s0 == q0 or sn == 0:
+        xc, qoff, keeps = x_local, 0, [(0, nq, q0)]
     elif s0 < q0:
-        xc, qoff, keep_lo, keep_hi, goff = torch.cat([shard, x_local]), sn, 0, sn, s0
+        xc, qoff, keeps = torch.cat([shard, x_local]), sn, [(0, sn, s0)] + ([(sn, sn + nq, q0 - sn)] if with_own else [])
     else:
-        xc, qoff, keep_lo, keep_hi, goff = torch.cat([x_local, shard]), 0, nq, nq + sn, s0 - nq
+        xc, qoff, keeps = torch.cat([x_local, shard]), 0, [(nq, nq + sn, s0 - nq)] + ([(0, nq, q0)] if with_own else [])
     kn = min(k, xc.shape[0] - 1)
     if kn >= 1:
         new_idx, _ = ops.knn(xc, kn, qoff, nq, algo)
-        ops.merge(xc, qoff, nq, new_idx, keep_lo, keep_hi, goff, run_idx, run_d2)
+        for keep_lo, keep_hi, goff in keeps:  # (rows of xc to keep, global index of xc row 0 for that range)
+            ops.merge(xc, qoff, nq, new_idx, keep_lo, keep_hi, goff, run_idx, run_d2)
 
 
 def make_knn_ring(x_local: torch.Tensor, n: int, k: int, group=None, algo: str = "auto", _ops=None):
@@ -313,7 +316,8 @@ def make_knn_ring(x_local: torch.Tensor, n: int, k: int, group=None, algo: str =
     `world` ring steps.  In step s the rank holds the shard of rank (rank+s) % world; it forwards it to rank-1
     while the graph builder runs on [shard ; own rows] stacked in global row order (so the builder's tie-break by
     local index is the contract's tie-break by global index), and the merge kernel folds the shard's rows of the
-    result into the running lists (`csrc/knn_merge.cu` explains why that is exact).  Step 0 ranks the own rows."""
+    result into the running lists (`csrc/knn_merge.cu` explains why that is exact).  Step 0 only starts the exchange;
+    the own rows are ranked by step 1's sweep, which covers them anyway (world = 2: ONE sweep of the whole matrix)."""
     ops = _ops or _DeviceOps()
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -336,7 +340,9 @@ def make_knn_ring(x_local: torch.Tensor, n: int, k: int, group=None, algo: str =
             if group is not None:
                 to, frm = dist.get_global_rank(group, to), dist.get_global_rank(group, frm)
             reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, cur, to, group), dist.P2POp(dist.irecv, nxt, frm, group)])
-        ring_fold(ops, x_local, q0, cur[:sn], s0, run_idx, run_d2, algo)
+        # own x own is settled together with the first foreign shard (one sweep of [shard ; own] instead of two)
+        if world == 1 or s > 0:
+            ring_fold(ops, x_local, q0, cur[:sn], s0, run_idx, run_d2, algo, with_own=(s == 1))
         for r in reqs:
             r.wait()
         cur, nxt = nxt, cur
