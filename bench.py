@@ -587,9 +587,9 @@ def run_ours(args) -> None:
                         "step's sweep), running top-k merge; graph only, no smoother",
                 "ms_knn": ms_ring, "ms_knn_replicated_layout": max_over_ranks(ms_knn), "steps": 2, "warmup": 1,
                 "identical_to_replicated_layout": bool(same.item()),
-                "note": "N - 1 sweeps of own x [shard ; own] (own x own is settled by the first of them); a sweep pruned by "
-                        "the cell bounds costs about the same per query block whatever the database size, so this is "
-                        "about N - 1 replicated builds (DESIGN.md section 8 item 3: what a seeded, bipartite sweep needs)"}
+                "note": "a sweep of own x [shards ; own] takes as many foreign shards as fit in device memory (here: all of "
+                        "them, one sweep); a sweep pruned by the cell bounds costs about the same per query block whatever "
+                        "the database size, so the number of sweeps is what counts (DESIGN.md section 6)"}
         del xl, r_idx, r_dist
 
     # ---- the north-star configurations beside the headline (device-generated data, a few steps)

@@ -59,9 +59,9 @@ if "ring" in which:
         q0, nq = shard_bounds(n, world, rank)
         own = xd[q0:q0 + nq].contiguous()
         ri, rd = ops.init(nq, k, q0, xd.device)
-        for s in range(world):
+        for s in range(1, world):
             s0, sn = shard_bounds(n, world, (rank + s) % world)
-            ring_fold(ops, own, q0, xd[s0:s0 + sn].contiguous(), s0, ri, rd)
+            ring_fold(ops, own, q0, [(s0, xd[s0:s0 + sn].contiguous())], ri, rd, with_own=(s == 1))
         assert torch.equal(ri, wi[q0:q0 + nq]) and torch.equal(ops.finish(rd), wd[q0:q0 + nq])
     print("ring ok", flush=True)
 torch.cuda.synchronize()

@@ -711,9 +711,10 @@ def test_cell_sweep_skips_far_clusters_and_stays_exact(monkeypatch):
 @pytest.mark.parametrize("kind,n,d,k,world", [("clustered", 30_000, 50, 50, 3), ("ties", 6_000, 6, 20, 4),
                                                ("clustered", 5_000, 130, 100, 2), ("iid", 700, 20, 300, 3)])
 def test_ring_steps_with_merge_kernel_equal_whole_matrix_build(kind, n, d, k, world):
-    """The ring build's per-step work (builder on [shard ; own rows] + csrc/knn_merge.cu), run here for every
-    'rank' in one process, is bit-identical to one build over the whole matrix -- including tie-breaks across
-    shard borders and k larger than a shard."""
+    """The ring build's sweeps (builder on [shards ; own rows] in global row order + csrc/knn_merge.cu per contiguous
+    range), run here for every 'rank' in one process and for one / two / all foreign shards per sweep, are
+    bit-identical to one build over the whole matrix -- including tie-breaks across shard borders and k larger than
+    a shard."""
     from vivae_b200.sharded import _DeviceOps, ring_fold, shard_bounds
 
     x = {"clustered": lambda: clustered(n, d, 8, seed=21), "ties": lambda: tie_data(n, d, seed=22),
@@ -725,11 +726,15 @@ def test_ring_steps_with_merge_kernel_equal_whole_matrix_build(kind, n, d, k, wo
     for rank in range(world):
         q0, nq = shard_bounds(n, world, rank)
         own = xd[q0:q0 + nq].contiguous()
-        run_idx, run_d2 = ops.init(nq, k, q0, xd.device)
-        for s in range(world):
+        foreign = []
+        for s in range(1, world):
             s0, sn = shard_bounds(n, world, (rank + s) % world)
-            ring_fold(ops, own, q0, xd[s0:s0 + sn].contiguous(), s0, run_idx, run_d2)
-        dist = ops.finish(run_d2)
-        assert torch.equal(run_idx, whole_idx[q0:q0 + nq])
-        assert torch.equal(dist, whole_dist[q0:q0 + nq])
+            foreign.append((s0, xd[s0:s0 + sn].contiguous()))
+        for per_sweep in sorted({1, 2, world - 1}):  # shards per sweep: the schedules make_knn_ring can choose
+            run_idx, run_d2 = ops.init(nq, k, q0, xd.device)
+            for g0 in range(0, len(foreign), per_sweep):
+                ring_fold(ops, own, q0, foreign[g0:g0 + per_sweep], run_idx, run_d2, with_own=(g0 == 0))
+            dist = ops.finish(run_d2)
+            assert torch.equal(run_idx, whole_idx[q0:q0 + nq]), (rank, per_sweep)
+            assert torch.equal(dist, whole_dist[q0:q0 + nq]), (rank, per_sweep)
     assert vv._lib.launch_count() > before

@@ -157,25 +157,29 @@ def _ring_data(n, kind):
     return x
 
 
-def _ring_worker(rank, world, port, n, k, kind, out_dir):
+def _ring_worker(rank, world, port, n, k, kind, out_dir, per_sweep=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         x = torch.from_numpy(_ring_data(n, kind))
         q0, nq = shard_bounds(n, world, rank)
-        idx, dst = make_knn_ring(x[q0:q0 + nq].clone(), n, k, _ops=_CpuRingOps())
+        idx, dst = make_knn_ring(x[q0:q0 + nq].clone(), n, k, _ops=_CpuRingOps(), shards_per_sweep=per_sweep)
         np.savez(os.path.join(out_dir, f"ring{rank}.npz"), idx=idx.numpy(), dist=dst.numpy(), q0=q0, nq=nq)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,k,kind", [(2, 150, 7, "normal"), (3, 100, 5, "ties"), (2, 90, 60, "ties"), (3, 7, 4, "normal")])
-def test_ring_build_equals_whole_matrix_build(tmp_path, world, n, k, kind):
+@pytest.mark.parametrize("world,n,k,kind,per_sweep", [(2, 150, 7, "normal", None), (3, 100, 5, "ties", 1),
+                                                      (3, 100, 5, "ties", None), (2, 90, 60, "ties", 1),
+                                                      (3, 7, 4, "normal", 1), (4, 61, 9, "ties", 2),
+                                                      (4, 61, 9, "normal", 1)])
+def test_ring_build_equals_whole_matrix_build(tmp_path, world, n, k, kind, per_sweep):
     """Shards passed around the ring + running merge == one build over the whole matrix, byte for byte
-    (k larger than a shard, ragged and short shards, ties and duplicate rows across shard borders)."""
+    (k larger than a shard, ragged and short shards, ties and duplicate rows across shard borders; one shard per
+    sweep, two, and as many as fit -- on the CPU: all of them)."""
     port = _free_port()
-    mp.spawn(_ring_worker, args=(world, port, n, k, kind, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_ring_worker, args=(world, port, n, k, kind, str(tmp_path), per_sweep), nprocs=world, join=True)
     wi, wd = orc.knn(_ring_data(n, kind), k)
     for r in range(world):
         g = np.load(tmp_path / f"ring{r}.npz")

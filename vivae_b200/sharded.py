@@ -287,21 +287,29 @@ class _DeviceOps:
                                                         device.knn_merge_finish)
 
 
-def ring_fold(ops, x_local: torch.Tensor, q0: int, shard: torch.Tensor, s0: int, run_idx: torch.Tensor,
-              run_d2: torch.Tensor, algo: str = "auto", with_own: bool = False) -> None:
-    """One ring step: fold database rows [s0, s0+len(shard)) into the running lists of query rows
-    [q0, q0+len(x_local)).  `s0 == q0` means the shard IS the rank's own rows.  `with_own`: the rank's own rows are
-    folded in by the same call (the builder sweeps [shard ; own] anyway, so the first step with a foreign shard also
-    settles own x own and no separate step is spent on it)."""
-    nq, sn, k = x_local.shape[0], shard.shape[0], run_idx.shape[1] - 1
-    if nq == 0 or (sn == 0 and not with_own):
+def ring_fold(ops, x_local: torch.Tensor, q0: int, shards, run_idx: torch.Tensor, run_d2: torch.Tensor,
+              algo: str = "auto", with_own: bool = False) -> None:
+    """One sweep of the ring build: fold the database shards `shards` = [(first global row, rows tensor), ...] into the
+    running lists of query rows [q0, q0+len(x_local)).  The builder runs on the shards and the own rows stacked in
+    GLOBAL row order (its tie-break by local index is then the contract's tie-break by global index); every contiguous
+    range of global indices is folded by one merge call.  `with_own`: the rank's own rows are folded in as well (the
+    sweep covers own x own anyway, so no sweep is spent on the own rows alone).  A shard that starts at `q0` IS the
+    rank's own rows (a one-rank "ring")."""
+    nq, k = x_local.shape[0], run_idx.shape[1] - 1
+    shards = [(s0, t) for s0, t in shards if t.shape[0] > 0 and s0 != q0]
+    if nq == 0 or (not shards and not with_own):
         return
-    if s0 == q0 or sn == 0:
-        xc, qoff, keeps = x_local, 0, [(0, nq, q0)]
-    elif s0 < q0:
-        xc, qoff, keeps = torch.cat([shard, x_local]), sn, [(0, sn, s0)] + ([(sn, sn + nq, q0 - sn)] if with_own else [])
-    else:
-        xc, qoff, keeps = torch.cat([x_local, shard]), 0, [(nq, nq + sn, s0 - nq)] + ([(0, nq, q0)] if with_own else [])
+    pieces = sorted(shards + [(q0, x_local)], key=lambda p_: p_[0])
+    xc = torch.cat([t for _, t in pieces]) if len(pieces) > 1 else x_local
+    keeps, qoff, pos = [], 0, 0
+    for s0, t in pieces:
+        if s0 == q0:
+            qoff = pos
+            if with_own:
+                keeps.append((pos, pos + nq, q0 - pos))
+        else:
+            keeps.append((pos, pos + t.shape[0], s0 - pos))
+        pos += t.shape[0]
     kn = min(k, xc.shape[0] - 1)
     if kn >= 1:
         new_idx, _ = ops.knn(xc, kn, qoff, nq, algo)
@@ -309,15 +317,30 @@ def ring_fold(ops, x_local: torch.Tensor, q0: int, shard: torch.Tensor, s0: int,
             ops.merge(xc, qoff, nq, new_idx, keep_lo, keep_hi, goff, run_idx, run_d2)
 
 
-def make_knn_ring(x_local: torch.Tensor, n: int, k: int, group=None, algo: str = "auto", _ops=None):
+def _ring_shards_per_sweep(per: int, d: int, device: torch.device, world: int) -> int:
+    """How many foreign shards one sweep of the ring build may hold: as many as fit in about a third of the free device
+    memory next to the own rows (matrix rows, fp16 hi/lo operand rows, cell-sorted order), at least one.  A sweep pruned
+    by the cell bounds costs about the same per query block whatever the size of its database, so fewer, larger sweeps
+    are cheaper: with everything in memory the ring is one sweep, i.e. the replicated layout."""
+    if device.type != "cuda":
+        return world - 1
+    free, _ = torch.cuda.mem_get_info(device)
+    ka = (d + 3 + 63) // 64
+    per_row = 4 * d + 512 * ka + 64
+    return max(1, min(world - 1, int(free / 3 // (per_row * max(per, 1))) - 1))
+
+
+def make_knn_ring(x_local: torch.Tensor, n: int, k: int, group=None, algo: str = "auto", _ops=None,
+                  shards_per_sweep: Optional[int] = None):
     """Exact kNN graph of an (n, d) matrix whose rows are spread over the ranks: `x_local` holds this rank's rows
     [q0, q0+nq) = `shard_bounds(n, world, rank)`.  Returns `(idx, dist)` of those rows, global indices.
 
-    `world` ring steps.  In step s the rank holds the shard of rank (rank+s) % world; it forwards it to rank-1
-    while the graph builder runs on [shard ; own rows] stacked in global row order (so the builder's tie-break by
-    local index is the contract's tie-break by global index), and the merge kernel folds the shard's rows of the
-    result into the running lists (`csrc/knn_merge.cu` explains why that is exact).  Step 0 only starts the exchange;
-    the own rows are ranked by step 1's sweep, which covers them anyway (world = 2: ONE sweep of the whole matrix)."""
+    `world` ring steps.  In step s the rank holds the shard of rank (rank+s) % world and forwards it to rank-1.  The
+    graph builder runs on [shards ; own rows] stacked in global row order (so the builder's tie-break by local index is
+    the contract's tie-break by global index) once `shards_per_sweep` foreign shards have arrived (default: as many
+    as fit in memory, `_ring_shards_per_sweep`; 1 = a sweep per ring step, overlapped with the next transfer), and the
+    merge kernel folds the shards' rows of the result into the running lists (`csrc/knn_merge.cu` explains why that is
+    exact).  The own rows are ranked by the first sweep, which covers them anyway."""
     ops = _ops or _DeviceOps()
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -329,9 +352,15 @@ def make_knn_ring(x_local: torch.Tensor, n: int, k: int, group=None, algo: str =
     per = (n + world - 1) // world
     d = x_local.shape[1]
     run_idx, run_d2 = ops.init(nq, k, q0, x_local.device)
+    if world == 1:
+        ring_fold(ops, x_local, q0, [], run_idx, run_d2, algo, with_own=True)
+        return run_idx, ops.finish(run_d2)
+    m = shards_per_sweep if shards_per_sweep else _ring_shards_per_sweep(per, d, x_local.device, world)
+    m = max(1, min(int(m), world - 1))
     cur = torch.zeros((per, d), dtype=x_local.dtype, device=x_local.device)
     cur[:nq] = x_local
     nxt = torch.empty_like(cur)
+    held, first = [], True
     for s in range(world):
         s0, sn = shard_bounds(n, world, (rank + s) % world)
         reqs = []
@@ -340,9 +369,12 @@ def make_knn_ring(x_local: torch.Tensor, n: int, k: int, group=None, algo: str =
             if group is not None:
                 to, frm = dist.get_global_rank(group, to), dist.get_global_rank(group, frm)
             reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, cur, to, group), dist.P2POp(dist.irecv, nxt, frm, group)])
-        # own x own is settled together with the first foreign shard (one sweep of [shard ; own] instead of two)
-        if world == 1 or s > 0:
-            ring_fold(ops, x_local, q0, cur[:sn], s0, run_idx, run_d2, algo, with_own=(s == 1))
+        if s > 0:
+            # (a held shard is copied out of the exchange buffers unless it is swept right away)
+            held.append((s0, cur[:sn] if m == 1 else cur[:sn].clone()))
+            if len(held) == m or s == world - 1:
+                ring_fold(ops, x_local, q0, held, run_idx, run_d2, algo, with_own=first)
+                held, first = [], False
         for r in reqs:
             r.wait()
         cur, nxt = nxt, cur
