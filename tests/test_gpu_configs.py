@@ -424,6 +424,27 @@ def test_one_product_pre_pass_never_changes_the_graph(monkeypatch, env):
     print("pre-pass", env, {key: st[key] for key in ("tiles_swept", "tiles_pre", "rows_refined", "rows_fallback")})
 
 
+@pytest.mark.parametrize("n,d,k", [(150_000, 50, 50), (40_000, 100, 30), (60_000, 20, 100)])
+def test_deferred_halves_merge_equals_the_in_kernel_merge(monkeypatch, n, d, k):
+    """The join of a row's two half lists runs in `halves_merge_kernel` (full occupancy) by default and inside the
+    screening kernel with VVB_TC_DEFER_MERGE=0: same lists, same thresholds, hence the same graph and the same rows
+    sent to the refine pass -- resident variant (d = 50, 20) and K-loop variant (d = 100)."""
+    x = pca_syn(n, d, seed=31)
+    got = []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("VVB_TC_DEFER_MERGE", mode)
+        st = {}
+        idx, dist = vv.make_knn(x, k=k, verbose=False, algo="tensor", stats=st)
+        assert st["algo_used"] == 2, st
+        got.append((idx.copy(), dist.copy(), st["rows_refined"], st["rows_fallback"]))
+    check_properties(got[0][0], got[0][1], n)
+    assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+    # (tiles_swept is not compared: where a block's sweep stops depends on when its warps publish their thresholds)
+    assert got[0][2:] == got[1][2:], (got[0][2:], got[1][2:])
+    orc.set_threads(os.cpu_count() or 1)
+    check_slices(x, got[0][0], got[0][1], k, (0, n // 2, n - 256), 256)
+
+
 @pytest.mark.parametrize("dtype,d,k,order", [(np.float32, 8, 50, "random"), (np.float32, 6, 50, "sorted"),
                                              (np.float32, 14, 100, "sorted"), (np.float64, 10, 30, "sorted"),
                                              (np.float32, 26, 50, "sorted"), (np.float64, 32, 20, "random"),

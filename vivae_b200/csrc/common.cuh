@@ -344,6 +344,72 @@ __device__ __forceinline__ float warp_select_truncate_core(Load load, uint2 *lis
   *new_cnt = base;
   return ord2f(cut);
 }
+// The same selection on entries that are already in registers: entry e of this lane is (key bits kv[e].x, index
+// kv[e].y) and takes part iff bit e of `valid` is set; the kept entries are written to list[0 .. *new_cnt) in
+// (e, lane) order.  Requires at least m valid entries in the warp.  (halves_merge_kernel loads both half lists of a
+// row speculatively, before their lengths have arrived: one DRAM round trip per row instead of two.)
+template <int E>
+__device__ __forceinline__ float warp_select_truncate_regs(const uint2 (&kv)[E], unsigned valid, uint2 *list, int m,
+                                                           int keep_max, int lane, int *new_cnt) {
+  uint32_t u[E];
+  uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const bool v = (valid >> e) & 1u;
+    u[e] = v ? f2ord(__uint_as_float(kv[e].x)) : 0xffffffffu;
+    lo = v ? min(lo, u[e]) : lo;
+    hi = v ? max(hi, u[e]) : hi;
+  }
+  lo = __reduce_min_sync(FULL, lo);
+  hi = __reduce_max_sync(FULL, hi);
+  const int top = 31 - __clz(static_cast<int>((lo ^ hi) | 1u));  // highest bit in which two keys differ
+  const int slack = (keep_max - m) < 24 ? (keep_max - m) : 24;
+  uint32_t T = (top >= 31) ? 0u : (lo & ~((2u << top) - 1u));  // invariant: count(valid u < T) < m
+  uint32_t cut = 0;
+  bool exact = true;
+  for (int b = top; b >= 0; --b) {
+    const uint32_t trial = T | (1u << b);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c += (((valid >> e) & 1u) && u[e] < trial) ? 1 : 0;
+    c = __reduce_add_sync(FULL, c);
+    if (c < m) {
+      T = trial;
+    } else if (c <= m + slack) {
+      cut = trial;
+      exact = false;
+      break;
+    }
+  }
+  int ties_allowed = 0;
+  if (exact) {
+    int c_less = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c_less += (((valid >> e) & 1u) && u[e] < T) ? 1 : 0;
+    c_less = __reduce_add_sync(FULL, c_less);
+    cut = T;
+    ties_allowed = keep_max - c_less;
+  }
+  int base = 0, ties_seen = 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const bool v = (valid >> e) & 1u;
+    const bool below = v && (u[e] < cut);
+    const bool tie = exact && v && (u[e] == cut);
+    const unsigned tb = __ballot_sync(FULL, tie);
+    const bool tie_kept = tie && (ties_seen + __popc(tb & lt_mask) < ties_allowed);
+    ties_seen += __popc(tb);
+    const bool keep = below || tie_kept;
+    const unsigned kb = __ballot_sync(FULL, keep);
+    if (keep) list[base + __popc(kb & lt_mask)] = kv[e];
+    base += __popc(kb);
+  }
+  __syncwarp();
+  *new_cnt = base;
+  return ord2f(cut);
+}
+
 template <int E>
 __device__ __forceinline__ float warp_select_truncate_pairs(uint2 *list, int cnt, int m, int keep_max, int lane,
                                                             int *new_cnt) {

@@ -520,6 +520,12 @@ struct TcParams {
   // still bounds the m-th full-precision key from above.  Exactness never depends on the starting threshold.
   int pre_hi;
   float pre_slack;   // what the one-product threshold is raised by, relative to (|x^| + Ymax)^2
+  // Non-refine, non-WIDE launches: the join of a row's two half lists (final truncation to the m best) is left to
+  // halves_merge_kernel, which runs at full occupancy, instead of 16 warps doing it row by row while the SM's tensor
+  // pipe waits (86k of 1,046k clocks per block at 1M x 50).  The halves' lengths go to slice_cnt[2 t + half], their
+  // final thresholds to half_tau[2 t + half].
+  int defer_merge;
+  float *half_tau;
   const float *x;    // (n, d) the original rows
   const int *perm;   // permuted database row -> original row
   int d, k1;         // k1 = k + 1 (self included)
@@ -1235,10 +1241,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
     // final: the second half's list is appended to the first, the best m are kept, count and threshold published
     // (a sliced refine launch leaves that to refine_concat_kernel: the lists are complete only when every slice is)
     stamp(5);
-    half_cnt[half * TC_M + prow] = cnt;
-    half_tau[half * TC_M + prow] = tau;
-    pair_sync();
-    const bool sliced = REFINE && p.slices > 1;
+    const bool deferred = !REFINE && !WIDE && p.defer_merge != 0;
+    if (deferred) {  // halves_merge_kernel finishes the row
+      p.slice_cnt[t_row * 2 + half] = cnt;
+      p.half_tau[t_row * 2 + half] = tau;
+    } else {
+      half_cnt[half * TC_M + prow] = cnt;
+      half_tau[half * TC_M + prow] = tau;
+      pair_sync();
+    }
+    const bool sliced = (REFINE && p.slices > 1) || deferred;
     for (int src = half * 16; src < half * 16 + 16 && !sliced; ++src) {
       const int64_t tt = __shfl_sync(FULL, t_row, src);
       if (tt >= p.nq) continue;  // warp-uniform
@@ -1283,6 +1295,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// After a launch with TcParams::defer_merge: one warp per query-list entry joins the row's two half lists -- the m
+// smallest keys of the union (and at most 8 more) stay, the threshold is the smaller of the halves' final thresholds and
+// the truncation cut: exactly what the screening kernel's own final merge computes, at full occupancy.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) halves_merge_kernel(uint2 *__restrict__ cand, const int *__restrict__ half_cnt,
+                                                          const float *__restrict__ half_tau, int64_t nq, int keep,
+                                                          int *__restrict__ cand_cnt, float *__restrict__ cand_thr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (t >= nq) return;
+  uint2 *la = cand + t * 2 * TC_CAP, *lb = la + TC_CAP;
+  // the first 64 entries of both halves are fetched before the lengths have arrived (the buffers exist whatever the
+  // lengths are): one DRAM round trip per row instead of two -- the kernel is bound by that latency
+  uint2 kv[4];
+  kv[0] = la[lane];
+  kv[1] = la[32 + lane];
+  kv[2] = lb[lane];
+  kv[3] = lb[32 + lane];
+  const int2 cc = *reinterpret_cast<const int2 *>(half_cnt + 2 * t);
+  const float2 tt = *reinterpret_cast<const float2 *>(half_tau + 2 * t);
+  const int ca = cc.x, cb = cc.y;
+  float thr = fminf(tt.x, tt.y);
+  const int c = ca + cb;
+  const int keep_max = min((keep + 31) & ~31, keep + 8);
+  int nc = c;
+  if (c > keep_max && ca <= 64 && cb <= 64) {  // the common case: everything is in registers already
+    const unsigned valid = (lane < ca ? 1u : 0u) | (32 + lane < ca ? 2u : 0u) | (lane < cb ? 4u : 0u) |
+                           (32 + lane < cb ? 8u : 0u);
+    thr = fminf(thr, warp_select_truncate_regs<4>(kv, valid, la, keep, keep_max, lane, &nc));
+  } else if (c > keep_max && c <= TC_CAP) {
+    if (c > 16 * TC_CAP_E) thr = fminf(thr, tc_select_truncate_halves(la, ca, lb, cb, keep, keep_max, lane, &nc));
+    else thr = fminf(thr, tc_select_truncate_halves_short(la, ca, lb, cb, keep, keep_max, lane, &nc));
+  } else {
+    for (int i0 = 0; i0 < cb; i0 += 32) {  // (same in-place append as the screening kernel's final merge)
+      uint2 v = make_uint2(0u, 0u);
+      if (i0 + lane < cb) v = lb[i0 + lane];
+      __syncwarp();
+      if (i0 + lane < cb) la[ca + i0 + lane] = v;
+      __syncwarp();
+    }
+    if (c > TC_CAP) thr = fminf(thr, tc_select_truncate_wide(la, c, keep, keep_max, lane, &nc));
+  }
+  if (lane == 0) {
+    cand_cnt[t] = nc;
+    cand_thr[t] = thr;
   }
 }
 
@@ -1622,7 +1682,8 @@ struct TcLayout {
   float *cand_thr;
   int *fb_count;
   int64_t *fb_rows;
-  int *slice_cnt;   // (2 * chunk) list lengths of a sliced refine launch
+  int *slice_cnt;   // (2 * chunk) list lengths of a sliced refine launch / of the halves of a deferred merge
+  float *half_tau;  // (2 * chunk) final thresholds of the halves of a deferred merge
   int wslices;      // database slices of the wide-row first tier (tc_wide_slices); > 1: the three arrays below exist
   uint2 *cand_v;    // (chunk * wslices, 2 * TC_CAP) per-slice lists
   int *cand_cnt_v;  // (chunk * wslices)
@@ -1680,6 +1741,7 @@ static TcLayout tc_layout(void *ws, int64_t n, int d, int k, int64_t chunk) {
   L.fb_rows = cv.take<int64_t>(static_cast<size_t>(L.chunk_pad));
   L.fb_thr = cv.take<float>(static_cast<size_t>(L.chunk_pad));
   L.slice_cnt = cv.take<int>(2 * static_cast<size_t>(L.chunk_pad));
+  L.half_tau = cv.take<float>(2 * static_cast<size_t>(L.chunk_pad));
   L.cta_order = cv.take<int>(static_cast<size_t>(L.chunk_pad / TC_M));
   L.cta_scratch = cv.take<int>(cells_cta_order_scratch_ints(L.chunk_pad / TC_M));
   L.cand = cv.take<uint2>(static_cast<size_t>(L.chunk_pad) * 2 * TC_CAP);  // two lists per row (one per column half)
@@ -1954,6 +2016,11 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     p.pre_slack = ldexpf(1.0f, -(ps ? atoi(ps) : 13));
   }
   p.slice_cnt = L.slice_cnt;
+  p.half_tau = L.half_tau;
+  {
+    const char *dm = getenv("VVB_TC_DEFER_MERGE");  // 0 = the screening kernel joins the halves itself
+    p.defer_merge = (dm ? atoi(dm) != 0 : 1) ? 1 : 0;
+  }
   p.cta_order = nullptr;
   {
     // longest-first launch order: pays when the launch is only a few waves long (the shards of a multi-GPU build).
@@ -2018,14 +2085,19 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
                                                                                  L.cand_thr);
       }
     }
-    else if (L.ka == 1 && !dbg)
-      knn_screen_kernel<false, false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, pp);
-    else if (L.ka == 1)
-      knn_screen_kernel<false, true, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, pp);
-    else if (!dbg)
-      knn_screen_kernel<true, false, false><<<grid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, pp);
-    else
-      knn_screen_kernel<true, true, false><<<grid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, pp);
+    else {
+      if (L.ka == 1 && !dbg)
+        knn_screen_kernel<false, false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, pp);
+      else if (L.ka == 1)
+        knn_screen_kernel<false, true, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(S->map_a, S->map_b, pp);
+      else if (!dbg)
+        knn_screen_kernel<true, false, false><<<grid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, pp);
+      else
+        knn_screen_kernel<true, true, false><<<grid, TC_THREADS, TC_SMEM_BYTES_K, st>>>(S->map_a, S->map_b, pp);
+      if (pp.defer_merge)  // compiled for 8 CTAs per SM (32 registers): 0.97 ms at 4, 0.73 at 6, 0.63 at 8 for 1M rows
+        halves_merge_kernel<8><<<static_cast<unsigned>((pp.nq + 7) / 8), 256, 0, st>>>(L.cand, L.slice_cnt, L.half_tau, pp.nq,
+                                                                                      pp.keep, L.cand_cnt, L.cand_thr);
+    }
   };
   launch_screen(p, sgrid);
   VVB_CHECK_LAUNCH();
