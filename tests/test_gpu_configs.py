@@ -424,6 +424,35 @@ def test_one_product_pre_pass_never_changes_the_graph(monkeypatch, env):
     print("pre-pass", env, {key: st[key] for key in ("tiles_swept", "tiles_pre", "rows_refined", "rows_fallback")})
 
 
+@pytest.mark.parametrize("n,d,k", [(150_000, 50, 50), (100_000, 300, 20), (60_000, 20, 30), (70_001, 7, 10)])
+def test_tiled_cell_plan_kernels_give_the_same_graph(monkeypatch, n, d, k):
+    """The TF32 tensor-core pivot assignment and the register-tiled extent kernel (default) against the tiled FP32
+    assignment (VVB_CELLS_ASSIGN=1) and the two-rows-per-thread kernels (VVB_CELLS_TILED=0): the partitions and bounds
+    may differ (TF32 moves rows that sit between two pivots), the graph may not -- all are the oracle's.  d > 64 exercises the selected coordinates, d < 64 the zero-padded ones, n = 70,001 a ragged last tile."""
+    x = pca_syn(n, d, seed=41)
+    got = []
+    # default: TF32 tensor-core assignment + tiled FP32 extents; then tiled FP32 for both; then the round-2a kernels
+    for mode, assign in (("1", None), ("1", "1"), ("0", None)):
+        monkeypatch.setenv("VVB_CELLS_TILED", mode)
+        if assign is None:
+            monkeypatch.delenv("VVB_CELLS_ASSIGN", raising=False)
+        else:
+            monkeypatch.setenv("VVB_CELLS_ASSIGN", assign)
+        st = {}
+        idx, dist = vv.make_knn(x, k=k, verbose=False, algo="tensor", stats=st)
+        assert st["algo_used"] == 2 and st["cells"] > 1, st
+        got.append((idx.copy(), dist.copy(), st["tiles_swept"], st["tiles_dense"]))
+    check_properties(got[0][0], got[0][1], n)
+    for other in got[1:]:
+        assert np.array_equal(got[0][0], other[0]) and np.array_equal(got[0][1], other[1])
+    orc.set_threads(os.cpu_count() or 1)
+    check_slices(x, got[0][0], got[0][1], k, (0, n // 2, n - 256), 256)
+    # the bounds prune about as well either way (same geometry, rounding aside)
+    for other in got[1:]:
+        assert abs(got[0][2] - other[2]) <= 0.05 * other[2] + 64, (got[0][2:], other[2:])
+    print("tiled plan", (n, d, k), [g[2:] for g in got])
+
+
 @pytest.mark.parametrize("n,d,k", [(150_000, 50, 50), (40_000, 100, 30), (60_000, 20, 100)])
 def test_deferred_halves_merge_equals_the_in_kernel_merge(monkeypatch, n, d, k):
     """The join of a row's two half lists runs in `halves_merge_kernel` (full occupancy) by default and inside the

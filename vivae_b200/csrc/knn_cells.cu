@@ -513,6 +513,389 @@ __global__ void __launch_bounds__(64) cell_extent_kernel(const float *__restrict
   }
 }
 
+// ------------------------------------------------------------------ register-tiled variants of the two O(n P 64) kernels
+// cell_assign_kernel / cell_extent_kernel above read every table value from shared memory once per TWO rows: a
+// warp-wide 16-byte read occupies the shared-memory pipe for four cycles and feeds four packed FMAs, which bounds them at
+// half the FP32 rate (measured 0.96 / 1.35 ms at 1M x 50, P = 256: a third).  Here a CTA of 256 threads multiplies a
+// tile of 128 rows x 128 table entries x 64 coordinates SGEMM-style: both operands lie k-major in shared memory, a
+// thread owns 8 rows x 8 entries (64 accumulators as 32 packed pairs) and reads 8 + 8 values per coordinate for 64
+// FMAs -- a quarter of the shared-memory bytes per FMA.  The sums are single left-to-right chains over the 64
+// coordinates (the kernels above use four interleaved chains); neither result needs a particular rounding: the
+// partition may be ANY partition, and the extents' FP32 evaluation error is covered ~50x by cell_lb_kernel's margin.
+// A rank of a multi-GPU build runs the same code on its rows / cells, so all ranks still agree bit for bit.
+constexpr int TL_LD = 128;                                        // rows / table entries per tile
+constexpr int TL_SMEM_BYTES = 2 * CELL_DIMS * TL_LD * 4;          // As[64][128] + Bs[64][128]
+
+// acc[i][jp]: row (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4), entries (jp < 2 ? tx * 4 + 2 jp : 64 + tx * 4 + 2 (jp - 2)) + {0, 1}
+__device__ __forceinline__ void tile_fma(const float *__restrict__ As, const float *__restrict__ Bs, int ty, int tx,
+                                         unsigned long long (&acc)[8][4]) {
+#pragma unroll 4
+  for (int k = 0; k < CELL_DIMS; ++k) {
+    const float4 a0 = *reinterpret_cast<const float4 *>(As + k * TL_LD + ty * 4);
+    const float4 a1 = *reinterpret_cast<const float4 *>(As + k * TL_LD + 64 + ty * 4);
+    const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(Bs + k * TL_LD + tx * 4);
+    const ulonglong2 b1 = *reinterpret_cast<const ulonglong2 *>(Bs + k * TL_LD + 64 + tx * 4);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const unsigned long long ad = pack_f32x2(av[i], av[i]);
+      fma_f32x2(acc[i][0], ad, b0.x);
+      fma_f32x2(acc[i][1], ad, b0.y);
+      fma_f32x2(acc[i][2], ad, b1.x);
+      fma_f32x2(acc[i][3], ad, b1.y);
+    }
+  }
+}
+__device__ __forceinline__ int tile_row(int ty, int i) { return i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4; }
+__device__ __forceinline__ int tile_col(int tx, int jp, int e) {
+  return (jp < 2 ? tx * 4 + 2 * jp : 64 + tx * 4 + 2 * (jp - 2)) + e;
+}
+// table rows [b0, b0 + nb) (64 floats each), minus `sub` (64 floats, or nullptr) -> Bs[k][b]; threads t0, t0 + nt, ...
+__device__ __forceinline__ void tile_fill_table(float *Bs, const float *__restrict__ table, int b0, int nb,
+                                                const float *__restrict__ sub, int t0, int nt) {
+  for (int i4 = t0; i4 < TL_LD * (CELL_DIMS / 4); i4 += nt) {
+    const int b = i4 & (TL_LD - 1), k4 = i4 >> 7;
+    float4 w = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (b < nb) {
+      w = __ldg(reinterpret_cast<const float4 *>(table + static_cast<size_t>(b0 + b) * CELL_DIMS) + k4);
+      if (sub) {
+        const float4 u = __ldg(reinterpret_cast<const float4 *>(sub) + k4);
+        w.x -= u.x;
+        w.y -= u.y;
+        w.z -= u.z;
+        w.w -= u.w;
+      }
+    }
+    Bs[(4 * k4 + 0) * TL_LD + b] = w.x;
+    Bs[(4 * k4 + 1) * TL_LD + b] = w.y;
+    Bs[(4 * k4 + 2) * TL_LD + b] = w.z;
+    Bs[(4 * k4 + 3) * TL_LD + b] = w.w;
+  }
+}
+
+// nearest pivot of 128 rows per CTA (ties -> lowest pivot)
+__global__ void __launch_bounds__(256, 2) cell_assign_tiled_kernel(const float *__restrict__ x, int64_t row0, int64_t n, int d,
+                                                                  int dsub, const int *__restrict__ dims,
+                                                                  const float *__restrict__ mu, int P,
+                                                                  const float *__restrict__ pivots,
+                                                                  int *__restrict__ cell_of, int *__restrict__ cnt) {
+  extern __shared__ __align__(16) float tl_smem[];
+  float *As = tl_smem, *Bs = tl_smem + CELL_DIMS * TL_LD;
+  __shared__ float pn[TL_LD];
+  __shared__ int hist[CELL_MAX];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int i = tid; i < P; i += 256) hist[i] = 0;
+  const int64_t row_base = row0 + static_cast<int64_t>(blockIdx.x) * TL_LD;
+  if (tid < TL_LD) {
+    const int64_t row = row_base + tid;
+#pragma unroll 8
+    for (int c = 0; c < CELL_DIMS; ++c) {
+      const bool on = c < dsub;
+      const int col = on ? __ldg(dims + c) : 0;
+      const float m = on ? __ldg(mu + col) : 0.0f;
+      As[c * TL_LD + tid] = (on && row < n) ? __ldg(x + row * d + col) - m : 0.0f;
+    }
+  } else {  // the other half of the CTA stages the first block of pivots meanwhile
+    tile_fill_table(Bs, pivots, 0, min(TL_LD, P), nullptr, tid - TL_LD, 128);
+  }
+  float best[8];
+  int best_p[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) best[i] = __int_as_float(0x7f800000), best_p[i] = 0;
+  for (int p0 = 0; p0 < P; p0 += TL_LD) {
+    const int np = min(TL_LD, P - p0);
+    __syncthreads();
+    if (p0 > 0) tile_fill_table(Bs, pivots, p0, np, nullptr, tid, 256);
+    __syncthreads();
+    if (tid < TL_LD) {
+      float sq = 0.0f;
+      for (int c = 0; c < CELL_DIMS; ++c) sq = fmaf(Bs[c * TL_LD + tid], Bs[c * TL_LD + tid], sq);
+      pn[tid] = sq;
+    }
+    __syncthreads();
+    unsigned long long acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+    tile_fma(As, Bs, ty, tx, acc);
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {  // columns in increasing order: a strict < keeps the lowest pivot among equals
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = tile_col(tx, jp, e);
+        const float pnc = pn[col];
+        if (col < np) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float lo, hi;
+            unpack_f32x2(acc[i][jp], lo, hi);
+            const float score = fmaf(-2.0f, e ? hi : lo, pnc);
+            if (score < best[i]) {
+              best[i] = score;
+              best_p[i] = p0 + col;
+            }
+          }
+        }
+      }
+    }
+  }
+  // the 16 threads that share a row (same ty: the lanes of a half-warp) agree on (score, pivot), lowest pivot among equals
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(FULL, best[i], o);
+      const int op = __shfl_xor_sync(FULL, best_p[i], o);
+      if (os < best[i] || (os == best[i] && op < best_p[i])) {
+        best[i] = os;
+        best_p[i] = op;
+      }
+    }
+    const int64_t row = row_base + tile_row(ty, i);
+    if (tx == 0 && row < n) {
+      cell_of[row] = best_p[i];
+      atomicAdd(&hist[best_p[i]], 1);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < P; i += 256)
+    if (hist[i]) atomicAdd(cnt + i, hist[i]);
+}
+
+// one CTA per group of 128 permuted rows of cell a: for every other cell b the largest projection of (x - c_a) on the
+// direction a -> b, and the largest squared distance to the centre (same quantities as cell_extent_kernel)
+__global__ void __launch_bounds__(256, 2) cell_extent_tiled_kernel(const float *__restrict__ x, int d, int dsub,
+                                                                  const int *__restrict__ dims,
+                                                                  const float *__restrict__ mu, const int *__restrict__ perm,
+                                                                  const int *__restrict__ off, int P,
+                                                                  const int *__restrict__ cell_of,
+                                                                  const float *__restrict__ cen, const float *__restrict__ cw,
+                                                                  const float *__restrict__ inv_norm,
+                                                                  unsigned int *__restrict__ ext,
+                                                                  unsigned int *__restrict__ rad2, int part, int parts) {
+  extern __shared__ __align__(16) float tl_smem[];
+  float *As = tl_smem, *Bs = tl_smem + CELL_DIMS * TL_LD;
+  __shared__ unsigned int emax[TL_LD];
+  __shared__ int row_ok[TL_LD];
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * CELL_GROUP;
+  if (p0 >= off[P]) return;
+  const int tid = threadIdx.x, lane = tid & 31, tx = tid & 15, ty = tid >> 4;
+  const int a = cell_of[perm[p0]];
+  if (a % parts != part) return;  // another rank owns this cell; extents and radii are max-reduced
+  if (tid < TL_LD) {
+    const int r = perm[p0 + tid];
+    row_ok[tid] = r >= 0;
+    float r2 = 0.0f;
+#pragma unroll 8
+    for (int c = 0; c < CELL_DIMS; ++c) {
+      const bool on = c < dsub;
+      const int col = on ? __ldg(dims + c) : 0;
+      const float m = on ? __ldg(mu + col) : 0.0f, ce = __ldg(cen + a * CELL_DIMS + c);
+      const float v = (on && r >= 0) ? (__ldg(x + static_cast<int64_t>(r) * d + col) - m) - ce : 0.0f;
+      r2 = fmaf(v, v, r2);
+      As[c * TL_LD + tid] = v;
+    }
+    const unsigned int m = __reduce_max_sync(FULL, f2ord(r2));
+    if (lane == 0) atomicMax(rad2 + a, m);
+  } else {  // the other half of the CTA stages the first block of directions meanwhile
+    // w_ab = cw_b - cw_a, formed exactly as cell_pairs_kernel forms it
+    tile_fill_table(Bs, cw, 0, min(TL_LD, P), cw + a * CELL_DIMS, tid - TL_LD, 128);
+  }
+  const unsigned int neg_inf = f2ord(-__int_as_float(0x7f800000));
+  const float ninf = -__int_as_float(0x7f800000);
+  for (int b0 = 0; b0 < P; b0 += TL_LD) {
+    const int nb = min(TL_LD, P - b0);
+    __syncthreads();
+    if (b0 > 0) tile_fill_table(Bs, cw, b0, nb, cw + a * CELL_DIMS, tid, 256);
+    if (tid < TL_LD) emax[tid] = neg_inf;
+    __syncthreads();
+    unsigned long long acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+    tile_fma(As, Bs, ty, tx, acc);
+    bool ok[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ok[i] = row_ok[tile_row(ty, i)] != 0;
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float m = ninf;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float lo, hi;
+          unpack_f32x2(acc[i][jp], lo, hi);
+          if (ok[i]) m = fmaxf(m, e ? hi : lo);
+        }
+        m = fmaxf(m, __shfl_xor_sync(FULL, m, 16));  // the warp's other eight rows of the same entries
+        const int col = tile_col(tx, jp, e);
+        // (inv_norm >= 0 and rounding is monotone: the largest projection is the largest sum times inv_norm)
+        if (lane < 16 && col < nb && m > ninf)
+          atomicMax(&emax[col], f2ord(m * __ldg(inv_norm + static_cast<size_t>(a) * P + b0 + col)));
+      }
+    }
+    __syncthreads();
+    if (tid < nb && emax[tid] != neg_inf) atomicMax(ext + static_cast<size_t>(a) * P + b0 + tid, emax[tid]);
+  }
+}
+
+// ---- pivot assignment on the tensor cores (TF32).  The partition may be ANY partition (the bounds are computed from the
+// rows each cell actually received, and the sweep is exact for whatever they are), so the nearest-pivot search needs no
+// FP32 arithmetic: mma.sync.m16n8k8 with 10-bit mantissas moves the odd row that sits between two pivots, nothing else.
+// CTA = 8 warps x 32 rows; the pivot block (256 x 64, rounded to TF32) lies in shared memory with a row stride of 68
+// floats (conflict-free B-fragment reads); a warp keeps its rows' A fragments (2 m-tiles x 8 k-steps) in registers.
+// FP32 FFMA on this chip issues at 64 lanes per clock and SM, packed or not (both FP32 variants above measure
+// 0.91-0.96 ms at 1M x 50, P = 256 = exactly that rate): this kernel is what lifts the assignment off that ceiling.
+constexpr int AM_ROWS = 256;     // rows per CTA
+constexpr int AM_PIV = 256;      // pivots per shared-memory block
+constexpr int AM_LD = CELL_DIMS + 4;
+constexpr int AM_SMEM_BYTES = AM_PIV * AM_LD * 4 + AM_PIV * 4;
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 2) cell_assign_mma_kernel(const float *__restrict__ x, int64_t row0, int64_t n, int d,
+                                                                int dsub, const int *__restrict__ dims,
+                                                                const float *__restrict__ mu, int P,
+                                                                const float *__restrict__ pivots,
+                                                                int *__restrict__ cell_of, int *__restrict__ cnt) {
+  extern __shared__ __align__(16) float am_smem[];
+  float *Ps = am_smem;                   // [AM_PIV][AM_LD], TF32 bit patterns
+  float *pn = am_smem + AM_PIV * AM_LD;  // [AM_PIV] squared norms of the rounded pivots
+  __shared__ int hist[CELL_MAX];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
+  for (int i = tid; i < P; i += 256) hist[i] = 0;
+  const int64_t wbase = row0 + static_cast<int64_t>(blockIdx.x) * AM_ROWS + warp * 32;
+  // A fragments: m-tile mt, k-step ks: a0 (row gid, col tig) a1 (row gid + 8, col tig) a2 (gid, tig + 4) a3 (gid + 8, tig + 4)
+  uint32_t af[2][8][4];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = ks * 8 + tig + 4 * h;
+      const bool on = c < dsub;
+      const int col = on ? __ldg(dims + c) : 0;
+      const float m = on ? __ldg(mu + col) : 0.0f;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int64_t r0 = wbase + mt * 16 + gid, r1 = r0 + 8;
+        af[mt][ks][2 * h + 0] = to_tf32((on && r0 < n) ? __ldg(x + r0 * d + col) - m : 0.0f);
+        af[mt][ks][2 * h + 1] = to_tf32((on && r1 < n) ? __ldg(x + r1 * d + col) - m : 0.0f);
+      }
+    }
+  }
+  float best[2][2];
+  int best_p[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) best[mt][h] = __int_as_float(0x7f800000), best_p[mt][h] = 0;
+  for (int p0 = 0; p0 < P; p0 += AM_PIV) {
+    const int np = min(AM_PIV, P - p0);
+    __syncthreads();
+    for (int i4 = tid; i4 < AM_PIV * (CELL_DIMS / 4); i4 += 256) {
+      const int pl = i4 >> 4, k4 = i4 & 15;
+      float4 w = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (pl < np) w = __ldg(reinterpret_cast<const float4 *>(pivots + static_cast<size_t>(p0 + pl) * CELL_DIMS) + k4);
+      uint4 t;
+      t.x = to_tf32(w.x);
+      t.y = to_tf32(w.y);
+      t.z = to_tf32(w.z);
+      t.w = to_tf32(w.w);
+      *reinterpret_cast<uint4 *>(Ps + pl * AM_LD + 4 * k4) = t;
+    }
+    __syncthreads();
+    {
+      float sq = 0.0f;
+      for (int c = 0; c < CELL_DIMS; ++c) sq = fmaf(Ps[tid * AM_LD + c], Ps[tid * AM_LD + c], sq);
+      pn[tid] = sq;
+    }
+    __syncthreads();
+    for (int nt = 0; nt < (np + 7) / 8; ++nt) {
+      float acc[2][4] = {{0.0f, 0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};
+      const float *prow = Ps + (nt * 8 + gid) * AM_LD + tig;  // B fragment: b0 (k tig, n gid), b1 (k tig + 4, n gid)
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t b0 = __float_as_uint(prow[ks * 8]), b1 = __float_as_uint(prow[ks * 8 + 4]);
+        mma_tf32(acc[0], af[0][ks], b0, b1);
+        mma_tf32(acc[1], af[1][ks], b0, b1);
+      }
+      // c0 (row gid, col 2 tig) c1 (gid, 2 tig + 1) c2 (gid + 8, 2 tig) c3 (gid + 8, 2 tig + 1); increasing pivot order
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int pl = nt * 8 + 2 * tig + e;
+        const float pnc = pn[pl];
+        if (pl < np) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float score = fmaf(-2.0f, acc[mt][2 * h + e], pnc);
+              if (score < best[mt][h]) {
+                best[mt][h] = score;
+                best_p[mt][h] = p0 + pl;
+              }
+            }
+        }
+      }
+    }
+  }
+  // the four lanes that share a row agree on (score, pivot), lowest pivot among equals
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int o = 1; o < 4; o <<= 1) {
+        const float os = __shfl_xor_sync(FULL, best[mt][h], o);
+        const int op = __shfl_xor_sync(FULL, best_p[mt][h], o);
+        if (os < best[mt][h] || (os == best[mt][h] && op < best_p[mt][h])) {
+          best[mt][h] = os;
+          best_p[mt][h] = op;
+        }
+      }
+      const int64_t row = wbase + mt * 16 + h * 8 + gid;
+      if (tig == 0 && row < n) {
+        cell_of[row] = best_p[mt][h];
+        atomicAdd(&hist[best_p[mt][h]], 1);
+      }
+    }
+  __syncthreads();
+  for (int i = tid; i < P; i += 256)
+    if (hist[i]) atomicAdd(cnt + i, hist[i]);
+}
+
+static bool cells_use_tiled() {
+  const char *e = getenv("VVB_CELLS_TILED");  // 0 = the two-rows-per-thread kernels
+  return !(e && atoi(e) == 0);
+}
+static int cells_assign_mode() {
+  const char *e = getenv("VVB_CELLS_ASSIGN");  // 2 = TF32 tensor cores (default), 1 = register-tiled FP32, 0 = two rows per thread
+  if (e) return atoi(e);
+  return cells_use_tiled() ? 2 : 0;
+}
+static int cells_tiled_attr() {
+  static bool done = false;
+  if (!done) {
+    VVB_CUDA(cudaFuncSetAttribute(cell_assign_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES));
+    VVB_CUDA(cudaFuncSetAttribute(cell_assign_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM_BYTES));
+    VVB_CUDA(cudaFuncSetAttribute(cell_extent_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM_BYTES));
+    done = true;
+  }
+  return VVB_OK;
+}
+
 // lb(a, b) = scale * max(discriminant bound, ball bound) - margin; +inf for empty b, -inf on the diagonal
 __global__ void __launch_bounds__(128) cell_lb_kernel(const int *__restrict__ cnt, int P, const float *__restrict__ gap,
                                                      const float *__restrict__ cdist,
@@ -561,7 +944,17 @@ int cells_build_phase(const CellPlan &L, const float *x, int d, const float *mu,
     cell_pivots_kernel<<<P, CELL_DIMS, 0, st>>>(x, n, d, L.dsub, dims, mu, P, L.cen);
     VVB_CHECK_LAUNCH();
     VVB_CUDA(cudaMemsetAsync(L.cnt, 0, sizeof(int) * P, st));
-    if (row_hi > row_lo) {
+    if (row_hi > row_lo && cells_assign_mode() == 2) {
+      if (int rc = cells_tiled_attr()) return rc;
+      cell_assign_mma_kernel<<<static_cast<unsigned>((row_hi - row_lo + AM_ROWS - 1) / AM_ROWS), 256, AM_SMEM_BYTES, st>>>(
+          x, row_lo, row_hi, d, L.dsub, dims, mu, P, L.cen, L.cell_of, L.cnt);
+      VVB_CHECK_LAUNCH();
+    } else if (row_hi > row_lo && cells_assign_mode() == 1) {
+      if (int rc = cells_tiled_attr()) return rc;
+      cell_assign_tiled_kernel<<<static_cast<unsigned>((row_hi - row_lo + TL_LD - 1) / TL_LD), 256, TL_SMEM_BYTES, st>>>(
+          x, row_lo, row_hi, d, L.dsub, dims, mu, P, L.cen, L.cell_of, L.cnt);
+      VVB_CHECK_LAUNCH();
+    } else if (row_hi > row_lo) {
       cell_assign_kernel<<<static_cast<unsigned>((row_hi - row_lo + ASSIGN_ROWS - 1) / ASSIGN_ROWS), 128, 0, st>>>(
           x, row_lo, row_hi, d, L.dsub, dims, mu, P, L.cen, L.cell_of, L.cnt);
       VVB_CHECK_LAUNCH();
@@ -591,8 +984,14 @@ int cells_build_phase(const CellPlan &L, const float *x, int d, const float *mu,
     VVB_CHECK_LAUNCH();
     cell_pairs_kernel<<<P, 128, 0, st>>>(L.cen, L.cw, P, L.inv_norm, L.gap, L.cdist, L.ext, L.rad2);
     VVB_CHECK_LAUNCH();
-    cell_extent_kernel<<<groups, 64, 0, st>>>(x, d, L.dsub, dims, mu, L.perm, L.off, P, L.cell_of, L.cen, L.cw,
-                                               L.inv_norm, L.ext, L.rad2, part, parts);
+    if (cells_use_tiled()) {
+      if (int rc = cells_tiled_attr()) return rc;
+      cell_extent_tiled_kernel<<<groups, 256, TL_SMEM_BYTES, st>>>(x, d, L.dsub, dims, mu, L.perm, L.off, P, L.cell_of, L.cen,
+                                                                    L.cw, L.inv_norm, L.ext, L.rad2, part, parts);
+    } else {
+      cell_extent_kernel<<<groups, 64, 0, st>>>(x, d, L.dsub, dims, mu, L.perm, L.off, P, L.cell_of, L.cen, L.cw,
+                                                 L.inv_norm, L.ext, L.rad2, part, parts);
+    }
     VVB_CHECK_LAUNCH();
   } else {
     cell_lb_kernel<<<P, 128, 0, st>>>(L.cnt, P, L.gap, L.cdist, L.ext, L.rad2, scale_dev, L.lb);

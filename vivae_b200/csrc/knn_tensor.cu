@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   stamp(1);
-  const bool pre_pass = (dbg_mode == 0 || dbg_mode == 4) && p.ka <= TC_PRE_MAX_KA && !REFINE;
+  const bool pre_pass = (dbg_mode == 0 || dbg_mode >= 4) && p.ka <= TC_PRE_MAX_KA && !REFINE;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -769,6 +769,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
             mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
             tile_seq[t % TC_RING] = row_b;
             const int natoms = (pass == 0 && p.pre_hi) ? 1 : 2;  // pre-pass with one product: the hi atom only
+            if (DBG && dbg_mode == 7 && pass == 0) {  // profiling only: no loads in the pre-pass (MMA rate alone)
+              mbar_arrive(bar_b_full + 8 * s);
+              continue;
+            }
             mbar_expect_tx(bar_b_full + 8 * s, natoms * TC_ATOM_BYTES);
             for (int atom = 0; atom < natoms; ++atom)
               tma_load_2d(smem_b + (s * 2 + atom) * TC_ATOM_BYTES, &map_b, bar_b_full + 8 * s, atom * 64, row_b);
@@ -1202,15 +1206,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_screen_kernel(const __grid_
             m4[(q >> 1) & 3] = fminf(fminf(__uint_as_float(r[q]), __uint_as_float(r[q + 1])), m4[(q >> 1) & 3]);
           tmin = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
         };
-        tc_ld32_issue(t_acc, ra);
-        tc_ld32_wait(ra);
-        fold(ra);
-        tc_ld32_issue(t_acc + 32, ra);
-        tc_ld32_wait(ra);
+        // (profiling only, results are garbage: VVB_TC_DEBUG=6 hands the accumulator straight back, 5 drains half of it)
+        if (!(DBG && dbg_mode >= 6)) {
+          tc_ld32_issue(t_acc, ra);
+          tc_ld32_wait(ra);
+          fold(ra);
+        }
+        if (!(DBG && dbg_mode >= 5)) {
+          tc_ld32_issue(t_acc + 32, ra);
+          tc_ld32_wait(ra);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
-        fold(ra);
+        if (!(DBG && dbg_mode >= 5)) fold(ra);
         if (active) pre_buf[2 * n_pre + half] = tmin;
         ++n_pre;
       } else if (dbg_mode == 3) {  // profiling only: hand the accumulator straight back (MMA/TMA rate alone)
