@@ -416,7 +416,9 @@ def run_ours(args) -> None:
     torch.cuda.synchronize()
     ms_smooth = max_over_ranks(e1.elapsed_time(e2))
     roofline = screen_roofline(st, nq, n, d, peaks)
-    cap = os.path.join(ROOT, "profiles", "r02b_c2_raw.csv")
+    cap = os.path.join(ROOT, "profiles", "r02c_c2_raw.csv")
+    if not os.path.isfile(cap):
+        cap = os.path.join(ROOT, "profiles", "r02b_c2_raw.csv")
     if world == 1 and st.get("algo_used") == 2 and (n, d, k) == (1_000_000, 50, 50) and os.path.isfile(cap):
         import csv
         with open(cap) as f:
@@ -428,7 +430,7 @@ def run_ours(args) -> None:
             roofline["traffic"] = sum(float(srow[col[m]]) * gb[rows_[1][col[m]]]
                                       for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
             roofline["traffic_note"] = ("dram__bytes_read + dram__bytes_write of this launch (1,000,000 query rows, one "
-                                        "GPU) from the committed ncu --set full capture profiles/r02b_c2_raw.csv")
+                                        "GPU) from the committed ncu --set full capture profiles/" + os.path.basename(cap))
     dense_roof = None
     if st.get("algo_used") == 2 and world == 1 and not args.skip_dense:
         # the same kernel with the partition switched off (every tile swept): the dense tensor roofline

@@ -53,8 +53,8 @@ typedef struct vvb_knn_stats {
                               certificate failed AND their refine list overflowed)  */
   int32_t algo_used;       /* VVB_KNN_BRUTE or VVB_KNN_TENSOR                       */
   int32_t candidates;      /* m: candidates kept per row by the screening kernel    */
-  float ms_prepare;        /* device time, operand preparation (centre/scale/split) */
-  float ms_screen;         /* device time, tensor-core distance GEMM + select       */
+  float ms_prepare;        /* device time, preparation (centre/scale/split, cell plan, operands) */
+  float ms_screen;         /* device time, screening launch + join of the half lists */
   float ms_rerank;         /* device time, FP32 re-rank + certify                   */
   float ms_fallback;       /* device time, refine pass + brute-force fallback       */
   int64_t kernel_launches; /* kernels launched by this call                         */

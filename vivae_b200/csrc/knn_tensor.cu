@@ -1806,7 +1806,7 @@ size_t knn_tensor_session_bytes() { return sizeof(TcSession); }
 
 namespace {
 struct ChunkEvents {  // released on every return path
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool on = false;
   int init() {
     for (auto &e : ev) VVB_CUDA(cudaEventCreate(&e));
@@ -1996,7 +1996,7 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   mark(0);
   int rc = cells_query_list(L.cells, q0, nq, nq_pad, L.qlist, nullptr, st);
   if (rc) return rc;
-  build_operands_kernel<true><<<sm_count() * 4, 256, 0, st>>>(S->x, S->d, L.ka, L.mu, L.scalars, L.qlist, nq_pad, L.opA,
+  build_operands_kernel<true><<<sm_count() * 8, 256, 0, st>>>(S->x, S->d, L.ka, L.mu, L.scalars, L.qlist, nq_pad, L.opA,
                                                               L.xnorm);
   VVB_CHECK_LAUNCH();
   VVB_CUDA(cudaMemsetAsync(L.fb_count, 0, sizeof(int), st));
@@ -2108,6 +2108,7 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
                                                                                       pp.keep, L.cand_cnt, L.cand_thr);
     }
   };
+  mark(4);  // query list and query operand of the chunk count as preparation; ms_screen = screening launch + join of the halves
   launch_screen(p, sgrid);
   VVB_CHECK_LAUNCH();
   S->blocks_since += sgrid;
@@ -2196,7 +2197,7 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
     const int64_t nr = fb, nr_pad = (nr + TC_M - 1) / TC_M * TC_M;
     rc = cells_query_list(L.cells, q0, nr, nr_pad, L.qlist, L.fb_rows, st);
     if (rc) return rc;
-    build_operands_kernel<true><<<sm_count() * 4, 256, 0, st>>>(S->x, S->d, L.ka, L.mu, L.scalars, L.qlist, nr_pad,
+    build_operands_kernel<true><<<sm_count() * 8, 256, 0, st>>>(S->x, S->d, L.ka, L.mu, L.scalars, L.qlist, nr_pad,
                                                                 L.opA, L.xnorm);
     VVB_CHECK_LAUNCH();
     VVB_CUDA(cudaMemsetAsync(L.fb_count, 0, sizeof(int), st));
@@ -2237,7 +2238,9 @@ int knn_tensor_chunk(void *session_mem, int64_t q0, int64_t nq, int64_t *out_idx
   if (stats) {
     VVB_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ce.ev[0], ce.ev[1]);
+    cudaEventElapsedTime(&ms, ce.ev[0], ce.ev[4]);
+    stats->ms_prepare += ms;
+    cudaEventElapsedTime(&ms, ce.ev[4], ce.ev[1]);
     stats->ms_screen += ms;
     cudaEventElapsedTime(&ms, ce.ev[1], ce.ev[2]);
     stats->ms_rerank += ms;
