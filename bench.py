@@ -637,6 +637,22 @@ def run_ours(args) -> None:
     if not args.skip_c3 and args.c3_rows > 0:
         xs = synth_pca_device(args.c3_rows, 50, dev)
         sub_config("config_c3", xs, 100, args.sub_steps)
+        if world > 1 and not args.skip_ring:
+            # the ring build at the north star's size too ("ring <= 1.15 x replicated at 10M")
+            a0, an = shard_bounds(args.c3_rows, world, rank)
+            xl = xs[a0:a0 + an].contiguous()
+            i_rep, d_rep = knn_step(xs, 100, a0, an)
+            ms_rep, _ = timed(lambda: knn_step(xs, 100, a0, an), 1, 0)
+            ms_ring3, _ = timed(lambda: make_knn_ring(xl, args.c3_rows, 100, algo=args.algo), 1, 1)
+            r_idx, r_dist = make_knn_ring(xl, args.c3_rows, 100, algo=args.algo)
+            same = torch.tensor([int(torch.equal(r_idx, i_rep) and torch.equal(r_dist, d_rep))], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            sub["config_c3"]["ring"] = {"ms_knn": ms_ring3, "ms_knn_replicated_layout": ms_rep,
+                                        "ratio": ms_ring3 / ms_rep, "steps": 1, "warmup": 1,
+                                        "identical_to_replicated_layout": bool(same.item()),
+                                        "what": "make_knn_ring (every rank holds only its n/N rows) beside the replicated "
+                                                "layout, graph only, max over ranks"}
+            del xl, r_idx, r_dist, i_rep, d_rep
         del xs
         torch.cuda.empty_cache()
     if not args.skip_overlap:

@@ -317,8 +317,12 @@ def test_smooth_rows_entry_point_jacobi_shards_equal_whole_sweep(dtype):
 
 
 # ======================================================================== quartet
+# `big`: VVB_QUARTET_BIG forces the kernel -- "0" eight lanes per quartet (training-size batches), "1" 32 quartets per warp
+# (bandwidth-sized batches; the launcher picks it from 2^17-ish quartets on): both must meet every fixture.
+@pytest.mark.parametrize("big", ["0", "1"])
 @pytest.mark.parametrize("name", QUARTET)
-def test_quartet_loss_and_grad_vs_reference_golden(name):
+def test_quartet_loss_and_grad_vs_reference_golden(monkeypatch, name, big):
+    monkeypatch.setenv("VVB_QUARTET_BIG", big)
     g = np.load(os.path.join(GOLDEN, name))
     ns = int(g["n_sampling"])
     dev = torch.device("cuda")
@@ -338,7 +342,9 @@ def test_quartet_loss_and_grad_vs_reference_golden(name):
     np.testing.assert_allclose(grad, og, rtol=1e-4, atol=1e-4 * scale)
 
 
-def test_quartet_small_batches_nan_and_zero_grad_rows():
+@pytest.mark.parametrize("big", ["0", "1"])
+def test_quartet_small_batches_nan_and_zero_grad_rows(monkeypatch, big):
+    monkeypatch.setenv("VVB_QUARTET_BIG", big)
     dev = torch.device("cuda")
     x = torch.randn(3, 5, device=dev)
     z = torch.randn(3, 2, device=dev, requires_grad=True)
@@ -354,7 +360,9 @@ def test_quartet_small_batches_nan_and_zero_grad_rows():
         vv.MDSLoss()(x, z, distf_hd="manhattan")
 
 
-def test_quartet_is_deterministic_and_resampling_uses_global_rng():
+@pytest.mark.parametrize("big", ["0", "1"])
+def test_quartet_is_deterministic_and_resampling_uses_global_rng(monkeypatch, big):
+    monkeypatch.setenv("VVB_QUARTET_BIG", big)
     dev = torch.device("cuda")
     x = torch.randn(1024, 50, device=dev)
     z0 = torch.randn(1024, 2, device=dev)
@@ -374,9 +382,16 @@ def test_quartet_is_deterministic_and_resampling_uses_global_rng():
     assert vv.quartet_loss(x, z, perms=perms).item() == outs[0][0]
 
 
-def test_quartet_large_batch_against_oracle():
+@pytest.mark.parametrize("B,D,L,big", [(1 << 16, 50, 2, "0"), (1 << 16, 50, 2, "1"), ((1 << 18) + 6, 37, 3, None),
+                                       ((1 << 20) + 3, 50, 2, None)])
+def test_quartet_large_batch_against_oracle(monkeypatch, B, D, L, big):
+    """big=None: the launcher's own choice (eight lanes per quartet at 2^18 rows, 32 quartets per warp at 2^20); odd D
+    (no 8-byte loads), L = 3, B mod 4 != 0 and a last round with idle lanes included."""
+    if big is None:
+        monkeypatch.delenv("VVB_QUARTET_BIG", raising=False)
+    else:
+        monkeypatch.setenv("VVB_QUARTET_BIG", big)
     rng = np.random.default_rng(3)
-    B, D, L = 1 << 16, 50, 2
     x = clustered(B, D, 10, seed=6)
     z = rng.standard_normal((B, L)).astype(np.float32)
     zt = torch.tensor(z, device="cuda", requires_grad=True)
