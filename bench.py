@@ -603,15 +603,21 @@ def run_ours(args) -> None:
         ms_ring, _ = timed(lambda: make_knn_ring(xl, n, k, algo=args.algo), 2, 1)
         r_idx, r_dist = make_knn_ring(xl, n, k, algo=args.algo)
         same = torch.tensor([int(torch.equal(r_idx, idx_s) and torch.equal(r_dist, dist_s))], device=dev)
+        # the ring schedule proper (what a matrix beyond one GPU's memory pays): one foreign shard per sweep
+        ms_ring1, _ = timed(lambda: make_knn_ring(xl, n, k, algo=args.algo, shards_per_sweep=1), 2, 1)
+        r1_idx, r1_dist = make_knn_ring(xl, n, k, algo=args.algo, shards_per_sweep=1)
+        same &= int(torch.equal(r1_idx, idx_s) and torch.equal(r1_dist, dist_s))
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
-        ring = {"what": "make_knn_ring: each rank holds n/N rows, N ring steps (isend/irecv of the shard overlapped with the "
-                        "step's sweep), running top-k merge; graph only, no smoother",
-                "ms_knn": ms_ring, "ms_knn_replicated_layout": max_over_ranks(ms_knn), "steps": 2, "warmup": 1,
+        ring = {"what": "make_knn_ring: each rank holds only its n/N rows; graph only, no smoother.  ms_knn: the default "
+                        "schedule -- every shard fits next to the own rows here, so they arrive with one all-gather and ONE "
+                        "sweep ranks the own rows (no running lists, no merges); ms_knn_one_shard_per_sweep: the ring "
+                        "schedule (isend/irecv of the shard overlapped with the step's sweep, running top-k merge)",
+                "ms_knn": ms_ring, "ms_knn_one_shard_per_sweep": ms_ring1,
+                "ms_knn_replicated_layout": max_over_ranks(ms_knn), "steps": 2, "warmup": 1,
                 "identical_to_replicated_layout": bool(same.item()),
-                "note": "a sweep of own x [shards ; own] takes as many foreign shards as fit in device memory (here: all of "
-                        "them, one sweep); a sweep pruned by the cell bounds costs about the same per query block whatever "
-                        "the database size, so the number of sweeps is what counts (DESIGN.md section 6)"}
-        del xl, r_idx, r_dist
+                "note": "a sweep pruned by the cell bounds costs about the same per query block whatever the database "
+                        "size, so the number of sweeps is what counts (DESIGN.md section 6)"}
+        del xl, r_idx, r_dist, r1_idx, r1_dist
 
     # ---- the north-star configurations beside the headline (device-generated data, a few steps)
     del idx_s, dist_s, idx_full

@@ -357,6 +357,17 @@ def make_knn_ring(x_local: torch.Tensor, n: int, k: int, group=None, algo: str =
         return run_idx, ops.finish(run_d2)
     m = shards_per_sweep if shards_per_sweep else _ring_shards_per_sweep(per, d, x_local.device, world)
     m = max(1, min(int(m), world - 1))
+    if not shards_per_sweep and m >= world - 1:
+        # Everything fits next to the own rows: ONE sweep ranks them against the whole matrix in global row order, so
+        # there is nothing to merge (running lists exist to carry results from one sweep to the next) and nothing to
+        # pass on -- the shards arrive with one all-gather instead of N - 1 ring rounds, and the cell plan is prepared
+        # across the ranks like in the replicated layout.  Round 2b ran this case through the ring machinery (N - 1
+        # waited transfers, a stacked copy, N merge calls that each re-ranked k rows per query): 1.29x / 1.48x the
+        # replicated layout at 1M x 50 on 2 / 4 GPUs.  An explicit `shards_per_sweep` keeps the ring schedule.
+        x_all = all_gather_rows(x_local, n, group)
+        if _ops is None:
+            return ops.knn(x_all, k, q0, nq, algo, group=(group if group is not None else dist.group.WORLD))
+        return ops.knn(x_all, k, q0, nq, algo)
     cur = torch.zeros((per, d), dtype=x_local.dtype, device=x_local.device)
     cur[:nq] = x_local
     nxt = torch.empty_like(cur)
