@@ -600,11 +600,11 @@ def run_ours(args) -> None:
     ring = None
     if world > 1 and not args.skip_ring and args.exchange != "ring":
         xl = x_dev[q0:q0 + nq].contiguous()
-        ms_ring, _ = timed(lambda: make_knn_ring(xl, n, k, algo=args.algo), 2, 1)
+        ms_ring, _ = timed(lambda: make_knn_ring(xl, n, k, algo=args.algo), 5, 3)
         r_idx, r_dist = make_knn_ring(xl, n, k, algo=args.algo)
         same = torch.tensor([int(torch.equal(r_idx, idx_s) and torch.equal(r_dist, dist_s))], device=dev)
         # the ring schedule proper (what a matrix beyond one GPU's memory pays): one foreign shard per sweep
-        ms_ring1, _ = timed(lambda: make_knn_ring(xl, n, k, algo=args.algo, shards_per_sweep=1), 2, 1)
+        ms_ring1, _ = timed(lambda: make_knn_ring(xl, n, k, algo=args.algo, shards_per_sweep=1), 5, 3)
         r1_idx, r1_dist = make_knn_ring(xl, n, k, algo=args.algo, shards_per_sweep=1)
         same &= int(torch.equal(r1_idx, idx_s) and torch.equal(r1_dist, dist_s))
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
@@ -613,7 +613,7 @@ def run_ours(args) -> None:
                         "sweep ranks the own rows (no running lists, no merges); ms_knn_one_shard_per_sweep: the ring "
                         "schedule (isend/irecv of the shard overlapped with the step's sweep, running top-k merge)",
                 "ms_knn": ms_ring, "ms_knn_one_shard_per_sweep": ms_ring1,
-                "ms_knn_replicated_layout": max_over_ranks(ms_knn), "steps": 2, "warmup": 1,
+                "ms_knn_replicated_layout": max_over_ranks(ms_knn), "steps": 5, "warmup": 3,
                 "identical_to_replicated_layout": bool(same.item()),
                 "note": "a sweep pruned by the cell bounds costs about the same per query block whatever the database "
                         "size, so the number of sweeps is what counts (DESIGN.md section 6)"}
@@ -648,13 +648,13 @@ def run_ours(args) -> None:
             a0, an = shard_bounds(args.c3_rows, world, rank)
             xl = xs[a0:a0 + an].contiguous()
             i_rep, d_rep = knn_step(xs, 100, a0, an)
-            ms_rep, _ = timed(lambda: knn_step(xs, 100, a0, an), 1, 0)
-            ms_ring3, _ = timed(lambda: make_knn_ring(xl, args.c3_rows, 100, algo=args.algo), 1, 1)
+            ms_rep, _ = timed(lambda: knn_step(xs, 100, a0, an), 2, 1)
+            ms_ring3, _ = timed(lambda: make_knn_ring(xl, args.c3_rows, 100, algo=args.algo), 2, 2)
             r_idx, r_dist = make_knn_ring(xl, args.c3_rows, 100, algo=args.algo)
             same = torch.tensor([int(torch.equal(r_idx, i_rep) and torch.equal(r_dist, d_rep))], device=dev)
             dist.all_reduce(same, op=dist.ReduceOp.MIN)
             sub["config_c3"]["ring"] = {"ms_knn": ms_ring3, "ms_knn_replicated_layout": ms_rep,
-                                        "ratio": ms_ring3 / ms_rep, "steps": 1, "warmup": 1,
+                                        "ratio": ms_ring3 / ms_rep, "steps": 2, "warmup": 2,
                                         "identical_to_replicated_layout": bool(same.item()),
                                         "what": "make_knn_ring (every rank holds only its n/N rows) beside the replicated "
                                                 "layout, graph only, max over ranks"}
