@@ -43,7 +43,7 @@ struct VsParams {
   VsLayer layer[VS_MAX_LAYERS];  // encoder layers, mu head, logvar head, decoder layers
   int n_enc, n_dec;
   int B, D, L, nq, P;
-  int off_x, off_eps, off_z, off_dzq, off_t, off_w;  // shared-memory offsets (floats)
+  int off_x, off_eps, off_z, off_dzq, off_t, off_w, off_w2;  // shared-memory offsets (floats); two weight buffers
   float lam_recon, lam_kldiv, lam_mds;
   const float *x, *eps;
   float *gpart;  // (gridDim.x, P)
@@ -63,17 +63,39 @@ __device__ __forceinline__ void act_into(float *T, const float *U, int dim) {
   }
 }
 
-// the layer's weight matrix (out x in, row-major) and bias into shared memory; the caller synchronises
-__device__ __forceinline__ void stage_weights(const VsLayer &ly, float *Wsm) {
+// A layer's weight matrix (out x in, row-major) and bias into shared memory, with cp.async (round 2c): the weights of
+// the NEXT layer travel into the other of two buffers while the current layer is computed -- the step is a chain of
+// ~22 short phases on 16 SMs, and every phase used to begin with an exposed L2 round trip for its weights (a plain
+// load + store staging loop in front of a barrier).
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void stage_weights_async(const VsLayer &ly, float *Wsm) {
   const int nw = ly.in * ly.out;
+  const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(Wsm));
   if ((nw % 4 == 0) && ((reinterpret_cast<uintptr_t>(ly.W) & 15) == 0)) {
-    const float4 *src = reinterpret_cast<const float4 *>(ly.W);
-    float4 *dst = reinterpret_cast<float4 *>(Wsm);
-    for (int i = threadIdx.x; i < nw / 4; i += VS_THREADS) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < nw / 4; i += VS_THREADS) cp_async_16(dst + 16u * i, ly.W + 4 * i);
   } else {
-    for (int i = threadIdx.x; i < nw; i += VS_THREADS) Wsm[i] = __ldg(ly.W + i);
+    for (int i = threadIdx.x; i < nw; i += VS_THREADS) cp_async_4(dst + 4u * i, ly.W + i);
   }
-  for (int i = threadIdx.x; i < ly.out; i += VS_THREADS) Wsm[nw + i] = __ldg(ly.b + i);
+  for (int i = threadIdx.x; i < ly.out; i += VS_THREADS) cp_async_4(dst + 4u * (nw + i), ly.b + i);
+}
+// the order in which the step needs its layers' weights: forward through all layers, then backward through the decoder,
+// the two heads, and the encoder down to its second layer (the first layer's backward needs no weights)
+__device__ __forceinline__ int vs_seq(const VsParams &p, int si) {
+  const int nl = p.n_enc + 2 + p.n_dec;
+  if (si < nl) return si;
+  si -= nl;
+  if (si < p.n_dec) return nl - 1 - si;
+  si -= p.n_dec;
+  if (si < 2) return p.n_enc + si;
+  si -= 2;
+  if (si < p.n_enc - 1) return p.n_enc - 1 - si;
+  return -1;
 }
 
 // out[o][lane] = b[o] + sum_i W[o][i] * in[i][lane]; a warp computes four outputs at a time.  Wsm: staged weights.
@@ -207,6 +229,24 @@ __global__ void __launch_bounds__(VS_THREADS, 1) vae_step_kernel(const __grid_co
   // local row r = a * 8 + ql  <->  batch row a * nq + 8 * blockIdx.x + ql   (quartet 8 * blockIdx.x + ql, member a)
   const int q0 = blockIdx.x * 8;
 
+  // ---- weights: double-buffered, prefetched one layer ahead.  acquire(li) replaces the synchronous staging of layer li
+  // (the caller's __syncthreads follows it); prefetch() right after that barrier starts the next layer's copy into the
+  // buffer the PREVIOUS phase read, which every thread has left by then.
+  float *const Wbuf0 = sm + p.off_w, *const Wbuf1 = sm + p.off_w2;
+  int w_si = 0, w_cur = 0;
+  stage_weights_async(p.layer[0], Wbuf0);
+  auto acquire = [&](int li) -> float * {
+    if (vs_seq(p, w_si) != li) __trap();  // the call order and vs_seq must agree
+    cp_async_wait_all();
+    return w_cur ? Wbuf1 : Wbuf0;
+  };
+  auto prefetch = [&]() {
+    ++w_si;
+    w_cur ^= 1;
+    const int nx = vs_seq(p, w_si);
+    if (nx >= 0) stage_weights_async(p.layer[nx], w_cur ? Wbuf1 : Wbuf0);
+  };
+
   // ---- load the batch rows (transposed); rows of quartets beyond nq are zero and take no part
   for (int idx = threadIdx.x; idx < VS_R * D; idx += VS_THREADS) {
     const int r = idx / D, c = idx - r * D;
@@ -221,25 +261,28 @@ __global__ void __launch_bounds__(VS_THREADS, 1) vae_step_kernel(const __grid_co
   __syncthreads();
 
   // ---- encoder (every layer: activation of the previous one into T, weights into Wsm, then the product)
-  float *Wsm = sm + p.off_w;
+  float *Wsm;
   for (int l = 0; l < p.n_enc; ++l) {
     const float *in = X;
     if (l > 0) {
       act_into(T, sm + p.layer[l - 1].ubuf, p.layer[l - 1].out);
       in = T;
     }
-    stage_weights(p.layer[l], Wsm);
+    Wsm = acquire(l);
     __syncthreads();
+    prefetch();
     gemm_fwd(p.layer[l], Wsm, in, sm + p.layer[l].ubuf, warp, lane);
     __syncthreads();
   }
   act_into(T, sm + p.layer[p.n_enc - 1].ubuf, p.layer[p.n_enc - 1].out);
-  stage_weights(ly_mu, Wsm);
+  Wsm = acquire(p.n_enc);
   __syncthreads();
+  prefetch();
   gemm_fwd(ly_mu, Wsm, T, MU, warp, lane);
   __syncthreads();
-  stage_weights(ly_lv, Wsm);
+  Wsm = acquire(p.n_enc + 1);
   __syncthreads();
+  prefetch();
   gemm_fwd(ly_lv, Wsm, T, LV, warp, lane);
   __syncthreads();
   // z = mu + eps * exp(logvar / 2)   (network.py:113-130)
@@ -256,8 +299,9 @@ __global__ void __launch_bounds__(VS_THREADS, 1) vae_step_kernel(const __grid_co
       act_into(T, sm + p.layer[li - 1].ubuf, p.layer[li - 1].out);
       in = T;
     }
-    stage_weights(p.layer[li], Wsm);
+    Wsm = acquire(li);
     __syncthreads();
+    prefetch();
     gemm_fwd(p.layer[li], Wsm, in, sm + p.layer[li].ubuf, warp, lane);
     __syncthreads();
   }
@@ -375,8 +419,9 @@ __global__ void __launch_bounds__(VS_THREADS, 1) vae_step_kernel(const __grid_co
       act_into(T, sm + p.layer[li - 1].ubuf, p.layer[li - 1].out);
       A = T;
     }
-    stage_weights(p.layer[li], Wsm);
+    Wsm = acquire(li);
     __syncthreads();
+    prefetch();
     const float *dU = sm + p.layer[li].ubuf;
     gemm_dw(p.layer[li], dU, A, g, warp, lane);
     if (l > 0) gemm_dx<0>(p.layer[li], Wsm, dU, sm + p.layer[li - 1].ubuf, warp, lane);
@@ -397,8 +442,9 @@ __global__ void __launch_bounds__(VS_THREADS, 1) vae_step_kernel(const __grid_co
     }
   }
   act_into(T, sm + p.layer[p.n_enc - 1].ubuf, p.layer[p.n_enc - 1].out);
-  stage_weights(ly_mu, Wsm);
+  Wsm = acquire(p.n_enc);
   __syncthreads();
+  prefetch();
   gemm_dw(ly_mu, MU, T, g, warp, lane);
   gemm_dw(ly_lv, LV, T, g, warp, lane);
   {
@@ -407,8 +453,9 @@ __global__ void __launch_bounds__(VS_THREADS, 1) vae_step_kernel(const __grid_co
     float *ACC = X;
     gemm_dx<2>(ly_mu, Wsm, MU, ACC, warp, lane);
     __syncthreads();
-    stage_weights(ly_lv, Wsm);
+    Wsm = acquire(p.n_enc + 1);
     __syncthreads();
+    prefetch();
     gemm_dx<1>(ly_lv, Wsm, LV, ACC, warp, lane);
     __syncthreads();
     float *U = sm + p.layer[p.n_enc - 1].ubuf;
@@ -423,7 +470,7 @@ __global__ void __launch_bounds__(VS_THREADS, 1) vae_step_kernel(const __grid_co
     const float *A;
     if (l > 0) {
       act_into(T, sm + p.layer[l - 1].ubuf, p.layer[l - 1].out);
-      stage_weights(p.layer[l], Wsm);
+      Wsm = acquire(l);
       A = T;
     } else {
       for (int idx = threadIdx.x; idx < VS_R * D; idx += VS_THREADS) {
@@ -434,6 +481,7 @@ __global__ void __launch_bounds__(VS_THREADS, 1) vae_step_kernel(const __grid_co
       A = X;
     }
     __syncthreads();
+    if (l > 0) prefetch();
     const float *dU = sm + p.layer[l].ubuf;
     gemm_dw(p.layer[l], dU, A, g, warp, lane);
     if (l > 0) gemm_dx<0>(p.layer[l], Wsm, dU, sm + p.layer[l - 1].ubuf, warp, lane);
@@ -512,6 +560,8 @@ int launch_vae_step(const float *const *w_ptrs, const float *const *b_ptrs, cons
     for (int l = 0; l < n_layers; ++l) wmax = std::max(wmax, in_dims[l] * out_dims[l] + out_dims[l]);
     off = (off + 3) / 4 * 4;
     p.off_w = off;
+    off += (wmax + 3) / 4 * 4;
+    p.off_w2 = off;  // second buffer: the next layer's weights arrive (cp.async) while this layer is computed
     off += (wmax + 3) / 4 * 4;
   }
   // shape checks: the chain must be consistent
