@@ -251,6 +251,8 @@ __global__ void __launch_bounds__(QT_THREADS) quartet_fwd_kernel(
 // gradient rows written by that lane.  Same arithmetic per quartet, 2.8x fewer instructions.  Used when there are enough
 // quartets to fill the GPU that way (launch_quartet_fwd); training-size batches keep the kernel above (latency counts
 // there, not issue slots).
+// (compiled for 4 CTAs per SM = 64 registers, the compiler's own choice; measured at B = 2^20: forcing 5 CTAs (48
+// registers, 160 bytes of spills) 84.9 us, 6 CTAs (40 registers) 99.4 us, no bound on the registers 92.2 us, against 70.4)
 template <int MHD, int MLD, bool VEC2>
 __global__ void __launch_bounds__(QT_THREADS) quartet_fwd_big_kernel(
     const float *__restrict__ x, const float *__restrict__ z, int64_t B, int D, int L,
